@@ -1,0 +1,223 @@
+/*
+ * tsdf_b200.h — C ABI of the B200-native track + fuse hot path (libtsdf_b200.so).
+ *
+ * Drop-in boundary for the per-frame path of mees/tracking_sdf (Bylow et al. 2013).  The
+ * reference has no FFI/plugin layer: the boundary is the public surface of its two C++
+ * classes, `SDF` and `CameraTracking`, as called from `SDF_Reconstruction` (the ROS node).
+ * Each entry point below names the reference interface it replaces; paths are relative to
+ * /root/reference/src/.  The C++ classes with the reference's own method names are in
+ * include/tracking_sdf_b200.hpp (header-only, over this ABI); INTEGRATION.md shows the
+ * binding a maintainer of the ROS node would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no exceptions cross the ABI; every call returns a
+ *    tsdf_status (0 = ok) and tsdf_last_error() gives the text of the last failure.
+ *  - R is a row-major 3x3 camera->world rotation, t the camera centre in world (the
+ *    reference's `rot` / `trans`, camera_tracking.h:42-47).  K is row-major 3x3.
+ *  - depth images are float32 metres along the camera z axis, row-major [height][width],
+ *    NaN / inf / <= 0 = invalid.  `mem` says whether the pointer is host or device memory.
+ *  - voxel (i,j,k) = (x,y,z) index exactly as in the reference (sdf.h:113-157).  The device
+ *    layout is private (x-fastest, {D,W} interleaved); grids cross the ABI in one of the
+ *    two documented layouts of tsdf_layout.
+ *  - there is NO CPU fallback: every compute entry point needs a CUDA device and fails
+ *    with TSDF_ERR_CUDA otherwise.
+ */
+#ifndef TSDF_B200_H_
+#define TSDF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSDF_ABI_VERSION 1
+
+typedef enum tsdf_status {
+    TSDF_OK = 0,
+    TSDF_ERR_BAD_ARG = 1,
+    TSDF_ERR_NO_INTRINSICS = 2,   /* the reference exit(0)s here, sdf.cpp:227-229 */
+    TSDF_ERR_CUDA = 3,
+    TSDF_ERR_TRACKING_LOST = 4,   /* singular normal equations / non-finite twist (unguarded at camera_tracking.cpp:191) */
+    TSDF_ERR_HALO = 5,            /* sharded: a tracking sample needed a voxel outside slab+halo */
+    TSDF_ERR_NOMEM = 6
+} tsdf_status;
+
+typedef enum tsdf_metric {
+    TSDF_POINT_TO_PLANE = 0,      /* active in the reference, sdf.cpp:272, sdf.h:177-181 */
+    TSDF_POINT_TO_POINT = 1       /* defined, call commented out, sdf.cpp:267, sdf.h:169-172 */
+} tsdf_metric;
+
+typedef enum tsdf_mem { TSDF_HOST = 0, TSDF_DEVICE = 1 } tsdf_mem;
+
+typedef enum tsdf_layout {
+    TSDF_LAYOUT_REFERENCE = 0,    /* separate D[], W[]; z-fastest idx = m*m*i + m*j + k (sdf.h:120) */
+    TSDF_LAYOUT_XFASTEST = 1      /* separate D[], W[]; x-fastest idx = (k*m + j)*m + i */
+} tsdf_layout;
+
+/* Replaces the ctor arguments of SDF (sdf.h:78-79) and CameraTracking
+ * (camera_tracking.cpp:3-4), which the node hard-codes at sdf_reconstruction.cpp:83-88. */
+typedef struct tsdf_config {
+    int32_t m;                          /* voxels per axis (256)                       */
+    float width, height, depth;         /* metric extents x,y,z (6, 6, 3.5)             */
+    double origin[3];                   /* grid corner in world (-3,-3,-0.5)            */
+    float distance_delta;               /* truncation delta (0.3)                       */
+    float distance_epsilon;             /* weight plateau epsilon (0.025)               */
+    int32_t gauss_newton_max_iteration; /* 20                                           */
+    float maximum_twist_diff;           /* signed stop threshold 0.001; -INFINITY = fixed iteration count */
+    float v_h;                          /* translational step in voxels (1.0)           */
+    float w_h;                          /* rotational step in rad (0.01)                */
+    int32_t pixel_stride;               /* 3 (camera_tracking.cpp:162-163)              */
+    int32_t metric;                     /* tsdf_metric                                  */
+    int32_t image_width, image_height;  /* 640 x 480                                    */
+    int32_t device;                     /* CUDA device ordinal                          */
+    /* z-slab sharding.  n_shards = 1: the whole volume on `device`.     */
+    int32_t n_shards;                   /* slabs the volume is cut into along z         */
+    int32_t shard_rank;                 /* which slab this handle owns                  */
+    int32_t halo;                       /* extra z layers kept (and fused) on each side; <0 = auto */
+    int32_t reserved[4];
+} tsdf_config;
+
+typedef struct tsdf_track_stats {
+    int32_t iterations;                 /* GN iterations executed                       */
+    int32_t stopped;                    /* the signed stop test fired                   */
+    int32_t n_valid;                    /* pixels in the last iteration's sums (all shards) */
+    int32_t n_oob;                      /* pixels whose centre sample left the volume   */
+    int32_t singular;                   /* normal equations singular / twist non-finite */
+    int32_t halo_miss;                  /* sharded: samples that needed a voxel we do not hold */
+    double residual;                    /* sum psi^2 of the last iteration              */
+    double A[36];                       /* last iteration's J^T J (row-major, symmetric) */
+    double b[6];                        /* last iteration's J^T r                       */
+    double twist[6];                    /* last solved twist (v, w)                     */
+} tsdf_track_stats;
+
+typedef struct tsdf_handle_s* tsdf_handle;
+
+int32_t     tsdf_abi_version(void);
+const char* tsdf_last_error(void);
+int32_t     tsdf_device_count(void);
+
+void        tsdf_default_config(tsdf_config* cfg);          /* sdf_reconstruction.cpp:83-88 */
+
+/* SDF::SDF + CameraTracking::CameraTracking (sdf.cpp:8-51, camera_tracking.cpp:3-18):
+ * allocates the grid in HBM, D = width+height+depth, W = 0, pose = the reference's initial pose. */
+tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out);
+tsdf_status tsdf_destroy(tsdf_handle h);
+tsdf_status tsdf_reset(tsdf_handle h);                      /* re-run the grid init of sdf.cpp:28-31 */
+tsdf_status tsdf_get_config(tsdf_handle h, tsdf_config* cfg);
+
+/* CameraTracking::camera_info_cb (camera_tracking.cpp:22-36) */
+tsdf_status tsdf_set_intrinsics(tsdf_handle h, const double K[9]);
+
+/* CameraTracking::set_camera_transformation (camera_tracking.cpp:59-65) and the public
+ * rot / trans / rot_inv / rot_inv_trans members the node reads (sdf_reconstruction.cpp:71). */
+tsdf_status tsdf_set_pose(tsdf_handle h, const double R[9], const double t[3]);
+tsdf_status tsdf_get_pose(tsdf_handle h, double R[9], double t[3]);
+tsdf_status tsdf_get_pose_inv(tsdf_handle h, double Rinv[9], double tinv[3]);
+
+/* CameraTracking::estimate_new_position (camera_tracking.cpp:66-245): Gauss-Newton on the
+ * SDF from the current pose; returns the new pose.  stats may be NULL. */
+tsdf_status tsdf_track(tsdf_handle h, const float* depth, int32_t mem,
+                       double R_out[9], double t_out[3], tsdf_track_stats* stats);
+
+/* SDF::update (sdf.cpp:224-305, D/W part).  R,t = NULL,NULL: fuse at the current pose
+ * (what the node does, sdf_reconstruction.cpp:74); otherwise set the pose first (the
+ * _useGroundTruth branch, sdf_reconstruction.cpp:61-66).  n_updated may be NULL. */
+tsdf_status tsdf_fuse(tsdf_handle h, const float* depth, int32_t mem,
+                      const double R[9], const double t[3], int64_t* n_updated);
+
+/* kinect_callback's else-branch + update in one call (sdf_reconstruction.cpp:69-74):
+ * track then fuse at the tracked pose; the pose never visits the host in between. */
+tsdf_status tsdf_track_and_fuse(tsdf_handle h, const float* depth, int32_t mem,
+                                double R_out[9], double t_out[3],
+                                tsdf_track_stats* stats, int64_t* n_updated);
+
+/* Asynchronous variant for streaming: enqueue track+fuse of a DEVICE-resident frame; the
+ * pose of frame `slot` lands in an internal pinned ring (capacity tsdf_pose_ring_capacity)
+ * and is read back after tsdf_sync with tsdf_read_pose_ring.  track = 0: fuse only. */
+tsdf_status tsdf_enqueue_frame(tsdf_handle h, const float* depth_dev, int32_t track, int32_t slot);
+tsdf_status tsdf_sync(tsdf_handle h);
+int32_t     tsdf_pose_ring_capacity(void);
+tsdf_status tsdf_read_pose_ring(tsdf_handle h, int32_t slot, double R[9], double t[3], tsdf_track_stats* stats);
+
+/* One linearisation at the current pose with NO pose update (the body of the loop at
+ * camera_tracking.cpp:81-189): A row-major 6x6, b 6.  For parity tests. */
+tsdf_status tsdf_linearize(tsdf_handle h, const float* depth, int32_t mem,
+                           double A[36], double b[6], tsdf_track_stats* stats);
+/* per-pixel records of that linearisation in the reference's loop order (column outer, row
+ * inner): J [n*6], psi [n], flag [n] (0 NaN point, 1 ok, 2 out of volume, 3 not interpolated).
+ * n must equal tsdf_num_strided_pixels(). */
+int32_t     tsdf_num_strided_pixels(tsdf_handle h);
+tsdf_status tsdf_linearize_pixels(tsdf_handle h, const float* depth, int32_t mem,
+                                  float* J, float* psi, uint8_t* flag);
+
+/* K1 (not in the reference; upstream ROS depth_image_proc + PCL normals): organised cloud
+ * and normals, each [height*width*3] floats on the host, NaN = invalid. normals may be NULL. */
+tsdf_status tsdf_backproject(tsdf_handle h, const float* depth, int32_t mem, float* cloud, float* normals);
+
+/* SDF::interpolate_distance (sdf.cpp:127-163) evaluated on the device: pts n x 3 doubles in
+ * continuous voxel coordinates (host), out n floats, ok n bytes (host). */
+tsdf_status tsdf_interpolate_distance(tsdf_handle h, int64_t n, const double* pts, float* out, uint8_t* ok);
+
+/* Grid accessors: SDF::get_number_of_voxels (sdf.h:107) and the raw D/W arrays the reference
+ * hands to its mesher (sdf.cpp:47-48).  Host buffers hold this handle's stored z range
+ * [k_begin, k_end) (the whole grid when n_shards = 1) in the requested layout. */
+int64_t     tsdf_number_of_voxels(tsdf_handle h);
+tsdf_status tsdf_stored_range(tsdf_handle h, int32_t* k_begin, int32_t* k_end, int32_t* k_own_begin, int32_t* k_own_end);
+tsdf_status tsdf_download(tsdf_handle h, float* D, float* W, int32_t layout);
+tsdf_status tsdf_upload(tsdf_handle h, const float* D, const float* W, int32_t layout);
+/* device pointer to the private interleaved store: float2{D,W} at ((k-k_begin)*m + j)*m + i */
+tsdf_status tsdf_device_grid(tsdf_handle h, void** dw_interleaved, int64_t* n_voxels_stored);
+
+/* Pure index / coordinate maps, identical (i,j,k) semantics to sdf.h:113-157 */
+int64_t     tsdf_get_array_index(tsdf_handle h, int32_t i, int32_t j, int32_t k);        /* reference (z-fastest) index or -1 */
+void        tsdf_get_voxel_coordinates_idx(tsdf_handle h, int64_t idx, int32_t ijk[3]);
+void        tsdf_get_voxel_coordinates(tsdf_handle h, const double g[3], double v[3]);
+void        tsdf_get_global_coordinates(tsdf_handle h, const int32_t ijk[3], double g[3]);
+
+/* eigen_utils::direct_exponential_map (eigen_utils.cpp:85-128) evaluated on the device */
+tsdf_status tsdf_exp_map(tsdf_handle h, const double twist[6], double R[9], double t[3]);
+
+/* Device-memory helpers so callers without a CUDA runtime binding (ctypes, cgo) can keep
+ * frames resident in HBM. */
+tsdf_status tsdf_dev_alloc(tsdf_handle h, int64_t bytes, void** dev_ptr);
+tsdf_status tsdf_dev_free(tsdf_handle h, void* dev_ptr);
+tsdf_status tsdf_dev_upload(tsdf_handle h, void* dev_dst, const void* host_src, int64_t bytes);
+tsdf_status tsdf_host_alloc_pinned(int64_t bytes, void** host_ptr);
+tsdf_status tsdf_host_free_pinned(void* host_ptr);
+
+/* Timing of the last enqueued work, CUDA events on the handle's stream (milliseconds):
+ * out[0] prep (back-projection+normals), out[1] tracking (all GN iterations), out[2] fusion. */
+tsdf_status tsdf_last_stage_ms(tsdf_handle h, float out[3]);
+tsdf_status tsdf_event_timer_begin(tsdf_handle h);              /* record start on the stream   */
+tsdf_status tsdf_event_timer_end(tsdf_handle h, float* ms);     /* record stop, sync, elapsed   */
+int64_t     tsdf_kernel_launch_count(tsdf_handle h);            /* kernels launched so far      */
+tsdf_status tsdf_flush_l2(tsdf_handle h);                       /* overwrite a >L2-sized scratch buffer */
+
+/* Sharded tracking across processes (one process per GPU): each rank exports a handle to
+ * its 30-double mailbox, the caller exchanges them (e.g. torch.distributed all_gather) and
+ * attaches all of them; the per-iteration all-reduce of the normal equations then runs
+ * inside the tracking kernels over NVLink peer stores, summed in rank order. */
+#define TSDF_IPC_HANDLE_BYTES 64
+tsdf_status tsdf_shard_ipc_export(tsdf_handle h, uint8_t out[TSDF_IPC_HANDLE_BYTES]);
+tsdf_status tsdf_shard_ipc_attach(tsdf_handle h, int32_t world, const uint8_t* handles /* world x 64 */);
+/* Same, for shards living in one process: `handles` ordered by shard_rank.  Shards on
+ * different devices exchange in-kernel over peer memory; shards that share one device
+ * (testing the slab logic on a single GPU) run on one stream with a deferred rank-order sum. */
+tsdf_status tsdf_shard_attach_local(tsdf_handle* handles, int32_t world);
+/* Group entry points for in-process shards: the same operations as tsdf_set_pose /
+ * tsdf_linearize / tsdf_track_and_fuse, issued to every shard in lock step.  depth is a HOST
+ * buffer, or a device buffer when all shards share one device.  Results are shard 0's (all
+ * shards hold identical poses); n_updated sums the voxels each shard owns. */
+tsdf_status tsdf_group_set_intrinsics(tsdf_handle* handles, int32_t world, const double K[9]);
+tsdf_status tsdf_group_set_pose(tsdf_handle* handles, int32_t world, const double R[9], const double t[3]);
+tsdf_status tsdf_group_linearize(tsdf_handle* handles, int32_t world, const float* depth, int32_t mem,
+                                 double A[36], double b[6], tsdf_track_stats* stats);
+tsdf_status tsdf_group_frame(tsdf_handle* handles, int32_t world, const float* depth, int32_t mem,
+                             int32_t track, int32_t fuse, double R_out[9], double t_out[3],
+                             tsdf_track_stats* stats, int64_t* n_updated);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSDF_B200_H_ */

@@ -1,0 +1,194 @@
+/*
+ * core_emul.cpp — HOST compile of the kernels' __host__ __device__ core (tsdf_core.cuh).
+ *
+ * TEST INFRASTRUCTURE ONLY (tests/ -m "not gpu").  There is no GPU in the build container, so
+ * this lets the CPU suite check the exact-arithmetic building blocks the CUDA kernels are made
+ * of — the hoisted camera-space sums, the scan-line clip, the per-sample interpolation, the
+ * J/psi construction, the 6x6 solve / exp map / pose update — against the oracle, bit for bit.
+ * The loops below mirror the kernels' work decomposition serially.  It is never loaded by the
+ * tracking_sdf_b200 package and is not a fallback.
+ */
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "tsdf_core.cuh"
+
+using namespace tsdf;
+
+extern "C" {
+
+/* fills a GridParams the same way tsdf_abi.cu:build_params does (kept in sync by
+ * tests/test_core_emul.py::test_params_match_oracle_constants) */
+void emul_params(int m, float width, float height, float depth, const double origin[3], float delta, float eps,
+                 float v_h, float w_h, int stride, int metric, int img_w, int img_h, const double K[9],
+                 float max_twist_diff, int max_iter, GridParams* g) {
+    memset(g, 0, sizeof *g);
+    g->m = m; g->ks0 = 0; g->ks1 = m; g->ko0 = 0; g->ko1 = m;
+    g->metric = metric; g->img_w = img_w; g->img_h = img_h; g->stride = stride;
+    g->ni = (img_w + stride - 1) / stride; g->nj = (img_h + stride - 1) / stride;
+    g->m_div_height = m / height; g->m_div_width = m / width; g->m_div_depth = m / depth;
+    g->vs_x = width / ((float)m); g->vs_y = height / ((float)m); g->vs_z = depth / ((float)m);
+    g->delta = delta; g->eps = eps; g->v_h = v_h; g->w_h = w_h;
+    const float v_h2 = 2 * v_h;
+    g->v_h2_width = v_h2 / g->m_div_width; g->v_h2_height = v_h2 / g->m_div_height; g->v_h2_depth = v_h2 / g->m_div_depth;
+    g->two_w_h = 2 * (w_h);
+    g->max_twist_diff = max_twist_diff; g->max_iter = max_iter;
+    for (int q = 0; q < 3; q++) g->origin[q] = origin[q];
+    for (int q = 0; q < 9; q++) g->K[q] = K[q];
+    g->k_simple = (K[1] == 0.0 && K[3] == 0.0 && K[6] == 0.0 && K[7] == 0.0 && K[8] == 1.0) ? 1 : 0;
+}
+int emul_sizeof_params() { return (int)sizeof(GridParams); }
+int emul_sizeof_pose() { return (int)sizeof(PoseState); }
+
+void emul_pose_set(PoseState* p, const double R[9], const double t[3]) { memset(p, 0, sizeof *p); pose_set(*p, R, t); }
+void emul_pose_get(const PoseState* p, double R[9], double t[3], double Rinv[9], double tinv[3]) {
+    memcpy(R, p->R, sizeof p->R); memcpy(t, p->t, sizeof p->t);
+    memcpy(Rinv, p->Rinv, sizeof p->Rinv); memcpy(tinv, p->tinv, sizeof p->tinv);
+}
+
+/* K1 */
+void emul_prep(const GridParams* g, const float* depth, float* pix /* [h*w*4] */) {
+    const K1Params kp = k1_params(g->K);
+    const float qnan = std::nanf("");
+    for (int v = 0; v < g->img_h; v++)
+        for (int u = 0; u < g->img_w; u++) {
+            const size_t o = (size_t)v * g->img_w + u;
+            const float zc = depth[o];
+            float r[4] = {depth_valid(zc) ? zc : qnan, qnan, qnan, qnan};
+            if (u > 0 && v > 0 && u < g->img_w - 1 && v < g->img_h - 1) {
+                float nx, ny, nz;
+                if (normal_px(kp, u, v, zc, depth[o - 1], depth[o + 1], depth[o - g->img_w], depth[o + g->img_w], nx, ny, nz)) {
+                    r[1] = nx; r[2] = ny; r[3] = nz;
+                }
+            }
+            memcpy(pix + 4 * o, r, sizeof r);
+        }
+}
+void emul_cloud(const GridParams* g, const float* pix, float* cloud, float* normals) {
+    const K1Params kp = k1_params(g->K);
+    for (int o = 0; o < g->img_w * g->img_h; o++) {
+        const int u = o % g->img_w, v = o / g->img_w;
+        float x, y;
+        backproject_px(kp, u, v, pix[4 * o], x, y);
+        cloud[3 * o] = x; cloud[3 * o + 1] = y; cloud[3 * o + 2] = pix[4 * o];
+        normals[3 * o] = pix[4 * o + 1]; normals[3 * o + 2] = pix[4 * o + 3]; normals[3 * o + 1] = pix[4 * o + 2];
+    }
+}
+
+/* grid here: x-fastest interleaved {D,W}, like the device store */
+struct HostFetch {
+    const float* grid; int m;
+    bool operator()(int ci, int cj, int ck, float& d, float& w) const {
+        if ((unsigned)ci >= (unsigned)m || (unsigned)cj >= (unsigned)m || (unsigned)ck >= (unsigned)m) return false;
+        const size_t o = (((size_t)ck * m + cj) * m + ci) * 2;
+        d = grid[o]; w = grid[o + 1];
+        return true;
+    }
+};
+
+void emul_interpolate(const GridParams* g, const float* grid, int64_t n, const double* pts, float* out, uint8_t* ok) {
+    HostFetch f{grid, g->m};
+    for (int64_t q = 0; q < n; q++) {
+        bool is_interp;
+        out[q] = interpolate_distance(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2], f, is_interp);
+        ok[q] = is_interp;
+    }
+}
+
+/* K3, mirroring k_fuse: rows clipped, products hoisted exactly like the kernel.
+ * use_clip = 0 visits every voxel (checks that clipping never drops an accepted voxel). */
+int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const PoseState* pose, int use_clip) {
+    const GridParams& g = *gp;
+    const int m = g.m;
+    const double* Ri = pose->Rinv; const double* ti = pose->tinv;
+    const K1Params kp = k1_params(g.K);
+    int64_t n_updated = 0;
+#pragma omp parallel for reduction(+ : n_updated) schedule(dynamic, 1)
+    for (int k = g.ks0; k < g.ks1; k++) {
+        const double gz = voxel_centre(g.vs_z, k, g.origin[2]);
+        const double pz0 = Ri[2] * gz, pz1 = Ri[5] * gz, pz2 = Ri[8] * gz;
+        for (int j = 0; j < m; j++) {
+            const double gy = voxel_centre(g.vs_y, j, g.origin[1]);
+            const double py0 = Ri[1] * gy, py1 = Ri[4] * gy, py2 = Ri[7] * gy;
+            int ilo = 0, ihi = m;
+            if (use_clip) row_clip(g, Ri, ti, py0, py1, py2, pz0, pz1, pz2, ilo, ihi);
+            for (int x = ilo; x < ihi; x++) {
+                const double gx = voxel_centre(g.vs_x, x, g.origin[0]);
+                const double px0 = Ri[0] * gx, px1 = Ri[3] * gx, px2 = Ri[6] * gx;
+                const double cx = ((px0 + py0) + pz0) + ti[0];
+                const double cy = ((px1 + py1) + pz1) + ti[1];
+                const double cz = ((px2 + py2) + pz2) + ti[2];
+                int iu, iv;
+                if (!fuse_project(g, cx, cy, cz, iu, iv)) continue;
+                const float* rr = pix + 4 * ((size_t)iv * g.img_w + iu);
+                PixRec rec; rec.z = rr[0]; rec.nx = rr[1]; rec.ny = rr[2]; rec.nz = rr[3];
+                float fx_, fy_, dn, wn;
+                backproject_px(kp, iu, iv, rec.z, fx_, fy_);
+                if (!fuse_distance(g, cx, cy, cz, fx_, fy_, rec, dn, wn)) continue;
+                const size_t o = (((size_t)(k - g.ks0) * m + j) * m + x) * 2;
+                fuse_apply(grid[o], grid[o + 1], dn, wn);
+                n_updated++;
+            }
+        }
+    }
+    return n_updated;
+}
+
+/* K2, mirroring k_linearize's lanes serially: per pixel 13 samples, J, psi, flag; sums in double */
+void emul_linearize(const GridParams* gp, const float* grid, const float* pix, const PoseState* pose,
+                    float* J /* [P*6] */, float* psi /* [P] */, uint8_t* flag /* [P] */, double* sums /* [30] */) {
+    const GridParams& g = *gp;
+    double M[7][9];
+    for (int q = 0; q < 9; q++) M[0][q] = pose->R[q];
+    for (int q = 0; q < 6; q++) perturbed_rot(g, pose->R, q, M[1 + q]);
+    const K1Params kp = k1_params(g.K);
+    HostFetch f{grid, g.m};
+    const int P = g.ni * g.nj;
+    for (int q = 0; q < N_SLOTS; q++) sums[q] = 0.0;
+    for (int p = 0; p < P; p++) {
+        const int ii = p / g.nj, jj = p - ii * g.nj;
+        const int u = ii * g.stride, v = jj * g.stride;
+        const float z = pix[4 * ((size_t)v * g.img_w + u)];
+        for (int a = 0; a < 6; a++) J[(size_t)p * 6 + a] = 0.0f;
+        psi[p] = 0.0f;
+        if (!(z == z)) { flag[p] = 0; continue; }
+        float x, y;
+        backproject_px(kp, u, v, z, x, y);
+        float val[13]; bool ok[13]; bool oob = false;
+        for (int s = 0; s < 13; s++) {
+            double vx, vy, vz;
+            sample_coords(g, M[(s < 7) ? 0 : (s - 6)], pose->t, s, (double)x, (double)y, (double)z, vx, vy, vz);
+            if (s == 0) { const double dm = (double)g.m; oob = (vx < 0 || vy < 0 || vz < 0 || vx >= dm || vy >= dm || vz >= dm); }
+            val[s] = interpolate_distance(vx, vy, vz, f, ok[s]);
+        }
+        bool allok = true;
+        for (int s = 0; s < 13; s++) allok = allok && ok[s];
+        const int fl = oob ? 2 : (allok ? 1 : 3);
+        flag[p] = (uint8_t)fl;
+        if (fl == 2) sums[SLOT_NOOB] += 1.0;
+        if (fl != 1) continue;
+        double xv[7];
+        for (int a = 0; a < 6; a++) {
+            const float step = (a == 0) ? g.v_h2_width : (a == 1) ? g.v_h2_height : (a == 2) ? g.v_h2_depth : g.two_w_h;
+            const float Ja = (val[2 * a + 1] - val[2 * a + 2]) / step;
+            J[(size_t)p * 6 + a] = Ja; xv[a] = (double)Ja;
+        }
+        psi[p] = val[0]; xv[6] = (double)val[0];
+        int q = 0;
+        for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) { sums[SLOT_A + q] += xv[r] * xv[c]; q++; }
+        for (int r = 0; r < 6; r++) sums[SLOT_B + r] += xv[6] * xv[r];
+        sums[SLOT_RES] += xv[6] * xv[6];
+        sums[SLOT_NVALID] += 1.0;
+    }
+}
+
+void emul_gn_update(const GridParams* g, PoseState* pose, const double* sums) { gn_update(*g, *pose, sums); }
+void emul_pose_stats(const PoseState* p, int32_t out[4], double twist[6]) {
+    out[0] = p->iterations; out[1] = p->stopped; out[2] = p->singular; out[3] = p->halo_miss;
+    memcpy(twist, p->twist, sizeof p->twist);
+}
+void emul_exp_map(const double twist[6], double R[9], double t[3]) { exp_map(twist, R, t); }
+double emul_weight_exp(double x) { return weight_exp(x); }
+int emul_trunc_f2i(float v) { return trunc_f2i(v); }
+
+}  // extern "C"

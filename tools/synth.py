@@ -1,0 +1,81 @@
+"""Synthetic inputs: fr1/plant camera path + analytic-scene depth frames (host tool)."""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TRAJ = os.path.join(ROOT, "data", "fr1_plant_gt_every4.txt")
+
+# ROS/TUM default intrinsics: fx = fy = 525, cx = 319.5, cy = 239.5
+K_DEFAULT = np.array([525.0, 0.0, 319.5, 0.0, 525.0, 239.5, 0.0, 0.0, 1.0])
+WIDTH, HEIGHT = 640, 480
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(_build.build_synth())
+        dp = ctypes.POINTER(ctypes.c_double)
+        _lib.synth_render_depth.argtypes = [dp, dp, dp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+        _lib.synth_render_depth.restype = None
+        _lib.synth_clearance.argtypes = [dp]
+        _lib.synth_clearance.restype = ctypes.c_double
+    return _lib
+
+
+def quat_to_rot(q):
+    """(qx,qy,qz,qw) -> 3x3 rotation, camera optical frame -> world."""
+    x, y, z, w = q
+    return np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+        [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+        [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], dtype=np.float64)
+
+
+def load_trajectory(path=TRAJ):
+    """-> (stamps [n], R [n,3,3], t [n,3]); pose = camera->world (x_w = R p + t)."""
+    a = np.loadtxt(path, comments="#")
+    stamps = a[:, 0]
+    t = a[:, 1:4].copy()
+    R = np.stack([quat_to_rot(q / np.linalg.norm(q)) for q in a[:, 4:8]])
+    return stamps, R, t
+
+
+def frame_index(i, n):
+    """Ping-pong index so that arbitrarily long runs stay on the (continuous) path."""
+    period = 2 * (n - 1)
+    j = i % period
+    return j if j < n else period - j
+
+
+def render_depth(R, t, K=K_DEFAULT, w=WIDTH, h=HEIGHT, out=None):
+    R = np.ascontiguousarray(R, dtype=np.float64).reshape(9)
+    t = np.ascontiguousarray(t, dtype=np.float64).reshape(3)
+    K = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
+    if out is None:
+        out = np.empty((h, w), dtype=np.float32)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib().synth_render_depth(R.ctypes.data_as(dp), t.ctypes.data_as(dp), K.ctypes.data_as(dp), w, h,
+                             out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    return out
+
+
+def clearance(p):
+    p = np.ascontiguousarray(p, dtype=np.float64).reshape(3)
+    return lib().synth_clearance(p.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+
+
+def render_sequence(n_frames, start=0, K=K_DEFAULT, w=WIDTH, h=HEIGHT, out=None):
+    """-> (depth [n,h,w] float32, R [n,3,3], t [n,3]) along the GT path (ping-pong beyond its end)."""
+    _, Rs, ts = load_trajectory()
+    idx = [frame_index(start + i, len(Rs)) for i in range(n_frames)]
+    if out is None:
+        out = np.empty((n_frames, h, w), dtype=np.float32)
+    for q, i in enumerate(idx):
+        render_depth(Rs[i], ts[i], K, w, h, out[q])
+    return out, Rs[idx].copy(), ts[idx].copy()

@@ -1,0 +1,922 @@
+/*
+ * tsdf_abi.cu — the C ABI of include/tsdf_b200.h: handle management, stream orchestration
+ * of the K1/K2/K3 kernels, accessors.  Host C++ only; no PyTorch, no CPU compute path.
+ */
+#include "tsdf_b200.h"
+#include "tsdf_internal.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace tsdf;
+
+namespace {
+
+thread_local std::string g_err;
+
+constexpr int POSE_RING = 4096;
+constexpr int64_t FLUSH_BYTES = 256ll << 20;   /* > 126 MB L2 */
+
+struct Impl {
+    tsdf_config cfg;
+    GridParams g;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    float2* grid = nullptr;
+    int64_t n_stored = 0;
+    PixRec* pix = nullptr;
+    float* depth_stage = nullptr;
+    PoseState* pose_dev = nullptr;
+    PoseState* pose_pin = nullptr;          /* pinned: D2H landing zone for track results */
+    PoseState* ring_pin = nullptr;          /* pinned pose ring for the async path */
+    double* partials = nullptr;
+    unsigned int* ticket = nullptr;
+    unsigned long long* n_upd_dev = nullptr;
+    unsigned long long* n_upd_pin = nullptr;
+    float* dbgJ = nullptr; float* dbgPsi = nullptr; uint8_t* dbgFlag = nullptr;
+    Mailbox* mailbox = nullptr;
+    ShardLinks links;
+    int exchange_mode = 0;
+    unsigned long long seqno = 0;
+    std::vector<void*> ipc_opened;
+    bool have_K = false;
+    cudaEvent_t ev[4];
+    cudaEvent_t tmr[2];
+    bool stage_valid = false;
+    int lin_blocks = 0, px_per_block = 0, fuse_blocks = 0;
+    int64_t launches = 0;
+    float* flush_buf = nullptr;
+    double* scratch_d = nullptr;            /* 32 doubles */
+};
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return TSDF_ERR_CUDA;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+tsdf_status bad(const char* msg) { g_err = msg; return TSDF_ERR_BAD_ARG; }
+
+Impl* I(tsdf_handle h) { return reinterpret_cast<Impl*>(h); }
+
+/* the fp32/fp64 constants exactly as the reference's constructors build them */
+void build_params(const tsdf_config& c, GridParams& g) {
+    memset(&g, 0, sizeof g);
+    g.m = c.m;
+    g.metric = c.metric;
+    g.img_w = c.image_width; g.img_h = c.image_height;
+    g.stride = c.pixel_stride;
+    g.ni = (c.image_width + c.pixel_stride - 1) / c.pixel_stride;
+    g.nj = (c.image_height + c.pixel_stride - 1) / c.pixel_stride;
+    g.m_div_height = c.m / c.height;                       /* sdf.cpp:19-21 */
+    g.m_div_width = c.m / c.width;
+    g.m_div_depth = c.m / c.depth;
+    g.vs_x = c.width / ((float)c.m);                       /* sdf.h:154-156 */
+    g.vs_y = c.height / ((float)c.m);
+    g.vs_z = c.depth / ((float)c.m);
+    g.delta = c.distance_delta; g.eps = c.distance_epsilon;
+    g.v_h = c.v_h; g.w_h = c.w_h;                          /* camera_tracking.cpp:11-17 */
+    const float v_h2 = 2 * c.v_h;
+    g.v_h2_width = v_h2 / g.m_div_width;
+    g.v_h2_height = v_h2 / g.m_div_height;
+    g.v_h2_depth = v_h2 / g.m_div_depth;
+    g.two_w_h = 2 * (c.w_h);
+    g.max_twist_diff = c.maximum_twist_diff;
+    g.max_iter = c.gauss_newton_max_iteration;
+    for (int q = 0; q < 3; q++) g.origin[q] = c.origin[q];
+}
+
+/* z-slab partition: rank r owns [r*m/G, (r+1)*m/G); it also stores and
+ * fuses `halo` layers on each side so the tracker's stencil never leaves local memory. */
+void slab_range(const tsdf_config& c, int& ko0, int& ko1, int& ks0, int& ks1, int& halo) {
+    const int G = c.n_shards < 1 ? 1 : c.n_shards;
+    ko0 = (int)(((int64_t)c.m * c.shard_rank) / G);
+    ko1 = (int)(((int64_t)c.m * (c.shard_rank + 1)) / G);
+    halo = c.halo;
+    if (G == 1) halo = 0;
+    else if (halo < 0) {
+        /* centre cell (+1), +-v_h voxels, and the rotational perturbation: w_h * r_max metres
+         * along z, r_max = the volume's diagonal (no back-projected point can be further) */
+        const double diag = sqrt((double)c.width * c.width + (double)c.height * c.height + (double)c.depth * c.depth);
+        const double vz = (double)c.depth / c.m;
+        halo = 2 + (int)ceil(c.v_h) + (int)ceil(c.w_h * diag / vz);
+    }
+    ks0 = ko0 - halo < 0 ? 0 : ko0 - halo;
+    ks1 = ko1 + halo > c.m ? c.m : ko1 + halo;
+}
+
+tsdf_status upload_pose(Impl* p, const PoseState& ps) {
+    memcpy(p->pose_pin, &ps, sizeof ps);
+    CK(cudaMemcpyAsync(p->pose_dev, p->pose_pin, sizeof ps, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return TSDF_OK;
+}
+tsdf_status fetch_pose(Impl* p) {
+    CK(cudaMemcpyAsync(p->pose_pin, p->pose_dev, sizeof(PoseState), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return TSDF_OK;
+}
+
+tsdf_status stage_depth(Impl* p, const float* depth, int mem, const float** dptr) {
+    if (!depth) return bad("depth is NULL");
+    if (mem == TSDF_DEVICE) { *dptr = depth; return TSDF_OK; }
+    const size_t bytes = (size_t)p->g.img_w * p->g.img_h * sizeof(float);
+    CK(cudaMemcpyAsync(p->depth_stage, depth, bytes, cudaMemcpyHostToDevice, p->stream));
+    *dptr = p->depth_stage;
+    return TSDF_OK;
+}
+
+LinearizeArgs lin_args(Impl* p, int do_update, bool debug) {
+    LinearizeArgs a;
+    a.g = p->g;
+    a.grid = p->grid; a.pix = p->pix; a.pose = p->pose_dev;
+    a.partials = p->partials; a.ticket = p->ticket;
+    a.dbgJ = debug ? p->dbgJ : nullptr; a.dbgPsi = debug ? p->dbgPsi : nullptr; a.dbgFlag = debug ? p->dbgFlag : nullptr;
+    a.do_update = do_update;
+    a.px_per_block = p->px_per_block;
+    a.links = p->links;
+    return a;
+}
+
+void enqueue_prep(Impl* p, const float* dptr, int reset_track) {
+    launch_prep(p->g, dptr, p->pix, p->pose_dev, reset_track, p->stream);
+    p->launches++;
+}
+void enqueue_linearize(Impl* p, int do_update, bool debug) {
+    p->seqno++;
+    launch_linearize(lin_args(p, do_update, debug), p->lin_blocks, p->exchange_mode, p->seqno, p->stream);
+    p->launches++;
+}
+void enqueue_combine(Impl* p, int do_update) {
+    launch_gn_combine(lin_args(p, do_update, false), p->seqno, p->stream);
+    p->launches++;
+}
+void enqueue_fuse(Impl* p) {
+    cudaMemsetAsync(p->n_upd_dev, 0, sizeof(unsigned long long), p->stream);
+    launch_fuse(p->g, p->grid, p->pix, p->pose_dev, p->n_upd_dev, p->fuse_blocks, p->stream);
+    p->launches++;
+}
+
+/* the per-frame sequence of sdf_reconstruction.cpp:69-74 on the stream, no host round trip */
+tsdf_status enqueue_frame(Impl* p, const float* dptr, bool do_track, bool do_fuse) {
+    if (!p->have_K) { g_err = "camera matrix not set (tsdf_set_intrinsics)"; return TSDF_ERR_NO_INTRINSICS; }
+    if (p->exchange_mode == 2) return bad("same-device shard group: use tsdf_group_* entry points");
+    cudaEventRecord(p->ev[0], p->stream);
+    enqueue_prep(p, dptr, do_track ? 1 : 0);
+    cudaEventRecord(p->ev[1], p->stream);
+    if (do_track)
+        for (int it = 0; it < p->g.max_iter; it++) enqueue_linearize(p, 1, false);
+    cudaEventRecord(p->ev[2], p->stream);
+    if (do_fuse) enqueue_fuse(p);
+    cudaEventRecord(p->ev[3], p->stream);
+    p->stage_valid = true;
+    CK(cudaGetLastError());
+    return TSDF_OK;
+}
+
+void fill_stats(const PoseState& ps, tsdf_track_stats* st) {
+    if (!st) return;
+    memset(st, 0, sizeof *st);
+    st->iterations = ps.iterations; st->stopped = ps.stopped; st->singular = ps.singular; st->halo_miss = ps.halo_miss;
+    st->n_valid = (int32_t)ps.sums[SLOT_NVALID]; st->n_oob = (int32_t)ps.sums[SLOT_NOOB];
+    st->residual = ps.sums[SLOT_RES];
+    int q = 0;
+    for (int r = 0; r < 6; r++)
+        for (int c = r; c < 6; c++) { st->A[6 * r + c] = ps.sums[SLOT_A + q]; st->A[6 * c + r] = ps.sums[SLOT_A + q]; q++; }
+    for (int r = 0; r < 6; r++) { st->b[r] = ps.sums[SLOT_B + r]; st->twist[r] = ps.twist[r]; }
+}
+
+tsdf_status track_result(Impl* p, double R_out[9], double t_out[3], tsdf_track_stats* stats) {
+    const PoseState& ps = *p->pose_pin;
+    if (R_out) memcpy(R_out, ps.R, sizeof ps.R);
+    if (t_out) memcpy(t_out, ps.t, sizeof ps.t);
+    fill_stats(ps, stats);
+    if (ps.halo_miss) { g_err = "a tracking sample needed a voxel outside this shard's slab+halo (increase tsdf_config.halo)"; return TSDF_ERR_HALO; }
+    if (ps.singular) { g_err = "tracking lost: singular normal equations or non-finite twist"; return TSDF_ERR_TRACKING_LOST; }
+    return TSDF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t tsdf_abi_version(void) { return TSDF_ABI_VERSION; }
+const char* tsdf_last_error(void) { return g_err.c_str(); }
+int32_t tsdf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void tsdf_default_config(tsdf_config* c) {
+    memset(c, 0, sizeof *c);
+    c->m = 256; c->width = 6.0f; c->height = 6.0f; c->depth = 3.5f;      /* sdf_reconstruction.cpp:83-85 */
+    c->origin[0] = -3.0; c->origin[1] = -3.0; c->origin[2] = -0.5;
+    c->distance_delta = 0.3f; c->distance_epsilon = 0.025f;
+    c->gauss_newton_max_iteration = 20; c->maximum_twist_diff = 0.001f;  /* sdf_reconstruction.cpp:88 */
+    c->v_h = 1.0f; c->w_h = 0.01f;
+    c->pixel_stride = 3;                                                  /* camera_tracking.cpp:162-163 */
+    c->metric = TSDF_POINT_TO_PLANE;                                      /* sdf.cpp:272 */
+    c->image_width = 640; c->image_height = 480;
+    c->device = 0; c->n_shards = 1; c->shard_rank = 0; c->halo = -1;
+}
+
+tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
+    if (!cfg || !out) return bad("null argument");
+    *out = nullptr;
+    if (cfg->m < 8 || cfg->m > 4096 || (cfg->m % 4) != 0) return bad("m must be a multiple of 4 in [8, 4096]");
+    if (!(cfg->width > 0 && cfg->height > 0 && cfg->depth > 0)) return bad("extents must be positive");
+    if (cfg->image_width < 3 || cfg->image_height < 3 || cfg->image_width > 8192 || cfg->image_height > 8192) return bad("bad image size");
+    if (cfg->pixel_stride < 1) return bad("pixel_stride must be >= 1");
+    if (cfg->gauss_newton_max_iteration < 0 || cfg->gauss_newton_max_iteration > 1000) return bad("bad iteration count");
+    if (cfg->metric != TSDF_POINT_TO_PLANE && cfg->metric != TSDF_POINT_TO_POINT) return bad("bad metric");
+    if (cfg->n_shards < 1 || cfg->n_shards > MAX_WORLD || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->n_shards) return bad("bad shard configuration");
+    if (cfg->n_shards > cfg->m / 4) return bad("too many shards for this m");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_err = "no CUDA device: libtsdf_b200 has no CPU fallback";
+        return TSDF_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return bad("bad device ordinal");
+    CK(cudaSetDevice(cfg->device));
+
+    Impl* p = new Impl();
+    p->cfg = *cfg;
+    p->device = cfg->device;
+    build_params(*cfg, p->g);
+    int halo;
+    slab_range(*cfg, p->g.ko0, p->g.ko1, p->g.ks0, p->g.ks1, halo);
+    p->cfg.halo = halo;
+    p->n_stored = (int64_t)(p->g.ks1 - p->g.ks0) * cfg->m * cfg->m;
+    p->links.world = 1; p->links.rank = 0;
+    for (int r = 0; r < MAX_WORLD; r++) p->links.box[r] = nullptr;
+
+    const size_t npx = (size_t)cfg->image_width * cfg->image_height;
+    const int P = p->g.ni * p->g.nj;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    A(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    A(cudaMalloc(&p->grid, (size_t)p->n_stored * sizeof(float2)));
+    A(cudaMalloc(&p->pix, npx * sizeof(PixRec)));
+    A(cudaMalloc(&p->depth_stage, npx * sizeof(float)));
+    A(cudaMalloc(&p->pose_dev, sizeof(PoseState)));
+    A(cudaMallocHost(&p->pose_pin, sizeof(PoseState)));
+    A(cudaMallocHost(&p->ring_pin, sizeof(PoseState) * POSE_RING));
+    A(cudaMalloc(&p->ticket, sizeof(unsigned int)));
+    A(cudaMalloc(&p->n_upd_dev, sizeof(unsigned long long)));
+    A(cudaMallocHost(&p->n_upd_pin, sizeof(unsigned long long)));
+    A(cudaMalloc(&p->dbgJ, (size_t)P * 6 * sizeof(float)));
+    A(cudaMalloc(&p->dbgPsi, (size_t)P * sizeof(float)));
+    A(cudaMalloc(&p->dbgFlag, (size_t)P));
+    A(cudaMalloc(&p->mailbox, sizeof(Mailbox)));
+    A(cudaMalloc(&p->scratch_d, 64 * sizeof(double)));
+    for (int q = 0; q < 4; q++) A(cudaEventCreate(&p->ev[q]));
+    for (int q = 0; q < 2; q++) A(cudaEventCreate(&p->tmr[q]));
+    if (e != cudaSuccess) {
+        g_err = std::string("allocation failed: ") + cudaGetErrorString(e);
+        tsdf_destroy(reinterpret_cast<tsdf_handle>(p));
+        return e == cudaErrorMemoryAllocation ? TSDF_ERR_NOMEM : TSDF_ERR_CUDA;
+    }
+    cudaMemset(p->ticket, 0, sizeof(unsigned int));
+    cudaMemset(p->mailbox, 0, sizeof(Mailbox));
+    p->links.box[0] = p->mailbox;
+
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    const int sms = prop.multiProcessorCount;
+    /* K2: ~2 blocks per SM, every block a contiguous run of pixels (multiple of 16) */
+    int nb = sms * 2;
+    int ppb = (P + nb - 1) / nb;
+    ppb = ((ppb + 15) / 16) * 16;
+    nb = (P + ppb - 1) / ppb;
+    p->px_per_block = ppb; p->lin_blocks = nb;
+    A(cudaMalloc(&p->partials, (size_t)nb * LIN_PARTIAL_STRIDE * sizeof(double)));
+    /* K3: persistent grid, a whole number of resident blocks per SM */
+    int fb = fuse_blocks_per_sm();
+    if (fb < 1) fb = 1;
+    p->fuse_blocks = sms * fb;
+    if (e != cudaSuccess) { g_err = "allocation failed"; tsdf_destroy(reinterpret_cast<tsdf_handle>(p)); return TSDF_ERR_NOMEM; }
+
+    *out = reinterpret_cast<tsdf_handle>(p);
+    tsdf_status st = tsdf_reset(*out);
+    if (st != TSDF_OK) { tsdf_destroy(*out); *out = nullptr; return st; }
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_destroy(tsdf_handle h) {
+    if (!h) return TSDF_OK;
+    Impl* p = I(h);
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    for (void* q : p->ipc_opened) cudaIpcCloseMemHandle(q);
+    cudaFree(p->grid); cudaFree(p->pix); cudaFree(p->depth_stage); cudaFree(p->pose_dev);
+    cudaFreeHost(p->pose_pin); cudaFreeHost(p->ring_pin); cudaFree(p->partials); cudaFree(p->ticket);
+    cudaFree(p->n_upd_dev); cudaFreeHost(p->n_upd_pin);
+    cudaFree(p->dbgJ); cudaFree(p->dbgPsi); cudaFree(p->dbgFlag); cudaFree(p->mailbox);
+    cudaFree(p->flush_buf); cudaFree(p->scratch_d);
+    for (int q = 0; q < 4; q++) if (p->ev[q]) cudaEventDestroy(p->ev[q]);
+    for (int q = 0; q < 2; q++) if (p->tmr[q]) cudaEventDestroy(p->tmr[q]);
+    if (p->stream && p->own_stream) cudaStreamDestroy(p->stream);
+    cudaGetLastError();
+    delete p;
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_reset(tsdf_handle h) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    const float d0 = p->cfg.width + p->cfg.height + p->cfg.depth;        /* sdf.cpp:29 */
+    launch_fill(p->grid, p->n_stored, d0, p->stream);
+    p->launches++;
+    CK(cudaGetLastError());
+    /* camera_tracking.cpp:5-8 initial pose */
+    const double R0[9] = {1, 0, 0, 0, 0, -1, 0, -1, 0};
+    const double t0[3] = {0, 0, 1};
+    PoseState ps;
+    memset(&ps, 0, sizeof ps);
+    pose_set(ps, R0, t0);
+    return upload_pose(p, ps);
+}
+
+tsdf_status tsdf_get_config(tsdf_handle h, tsdf_config* cfg) {
+    if (!h || !cfg) return bad("null argument");
+    *cfg = I(h)->cfg;
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_set_intrinsics(tsdf_handle h, const double K[9]) {
+    if (!h || !K) return bad("null argument");
+    Impl* p = I(h);
+    for (int q = 0; q < 9; q++) p->g.K[q] = K[q];                        /* camera_tracking.cpp:24-32 */
+    p->g.k_simple = (K[1] == 0.0 && K[3] == 0.0 && K[6] == 0.0 && K[7] == 0.0 && K[8] == 1.0) ? 1 : 0;
+    p->have_K = true;
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_set_pose(tsdf_handle h, const double R[9], const double t[3]) {
+    if (!h || !R || !t) return bad("null argument");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    tsdf_status st = fetch_pose(p);
+    if (st != TSDF_OK) return st;
+    PoseState ps = *p->pose_pin;
+    pose_set(ps, R, t);                                                   /* camera_tracking.cpp:59-65 */
+    return upload_pose(p, ps);
+}
+tsdf_status tsdf_get_pose(tsdf_handle h, double R[9], double t[3]) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    tsdf_status st = fetch_pose(p);
+    if (st != TSDF_OK) return st;
+    if (R) memcpy(R, p->pose_pin->R, sizeof p->pose_pin->R);
+    if (t) memcpy(t, p->pose_pin->t, sizeof p->pose_pin->t);
+    return TSDF_OK;
+}
+tsdf_status tsdf_get_pose_inv(tsdf_handle h, double Rinv[9], double tinv[3]) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    tsdf_status st = fetch_pose(p);
+    if (st != TSDF_OK) return st;
+    if (Rinv) memcpy(Rinv, p->pose_pin->Rinv, sizeof p->pose_pin->Rinv);
+    if (tinv) memcpy(tinv, p->pose_pin->tinv, sizeof p->pose_pin->tinv);
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_track(tsdf_handle h, const float* depth, int32_t mem, double R_out[9], double t_out[3], tsdf_track_stats* stats) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    const float* dptr;
+    tsdf_status st = stage_depth(p, depth, mem, &dptr);
+    if (st != TSDF_OK) return st;
+    st = enqueue_frame(p, dptr, true, false);
+    if (st != TSDF_OK) return st;
+    st = fetch_pose(p);
+    if (st != TSDF_OK) return st;
+    return track_result(p, R_out, t_out, stats);
+}
+
+tsdf_status tsdf_fuse(tsdf_handle h, const float* depth, int32_t mem, const double R[9], const double t[3], int64_t* n_updated) {
+    if (!h) return bad("null handle");
+    if ((R == nullptr) != (t == nullptr)) return bad("R and t must both be given or both be NULL");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    if (!p->have_K) { g_err = "camera matrix not set (tsdf_set_intrinsics)"; return TSDF_ERR_NO_INTRINSICS; }
+    tsdf_status st;
+    if (R) { st = tsdf_set_pose(h, R, t); if (st != TSDF_OK) return st; }
+    const float* dptr;
+    st = stage_depth(p, depth, mem, &dptr);
+    if (st != TSDF_OK) return st;
+    st = enqueue_frame(p, dptr, false, true);
+    if (st != TSDF_OK) return st;
+    CK(cudaMemcpyAsync(p->n_upd_pin, p->n_upd_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (n_updated) *n_updated = (int64_t)*p->n_upd_pin;
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_track_and_fuse(tsdf_handle h, const float* depth, int32_t mem, double R_out[9], double t_out[3],
+                                tsdf_track_stats* stats, int64_t* n_updated) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    const float* dptr;
+    tsdf_status st = stage_depth(p, depth, mem, &dptr);
+    if (st != TSDF_OK) return st;
+    st = enqueue_frame(p, dptr, true, true);
+    if (st != TSDF_OK) return st;
+    CK(cudaMemcpyAsync(p->n_upd_pin, p->n_upd_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
+    st = fetch_pose(p);
+    if (st != TSDF_OK) return st;
+    if (n_updated) *n_updated = (int64_t)*p->n_upd_pin;
+    return track_result(p, R_out, t_out, stats);
+}
+
+int32_t tsdf_pose_ring_capacity(void) { return POSE_RING; }
+
+tsdf_status tsdf_enqueue_frame(tsdf_handle h, const float* depth_dev, int32_t track, int32_t slot) {
+    if (!h || !depth_dev) return bad("null argument");
+    if (slot < 0 || slot >= POSE_RING) return bad("slot out of range");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    tsdf_status st = enqueue_frame(p, depth_dev, track != 0, true);
+    if (st != TSDF_OK) return st;
+    CK(cudaMemcpyAsync(&p->ring_pin[slot], p->pose_dev, sizeof(PoseState), cudaMemcpyDeviceToHost, p->stream));
+    return TSDF_OK;
+}
+tsdf_status tsdf_sync(tsdf_handle h) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    return TSDF_OK;
+}
+tsdf_status tsdf_read_pose_ring(tsdf_handle h, int32_t slot, double R[9], double t[3], tsdf_track_stats* stats) {
+    if (!h) return bad("null handle");
+    if (slot < 0 || slot >= POSE_RING) return bad("slot out of range");
+    const PoseState& ps = I(h)->ring_pin[slot];
+    if (R) memcpy(R, ps.R, sizeof ps.R);
+    if (t) memcpy(t, ps.t, sizeof ps.t);
+    fill_stats(ps, stats);
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_linearize(tsdf_handle h, const float* depth, int32_t mem, double A[36], double b[6], tsdf_track_stats* stats) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    if (!p->have_K) { g_err = "camera matrix not set"; return TSDF_ERR_NO_INTRINSICS; }
+    if (p->exchange_mode == 2) return bad("same-device shard group: use tsdf_group_* entry points");
+    const float* dptr;
+    tsdf_status st = stage_depth(p, depth, mem, &dptr);
+    if (st != TSDF_OK) return st;
+    enqueue_prep(p, dptr, 1);
+    enqueue_linearize(p, 0, false);
+    CK(cudaGetLastError());
+    st = fetch_pose(p);
+    if (st != TSDF_OK) return st;
+    tsdf_track_stats s;
+    fill_stats(*p->pose_pin, &s);
+    if (A) memcpy(A, s.A, sizeof s.A);
+    if (b) memcpy(b, s.b, sizeof s.b);
+    if (stats) *stats = s;
+    if (p->pose_pin->halo_miss) { g_err = "halo too small for the tracking stencil"; return TSDF_ERR_HALO; }
+    return TSDF_OK;
+}
+
+int32_t tsdf_num_strided_pixels(tsdf_handle h) { return h ? I(h)->g.ni * I(h)->g.nj : 0; }
+
+tsdf_status tsdf_linearize_pixels(tsdf_handle h, const float* depth, int32_t mem, float* J, float* psi, uint8_t* flag) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    if (!p->have_K) { g_err = "camera matrix not set"; return TSDF_ERR_NO_INTRINSICS; }
+    if (p->links.world > 1) return bad("per-pixel records are a single-shard debugging aid");
+    const float* dptr;
+    tsdf_status st = stage_depth(p, depth, mem, &dptr);
+    if (st != TSDF_OK) return st;
+    const int P = p->g.ni * p->g.nj;
+    CK(cudaMemsetAsync(p->dbgFlag, 0, P, p->stream));
+    CK(cudaMemsetAsync(p->dbgJ, 0, (size_t)P * 6 * sizeof(float), p->stream));
+    CK(cudaMemsetAsync(p->dbgPsi, 0, (size_t)P * sizeof(float), p->stream));
+    enqueue_prep(p, dptr, 1);
+    enqueue_linearize(p, 0, true);
+    CK(cudaGetLastError());
+    if (J) CK(cudaMemcpyAsync(J, p->dbgJ, (size_t)P * 6 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    if (psi) CK(cudaMemcpyAsync(psi, p->dbgPsi, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    if (flag) CK(cudaMemcpyAsync(flag, p->dbgFlag, (size_t)P, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_backproject(tsdf_handle h, const float* depth, int32_t mem, float* cloud, float* normals) {
+    if (!h || !cloud) return bad("null argument");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    if (!p->have_K) { g_err = "camera matrix not set"; return TSDF_ERR_NO_INTRINSICS; }
+    const float* dptr;
+    tsdf_status st = stage_depth(p, depth, mem, &dptr);
+    if (st != TSDF_OK) return st;
+    const size_t n = (size_t)p->g.img_w * p->g.img_h * 3;
+    float *dc = nullptr, *dn = nullptr;
+    CK(cudaMalloc(&dc, n * sizeof(float)));
+    if (normals) CK(cudaMalloc(&dn, n * sizeof(float)));
+    enqueue_prep(p, dptr, 0);
+    launch_cloud(p->g, p->pix, dc, dn, p->stream);
+    p->launches++;
+    CK(cudaMemcpyAsync(cloud, dc, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    if (normals) CK(cudaMemcpyAsync(normals, dn, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    cudaFree(dc); cudaFree(dn);
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_interpolate_distance(tsdf_handle h, int64_t n, const double* pts, float* out, uint8_t* ok) {
+    if (!h || !pts || !out || !ok || n < 0) return bad("bad argument");
+    if (n == 0) return TSDF_OK;
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    double* dp = nullptr; float* dout = nullptr; uint8_t* dok = nullptr;
+    CK(cudaMalloc(&dp, (size_t)n * 3 * sizeof(double)));
+    CK(cudaMalloc(&dout, (size_t)n * sizeof(float)));
+    CK(cudaMalloc(&dok, (size_t)n));
+    CK(cudaMemcpyAsync(dp, pts, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    launch_sample(p->g, p->grid, n, dp, dout, dok, p->stream);
+    p->launches++;
+    CK(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(ok, dok, (size_t)n, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    cudaFree(dp); cudaFree(dout); cudaFree(dok);
+    return TSDF_OK;
+}
+
+int64_t tsdf_number_of_voxels(tsdf_handle h) {
+    if (!h) return 0;
+    const int64_t m = I(h)->cfg.m;
+    return m * m * m;                                                     /* sdf.h:107 (64-bit) */
+}
+tsdf_status tsdf_stored_range(tsdf_handle h, int32_t* k_begin, int32_t* k_end, int32_t* k_own_begin, int32_t* k_own_end) {
+    if (!h) return bad("null handle");
+    const GridParams& g = I(h)->g;
+    if (k_begin) *k_begin = g.ks0;
+    if (k_end) *k_end = g.ks1;
+    if (k_own_begin) *k_own_begin = g.ko0;
+    if (k_own_end) *k_own_end = g.ko1;
+    return TSDF_OK;
+}
+
+static tsdf_status xfer_grid(Impl* p, float* D, float* W, int layout, bool down) {
+    if (!D || !W) return bad("null argument");
+    if (layout != TSDF_LAYOUT_REFERENCE && layout != TSDF_LAYOUT_XFASTEST) return bad("bad layout");
+    CK(cudaSetDevice(p->device));
+    /* stage through device buffers in slabs of z so the extra footprint stays small */
+    const int m = p->g.m, nk = p->g.ks1 - p->g.ks0;
+    if (layout == TSDF_LAYOUT_XFASTEST) {
+        const int kstep = 16;
+        float *dD = nullptr, *dW = nullptr;
+        const size_t plane = (size_t)m * m;
+        CK(cudaMalloc(&dD, plane * kstep * sizeof(float)));
+        CK(cudaMalloc(&dW, plane * kstep * sizeof(float)));
+        for (int k0 = 0; k0 < nk; k0 += kstep) {
+            const int kn = nk - k0 < kstep ? nk - k0 : kstep;
+            GridParams gs = p->g;
+            gs.ks0 = 0; gs.ks1 = kn;
+            float2* sub = p->grid + plane * k0;
+            if (down) {
+                launch_export(gs, sub, dD, dW, 1, p->stream);
+                CK(cudaMemcpyAsync(D + plane * k0, dD, plane * kn * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+                CK(cudaMemcpyAsync(W + plane * k0, dW, plane * kn * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+            } else {
+                CK(cudaMemcpyAsync(dD, D + plane * k0, plane * kn * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+                CK(cudaMemcpyAsync(dW, W + plane * k0, plane * kn * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+                launch_import(gs, sub, dD, dW, 1, p->stream);
+            }
+            p->launches++;
+            CK(cudaStreamSynchronize(p->stream));
+        }
+        cudaFree(dD); cudaFree(dW);
+    } else {
+        float *dD = nullptr, *dW = nullptr;
+        CK(cudaMalloc(&dD, (size_t)p->n_stored * sizeof(float)));
+        CK(cudaMalloc(&dW, (size_t)p->n_stored * sizeof(float)));
+        if (down) {
+            launch_export(p->g, p->grid, dD, dW, 0, p->stream);
+            CK(cudaMemcpyAsync(D, dD, (size_t)p->n_stored * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+            CK(cudaMemcpyAsync(W, dW, (size_t)p->n_stored * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+        } else {
+            CK(cudaMemcpyAsync(dD, D, (size_t)p->n_stored * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+            CK(cudaMemcpyAsync(dW, W, (size_t)p->n_stored * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+            launch_import(p->g, p->grid, dD, dW, 0, p->stream);
+        }
+        p->launches++;
+        CK(cudaStreamSynchronize(p->stream));
+        cudaFree(dD); cudaFree(dW);
+    }
+    CK(cudaGetLastError());
+    return TSDF_OK;
+}
+tsdf_status tsdf_download(tsdf_handle h, float* D, float* W, int32_t layout) {
+    if (!h) return bad("null handle");
+    return xfer_grid(I(h), D, W, layout, true);
+}
+tsdf_status tsdf_upload(tsdf_handle h, const float* D, const float* W, int32_t layout) {
+    if (!h) return bad("null handle");
+    return xfer_grid(I(h), const_cast<float*>(D), const_cast<float*>(W), layout, false);
+}
+tsdf_status tsdf_device_grid(tsdf_handle h, void** dw, int64_t* n) {
+    if (!h) return bad("null handle");
+    if (dw) *dw = I(h)->grid;
+    if (n) *n = I(h)->n_stored;
+    return TSDF_OK;
+}
+
+/* ---- pure index / coordinate maps (host), sdf.h:113-157 ---- */
+int64_t tsdf_get_array_index(tsdf_handle h, int32_t i, int32_t j, int32_t k) {
+    if (!h) return -1;
+    const int64_t m = I(h)->cfg.m;
+    if (i < 0 || j < 0 || k < 0) return -1;
+    if (i >= m || j >= m || k >= m) return -1;
+    return m * m * i + m * j + k;
+}
+void tsdf_get_voxel_coordinates_idx(tsdf_handle h, int64_t idx, int32_t ijk[3]) {
+    const int64_t m = I(h)->cfg.m, m2 = m * m;
+    ijk[1] = (int32_t)((idx % m2) / m);
+    ijk[0] = (int32_t)(idx / m2);
+    ijk[2] = (int32_t)(idx % m);
+}
+void tsdf_get_voxel_coordinates(tsdf_handle h, const double gl[3], double v[3]) {
+    world_to_voxel(I(h)->g, gl[0], gl[1], gl[2], v[0], v[1], v[2]);
+}
+void tsdf_get_global_coordinates(tsdf_handle h, const int32_t ijk[3], double gl[3]) {
+    const GridParams& g = I(h)->g;
+    gl[0] = voxel_centre(g.vs_x, ijk[0], g.origin[0]);
+    gl[1] = voxel_centre(g.vs_y, ijk[1], g.origin[1]);
+    gl[2] = voxel_centre(g.vs_z, ijk[2], g.origin[2]);
+}
+
+tsdf_status tsdf_exp_map(tsdf_handle h, const double twist[6], double R[9], double t[3]) {
+    if (!h || !twist) return bad("null argument");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    double out[12];
+    CK(cudaMemcpyAsync(p->scratch_d, twist, 6 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    launch_exp_map(p->scratch_d, p->scratch_d + 8, p->stream);
+    p->launches++;
+    CK(cudaMemcpyAsync(out, p->scratch_d + 8, 12 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (R) memcpy(R, out, 9 * sizeof(double));
+    if (t) memcpy(t, out + 9, 3 * sizeof(double));
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_dev_alloc(tsdf_handle h, int64_t bytes, void** dev_ptr) {
+    if (!h || !dev_ptr || bytes <= 0) return bad("bad argument");
+    CK(cudaSetDevice(I(h)->device));
+    CK(cudaMalloc(dev_ptr, (size_t)bytes));
+    return TSDF_OK;
+}
+tsdf_status tsdf_dev_free(tsdf_handle h, void* dev_ptr) {
+    if (!h) return bad("null handle");
+    CK(cudaSetDevice(I(h)->device));
+    CK(cudaFree(dev_ptr));
+    return TSDF_OK;
+}
+tsdf_status tsdf_dev_upload(tsdf_handle h, void* dev_dst, const void* host_src, int64_t bytes) {
+    if (!h || !dev_dst || !host_src || bytes < 0) return bad("bad argument");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(dev_dst, host_src, (size_t)bytes, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return TSDF_OK;
+}
+tsdf_status tsdf_host_alloc_pinned(int64_t bytes, void** host_ptr) {
+    if (!host_ptr || bytes <= 0) return bad("bad argument");
+    CK(cudaMallocHost(host_ptr, (size_t)bytes));
+    return TSDF_OK;
+}
+tsdf_status tsdf_host_free_pinned(void* host_ptr) {
+    CK(cudaFreeHost(host_ptr));
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_last_stage_ms(tsdf_handle h, float out[3]) {
+    if (!h || !out) return bad("null argument");
+    Impl* p = I(h);
+    if (!p->stage_valid) return bad("no frame enqueued yet");
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventSynchronize(p->ev[3]));
+    for (int q = 0; q < 3; q++) CK(cudaEventElapsedTime(&out[q], p->ev[q], p->ev[q + 1]));
+    return TSDF_OK;
+}
+tsdf_status tsdf_event_timer_begin(tsdf_handle h) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventRecord(p->tmr[0], p->stream));
+    return TSDF_OK;
+}
+tsdf_status tsdf_event_timer_end(tsdf_handle h, float* ms) {
+    if (!h || !ms) return bad("null argument");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventRecord(p->tmr[1], p->stream));
+    CK(cudaEventSynchronize(p->tmr[1]));
+    CK(cudaEventElapsedTime(ms, p->tmr[0], p->tmr[1]));
+    return TSDF_OK;
+}
+int64_t tsdf_kernel_launch_count(tsdf_handle h) { return h ? I(h)->launches : 0; }
+
+tsdf_status tsdf_flush_l2(tsdf_handle h) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    if (!p->flush_buf) CK(cudaMalloc(&p->flush_buf, FLUSH_BYTES));
+    launch_flush(p->flush_buf, FLUSH_BYTES / sizeof(float), p->stream);
+    p->launches++;
+    CK(cudaGetLastError());
+    return TSDF_OK;
+}
+
+/* ---- sharding ------------------------------------------------------------------------------ */
+tsdf_status tsdf_shard_ipc_export(tsdf_handle h, uint8_t out[TSDF_IPC_HANDLE_BYTES]) {
+    if (!h || !out) return bad("null argument");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) <= TSDF_IPC_HANDLE_BYTES, "ipc handle size");
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, p->mailbox));
+    memset(out, 0, TSDF_IPC_HANDLE_BYTES);
+    memcpy(out, &mh, sizeof mh);
+    return TSDF_OK;
+}
+tsdf_status tsdf_shard_ipc_attach(tsdf_handle h, int32_t world, const uint8_t* handles) {
+    if (!h || !handles) return bad("null argument");
+    Impl* p = I(h);
+    if (world != p->cfg.n_shards) return bad("world must equal tsdf_config.n_shards");
+    CK(cudaSetDevice(p->device));
+    p->links.world = world; p->links.rank = p->cfg.shard_rank;
+    for (int r = 0; r < world; r++) {
+        if (r == p->cfg.shard_rank) { p->links.box[r] = p->mailbox; continue; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, handles + (size_t)r * TSDF_IPC_HANDLE_BYTES, sizeof mh);
+        void* ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+        p->ipc_opened.push_back(ptr);
+        p->links.box[r] = reinterpret_cast<Mailbox*>(ptr);
+    }
+    p->exchange_mode = world > 1 ? 1 : 0;
+    p->seqno = 0;
+    return TSDF_OK;
+}
+tsdf_status tsdf_shard_attach_local(tsdf_handle* handles, int32_t world) {
+    if (!handles || world < 1 || world > MAX_WORLD) return bad("bad argument");
+    bool same_dev = true;
+    for (int r = 0; r < world; r++) {
+        if (!handles[r]) return bad("null handle in group");
+        Impl* p = I(handles[r]);
+        if (p->cfg.n_shards != world || p->cfg.shard_rank != r) return bad("handles must be ordered by shard_rank with n_shards = world");
+        if (p->device != I(handles[0])->device) same_dev = false;
+    }
+    for (int r = 0; r < world; r++) {
+        Impl* p = I(handles[r]);
+        CK(cudaSetDevice(p->device));
+        p->links.world = world; p->links.rank = r;
+        for (int q = 0; q < world; q++) {
+            Impl* o = I(handles[q]);
+            if (!same_dev && o->device != p->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { g_err = "peer access unavailable"; return TSDF_ERR_CUDA; }
+                cudaGetLastError();
+            }
+            p->links.box[q] = o->mailbox;
+        }
+        p->exchange_mode = world > 1 ? (same_dev ? 2 : 1) : 0;
+        p->seqno = 0;
+        if (same_dev && r > 0) {
+            /* one stream for the whole group: program order is the cross-shard dependency */
+            CK(cudaStreamSynchronize(p->stream));
+            if (p->own_stream) cudaStreamDestroy(p->stream);
+            p->stream = I(handles[0])->stream;
+            p->own_stream = false;
+        }
+    }
+    return TSDF_OK;
+}
+
+
+static tsdf_status group_check(tsdf_handle* handles, int32_t world) {
+    if (!handles || world < 1 || world > MAX_WORLD) return bad("bad group");
+    for (int r = 0; r < world; r++) {
+        if (!handles[r]) return bad("null handle in group");
+        if (I(handles[r])->links.world != world || I(handles[r])->links.rank != r) return bad("group not attached (tsdf_shard_attach_local)");
+    }
+    return TSDF_OK;
+}
+tsdf_status tsdf_group_set_intrinsics(tsdf_handle* handles, int32_t world, const double K[9]) {
+    tsdf_status st = group_check(handles, world);
+    for (int r = 0; r < world && st == TSDF_OK; r++) st = tsdf_set_intrinsics(handles[r], K);
+    return st;
+}
+tsdf_status tsdf_group_set_pose(tsdf_handle* handles, int32_t world, const double R[9], const double t[3]) {
+    tsdf_status st = group_check(handles, world);
+    for (int r = 0; r < world && st == TSDF_OK; r++) st = tsdf_set_pose(handles[r], R, t);
+    return st;
+}
+static tsdf_status group_stage(tsdf_handle* handles, int32_t world, const float* depth, int32_t mem, std::vector<const float*>& dptr) {
+    dptr.resize(world);
+    for (int r = 0; r < world; r++) {
+        Impl* p = I(handles[r]);
+        if (!p->have_K) { g_err = "camera matrix not set"; return TSDF_ERR_NO_INTRINSICS; }
+        if (mem == TSDF_DEVICE && p->device != I(handles[0])->device) return bad("device depth needs all shards on one device");
+        CK(cudaSetDevice(p->device));
+        tsdf_status st = stage_depth(p, depth, mem, &dptr[r]);
+        if (st != TSDF_OK) return st;
+    }
+    return TSDF_OK;
+}
+static void group_gn_iteration(tsdf_handle* handles, int32_t world, int do_update) {
+    for (int r = 0; r < world; r++) { cudaSetDevice(I(handles[r])->device); enqueue_linearize(I(handles[r]), do_update, false); }
+    if (I(handles[0])->exchange_mode == 2)
+        for (int r = 0; r < world; r++) enqueue_combine(I(handles[r]), do_update);
+}
+tsdf_status tsdf_group_linearize(tsdf_handle* handles, int32_t world, const float* depth, int32_t mem,
+                                 double A[36], double b[6], tsdf_track_stats* stats) {
+    tsdf_status st = group_check(handles, world);
+    if (st != TSDF_OK) return st;
+    std::vector<const float*> dptr;
+    st = group_stage(handles, world, depth, mem, dptr);
+    if (st != TSDF_OK) return st;
+    for (int r = 0; r < world; r++) { cudaSetDevice(I(handles[r])->device); enqueue_prep(I(handles[r]), dptr[r], 1); }
+    group_gn_iteration(handles, world, 0);
+    CK(cudaGetLastError());
+    int miss = 0;
+    for (int r = world - 1; r >= 0; r--) {
+        Impl* p = I(handles[r]);
+        CK(cudaSetDevice(p->device));
+        st = fetch_pose(p);
+        if (st != TSDF_OK) return st;
+        miss |= p->pose_pin->halo_miss;
+    }
+    tsdf_track_stats s;
+    fill_stats(*I(handles[0])->pose_pin, &s);
+    s.halo_miss = miss;
+    if (A) memcpy(A, s.A, sizeof s.A);
+    if (b) memcpy(b, s.b, sizeof s.b);
+    if (stats) *stats = s;
+    if (miss) { g_err = "halo too small for the tracking stencil"; return TSDF_ERR_HALO; }
+    return TSDF_OK;
+}
+tsdf_status tsdf_group_frame(tsdf_handle* handles, int32_t world, const float* depth, int32_t mem,
+                             int32_t track, int32_t fuse, double R_out[9], double t_out[3],
+                             tsdf_track_stats* stats, int64_t* n_updated) {
+    tsdf_status st = group_check(handles, world);
+    if (st != TSDF_OK) return st;
+    std::vector<const float*> dptr;
+    st = group_stage(handles, world, depth, mem, dptr);
+    if (st != TSDF_OK) return st;
+    for (int r = 0; r < world; r++) { cudaSetDevice(I(handles[r])->device); enqueue_prep(I(handles[r]), dptr[r], track ? 1 : 0); }
+    if (track)
+        for (int it = 0; it < I(handles[0])->g.max_iter; it++) group_gn_iteration(handles, world, 1);
+    if (fuse)
+        for (int r = 0; r < world; r++) {
+            Impl* p = I(handles[r]);
+            cudaSetDevice(p->device);
+            enqueue_fuse(p);
+            cudaMemcpyAsync(p->n_upd_pin, p->n_upd_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream);
+        }
+    CK(cudaGetLastError());
+    int64_t nupd = 0;
+    int miss = 0;
+    for (int r = world - 1; r >= 0; r--) {
+        Impl* p = I(handles[r]);
+        CK(cudaSetDevice(p->device));
+        st = fetch_pose(p);
+        if (st != TSDF_OK) return st;
+        if (fuse) nupd += (int64_t)*p->n_upd_pin;
+        miss |= p->pose_pin->halo_miss;
+    }
+    if (n_updated) *n_updated = nupd;
+    I(handles[0])->pose_pin->halo_miss = miss;
+    if (!track) {
+        const PoseState& ps = *I(handles[0])->pose_pin;
+        if (R_out) memcpy(R_out, ps.R, sizeof ps.R);
+        if (t_out) memcpy(t_out, ps.t, sizeof ps.t);
+        if (stats) memset(stats, 0, sizeof *stats);
+        return TSDF_OK;
+    }
+    return track_result(I(handles[0]), R_out, t_out, stats);
+}
+
+}  // extern "C"

@@ -1,0 +1,441 @@
+/*
+ * tsdf_core.cuh — exact-arithmetic building blocks of the track + fuse kernels.
+ *
+ * Everything here is `__host__ __device__` and written as plain IEEE arithmetic: the
+ * library is compiled with nvcc -fmad=false (and default -prec-div/-prec-sqrt, no
+ * fast-math) so each + - * / rounds exactly as the reference's non-contracted x86 code does
+ * (SURVEY.md "hard part 1").  The host compile of this header (tests/host_emul, g++
+ * -ffp-contract=off) exists only so the CPU test-suite can check the kernels' per-voxel /
+ * per-sample logic against the oracle without a GPU; the product never runs it.
+ *
+ * Reference citations are relative to /root/reference/src/.
+ */
+#pragma once
+#include <stdint.h>
+#include <limits.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define TSDF_HD __host__ __device__ __forceinline__
+#else
+#define TSDF_HD inline
+#endif
+
+namespace tsdf {
+
+/* --- parameters shared by all kernels (built on the host in fp32/fp64 exactly like the
+ * reference's constructors, sdf.cpp:18-21, camera_tracking.cpp:11-17) ------------------- */
+struct GridParams {
+    int32_t m;                 /* voxels per axis */
+    int32_t ks0, ks1;          /* stored z range [ks0, ks1)  (slab + halo)  */
+    int32_t ko0, ko1;          /* owned  z range [ko0, ko1)                  */
+    int32_t metric;            /* 0 plane, 1 point */
+    int32_t img_w, img_h;
+    int32_t stride;            /* pixel stride of the tracker */
+    int32_t ni, nj;            /* strided pixel grid (columns, rows) */
+    float m_div_width, m_div_height, m_div_depth;      /* sdf.cpp:19-21 (fp32) */
+    float vs_x, vs_y, vs_z;    /* extent / (float)m, the fp32 quotient of sdf.h:154-156 */
+    float delta, eps;          /* sdf.cpp:8 */
+    float v_h, w_h;            /* camera_tracking.cpp:11-12 */
+    float v_h2_width, v_h2_height, v_h2_depth;         /* camera_tracking.cpp:15-17 */
+    float two_w_h;             /* 2 * w_h as float, camera_tracking.cpp:331 */
+    float max_twist_diff;
+    int32_t max_iter;
+    double origin[3];
+    double K[9];
+    int32_t k_simple;          /* 1 when K = [fx 0 cx; 0 fy cy; 0 0 1]: the zero products are exact no-ops */
+    int32_t pad;
+};
+
+/* pose block living in device memory; written by set_pose (host) and by the tracker's
+ * on-device update (camera_tracking.cpp:237-239) */
+struct PoseState {
+    double R[9], t[3];         /* rot, trans            camera_tracking.h:42-47 */
+    double Rinv[9], tinv[3];   /* rot_inv, rot_inv_trans */
+    double twist[6];
+    double sums[30];           /* last reduced normal equations: 21 A (upper, row-major), 6 b, psi^2, n_valid, n_oob */
+    int32_t iterations, stopped, singular, halo_miss;
+};
+
+struct PixRec { float z, nx, ny, nz; };     /* per-pixel record written by K1 (16 B) */
+
+/* ---- the reference's (int) casts: x86 cvttss2si — truncation toward zero, NaN and
+ * out-of-range give INT_MIN.  sdf.cpp:143-145 ---- */
+TSDF_HD int trunc_f2i(float v) {
+    if (!(v >= -2147483648.0f && v < 2147483648.0f)) return INT_MIN;
+    return (int)v;
+}
+
+/* `volume < 0.00001` compares the float promoted to double against a double literal
+ * (sdf.cpp:151).  float(1e-5) = 9.99999974737875e-06 < 1e-5, so the test is `volume <=`
+ * that float. */
+#define TSDF_VOL_EXACT_F 9.99999974737875163555145263671875e-06f
+
+/* sdf.h:143-147 */
+TSDF_HD void world_to_voxel(const GridParams& g, double wx, double wy, double wz,
+                            double& vx, double& vy, double& vz) {
+    vx = ((wx - g.origin[0]) * (double)g.m_div_width - 0.5);
+    vy = ((wy - g.origin[1]) * (double)g.m_div_height - 0.5);
+    vz = ((wz - g.origin[2]) * (double)g.m_div_depth - 0.5);
+}
+/* sdf.h:153-157, one axis */
+TSDF_HD double voxel_centre(float vs, int idx, double org) {
+    return (double)vs * ((double)idx + 0.5) + org;
+}
+
+/* Eigen fixed-size product coefficient: ((a0*b0 + a1*b1) + a2*b2) */
+TSDF_HD double dot3_seq(double a0, double a1, double a2, double b0, double b1, double b2) {
+    return (a0 * b0 + a1 * b1) + a2 * b2;
+}
+TSDF_HD void matvec3(const double* M, double x, double y, double z, double& ox, double& oy, double& oz) {
+    ox = dot3_seq(M[0], M[1], M[2], x, y, z);
+    oy = dot3_seq(M[3], M[4], M[5], x, y, z);
+    oz = dot3_seq(M[6], M[7], M[8], x, y, z);
+}
+TSDF_HD void matmul3(const double* A, const double* B, double* C) {
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++)
+            C[3 * r + c] = (A[3 * r + 0] * B[0 + c] + A[3 * r + 1] * B[3 + c]) + A[3 * r + 2] * B[6 + c];
+}
+/* Matrix3d::inverse(): cofactors * (1/det)  (camera_tracking.cpp:62) */
+TSDF_HD void inverse3(const double* M, double* inv) {
+    double c00 = M[4] * M[8] - M[5] * M[7];
+    double c01 = M[5] * M[6] - M[3] * M[8];
+    double c02 = M[3] * M[7] - M[4] * M[6];
+    double det = (M[0] * c00 + M[1] * c01) + M[2] * c02;
+    double id = 1.0 / det;
+    inv[0] = c00 * id;
+    inv[1] = (M[2] * M[7] - M[1] * M[8]) * id;
+    inv[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+    inv[3] = c01 * id;
+    inv[4] = (M[0] * M[8] - M[2] * M[6]) * id;
+    inv[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+    inv[6] = c02 * id;
+    inv[7] = (M[1] * M[6] - M[0] * M[7]) * id;
+    inv[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+}
+/* camera_tracking.cpp:59-65 */
+TSDF_HD void pose_set(PoseState& p, const double* R, const double* t) {
+    for (int q = 0; q < 9; q++) p.R[q] = R[q];
+    for (int q = 0; q < 3; q++) p.t[q] = t[q];
+    inverse3(p.R, p.Rinv);
+    double x, y, z;
+    matvec3(p.Rinv, p.t[0], p.t[1], p.t[2], x, y, z);
+    p.tinv[0] = -1 * x; p.tinv[1] = -1 * y; p.tinv[2] = -1 * z;
+}
+
+/* K1 back-projection (depth_image_proc convention, fp32): x = (u - cx) * z * (1/fx) */
+struct K1Params { float cx, cy, inv_fx, inv_fy; };
+TSDF_HD K1Params k1_params(const double* K) {
+    K1Params p;
+    p.cx = (float)K[2]; p.cy = (float)K[5];
+    p.inv_fx = 1.0f / (float)K[0]; p.inv_fy = 1.0f / (float)K[4];
+    return p;
+}
+TSDF_HD bool depth_valid(float z) { return (z > 0.0f) && (z <= 3.402823466e+38f); }   /* finite, > 0; false for NaN */
+TSDF_HD void backproject_px(const K1Params& p, int u, int v, float z, float& x, float& y) {
+    x = ((float)u - p.cx) * z * p.inv_fx;
+    y = ((float)v - p.cy) * z * p.inv_fy;
+}
+/* normal from central differences of the 4-neighbourhood; false = not computable (NaN) */
+TSDF_HD bool normal_px(const K1Params& p, int u, int v, float zc, float zl, float zr, float zu, float zd,
+                       float& nx, float& ny, float& nz) {
+    if (!(depth_valid(zc) && depth_valid(zl) && depth_valid(zr) && depth_valid(zu) && depth_valid(zd))) return false;
+    float thr = 0.02f * zc;        /* PCL MaxDepthChangeFactor, sdf_reconstruction.cpp:46 */
+    if (fabsf(zl - zc) > thr || fabsf(zr - zc) > thr || fabsf(zu - zc) > thr || fabsf(zd - zc) > thr) return false;
+    float xc, yc, xl, yl, xr, yr, xu, yu, xd, yd;
+    backproject_px(p, u, v, zc, xc, yc);
+    backproject_px(p, u - 1, v, zl, xl, yl);
+    backproject_px(p, u + 1, v, zr, xr, yr);
+    backproject_px(p, u, v - 1, zu, xu, yu);
+    backproject_px(p, u, v + 1, zd, xd, yd);
+    float ax = xr - xl, ay = yr - yl, az = zr - zl;
+    float bx = xd - xu, by = yd - yu, bz = zd - zu;
+    float cx_ = ay * bz - az * by;
+    float cy_ = az * bx - ax * bz;
+    float cz_ = ax * by - ay * bx;
+    float len = sqrtf((cx_ * cx_ + cy_ * cy_) + cz_ * cz_);
+    if (!(len > 0.0f)) return false;
+    cx_ = cx_ / len; cy_ = cy_ / len; cz_ = cz_ / len;
+    float dotp = (cx_ * xc + cy_ * yc) + cz_ * zc;
+    if (dotp > 0.0f) { cx_ = -cx_; cy_ = -cy_; cz_ = -cz_; }
+    nx = cx_; ny = cy_; nz = cz_;
+    return true;
+}
+
+/* ---- SDF::interpolate_distance, sdf.cpp:127-163 -----------------------------------------
+ * fetch(ci,cj,ck,D,W) -> true when the voxel is inside the grid (sdf.h:113-119).  The loop
+ * keeps the reference's neighbour order (i outer, j, k inner) and its early return. */
+template <class Fetch>
+TSDF_HD float interpolate_distance(double vx, double vy, double vz, Fetch&& fetch, bool& is_interpolated) {
+    const float i = (float)vx, j = (float)vy, k = (float)vz;
+    const int bi = trunc_f2i(i), bj = trunc_f2i(j), bk = trunc_f2i(k);
+    float w_sum = 0.0f, sum_d = 0.0f;
+    bool any = false, exact = false;
+    float exact_val = 0.0f;
+#pragma unroll
+    for (int io = 0; io < 2; io++) {
+#pragma unroll
+        for (int jo = 0; jo < 2; jo++) {
+#pragma unroll
+            for (int ko = 0; ko < 2; ko++) {
+                const int ci = bi + io, cj = bj + jo, ck = bk + ko;
+                const float volume = fabsf((float)ci - i) + fabsf((float)cj - j) + fabsf((float)ck - k);
+                float d, w;
+                const bool inb = fetch(ci, cj, ck, d, w);
+                if (inb && w > 0.0f && !exact) {
+                    any = true;
+                    if (volume <= TSDF_VOL_EXACT_F) {
+                        exact = true;
+                        exact_val = d;
+                    } else {
+                        const float wt = 1.0f / volume;       /* == (float)(1.0 / (double)volume) */
+                        w_sum = w_sum + wt;
+                        sum_d = sum_d + wt * d;
+                    }
+                }
+            }
+        }
+    }
+    is_interpolated = any;
+    return exact ? exact_val : sum_d / w_sum;
+}
+
+/* ---- fusion, per voxel: sdf.cpp:245-292 ---------------------------------------------------
+ * Stage 1 (projection): camera-space voxel centre -> pixel, or reject. */
+TSDF_HD bool fuse_project(const GridParams& g, double cx, double cy, double cz, int& iu, int& iv) {
+    if (cz < 0) return false;                                   /* sdf.cpp:247 */
+    double ij0, ij1, ij2;
+    if (g.k_simple) {       /* 0*x and +0 are exact no-ops for finite operands */
+        ij0 = g.K[0] * cx + g.K[2] * cz;
+        ij1 = g.K[4] * cy + g.K[5] * cz;
+        ij2 = cz;
+    } else {                /* camera_tracking.cpp:44 */
+        ij0 = dot3_seq(g.K[0], g.K[1], g.K[2], cx, cy, cz);
+        ij1 = dot3_seq(g.K[3], g.K[4], g.K[5], cx, cy, cz);
+        ij2 = dot3_seq(g.K[6], g.K[7], g.K[8], cx, cy, cz);
+    }
+    const double u = ij0 / ij2, v = ij1 / ij2;                  /* camera_tracking.cpp:45-46 */
+    /* (int) truncation then 0 <= i < width  <=>  -1 < u < width (false for NaN/inf);  sdf.cpp:251-254 */
+    if (!(u > -1.0 && u < (double)g.img_w && v > -1.0 && v < (double)g.img_h)) return false;
+    iu = (int)u; iv = (int)v;
+    return true;
+}
+
+/* exp(x) for the weight of sdf.cpp:278.  For x in [-0.04, 0] a degree-9 Taylor polynomial in
+ * double is accurate to < 2e-16 relative, i.e. it rounds to the same float as a correctly
+ * rounded exp except with probability ~1e-8 per call; outside that range call exp(). */
+TSDF_HD double weight_exp(double x) {
+    if (x >= -0.04) {
+        double p = 1.0 / 362880.0;
+        p = p * x + 1.0 / 40320.0;
+        p = p * x + 1.0 / 5040.0;
+        p = p * x + 1.0 / 720.0;
+        p = p * x + 1.0 / 120.0;
+        p = p * x + 1.0 / 24.0;
+        p = p * x + 1.0 / 6.0;
+        p = p * x + 0.5;
+        p = p * x + 1.0;
+        p = p * x + 1.0;
+        return p;
+    }
+    return exp(x);
+}
+
+/* Stage 2 (distance + weight): false = voxel skipped.  rec = the pixel's {z,n}; px,py =
+ * the pixel's back-projected x,y (recomputed with backproject_px, bit-identical to K1). */
+TSDF_HD bool fuse_distance(const GridParams& g, double cx, double cy, double cz,
+                           float px, float py, const PixRec& rec, float& d_out, float& w_out) {
+    float d_new;
+    if (g.metric == 0) {
+        /* sdf.cpp:260: isnan(point.x)|isnan(point.y)|isnan(normal.*) — z NaN makes x,y NaN */
+        if (!(rec.z == rec.z) || !(rec.nx == rec.nx)) return false;
+        /* sdf.h:177-181, Eigen dot = c0 + (c1 + c2) */
+        const double dx = (double)px - cx, dy = (double)py - cy, dz = (double)rec.z - cz;
+        const double pp = dx * (double)rec.nx + (dy * (double)rec.ny + dz * (double)rec.nz);
+        d_new = (float)pp;                                      /* sdf.cpp:274 */
+    } else {
+        if (!(rec.z == rec.z)) return false;
+        const double pp = cz - (double)rec.z;                   /* sdf.h:169-172 */
+        d_new = (float)pp;
+    }
+    float w_new = 1.0f;                                         /* sdf.cpp:276 */
+    if (d_new >= g.eps && d_new <= g.delta) {
+        const float e = d_new - g.eps;
+        w_new = (float)weight_exp(-0.5 * (double)e * (double)e);   /* sdf.cpp:278 */
+    }
+    if (d_new > g.delta) return false;                          /* sdf.cpp:280-283 */
+    if (d_new < -g.delta) d_new = -g.delta;                     /* sdf.cpp:285-287 */
+    d_out = d_new; w_out = w_new;
+    return true;
+}
+/* Stage 3 (running weighted mean): sdf.cpp:289-292 */
+TSDF_HD void fuse_apply(float& D, float& W, float d_new, float w_new) {
+    const float w_old = W;
+    W = w_old + w_new;
+    D = (w_old * D + w_new * d_new) / W;
+}
+
+/* ---- scan-line clipping for the fusion kernel ------------------------------------------------
+ * Along a grid row (fixed j,k; i = 0..m-1) the camera-space centre is affine in i, so each of
+ * the five acceptance tests of sdf.cpp:247-254 (z >= 0, -1 < u < width, -1 < v < height, the
+ * last four multiplied through by z > 0) is a linear inequality f(i) >= 0 and the accepted
+ * voxels form one interval.  This computes a CONSERVATIVE superset [ilo, ihi) of it (tolerance
+ * far above the rounding error of the evaluation, interval widened by a voxel); the exact
+ * per-voxel test still decides.  py*, pz* = Rinv(r,1)*gy, Rinv(r,2)*gz. */
+TSDF_HD void clip_constraint(double f0, double f1, double span, double& lo, double& hi, bool& empty) {
+    const double tol = 1e-6 * (fabs(f0) + fabs(f1)) + 1e-9;
+    const double g0 = f0 + tol, g1 = f1 + tol;
+    if (g0 < 0.0 && g1 < 0.0) { empty = true; return; }
+    if (g0 >= 0.0 && g1 >= 0.0) return;
+    const double sx = g0 / (g0 - g1) * span;
+    if (g0 < 0.0) lo = fmax(lo, sx); else hi = fmin(hi, sx);
+}
+TSDF_HD void row_clip(const GridParams& g, const double* Ri, const double* ti,
+                      double py0, double py1, double py2, double pz0, double pz1, double pz2,
+                      int& ilo, int& ihi) {
+    const int m = g.m;
+    ilo = 0; ihi = 0;
+    double lo = 0.0, hi = (double)(m - 1);
+    bool empty = false;
+    const double gx0 = voxel_centre(g.vs_x, 0, g.origin[0]), gx1 = voxel_centre(g.vs_x, m - 1, g.origin[0]);
+    const double ax = ((Ri[0] * gx0 + py0) + pz0) + ti[0], bx = ((Ri[0] * gx1 + py0) + pz0) + ti[0];
+    const double ay = ((Ri[3] * gx0 + py1) + pz1) + ti[1], by = ((Ri[3] * gx1 + py1) + pz1) + ti[1];
+    const double az = ((Ri[6] * gx0 + py2) + pz2) + ti[2], bz = ((Ri[6] * gx1 + py2) + pz2) + ti[2];
+    const double span = (double)(m - 1);
+    const double Wd = (double)g.img_w, Hd = (double)g.img_h;
+    clip_constraint(az, bz, span, lo, hi, empty);                               /* z >= 0 */
+    if (g.k_simple) {
+        const double a0 = g.K[0] * ax + g.K[2] * az, b0 = g.K[0] * bx + g.K[2] * bz;   /* ij0 */
+        const double a1 = g.K[4] * ay + g.K[5] * az, b1 = g.K[4] * by + g.K[5] * bz;   /* ij1 */
+        clip_constraint(a0 + az, b0 + bz, span, lo, hi, empty);                 /* u > -1     */
+        clip_constraint(Wd * az - a0, Wd * bz - b0, span, lo, hi, empty);       /* u < width  */
+        clip_constraint(a1 + az, b1 + bz, span, lo, hi, empty);                 /* v > -1     */
+        clip_constraint(Hd * az - a1, Hd * bz - b1, span, lo, hi, empty);       /* v < height */
+    }
+    if (!empty && lo <= hi) {
+        int l = (int)floor(lo) - 1, h = (int)ceil(hi) + 2;
+        ilo = l < 0 ? 0 : l;
+        ihi = h > m ? m : h;
+    }
+}
+
+/* ---- tracker: sample coordinates, camera_tracking.cpp:259-260, 273-361 -----------------------
+ * s = 0 centre; 1..6 = +x,-x,+y,-y,+z,-z voxel steps; 7..12 = r1p,r1m,r2p,r2m,r3p,r3m.
+ * M = rot for s < 7, the perturbed rotation otherwise.  cvx.. returns the UN-stepped voxel
+ * coordinate (the centre for s < 7) for the bounds test of :261-268. */
+TSDF_HD void sample_coords(const GridParams& g, const double* M, const double* t, int s,
+                           double px, double py, double pz,
+                           double& vx, double& vy, double& vz) {
+    double wx, wy, wz;
+    matvec3(M, px, py, pz, wx, wy, wz);
+    wx = wx + t[0]; wy = wy + t[1]; wz = wz + t[2];
+    world_to_voxel(g, wx, wy, wz, vx, vy, vz);
+    const double vh = (double)g.v_h;
+    if (s == 1) vx += vh; else if (s == 2) vx -= vh;
+    else if (s == 3) vy += vh; else if (s == 4) vy -= vh;
+    else if (s == 5) vz += vh; else if (s == 6) vz -= vh;
+}
+/* camera_tracking.cpp:92-145: perturbed rotation q (0..5) = (I +- w_h [e_k]x) * rot */
+TSDF_HD void perturbed_rot(const GridParams& g, const double* rot, int q, double* out) {
+    const double w_h = (double)g.w_h;
+    double Rd[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    switch (q) {
+        case 0: Rd[5] = -w_h; Rd[7] = w_h; break;
+        case 1: Rd[5] = w_h; Rd[7] = -w_h; break;
+        case 2: Rd[2] = w_h; Rd[6] = -w_h; break;
+        case 3: Rd[2] = -w_h; Rd[6] = w_h; break;
+        case 4: Rd[1] = -w_h; Rd[3] = w_h; break;
+        default: Rd[1] = w_h; Rd[3] = -w_h; break;
+    }
+    matmul3(Rd, rot, out);
+}
+
+/* slot layout of the reduced normal equations */
+enum { SLOT_A = 0, SLOT_B = 21, SLOT_RES = 27, SLOT_NVALID = 28, SLOT_NOOB = 29, N_SLOTS = 30 };
+
+/* ---- 6x6 partial-pivot LU solve, stands in for Eigen's A.inverse()*b (camera_tracking.cpp:191) */
+TSDF_HD int solve6(const double* Ain, const double* bin, double* x) {
+    double A[36], b[6];
+    for (int q = 0; q < 36; q++) A[q] = Ain[q];
+    for (int q = 0; q < 6; q++) b[q] = bin[q];
+    int singular = 0;
+    for (int c = 0; c < 6; c++) {
+        int piv = c;
+        double best = fabs(A[6 * c + c]);
+        for (int r = c + 1; r < 6; r++) {
+            double v = fabs(A[6 * r + c]);
+            if (v > best) { best = v; piv = r; }
+        }
+        if (!(best > 0.0)) { singular = 1; continue; }
+        if (piv != c) {
+            for (int q = 0; q < 6; q++) { double tt = A[6 * c + q]; A[6 * c + q] = A[6 * piv + q]; A[6 * piv + q] = tt; }
+            double tt = b[c]; b[c] = b[piv]; b[piv] = tt;
+        }
+        for (int r = c + 1; r < 6; r++) {
+            double f = A[6 * r + c] / A[6 * c + c];
+            A[6 * r + c] = f;
+            for (int q = c + 1; q < 6; q++) A[6 * r + q] = A[6 * r + q] - f * A[6 * c + q];
+            b[r] = b[r] - f * b[c];
+        }
+    }
+    for (int r = 5; r >= 0; r--) {
+        double s = b[r];
+        for (int q = r + 1; q < 6; q++) s = s - A[6 * r + q] * x[q];
+        x[r] = s / A[6 * r + r];
+    }
+    for (int q = 0; q < 6; q++) if (!(fabs(x[q]) <= 1.7976931348623157e308)) singular = 1;
+    return singular;
+}
+
+/* ---- eigen_utils.cpp:40-128 (delta_t = 1) */
+TSDF_HD void exp_map(const double* v, double* rd, double* dt) {
+    const double ang_min_sinc = 1.0e-8, ang_min_mc = 2.5e-4;
+    const double u0 = v[3], u1 = v[4], u2 = v[5];
+    const double theta = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
+    const double si = sin(theta), co = cos(theta);
+    const double sinc = (fabs(theta) < ang_min_sinc) ? 1.0 : (si / theta);
+    const double mcosc = (fabs(theta) < ang_min_mc) ? 0.5 : ((1.0 - co) / theta / theta);
+    const double msinc = (fabs(theta) < ang_min_mc) ? (1. / 6.0) : ((1.0 - si / theta) / theta / theta);
+    rd[0] = co + mcosc * u0 * u0;
+    rd[1] = -sinc * u2 + mcosc * u0 * u1;
+    rd[2] = sinc * u1 + mcosc * u0 * u2;
+    rd[3] = sinc * u2 + mcosc * u1 * u0;
+    rd[4] = co + mcosc * u1 * u1;
+    rd[5] = -sinc * u0 + mcosc * u1 * u2;
+    rd[6] = -sinc * u1 + mcosc * u2 * u0;
+    rd[7] = sinc * u0 + mcosc * u2 * u1;
+    rd[8] = co + mcosc * u2 * u2;
+    dt[0] = v[0] * (sinc + u0 * u0 * msinc) + v[1] * (u0 * u1 * msinc - u2 * mcosc) + v[2] * (u0 * u2 * msinc + u1 * mcosc);
+    dt[1] = v[0] * (u0 * u1 * msinc + u2 * mcosc) + v[1] * (sinc + u1 * u1 * msinc) + v[2] * (u1 * u2 * msinc - u0 * mcosc);
+    dt[2] = v[0] * (u0 * u2 * msinc - u1 * mcosc) + v[1] * (u1 * u2 * msinc + u0 * mcosc) + v[2] * (sinc + u2 * u2 * msinc);
+}
+
+/* Gauss-Newton step: solve, exp, pose update, signed stop test.
+ * camera_tracking.cpp:191-192, 216-224, 237-239.  sums = the 30 reduced slots. */
+TSDF_HD void gn_update(const GridParams& g, PoseState& p, const double* sums) {
+    double A[36], b[6];
+    int q = 0;
+    for (int r = 0; r < 6; r++)
+        for (int c = r; c < 6; c++) { A[6 * r + c] = sums[SLOT_A + q]; A[6 * c + r] = sums[SLOT_A + q]; q++; }
+    for (int r = 0; r < 6; r++) b[r] = sums[SLOT_B + r];
+    for (int s = 0; s < N_SLOTS; s++) p.sums[s] = sums[s];
+    double tw[6];
+    const int singular = solve6(A, b, tw);
+    p.iterations = p.iterations + 1;
+    if (singular) { p.singular = 1; p.stopped = 1; return; }    /* keep the previous pose, report */
+    for (int s = 0; s < 6; s++) p.twist[s] = tw[s];
+    double rd[9], td[3];
+    exp_map(tw, rd, td);
+    const double rdT[9] = {rd[0], rd[3], rd[6], rd[1], rd[4], rd[7], rd[2], rd[5], rd[8]};
+    double newR[9];
+    matmul3(rdT, p.R, newR);                                     /* :237 */
+    double x, y, z;
+    matvec3(rdT, td[0], td[1], td[2], x, y, z);
+    const double newt[3] = {p.t[0] - x, p.t[1] - y, p.t[2] - z};  /* :238 */
+    pose_set(p, newR, newt);                                     /* :239 */
+    const double mtd = (double)g.max_twist_diff;
+    if (tw[0] < mtd && tw[1] < mtd && tw[2] < mtd && tw[3] < mtd && tw[4] < mtd && tw[5] < mtd) p.stopped = 1;   /* :216-224 */
+}
+
+}  // namespace tsdf

@@ -1,0 +1,58 @@
+/* tsdf_internal.h — launcher declarations shared by tsdf_kernels.cu and tsdf_abi.cu */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tsdf_core.cuh"
+
+namespace tsdf {
+
+constexpr int LIN_THREADS = 256;          /* 8 warps, 16 pixels per sweep */
+constexpr int LIN_PARTIAL_STRIDE = 32;    /* doubles per block partial (30 used) */
+constexpr int MAX_WORLD = 16;
+constexpr int FUSE_ROWS = 8;              /* rows (j) per warp task */
+constexpr int FUSE_THREADS = 128;
+
+/* cross-shard exchange of the reduced normal equations (one slot per rank, double-buffered
+ * by sequence parity so a fast rank cannot overwrite a slot a slow rank still reads) */
+struct Mailbox {
+    double sums[2][MAX_WORLD][32];
+    unsigned long long seq[2][MAX_WORLD];   /* sequence number of the data in sums[parity][rank] */
+};
+
+struct ShardLinks {
+    int32_t world, rank;
+    Mailbox* box[MAX_WORLD];               /* box[r] = rank r's mailbox (peer-mapped), box[rank] = ours */
+};
+
+struct LinearizeArgs {
+    GridParams g;
+    const float2* grid;
+    const PixRec* pix;
+    PoseState* pose;
+    double* partials;                      /* nblk * LIN_PARTIAL_STRIDE */
+    unsigned int* ticket;
+    float* dbgJ; float* dbgPsi; uint8_t* dbgFlag;   /* optional per-pixel records */
+    int32_t do_update;                     /* 1: solve + pose update in the last block */
+    int32_t px_per_block;
+    ShardLinks links;                      /* world = 1: no exchange */
+};
+
+void launch_prep(const GridParams& g, const float* depth, PixRec* pix, PoseState* pose, int reset_track, cudaStream_t s);
+/* exchange_mode: 0 none, 1 in-kernel mailbox all-reduce over peer memory (one kernel per
+ * device, all running concurrently), 2 deferred (same-device shards: publish, then
+ * launch_gn_combine sums in rank order).  seqno labels the exchange. */
+void launch_linearize(const LinearizeArgs& a, int nblk, int exchange_mode, unsigned long long seqno, cudaStream_t s);
+void launch_gn_combine(const LinearizeArgs& a, unsigned long long seqno, cudaStream_t s);
+void launch_fuse(const GridParams& g, float2* grid, const PixRec* pix, const PoseState* pose,
+                 unsigned long long* n_updated, int nblk, cudaStream_t s);
+void launch_fill(float2* grid, int64_t n, float d0, cudaStream_t s);
+void launch_sample(const GridParams& g, const float2* grid, int64_t n, const double* pts, float* out, uint8_t* ok, cudaStream_t s);
+void launch_export(const GridParams& g, const float2* grid, float* D, float* W, int layout, cudaStream_t s);
+void launch_import(const GridParams& g, float2* grid, const float* D, const float* W, int layout, cudaStream_t s);
+void launch_cloud(const GridParams& g, const PixRec* pix, float* cloud, float* normals, cudaStream_t s);
+void launch_exp_map(const double* twist, double* out12, cudaStream_t s);
+void launch_flush(float* buf, int64_t n, cudaStream_t s);
+int  fuse_blocks_per_sm();
+int  linearize_blocks_per_sm();
+
+}  // namespace tsdf

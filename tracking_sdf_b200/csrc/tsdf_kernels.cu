@@ -1,0 +1,572 @@
+/*
+ * tsdf_kernels.cu — hand-written sm_100a kernels of the track + fuse hot path.
+ *
+ *   K1 k_prep       depth -> per-pixel {z, normal} records            
+ *   K2 k_linearize  13-sample central-difference linearisation, deterministic reduction,
+ *                   6x6 solve, exp map and pose update on the device  (camera_tracking.cpp:66-363)
+ *   K3 k_fuse       per-voxel TSDF integration, scan-line clipped     (sdf.cpp:224-292)
+ *
+ * Neither path is a dense contraction, so tensor cores are not used (BASELINE.json
+ * north_star); K3 is HBM/fp64-issue bound, K2 is L1/L2-gather-latency bound.
+ * Compiled with -fmad=false: see tsdf_core.cuh.
+ */
+#include "tsdf_internal.h"
+
+namespace tsdf {
+
+/* ------------------------------------------------------------------------------------------
+ * K1: back-projection + normals.  One thread per pixel; 5 depth reads (L1/L2 resident),
+ * one 16-byte record out.  Thread 0 also re-arms the tracker state for the coming frame.
+ * ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restrict__ depth,
+                                              PixRec* __restrict__ pix, PoseState* pose, int reset_track) {
+    const int u = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int v = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (reset_track && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        pose->iterations = 0; pose->stopped = 0; pose->singular = 0; pose->halo_miss = 0;
+    }
+    if (u >= g.img_w || v >= g.img_h) return;
+    const K1Params kp = k1_params(g.K);
+    const size_t o = (size_t)v * g.img_w + u;
+    const float zc = depth[o];
+    const float qnan = __int_as_float(0x7fc00000);
+    PixRec r;
+    r.z = depth_valid(zc) ? zc : qnan;
+    r.nx = r.ny = r.nz = qnan;
+    if (u > 0 && v > 0 && u < g.img_w - 1 && v < g.img_h - 1) {
+        float nx, ny, nz;
+        if (normal_px(kp, u, v, zc, depth[o - 1], depth[o + 1], depth[o - g.img_w], depth[o + g.img_w], nx, ny, nz)) {
+            r.nx = nx; r.ny = ny; r.nz = nz;
+        }
+    }
+    *reinterpret_cast<float4*>(&pix[o]) = make_float4(r.z, r.nx, r.ny, r.nz);
+}
+
+void launch_prep(const GridParams& g, const float* depth, PixRec* pix, PoseState* pose, int reset_track, cudaStream_t s) {
+    dim3 grid((g.img_w + 31) / 32, (g.img_h + 7) / 8);
+    k_prep<<<grid, 256, 0, s>>>(g, depth, pix, pose, reset_track);
+}
+
+/* organised cloud + normals for the accessor / tests */
+__global__ void k_cloud(GridParams g, const PixRec* __restrict__ pix, float* cloud, float* normals) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= g.img_w * g.img_h) return;
+    const int u = o % g.img_w, v = o / g.img_w;
+    const K1Params kp = k1_params(g.K);
+    const PixRec r = pix[o];
+    float x, y;
+    backproject_px(kp, u, v, r.z, x, y);
+    cloud[3 * o] = x; cloud[3 * o + 1] = y; cloud[3 * o + 2] = r.z;
+    if (normals) { normals[3 * o] = r.nx; normals[3 * o + 1] = r.ny; normals[3 * o + 2] = r.nz; }
+}
+void launch_cloud(const GridParams& g, const PixRec* pix, float* cloud, float* normals, cudaStream_t s) {
+    const int n = g.img_w * g.img_h;
+    k_cloud<<<(n + 255) / 256, 256, 0, s>>>(g, pix, cloud, normals);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * voxel fetch used by the tracker and the sampler: {D,W} interleaved, x-fastest, read-only path
+ * ------------------------------------------------------------------------------------------ */
+struct GridFetch {
+    const float2* __restrict__ grid;
+    int m, ks0, ks1;
+    int* miss;
+    __device__ __forceinline__ bool operator()(int ci, int cj, int ck, float& d, float& w) const {
+        if ((unsigned)ci >= (unsigned)m || (unsigned)cj >= (unsigned)m || (unsigned)ck >= (unsigned)m) return false;   /* sdf.h:114-119 */
+        if (ck < ks0 || ck >= ks1) { *miss = 1; d = 0.0f; w = 0.0f; return true; }   /* not held by this shard */
+        const float2 dw = __ldg(&grid[((size_t)(ck - ks0) * m + cj) * m + ci]);
+        d = dw.x; w = dw.y;
+        return true;
+    }
+};
+
+__global__ void k_sample(GridParams g, const float2* __restrict__ grid, int64_t n, const double* __restrict__ pts,
+                         float* out, uint8_t* ok) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int miss = 0;
+    GridFetch f{grid, g.m, g.ks0, g.ks1, &miss};
+    bool is_interp;
+    out[q] = interpolate_distance(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2], f, is_interp);
+    ok[q] = is_interp ? 1 : 0;
+}
+void launch_sample(const GridParams& g, const float2* grid, int64_t n, const double* pts, float* out, uint8_t* ok, cudaStream_t s) {
+    k_sample<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, grid, n, pts, out, ok);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K2: linearisation + reduction + (optionally) solve and pose update.
+ *
+ * Mapping: 16 lanes per pixel (13 samples + 3 idle), two pixels per warp, so the 104
+ * neighbour gathers of one pixel are issued by 13 lanes in parallel instead of one thread
+ * serially; each block owns a contiguous run of the strided pixels (reference loop order:
+ * column outer, row inner) so neighbouring pixels share voxel lines in L1.
+ *
+ * Reduction (deterministic, no float atomics): the 30 slots (21 upper-triangle J J^T, 6 psi J,
+ * psi^2, n_valid, n_oob) are spread over the 16 lanes of a pixel group (slots s and s+16);
+ * every product of two fp32-valued doubles is exact, sums are double in a fixed order:
+ * lane registers over the block's pixels -> half-warps -> warps -> blocks (last block, via a
+ * ticket) -> ranks (mailboxes, rank order).
+ * ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ void slot_operands(int slot, int& a, int& b, int& kind) {
+    /* kind 0: x[a]*x[b] with x = (J0..J5, psi); 1: n_valid; 2: n_oob; 3: unused */
+    kind = 0; a = 0; b = 0;
+    if (slot < SLOT_B) {
+        int q = 0;
+        for (int r = 0; r < 6; r++)
+            for (int c = r; c < 6; c++) { if (q == slot) { a = r; b = c; } q++; }
+    } else if (slot < SLOT_RES) { a = 6; b = slot - SLOT_B; }
+    else if (slot == SLOT_RES) { a = 6; b = 6; }
+    else if (slot == SLOT_NVALID) kind = 1;
+    else if (slot == SLOT_NOOB) kind = 2;
+    else kind = 3;
+}
+
+__device__ __forceinline__ double ld_volatile_f64(const double* p) { return *reinterpret_cast<const volatile double*>(p); }
+
+/* sum of the 30 slots over all ranks, rank order; runs in the last block after its local sums
+ * are in s_sums.  mode 1: in-kernel exchange over peer-mapped mailboxes. */
+__device__ void exchange_sums(const ShardLinks& L, unsigned long long seqno, double* s_sums, int tid) {
+    const int par = (int)(seqno & 1ull);
+    for (int r = 0; r < L.world; r++) {
+        if (tid < N_SLOTS) L.box[r]->sums[par][L.rank][tid] = s_sums[tid];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < L.world) {
+        *reinterpret_cast<volatile unsigned long long*>(&L.box[tid]->seq[par][L.rank]) = seqno;
+    }
+    if (tid < L.world) {
+        const volatile unsigned long long* flag = &L.box[L.rank]->seq[par][tid];
+        while (*flag != seqno) { __nanosleep(20); }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < N_SLOTS) {
+        double acc = 0.0;
+        for (int r = 0; r < L.world; r++) acc = acc + ld_volatile_f64(&L.box[L.rank]->sums[par][r][tid]);
+        s_sums[tid] = acc;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinearizeArgs a, int exchange_mode, unsigned long long seqno) {
+    __shared__ double sM[7][9];
+    __shared__ double sT[3];
+    __shared__ double sRed[LIN_THREADS / 32][32];
+    __shared__ double sSums[32];
+    __shared__ int sLast;
+    __shared__ int sMiss;
+
+    const GridParams& g = a.g;
+    PoseState* pose = a.pose;
+    if (a.do_update && pose->stopped) return;             /* loop condition of camera_tracking.cpp:79 */
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 9) sM[0][tid] = pose->R[tid];
+    if (tid < 3) sT[tid] = pose->t[tid];
+    if (tid == 0) sMiss = 0;
+    if (tid >= 32 && tid < 38) {                          /* camera_tracking.cpp:92-145 */
+        double R[9], out[9];
+        for (int q = 0; q < 9; q++) R[q] = pose->R[q];
+        perturbed_rot(g, R, tid - 32, out);
+        for (int q = 0; q < 9; q++) sM[1 + tid - 32][q] = out[q];
+    }
+    __syncthreads();
+
+    const int grp = lane >> 4, s = lane & 15, base = grp << 4;
+    int a0, b0, k0, a1, b1, k1;
+    slot_operands(s, a0, b0, k0);
+    slot_operands(s + 16, a1, b1, k1);
+    const K1Params kp = k1_params(g.K);
+    const float step = (s == 0) ? g.v_h2_width : (s == 1) ? g.v_h2_height : (s == 2) ? g.v_h2_depth : g.two_w_h;
+    const double* M = sM[(s < 7) ? 0 : (s - 6)];
+    int miss = 0;
+    GridFetch fetch{a.grid, g.m, g.ks0, g.ks1, &miss};
+
+    const bool sharded = (g.ko0 > 0 || g.ko1 < g.m);
+    const int P = g.ni * g.nj;
+    const int p_begin = blockIdx.x * a.px_per_block;
+    const int p_end = min(P, p_begin + a.px_per_block);
+    double acc0 = 0.0, acc1 = 0.0;
+
+    for (int pb = p_begin; pb < p_end; pb += (LIN_THREADS / 32) * 2) {     /* warp-uniform trip count */
+        const int p = pb + warp * 2 + grp;
+        const bool have = p < p_end;
+        float z = __int_as_float(0x7fc00000);
+        int u = 0, v = 0;
+        if (have) {
+            const int ii = p / g.nj, jj = p - ii * g.nj;                     /* camera_tracking.cpp:162-163 */
+            u = ii * g.stride; v = jj * g.stride;
+            z = __ldg(&a.pix[(size_t)v * g.img_w + u].z);
+        }
+        const bool valid_pt = have && (z == z);                              /* camera_tracking.cpp:168 */
+        float val = 0.0f;
+        bool ok = true, oob = false, mine = true;
+        float x = 0.0f, y = 0.0f;
+        if (valid_pt) backproject_px(kp, u, v, z, x, y);
+        if (sharded && valid_pt) {
+            /* pixel owner = the slab holding the centre sample's base cell */
+            const double wz = ((sM[0][6] * (double)x + sM[0][7] * (double)y) + sM[0][8] * (double)z) + sT[2];
+            const double vzc = ((wz - g.origin[2]) * (double)g.m_div_depth - 0.5);
+            int kc = trunc_f2i((float)vzc);
+            kc = kc < 0 ? 0 : (kc > g.m - 1 ? g.m - 1 : kc);
+            mine = (kc >= g.ko0 && kc < g.ko1);
+        }
+        if (s < 13) {
+            ok = false;
+            if (valid_pt && mine) {
+                double vx, vy, vz;
+                sample_coords(g, M, sT, s, (double)x, (double)y, (double)z, vx, vy, vz);
+                if (s == 0) {                                                /* camera_tracking.cpp:261-268 */
+                    const double dm = (double)g.m;
+                    oob = (vx < 0 || vy < 0 || vz < 0 || vx >= dm || vy >= dm || vz >= dm);
+                }
+                bool is_interp;
+                val = interpolate_distance(vx, vy, vz, fetch, is_interp);
+                ok = is_interp;
+            }
+        }
+        const unsigned okb = __ballot_sync(0xffffffffu, ok);
+        const unsigned oobb = __ballot_sync(0xffffffffu, oob);
+        const bool allok = ((okb >> base) & 0xffffu) == 0xffffu;
+        const bool is_oob = ((oobb >> base) & 1u) != 0u;
+        const int flag = !valid_pt ? 0 : (!mine ? 4 : (is_oob ? 2 : (allok ? 1 : 3)));
+
+        /* J_a = (plus - minus) / step  in fp32, camera_tracking.cpp:286,301,316,331,346,361 */
+        const int sa = (s < 6) ? s : 0;
+        const float vplus = __shfl_sync(0xffffffffu, val, base + 2 * sa + 1);
+        const float vminus = __shfl_sync(0xffffffffu, val, base + 2 * sa + 2);
+        const float psi = __shfl_sync(0xffffffffu, val, base);
+        const float Ja = (vplus - vminus) / step;
+        const float xv = (s < 6) ? Ja : psi;                                 /* lane 6 (and up) holds psi */
+        const double xa0 = (double)__shfl_sync(0xffffffffu, xv, base + a0);
+        const double xb0 = (double)__shfl_sync(0xffffffffu, xv, base + b0);
+        const double xa1 = (double)__shfl_sync(0xffffffffu, xv, base + a1);
+        const double xb1 = (double)__shfl_sync(0xffffffffu, xv, base + b1);
+        if (flag == 1) {                                                     /* camera_tracking.cpp:178-182 */
+            if (k0 == 0) acc0 = acc0 + xa0 * xb0;
+            if (k1 == 0) acc1 = acc1 + xa1 * xb1; else if (k1 == 1) acc1 = acc1 + 1.0;
+        } else if (flag == 2) {
+            if (k1 == 2) acc1 = acc1 + 1.0;
+        }
+        if (a.dbgFlag && have) {
+            if (s < 6) a.dbgJ[(size_t)p * 6 + s] = (flag == 1) ? Ja : 0.0f;
+            else if (s == 6) a.dbgPsi[p] = (flag == 1) ? psi : 0.0f;
+            else if (s == 7) a.dbgFlag[p] = (uint8_t)flag;
+        }
+    }
+    if (miss) sMiss = 1;
+
+    /* half-warps -> warp */
+    acc0 = acc0 + __shfl_xor_sync(0xffffffffu, acc0, 16);
+    acc1 = acc1 + __shfl_xor_sync(0xffffffffu, acc1, 16);
+    if (lane < 16) { sRed[warp][lane] = acc0; sRed[warp][lane + 16] = acc1; }
+    __syncthreads();
+    /* warps -> block partial */
+    if (tid < N_SLOTS) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < LIN_THREADS / 32; w++) v = v + sRed[w][tid];
+        a.partials[(size_t)blockIdx.x * LIN_PARTIAL_STRIDE + tid] = v;
+    }
+    if (tid == 0 && sMiss) atomicAdd(&pose->halo_miss, 1);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(a.ticket, 1u);
+        sLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!sLast) return;
+
+    /* ---- last block: blocks -> device sums, fixed order (8 chunks per slot, then chunk order) */
+    __threadfence();
+    {
+        const int slot = tid >> 3, chunk = tid & 7;
+        const int nb = gridDim.x;
+        const int per = (nb + 7) / 8;
+        double v = 0.0;
+        if (slot < N_SLOTS) {
+            const int b0_ = chunk * per, b1_ = min(nb, b0_ + per);
+            for (int b = b0_; b < b1_; b++) v = v + __ldcg(&a.partials[(size_t)b * LIN_PARTIAL_STRIDE + slot]);
+        }
+        /* combine the 8 chunk sums in chunk order on the chunk-0 lane */
+        double tot = v;
+#pragma unroll
+        for (int c = 1; c < 8; c++) {
+            const double o = __shfl_sync(0xffffffffu, v, (lane & ~7) + c);
+            tot = tot + o;
+        }
+        if (slot < N_SLOTS && chunk == 0) sSums[slot] = tot;
+    }
+    __syncthreads();
+    if (exchange_mode == 1 && a.links.world > 1) exchange_sums(a.links, seqno, sSums, tid);
+    if (exchange_mode == 2 && a.links.world > 1) {
+        /* deferred (single-process emulation): publish our sums into every mailbox; a separate
+         * k_gn_combine launch sums them in rank order and updates the pose */
+        const int par = (int)(seqno & 1ull);
+        for (int r = 0; r < a.links.world; r++)
+            if (tid < N_SLOTS) a.links.box[r]->sums[par][a.links.rank][tid] = sSums[tid];
+    } else if (tid == 0) {
+        if (a.do_update) gn_update(g, *pose, sSums);
+        else for (int q = 0; q < N_SLOTS; q++) pose->sums[q] = sSums[q];
+    }
+    if (tid == 0) *a.ticket = 0u;
+}
+
+/* deferred combine for in-process shards (exchange_mode 2) */
+__global__ void k_gn_combine(LinearizeArgs a, unsigned long long seqno) {
+    __shared__ double sSums[32];
+    PoseState* pose = a.pose;
+    if (a.do_update && pose->stopped) return;
+    const int tid = threadIdx.x;
+    const int par = (int)(seqno & 1ull);
+    if (tid < N_SLOTS) {
+        double acc = 0.0;
+        for (int r = 0; r < a.links.world; r++) acc = acc + a.links.box[a.links.rank]->sums[par][r][tid];
+        sSums[tid] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (a.do_update) gn_update(a.g, *pose, sSums);
+        else for (int q = 0; q < N_SLOTS; q++) pose->sums[q] = sSums[q];
+    }
+}
+
+void launch_linearize(const LinearizeArgs& a, int nblk, int exchange_mode, unsigned long long seqno, cudaStream_t s) {
+    k_linearize<<<nblk, LIN_THREADS, 0, s>>>(a, exchange_mode, seqno);
+}
+void launch_gn_combine(const LinearizeArgs& a, unsigned long long seqno, cudaStream_t s) {
+    k_gn_combine<<<1, 32, 0, s>>>(a, seqno);
+}
+
+int linearize_blocks_per_sm() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_linearize, LIN_THREADS, 0);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K3: TSDF fusion (sdf.cpp:232-292).
+ *
+ * Layout: float2 {D,W} per voxel, x fastest; a lane owns 4 consecutive x voxels = one 32-byte
+ * sector = two 16-byte vector loads/stores.  A warp task is FUSE_ROWS rows (same k, consecutive
+ * j); lane r first clips row r against the view frustum (the projection is affine along a
+ * row, so the in-image voxels form one interval; the clip is conservative by a voxel and the
+ * exact double-precision test still decides every voxel).  Rows and 128-voxel chunks outside
+ * the interval cost no memory traffic and almost no instructions.
+ *
+ * Exactness: the camera-space centre is ((Rinv_r0*gx + Rinv_r1*gy) + Rinv_r2*gz) + tinv_r in
+ * double, identical rounding sequence to the reference's Eigen product; the three products
+ * are hoisted (x per chunk, y per row, z per task), the three additions are per voxel.
+ * ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(FUSE_THREADS) k_fuse(GridParams g, float2* __restrict__ grid,
+                                                       const PixRec* __restrict__ pix,
+                                                       const PoseState* __restrict__ pose,
+                                                       unsigned long long* n_updated) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = FUSE_THREADS / 32;
+    const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int total_warps = gridDim.x * warps_per_block;
+    const int m = g.m;
+    const int jgroups = (m + FUSE_ROWS - 1) / FUSE_ROWS;
+    const int ntasks = (g.ks1 - g.ks0) * jgroups;
+    const int nchunks = (m + 127) / 128;
+
+    double Ri[9], ti[3];
+#pragma unroll
+    for (int q = 0; q < 9; q++) Ri[q] = pose->Rinv[q];
+#pragma unroll
+    for (int q = 0; q < 3; q++) ti[q] = pose->tinv[q];
+    const K1Params kp = k1_params(g.K);
+    unsigned int my_updates = 0;
+
+    for (int task = gw; task < ntasks; task += total_warps) {
+        const int k = g.ks0 + task / jgroups;
+        const int j0 = (task % jgroups) * FUSE_ROWS;
+        const double gz = voxel_centre(g.vs_z, k, g.origin[2]);
+        const double pz0 = Ri[2] * gz, pz1 = Ri[5] * gz, pz2 = Ri[8] * gz;
+
+        /* ---- per-row setup on lane r: y products and the conservative clip interval */
+        const int jrow = j0 + (lane & (FUSE_ROWS - 1));
+        const double gy = voxel_centre(g.vs_y, jrow, g.origin[1]);
+        const double py0 = Ri[1] * gy, py1 = Ri[4] * gy, py2 = Ri[7] * gy;
+        int ilo = 0, ihi = 0;
+        if (lane < FUSE_ROWS && jrow < m) row_clip(g, Ri, ti, py0, py1, py2, pz0, pz1, pz2, ilo, ihi);
+        /* union of the rows' intervals decides which chunks the warp visits at all */
+        int umin = ilo < ihi ? ilo : m, umax = ilo < ihi ? ihi : 0;
+#pragma unroll
+        for (int o = FUSE_ROWS / 2; o > 0; o >>= 1) {
+            umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+            umax = max(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+        }
+        umin = __shfl_sync(0xffffffffu, umin, 0);
+        umax = __shfl_sync(0xffffffffu, umax, 0);
+        if (umin >= umax) continue;
+
+        for (int c = umin / 128; c < nchunks && c * 128 < umax; c++) {
+            const int x0 = c * 128 + lane * 4;
+            double px0[4], px1[4], px2[4];
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const double gx = voxel_centre(g.vs_x, x0 + v, g.origin[0]);
+                px0[v] = Ri[0] * gx; px1[v] = Ri[3] * gx; px2[v] = Ri[6] * gx;
+            }
+            for (int r = 0; r < FUSE_ROWS; r++) {
+                const int rlo = __shfl_sync(0xffffffffu, ilo, r), rhi = __shfl_sync(0xffffffffu, ihi, r);
+                if (rlo >= rhi || rhi <= c * 128 || rlo >= c * 128 + 128) continue;     /* warp-uniform */
+                const double qy0 = __shfl_sync(0xffffffffu, py0, r);
+                const double qy1 = __shfl_sync(0xffffffffu, py1, r);
+                const double qy2 = __shfl_sync(0xffffffffu, py2, r);
+                const int j = j0 + r;
+                float dnew[4], wnew[4];
+                bool upd[4];
+                bool any = false;
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    upd[v] = false;
+                    const int x = x0 + v;
+                    if (x >= rlo && x < rhi && x < m) {
+                        /* camera_tracking.cpp:51-54 : rot_inv * g + rot_inv_trans */
+                        const double cx = ((px0[v] + qy0) + pz0) + ti[0];
+                        const double cy = ((px1[v] + qy1) + pz1) + ti[1];
+                        const double cz = ((px2[v] + qy2) + pz2) + ti[2];
+                        int iu, iv;
+                        if (fuse_project(g, cx, cy, cz, iu, iv)) {
+                            const float4 rr = __ldg(reinterpret_cast<const float4*>(&pix[(size_t)iv * g.img_w + iu]));
+                            PixRec rec; rec.z = rr.x; rec.nx = rr.y; rec.ny = rr.z; rec.nz = rr.w;
+                            float fx_, fy_;
+                            backproject_px(kp, iu, iv, rec.z, fx_, fy_);
+                            upd[v] = fuse_distance(g, cx, cy, cz, fx_, fy_, rec, dnew[v], wnew[v]);
+                        }
+                    }
+                    any = any || upd[v];
+                }
+                if (any) {
+                    const bool owned = (k >= g.ko0 && k < g.ko1);    /* halo layers are fused redundantly, counted once */
+                    float4* ptr = reinterpret_cast<float4*>(&grid[((size_t)(k - g.ks0) * m + j) * m + x0]);
+                    float4 q0 = ptr[0], q1 = ptr[1];
+                    if (upd[0]) { fuse_apply(q0.x, q0.y, dnew[0], wnew[0]); my_updates += owned; }
+                    if (upd[1]) { fuse_apply(q0.z, q0.w, dnew[1], wnew[1]); my_updates += owned; }
+                    if (upd[2]) { fuse_apply(q1.x, q1.y, dnew[2], wnew[2]); my_updates += owned; }
+                    if (upd[3]) { fuse_apply(q1.z, q1.w, dnew[3], wnew[3]); my_updates += owned; }
+                    if (upd[0] || upd[1]) ptr[0] = q0;
+                    if (upd[2] || upd[3]) ptr[1] = q1;
+                }
+            }
+        }
+    }
+    /* one atomic per warp */
+    unsigned int tot = my_updates;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0 && tot) atomicAdd(n_updated, (unsigned long long)tot);
+}
+
+void launch_fuse(const GridParams& g, float2* grid, const PixRec* pix, const PoseState* pose,
+                 unsigned long long* n_updated, int nblk, cudaStream_t s) {
+    k_fuse<<<nblk, FUSE_THREADS, 0, s>>>(g, grid, pix, pose, n_updated);
+}
+int fuse_blocks_per_sm() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fuse, FUSE_THREADS, 0);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * utilities: grid init (sdf.cpp:28-31), layout conversion for the accessors, exp map, L2 flush
+ * ------------------------------------------------------------------------------------------ */
+__global__ void k_fill(float4* grid, int64_t n4, float d0) {
+    const float4 v = make_float4(d0, 0.0f, d0, 0.0f);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) grid[q] = v;
+}
+void launch_fill(float2* grid, int64_t n, float d0, cudaStream_t s) {
+    k_fill<<<148 * 8, 256, 0, s>>>(reinterpret_cast<float4*>(grid), n / 2, d0);
+}
+
+/* out index: layout 0 = reference z-fastest over the stored slab: idx = (i*m + j)*nk + (k-ks0);
+ * layout 1 = x-fastest: idx = ((k-ks0)*m + j)*m + i.  Tiled through shared memory for layout 0. */
+__global__ void k_export_xfast(GridParams g, const float2* __restrict__ grid, float* D, float* W, int64_t n) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const float2 v = grid[q];
+        D[q] = v.x; W[q] = v.y;
+    }
+}
+__global__ void k_import_xfast(GridParams g, float2* grid, const float* __restrict__ D, const float* __restrict__ W, int64_t n) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
+        grid[q] = make_float2(D[q], W[q]);
+}
+/* transpose (k,i) planes for fixed j: tile 32x32 */
+__global__ void k_export_ref(GridParams g, const float2* __restrict__ grid, float* D, float* W) {
+    __shared__ float2 tile[32][33];
+    const int m = g.m, nk = g.ks1 - g.ks0;
+    const int j = blockIdx.z;
+    const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int kk = k0 + r, i = i0 + threadIdx.x;
+        if (kk < nk && i < m) tile[r][threadIdx.x] = grid[((size_t)kk * m + j) * m + i];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, kk = k0 + threadIdx.x;
+        if (kk < nk && i < m) {
+            const float2 v = tile[threadIdx.x][r];
+            const size_t o = ((size_t)i * m + j) * nk + kk;
+            D[o] = v.x; W[o] = v.y;
+        }
+    }
+}
+__global__ void k_import_ref(GridParams g, float2* grid, const float* __restrict__ D, const float* __restrict__ W) {
+    __shared__ float2 tile[32][33];
+    const int m = g.m, nk = g.ks1 - g.ks0;
+    const int j = blockIdx.z;
+    const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, kk = k0 + threadIdx.x;
+        if (kk < nk && i < m) {
+            const size_t o = ((size_t)i * m + j) * nk + kk;
+            tile[r][threadIdx.x] = make_float2(D[o], W[o]);
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int kk = k0 + r, i = i0 + threadIdx.x;
+        if (kk < nk && i < m) grid[((size_t)kk * m + j) * m + i] = tile[threadIdx.x][r];
+    }
+}
+void launch_export(const GridParams& g, const float2* grid, float* D, float* W, int layout, cudaStream_t s) {
+    const int nk = g.ks1 - g.ks0;
+    if (layout == 1) {
+        k_export_xfast<<<148 * 8, 256, 0, s>>>(g, grid, D, W, (int64_t)nk * g.m * g.m);
+    } else {
+        dim3 grid3((g.m + 31) / 32, (nk + 31) / 32, g.m);
+        k_export_ref<<<grid3, dim3(32, 8), 0, s>>>(g, grid, D, W);
+    }
+}
+void launch_import(const GridParams& g, float2* grid, const float* D, const float* W, int layout, cudaStream_t s) {
+    const int nk = g.ks1 - g.ks0;
+    if (layout == 1) {
+        k_import_xfast<<<148 * 8, 256, 0, s>>>(g, grid, D, W, (int64_t)nk * g.m * g.m);
+    } else {
+        dim3 grid3((g.m + 31) / 32, (nk + 31) / 32, g.m);
+        k_import_ref<<<grid3, dim3(32, 8), 0, s>>>(g, grid, D, W);
+    }
+}
+
+__global__ void k_exp_map(const double* twist, double* out12) {
+    double tw[6], rd[9], dt[3];
+    for (int q = 0; q < 6; q++) tw[q] = twist[q];
+    exp_map(tw, rd, dt);
+    for (int q = 0; q < 9; q++) out12[q] = rd[q];
+    for (int q = 0; q < 3; q++) out12[9 + q] = dt[q];
+}
+void launch_exp_map(const double* twist, double* out12, cudaStream_t s) { k_exp_map<<<1, 1, 0, s>>>(twist, out12); }
+
+__global__ void k_flush(float4* buf, int64_t n4) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x)
+        buf[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+void launch_flush(float* buf, int64_t n, cudaStream_t s) { k_flush<<<148 * 8, 256, 0, s>>>(reinterpret_cast<float4*>(buf), n / 4); }
+
+}  // namespace tsdf
