@@ -1,0 +1,378 @@
+#!/usr/bin/env python3
+"""bench.py — frames/s of the track + fuse hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          this repo's CUDA path
+  python bench.py --impl reference [...]                       the reference's CPU algorithm (oracle port)
+
+A step = one 640x480 depth frame tracked (10 fixed Gauss-Newton iterations) and fused into a
+512^3 grid (BASELINE.json configs[1]).  Frames are synthetic: raycast from an analytic scene
+along the bundled fr1/plant ground-truth camera path (tools/synth).
+
+N = 1   one sequence on one B200.
+N > 1   launched by torch.distributed.run, one process per GPU: N independent sequences of the
+        same shape, one per GPU (BASELINE.json configs[4]); no data-path collective; value is the
+        aggregate frames/s; scaling "weak".  (The z-slab sharded volumes of configs[2,3] are run
+        with --workload sharded.)
+
+Numbers in the JSON line
+  value      frames/s with every depth frame already resident in HBM, CUDA-event timed on the
+             library's stream, max over ranks.  The 1 GiB grid is > L2 (126 MB), so no L2 flush.
+  e2e        the same frames through tsdf_track_and_fuse() with HOST (pinned) depth buffers: each
+             step includes the H2D copy of its frame and the D2H read of pose + stats; wall clock.
+  roofline   the fusion kernel (k_fuse): 16 B per updated voxel / CUDA-event duration vs the
+             measured HBM copy peak; dense_fuse = the same kernel on the dense micro-benchmark
+             (every voxel of the 512^3 grid updated, 2.147 GB per launch) where north_star's
+             ">= 70 % of HBM peak" is defined; roofline_track = the linearisation kernel's
+             gather bytes (832 B per valid pixel-iteration, L2-resident) for information.
+  cpu_baseline  the oracle port of the reference (all host threads) on the first frames of the
+             same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/s (track+fuse) 640x480 @512^3"
+GN_ITERS = 10
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def init_dist(world, local, backend):
+    if world <= 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+    dist.init_process_group(backend=backend)
+    return dist
+
+
+def barrier_max(dist, value, device=None):
+    """barrier, then max over ranks of `value` (plumbing only: torch.distributed)."""
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.barrier()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def render_frames(n, start, pinned):
+    from tools import synth
+    import tracking_sdf_b200.capi as capi
+    t0 = time.time()
+    buf = capi.pinned_empty((n, synth.HEIGHT, synth.WIDTH), np.float32) if pinned else np.empty((n, synth.HEIGHT, synth.WIDTH), np.float32)
+    depth, Rs, ts = synth.render_sequence(n, start=start, out=buf)
+    log("[bench] rendered %d synthetic frames in %.1f s" % (n, time.time() - t0))
+    return depth, Rs, ts
+
+
+def run_cpu_baseline(depth, Rs, ts, m, budget_s, max_frames):
+    """The oracle port of the reference on the first frames of the workload, all host threads,
+    timed where the reference prints its own timings (camera_tracking.cpp:68,243; sdf.cpp:225,306)."""
+    from oracle import pyoracle as po
+    from tools import synth
+    t_setup = time.time()
+    o = po.Oracle(m=m, use_coord_table=1, gauss_newton_max_iteration=GN_ITERS, maximum_twist_diff=float("-inf"))
+    o.set_intrinsics(synth.K_DEFAULT)
+    o.set_pose(Rs[0], ts[0])
+    o.fuse(depth[0])
+    setup = time.time() - t_setup
+    t_track = t_fuse = 0.0
+    n = 0
+    n_upd = 0
+    t_begin = time.time()
+    for f in range(1, len(depth)):
+        t0 = time.time(); st = o.track(depth[f]); t1 = time.time(); n_upd += o.fuse(depth[f]); t2 = time.time()
+        t_track += t1 - t0; t_fuse += t2 - t1; n += 1
+        if n >= max_frames or (time.time() - t_begin) > budget_s:
+            break
+    R, t = o.get_pose()
+    err = float(np.linalg.norm(t - ts[n]))
+    o.close()
+    tot = t_track + t_fuse
+    return {"value": n / tot, "unit": "frames/s", "cores": po.num_threads(), "kind": "port",
+            "sample": "frames 1..%d of the same 512^3 workload (frame 0 fused untimed), %d GN iterations each; "
+                      "oracle port of the reference (it cannot be built here: ROS/PCL/Eigen absent), OpenMP, "
+                      "precomputed global_coords table like sdf.cpp:11" % (n, GN_ITERS),
+            "ms_per_frame_track": 1e3 * t_track / n, "ms_per_frame_fuse": 1e3 * t_fuse / n,
+            "voxels_visited_per_s": (m ** 3) * n / t_fuse, "voxel_updates_per_s": n_upd / t_fuse,
+            "frames": n, "setup_s": setup, "final_pos_err_m": err}
+
+
+def main_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return 0
+    n_need = min(args.steps + args.warmup, 64) + 1
+    depth, Rs, ts = render_frames(n_need, 0, pinned=False)
+    t0 = time.time()
+    cb = run_cpu_baseline(depth, Rs, ts, args.m, budget_s=args.ref_budget, max_frames=n_need - 1)
+    out = {"metric": METRIC if args.m == 512 else METRIC.replace("512", str(args.m)), "value": cb["value"], "unit": "frames/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 values / f64 geometry",
+           "data": "synthetic", "impl": "reference",
+           "config": {"workload": "%d^3 grid, 640x480 synthetic depth along fr1/plant GT path, %d GN iterations/frame (BASELINE.json configs[1])" % (args.m, GN_ITERS),
+                      "note": "rate measured on a bounded sample of the requested steps (%d frames, %.0f s budget); host CPU only" % (cb["frames"], args.ref_budget)},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "wall_s": time.time() - t0}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def dense_fuse_bench(T, m, K, reps, hbm):
+    """Dense micro-benchmark: camera outside the volume looking in, constant depth
+    behind the whole volume -> every voxel is in view and in front of the surface -> every voxel
+    is updated: traffic is exactly 16 B x m^3 per launch."""
+    g = T.Tsdf(T.default_config(m=m, gauss_newton_max_iteration=GN_ITERS, maximum_twist_diff=float("-inf")))
+    g.set_intrinsics(K)
+    R = np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0]], float)
+    t = np.array([0.0, -12.0, 1.25])
+    depth = np.full((480, 640), 40.0, np.float32)
+    dev = g.dev_alloc(depth.nbytes); g.dev_upload(dev, depth)
+    g.set_pose(R, t)
+    for _ in range(3):
+        g.enqueue_frame(dev, track=0, slot=0)
+    g.sync(); g.total_updates(reset=True)
+    g.stage_timing_begin(reps)
+    for _ in range(reps):
+        g.enqueue_frame(dev, track=0, slot=0)
+    ms = g.stage_timing_end()
+    upd = g.total_updates()
+    g.dev_free(dev); g.close()
+    t_fuse = float(ms[:, 2].mean()) * 1e-3
+    per_launch = upd / reps
+    ach = 16.0 * per_launch / t_fuse / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+            "ms_per_launch": t_fuse * 1e3, "voxels_updated_per_launch": per_launch, "all_voxels_updated": bool(per_launch == m ** 3),
+            "voxel_updates_per_s": per_launch / t_fuse}
+
+
+def main_cuda(args):
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        log("[bench] WORLD_SIZE %d != --gpus %d; using WORLD_SIZE" % (world, args.gpus))
+    n_gpus = max(world, 1)
+    import tracking_sdf_b200 as T
+    from tracking_sdf_b200 import capi
+    from tools import synth
+    L = T.load_library()                       # raises if the CUDA library is missing: no fallback
+    ndev = L.tsdf_device_count()
+    if ndev < 1:
+        raise SystemExit("bench.py: no CUDA device visible (the product has no CPU path)")
+    device = local % ndev
+    dist = init_dist(world, local, "nccl")
+    tdev = None
+    if dist is not None:
+        import torch
+        tdev = torch.device("cuda", device)
+    hbm, peak_src = peaks()
+    K = synth.K_DEFAULT
+    m = args.m
+    W, Ksteps = args.warmup, args.steps
+    n_frames = W + Ksteps
+    # config 5: independent sequences — each rank starts elsewhere on the path
+    depth, Rs, ts = render_frames(n_frames, start=rank * 37, pinned=True)
+    frame_bytes = depth[0].nbytes
+
+    cfg = T.default_config(m=m, device=device, gauss_newton_max_iteration=GN_ITERS, maximum_twist_diff=float("-inf"))
+    g = T.Tsdf(cfg)
+    g.set_intrinsics(K)
+    ring = g.pose_ring_capacity()
+
+    # ---------------- value: frames resident in HBM --------------------------------------------
+    dev = g.dev_alloc(depth.nbytes)
+    g.dev_upload(dev, depth)
+    g.set_pose(Rs[0], ts[0])
+    g.enqueue_frame(dev, track=0, slot=0)                       # frame 0: fuse at the GT pose
+    for f in range(1, W):
+        g.enqueue_frame(dev + f * frame_bytes, track=1, slot=f % ring)
+    g.sync()
+    g.total_updates(reset=True)
+    launches0 = g.kernel_launch_count()
+    sampler = ClockSampler(device); sampler.start()
+    if dist is not None:
+        import torch
+        dist.barrier(); torch.cuda.synchronize()
+    g.stage_timing_begin(Ksteps)
+    g.timer_begin()
+    for f in range(W, n_frames):
+        g.enqueue_frame(dev + f * frame_bytes, track=1, slot=f % ring)
+    ms_total = g.timer_end()
+    g.sync()
+    if dist is not None:
+        import torch
+        torch.cuda.synchronize()
+    ms_total = barrier_max(dist, ms_total, tdev)
+    clocks = sampler.stop()
+    launches = g.kernel_launch_count() - launches0
+    stage = g.stage_timing_end()
+    n_upd = g.total_updates()
+    poses_dev = [g.read_pose_ring(f % ring) for f in range(max(W, n_frames - min(ring, Ksteps)), n_frames)]
+    last_R, last_t, last_st = poses_dev[-1]
+    value = n_gpus * Ksteps / (ms_total * 1e-3)
+    t_prep, t_track, t_fuse = [float(x) * 1e-3 for x in stage.mean(axis=0)]
+    upd_per_frame = n_upd / Ksteps
+    ach = 16.0 * upd_per_frame / t_fuse / 1e9
+    n_valid = last_st["n_valid"]
+    gather = 832.0 * n_valid * GN_ITERS / t_track / 1e9
+    roof_fuse = {"bound": "hbm", "kernel": "k_fuse", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                 "traffic": None, "peak_source": peak_src, "ms_per_launch": t_fuse * 1e3,
+                 "voxels_updated_per_launch": upd_per_frame, "voxel_updates_per_s": upd_per_frame / t_fuse,
+                 "voxels_visited_per_s": m ** 3 / t_fuse,
+                 "note": "algorithmic bytes = 16 B x voxels updated (read+write D,W); skipped voxels move no bytes"}
+    roof_track = {"bound": "l2-gather-latency", "kernel": "k_linearize", "achieved": gather, "peak": hbm, "unit": "GB/s",
+                  "frac": gather / hbm, "ms_per_launch": t_track * 1e3 / GN_ITERS, "launches_per_frame": GN_ITERS,
+                  "note": "832 B gathered per valid pixel-iteration (13 samples x 8 neighbours x {D,W}); working set is L2-resident, "
+                          "so HBM peak is only a yardstick here"}
+    share = {"prep": t_prep, "track": t_track, "fuse": t_fuse}
+    tot = sum(share.values())
+    share = {k: v / tot for k, v in share.items()}
+    g.dev_free(dev)
+
+    # ---------------- e2e: host buffers through the public call --------------------------------
+    g.reset(); g.set_intrinsics(K)
+    g.fuse(depth[0], Rs[0], ts[0])
+    for f in range(1, W):
+        g.track_and_fuse(depth[f])
+    if dist is not None:
+        import torch
+        dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for f in range(W, n_frames):
+        R_e, t_e, st_e, nu_e = g.track_and_fuse(depth[f])
+    e2e_s = time.perf_counter() - t0
+    e2e_s = barrier_max(dist, e2e_s, tdev)
+    e2e = {"value": n_gpus * Ksteps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(frame_bytes),
+           "d2h_bytes_per_step": 496 + 8,      # sizeof(PoseState) (pose, twist, normal equations, counters) + n_updated
+           "ms_per_step": 1e3 * e2e_s / Ksteps, "timing": "host wall clock around K synchronous tsdf_track_and_fuse(HOST depth) calls"}
+    pose_agree = float(np.linalg.norm(t_e - last_t))
+    track_err = float(np.linalg.norm(last_t - ts[n_frames - 1]))
+    g.close()
+
+    out = {"metric": METRIC if m == 512 else METRIC.replace("512", str(m)), "value": value, "unit": "frames/s", "n_gpus": n_gpus,
+           "steps": Ksteps, "warmup": W, "ms_per_step": ms_total / Ksteps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32 values / f64 geometry", "data": "synthetic",
+           "config": {"workload": "%d^3 grid, 640x480 synthetic depth along fr1/plant GT path, %d GN iterations/frame, point-to-plane fusion "
+                                  "(BASELINE.json configs[1]%s)" % (m, GN_ITERS, "; one independent sequence per GPU, configs[4]" if n_gpus > 1 else ""),
+                      "grid_bytes": 8 * m ** 3, "l2": "inputs larger than L2 (1 GiB grid vs 126 MB); no flush",
+                      "gn_iterations": GN_ITERS, "pixel_stride": 3, "frames_source": "tools/synth.py + data/fr1_plant_gt_every4.txt"},
+           "roofline": roof_fuse, "roofline_track": roof_track, "stage_share": share,
+           "stage_ms": {"prep": t_prep * 1e3, "track": t_track * 1e3, "fuse": t_fuse * 1e3},
+           "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+           "tracking": {"final_pos_err_vs_gt_m": track_err, "n_valid_last": int(n_valid), "e2e_vs_resident_pose_diff_m": pose_agree}}
+
+    if rank == 0 and n_gpus == 1 and not args.no_dense:
+        out["dense_fuse"] = dense_fuse_bench(T, m, K, reps=20, hbm=hbm)
+    if rank == 0 and n_gpus == 1 and not args.no_cpu:
+        nb = min(n_frames, 40)
+        out["cpu_baseline"] = run_cpu_baseline(depth[:nb], Rs[:nb], ts[:nb], m, budget_s=args.cpu_budget, max_frames=nb - 1)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--m", type=int, default=512)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense fusion micro-benchmark")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--ref-budget", type=float, default=90.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

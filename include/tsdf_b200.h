@@ -192,7 +192,17 @@ tsdf_status tsdf_last_stage_ms(tsdf_handle h, float out[3]);
 tsdf_status tsdf_event_timer_begin(tsdf_handle h);              /* record start on the stream   */
 tsdf_status tsdf_event_timer_end(tsdf_handle h, float* ms);     /* record stop, sync, elapsed   */
 int64_t     tsdf_kernel_launch_count(tsdf_handle h);            /* kernels launched so far      */
+/* per-frame stage times over a run of enqueued frames: begin(n) arms n x 4 events, every
+ * following frame records into them, end() syncs and returns ms[n][3] = {prep, track, fuse} */
+tsdf_status tsdf_stage_timing_begin(tsdf_handle h, int32_t n_frames);
+tsdf_status tsdf_stage_timing_end(tsdf_handle h, int32_t* n_frames, float* ms);
+/* running total of voxels updated by fusion since the last reset (for GB/s accounting) */
+tsdf_status tsdf_total_updates(tsdf_handle h, int32_t reset, int64_t* total);
 tsdf_status tsdf_flush_l2(tsdf_handle h);                       /* overwrite a >L2-sized scratch buffer */
+
+/* Pure host function (no device needed): the z-slab plan tsdf_create would use for `cfg`:
+ * out = {k_own_begin, k_own_end, k_stored_begin, k_stored_end, halo}. */
+tsdf_status tsdf_slab_plan(const tsdf_config* cfg, int32_t out[5]);
 
 /* Sharded tracking across processes (one process per GPU): each rank exports a handle to
  * its 30-double mailbox, the caller exchanges them (e.g. torch.distributed all_gather) and

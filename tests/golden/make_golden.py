@@ -1,0 +1,63 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/track_fuse_m32.npz from the CPU oracle.
+
+The reference ships no golden vectors and cannot be built or imported in this
+image, so these fixtures are produced by the oracle restatement (oracle/oracle.cpp) on the
+deterministic synthetic frames (tools/synth).  They pin the oracle against silent drift and give
+the GPU tests a second, committed target.  Re-run only when the oracle is deliberately changed:
+    python tests/golden/make_golden.py
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as po   # noqa: E402
+from tools import synth             # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "track_fuse_m32.npz")
+
+
+def build():
+    depth, Rs, ts = synth.render_sequence(6)
+    out = {"K": synth.K_DEFAULT, "R_gt": Rs, "t_gt": ts,
+           "depth_sha256": np.frombuffer(hashlib.sha256(depth.tobytes()).digest(), np.uint8),
+           "depth_probe": depth[:, ::60, ::80].copy()}
+    for metric in (0, 1):
+        o = po.Oracle(m=32, use_coord_table=0, metric=metric, gauss_newton_max_iteration=10, maximum_twist_diff=float("-inf"))
+        o.set_intrinsics(synth.K_DEFAULT)
+        nupd = []
+        for f in range(3):                       # fuse three frames at ground-truth poses
+            o.set_pose(Rs[f], ts[f])
+            nupd.append(o.fuse(depth[f]))
+        out["m%d_n_updated" % metric] = np.array(nupd)
+        out["m%d_D" % metric] = o.D.copy()
+        out["m%d_W" % metric] = o.W.copy()
+        o.set_pose(Rs[3], ts[3])                 # one linearisation at the GT pose of frame 3
+        A, b, st = o.linearize(depth[3])
+        J, psi, flag = o.linearize_pixels(depth[3])
+        out["m%d_A" % metric] = A; out["m%d_b" % metric] = b
+        out["m%d_lin_stats" % metric] = np.array([st["n_valid"], st["n_oob"], st["residual"]])
+        out["m%d_flag" % metric] = flag; out["m%d_J" % metric] = J[::16].copy(); out["m%d_psi" % metric] = psi[::16].copy()
+        out["m%d_J_sha256" % metric] = np.frombuffer(hashlib.sha256(J.tobytes() + psi.tobytes()).digest(), np.uint8)
+        o.set_pose(Rs[2], ts[2])                 # track frame 3 from frame 2's pose, 10 fixed iterations
+        st = o.track(depth[3])
+        R, t = o.get_pose()
+        out["m%d_R_tracked" % metric] = R; out["m%d_t_tracked" % metric] = t
+        out["m%d_track_stats" % metric] = np.array([st["iterations"], st["n_valid"], st["residual"]])
+        pts = np.random.default_rng(7).uniform(-1, 33, (512, 3))
+        v, ok = o.interpolate_distance(pts)
+        out["m%d_sample_pts" % metric] = pts; out["m%d_sample_val" % metric] = v; out["m%d_sample_ok" % metric] = ok
+        o.close()
+    tw = np.random.default_rng(11).uniform(-0.5, 0.5, (16, 6)); tw[0] = 0; tw[1, 3:] = 1e-5; tw[2, 3:] = 1e-9
+    out["exp_twist"] = tw
+    out["exp_R"] = np.stack([po.exp_map(x)[0] for x in tw]); out["exp_t"] = np.stack([po.exp_map(x)[1] for x in tw])
+    return out
+
+
+if __name__ == "__main__":
+    np.savez_compressed(OUT, **build())
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")

@@ -99,6 +99,10 @@ PROTOTYPES = [
     ("tsdf_event_timer_end", _I32, [_VP, c_fp]),
     ("tsdf_kernel_launch_count", _I64, [_VP]),
     ("tsdf_flush_l2", _I32, [_VP]),
+    ("tsdf_stage_timing_begin", _I32, [_VP, _I32]),
+    ("tsdf_stage_timing_end", _I32, [_VP, c_i32p, c_fp]),
+    ("tsdf_total_updates", _I32, [_VP, _I32, c_i64p]),
+    ("tsdf_slab_plan", _I32, [_CFGP, c_i32p]),
     ("tsdf_shard_ipc_export", _I32, [_VP, c_u8p]),
     ("tsdf_shard_ipc_attach", _I32, [_VP, _I32, c_u8p]),
     ("tsdf_shard_attach_local", _I32, [_VPP, _I32]),
@@ -144,6 +148,16 @@ def default_config(**kw):
             assert hasattr(c, k), k
             setattr(c, k, v)
     return c
+
+
+def slab_plan(cfg):
+    """-> dict(own=(k0,k1), stored=(k0,k1), halo=h): pure host computation, no GPU needed."""
+    L = load_library()
+    out = (ctypes.c_int32 * 5)()
+    st = L.tsdf_slab_plan(ctypes.byref(cfg), out)
+    if st != 0:
+        raise TsdfError(st, L.tsdf_last_error().decode())
+    return {"own": (out[0], out[1]), "stored": (out[2], out[3]), "halo": out[4]}
 
 
 def _d(a):
@@ -355,6 +369,20 @@ class Tsdf:
     def kernel_launch_count(self):
         return self.L.tsdf_kernel_launch_count(self.h)
 
+    def stage_timing_begin(self, n_frames):
+        self._stage_n = n_frames
+        self._ck(self.L.tsdf_stage_timing_begin(self.h, n_frames))
+
+    def stage_timing_end(self):
+        ms = np.empty((self._stage_n, 3), np.float32); n = ctypes.c_int32()
+        self._ck(self.L.tsdf_stage_timing_end(self.h, ctypes.byref(n), _f(ms)))
+        return ms[:n.value]
+
+    def total_updates(self, reset=False):
+        v = ctypes.c_int64()
+        self._ck(self.L.tsdf_total_updates(self.h, int(reset), ctypes.byref(v)))
+        return v.value
+
     def flush_l2(self):
         self._ck(self.L.tsdf_flush_l2(self.h))
 
@@ -398,7 +426,7 @@ class ShardGroup:
             raise TsdfError(st, self.L.tsdf_last_error().decode())
 
     def close(self):
-        for s in self.shards:
+        for s in self.shards[::-1]:      # shard 0 owns the shared stream: destroy it last
             s.close()
 
     def set_intrinsics(self, K):

@@ -48,6 +48,8 @@ struct Impl {
     cudaEvent_t ev[4];
     cudaEvent_t tmr[2];
     bool stage_valid = false;
+    std::vector<cudaEvent_t> ring_ev;       /* optional per-frame stage events (4 per frame) */
+    int ring_frames = 0, ring_pos = 0;
     int lin_blocks = 0, px_per_block = 0, fuse_blocks = 0;
     int64_t launches = 0;
     float* flush_buf = nullptr;
@@ -169,14 +171,16 @@ void enqueue_fuse(Impl* p) {
 tsdf_status enqueue_frame(Impl* p, const float* dptr, bool do_track, bool do_fuse) {
     if (!p->have_K) { g_err = "camera matrix not set (tsdf_set_intrinsics)"; return TSDF_ERR_NO_INTRINSICS; }
     if (p->exchange_mode == 2) return bad("same-device shard group: use tsdf_group_* entry points");
-    cudaEventRecord(p->ev[0], p->stream);
+    cudaEvent_t* ev = p->ev;
+    if (p->ring_pos < p->ring_frames) { ev = &p->ring_ev[(size_t)4 * p->ring_pos]; p->ring_pos++; }
+    cudaEventRecord(ev[0], p->stream);
     enqueue_prep(p, dptr, do_track ? 1 : 0);
-    cudaEventRecord(p->ev[1], p->stream);
+    cudaEventRecord(ev[1], p->stream);
     if (do_track)
         for (int it = 0; it < p->g.max_iter; it++) enqueue_linearize(p, 1, false);
-    cudaEventRecord(p->ev[2], p->stream);
+    cudaEventRecord(ev[2], p->stream);
     if (do_fuse) enqueue_fuse(p);
-    cudaEventRecord(p->ev[3], p->stream);
+    cudaEventRecord(ev[3], p->stream);
     p->stage_valid = true;
     CK(cudaGetLastError());
     return TSDF_OK;
@@ -272,7 +276,7 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     A(cudaMallocHost(&p->pose_pin, sizeof(PoseState)));
     A(cudaMallocHost(&p->ring_pin, sizeof(PoseState) * POSE_RING));
     A(cudaMalloc(&p->ticket, sizeof(unsigned int)));
-    A(cudaMalloc(&p->n_upd_dev, sizeof(unsigned long long)));
+    A(cudaMalloc(&p->n_upd_dev, 2 * sizeof(unsigned long long)));
     A(cudaMallocHost(&p->n_upd_pin, sizeof(unsigned long long)));
     A(cudaMalloc(&p->dbgJ, (size_t)P * 6 * sizeof(float)));
     A(cudaMalloc(&p->dbgPsi, (size_t)P * sizeof(float)));
@@ -287,6 +291,7 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
         return e == cudaErrorMemoryAllocation ? TSDF_ERR_NOMEM : TSDF_ERR_CUDA;
     }
     cudaMemset(p->ticket, 0, sizeof(unsigned int));
+    cudaMemset(p->n_upd_dev, 0, 2 * sizeof(unsigned long long));
     cudaMemset(p->mailbox, 0, sizeof(Mailbox));
     p->links.box[0] = p->mailbox;
 
@@ -323,6 +328,7 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     cudaFree(p->n_upd_dev); cudaFreeHost(p->n_upd_pin);
     cudaFree(p->dbgJ); cudaFree(p->dbgPsi); cudaFree(p->dbgFlag); cudaFree(p->mailbox);
     cudaFree(p->flush_buf); cudaFree(p->scratch_d);
+    for (cudaEvent_t e : p->ring_ev) cudaEventDestroy(e);
     for (int q = 0; q < 4; q++) if (p->ev[q]) cudaEventDestroy(p->ev[q]);
     for (int q = 0; q < 2; q++) if (p->tmr[q]) cudaEventDestroy(p->tmr[q]);
     if (p->stream && p->own_stream) cudaStreamDestroy(p->stream);
@@ -738,6 +744,41 @@ tsdf_status tsdf_event_timer_end(tsdf_handle h, float* ms) {
 }
 int64_t tsdf_kernel_launch_count(tsdf_handle h) { return h ? I(h)->launches : 0; }
 
+tsdf_status tsdf_stage_timing_begin(tsdf_handle h, int32_t n_frames) {
+    if (!h || n_frames < 1 || n_frames > (1 << 20)) return bad("bad argument");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    for (cudaEvent_t e : p->ring_ev) cudaEventDestroy(e);
+    p->ring_ev.assign((size_t)4 * n_frames, nullptr);
+    for (auto& e : p->ring_ev) CK(cudaEventCreate(&e));
+    p->ring_frames = n_frames; p->ring_pos = 0;
+    return TSDF_OK;
+}
+tsdf_status tsdf_stage_timing_end(tsdf_handle h, int32_t* n_frames, float* ms /* n x 3 */) {
+    if (!h || !n_frames || !ms) return bad("null argument");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    const int n = p->ring_pos;
+    for (int f = 0; f < n; f++)
+        for (int q = 0; q < 3; q++) CK(cudaEventElapsedTime(&ms[3 * f + q], p->ring_ev[(size_t)4 * f + q], p->ring_ev[(size_t)4 * f + q + 1]));
+    *n_frames = n;
+    for (cudaEvent_t e : p->ring_ev) cudaEventDestroy(e);
+    p->ring_ev.clear(); p->ring_frames = 0; p->ring_pos = 0;
+    return TSDF_OK;
+}
+tsdf_status tsdf_total_updates(tsdf_handle h, int32_t reset, int64_t* total) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    unsigned long long v[2] = {0, 0};
+    CK(cudaMemcpyAsync(v, p->n_upd_dev, sizeof v, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (total) *total = (int64_t)v[1];
+    if (reset) { CK(cudaMemsetAsync(p->n_upd_dev + 1, 0, sizeof(unsigned long long), p->stream)); }
+    return TSDF_OK;
+}
+
 tsdf_status tsdf_flush_l2(tsdf_handle h) {
     if (!h) return bad("null handle");
     Impl* p = I(h);
@@ -750,6 +791,15 @@ tsdf_status tsdf_flush_l2(tsdf_handle h) {
 }
 
 /* ---- sharding ------------------------------------------------------------------------------ */
+tsdf_status tsdf_slab_plan(const tsdf_config* cfg, int32_t out[5]) {
+    if (!cfg || !out) return bad("null argument");
+    if (cfg->m < 8 || (cfg->m % 4) != 0) return bad("m must be a multiple of 4, >= 8");
+    if (cfg->n_shards < 1 || cfg->n_shards > MAX_WORLD || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->n_shards) return bad("bad shard configuration");
+    int ko0, ko1, ks0, ks1, halo;
+    slab_range(*cfg, ko0, ko1, ks0, ks1, halo);
+    out[0] = ko0; out[1] = ko1; out[2] = ks0; out[3] = ks1; out[4] = halo;
+    return TSDF_OK;
+}
 tsdf_status tsdf_shard_ipc_export(tsdf_handle h, uint8_t out[TSDF_IPC_HANDLE_BYTES]) {
     if (!h || !out) return bad("null argument");
     Impl* p = I(h);

@@ -364,7 +364,7 @@ int linearize_blocks_per_sm() {
 __global__ void __launch_bounds__(FUSE_THREADS) k_fuse(GridParams g, float2* __restrict__ grid,
                                                        const PixRec* __restrict__ pix,
                                                        const PoseState* __restrict__ pose,
-                                                       unsigned long long* n_updated) {
+                                                       unsigned long long* n_updated /* [0] this launch, [1] running total */) {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = FUSE_THREADS / 32;
     const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(FUSE_THREADS) k_fuse(GridParams g, float2* __r
     unsigned int tot = my_updates;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0 && tot) atomicAdd(n_updated, (unsigned long long)tot);
+    if (lane == 0 && tot) { atomicAdd(&n_updated[0], (unsigned long long)tot); atomicAdd(&n_updated[1], (unsigned long long)tot); }
 }
 
 void launch_fuse(const GridParams& g, float2* grid, const PixRec* pix, const PoseState* pose,
