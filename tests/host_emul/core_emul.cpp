@@ -84,6 +84,12 @@ struct HostFetch {
         d = grid[o]; w = grid[o + 1];
         return true;
     }
+    bool interior(int bi, int bj, int bk) const {
+        return bi >= 0 && bj >= 0 && bk >= 0 && bi < m - 1 && bj < m - 1 && bk < m - 1;
+    }
+    void load8(int bi, int bj, int bk, float* d, float* w) const {
+        for (int n = 0; n < 8; n++) (*this)(bi + (n >> 2), bj + ((n >> 1) & 1), bk + (n & 1), d[n], w[n]);
+    }
 };
 
 void emul_interpolate(const GridParams* g, const float* grid, int64_t n, const double* pts, float* out, uint8_t* ok) {

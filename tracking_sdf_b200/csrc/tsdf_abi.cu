@@ -35,7 +35,11 @@ struct Impl {
     PoseState* pose_pin = nullptr;          /* pinned: D2H landing zone for track results */
     PoseState* ring_pin = nullptr;          /* pinned pose ring for the async path */
     double* partials = nullptr;
-    unsigned int* ticket = nullptr;
+    double* group_partials = nullptr;
+    unsigned int* ticket = nullptr;         /* [0] final ticket, [1..] group tickets */
+    double* fuse_tables = nullptr;
+    unsigned long long* fuse_items = nullptr;
+    unsigned int* fuse_item_count = nullptr;
     unsigned long long* n_upd_dev = nullptr;
     unsigned long long* n_upd_pin = nullptr;
     float* dbgJ = nullptr; float* dbgPsi = nullptr; uint8_t* dbgFlag = nullptr;
@@ -141,6 +145,7 @@ LinearizeArgs lin_args(Impl* p, int do_update, bool debug) {
     a.g = p->g;
     a.grid = p->grid; a.pix = p->pix; a.pose = p->pose_dev;
     a.partials = p->partials; a.ticket = p->ticket;
+    a.group_ticket = p->ticket + 1; a.group_partials = p->group_partials;
     a.dbgJ = debug ? p->dbgJ : nullptr; a.dbgPsi = debug ? p->dbgPsi : nullptr; a.dbgFlag = debug ? p->dbgFlag : nullptr;
     a.do_update = do_update;
     a.px_per_block = p->px_per_block;
@@ -162,9 +167,12 @@ void enqueue_combine(Impl* p, int do_update) {
     p->launches++;
 }
 void enqueue_fuse(Impl* p) {
-    cudaMemsetAsync(p->n_upd_dev, 0, sizeof(unsigned long long), p->stream);
-    launch_fuse(p->g, p->grid, p->pix, p->pose_dev, p->n_upd_dev, p->fuse_blocks, p->stream);
-    p->launches++;
+    FuseArgs f;
+    f.g = p->g; f.grid = p->grid; f.pix = p->pix; f.pose = p->pose_dev;
+    f.tables = p->fuse_tables; f.items = p->fuse_items; f.item_count = p->fuse_item_count;
+    f.n_updated = p->n_upd_dev; f.nblk = p->fuse_blocks;
+    launch_fuse(f, p->stream);
+    p->launches += FUSE_LAUNCHES;
 }
 
 /* the per-frame sequence of sdf_reconstruction.cpp:69-74 on the stream, no host round trip */
@@ -236,7 +244,7 @@ void tsdf_default_config(tsdf_config* c) {
 tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     if (!cfg || !out) return bad("null argument");
     *out = nullptr;
-    if (cfg->m < 8 || cfg->m > 4096 || (cfg->m % 4) != 0) return bad("m must be a multiple of 4 in [8, 4096]");
+    if (cfg->m < 8 || cfg->m > 4092 || (cfg->m % 4) != 0) return bad("m must be a multiple of 4 in [8, 4092]");
     if (!(cfg->width > 0 && cfg->height > 0 && cfg->depth > 0)) return bad("extents must be positive");
     if (cfg->image_width < 3 || cfg->image_height < 3 || cfg->image_width > 8192 || cfg->image_height > 8192) return bad("bad image size");
     if (cfg->pixel_stride < 1) return bad("pixel_stride must be >= 1");
@@ -275,7 +283,10 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     A(cudaMalloc(&p->pose_dev, sizeof(PoseState)));
     A(cudaMallocHost(&p->pose_pin, sizeof(PoseState)));
     A(cudaMallocHost(&p->ring_pin, sizeof(PoseState) * POSE_RING));
-    A(cudaMalloc(&p->ticket, sizeof(unsigned int)));
+    A(cudaMalloc(&p->ticket, 1024 * sizeof(unsigned int)));
+    A(cudaMalloc(&p->fuse_tables, ((size_t)9 * cfg->m + 8) * sizeof(double)));
+    A(cudaMalloc(&p->fuse_items, (size_t)(p->g.ks1 - p->g.ks0) * cfg->m * ((cfg->m + 127) / 128 + 1) * sizeof(unsigned long long)));
+    A(cudaMalloc(&p->fuse_item_count, sizeof(unsigned int)));
     A(cudaMalloc(&p->n_upd_dev, 2 * sizeof(unsigned long long)));
     A(cudaMallocHost(&p->n_upd_pin, sizeof(unsigned long long)));
     A(cudaMalloc(&p->dbgJ, (size_t)P * 6 * sizeof(float)));
@@ -290,7 +301,7 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
         tsdf_destroy(reinterpret_cast<tsdf_handle>(p));
         return e == cudaErrorMemoryAllocation ? TSDF_ERR_NOMEM : TSDF_ERR_CUDA;
     }
-    cudaMemset(p->ticket, 0, sizeof(unsigned int));
+    cudaMemset(p->ticket, 0, 1024 * sizeof(unsigned int));
     cudaMemset(p->n_upd_dev, 0, 2 * sizeof(unsigned long long));
     cudaMemset(p->mailbox, 0, sizeof(Mailbox));
     p->links.box[0] = p->mailbox;
@@ -298,13 +309,17 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     const int sms = prop.multiProcessorCount;
-    /* K2: ~2 blocks per SM, every block a contiguous run of pixels (multiple of 16) */
-    int nb = sms * 2;
+    /* K2: one resident wave; every block a contiguous run of pixels (multiple of 16) */
+    int lb = linearize_blocks_per_sm();
+    if (lb < 1) lb = 1;
+    int nb = sms * lb;
     int ppb = (P + nb - 1) / nb;
     ppb = ((ppb + 15) / 16) * 16;
     nb = (P + ppb - 1) / ppb;
+    if ((nb + LIN_GROUP - 1) / LIN_GROUP > 1000) { g_err = "image too large for the reduction tree"; tsdf_destroy(reinterpret_cast<tsdf_handle>(p)); return TSDF_ERR_BAD_ARG; }
     p->px_per_block = ppb; p->lin_blocks = nb;
     A(cudaMalloc(&p->partials, (size_t)nb * LIN_PARTIAL_STRIDE * sizeof(double)));
+    A(cudaMalloc(&p->group_partials, (size_t)((nb + LIN_GROUP - 1) / LIN_GROUP) * LIN_PARTIAL_STRIDE * sizeof(double)));
     /* K3: persistent grid, a whole number of resident blocks per SM */
     int fb = fuse_blocks_per_sm();
     if (fb < 1) fb = 1;
@@ -325,6 +340,7 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     for (void* q : p->ipc_opened) cudaIpcCloseMemHandle(q);
     cudaFree(p->grid); cudaFree(p->pix); cudaFree(p->depth_stage); cudaFree(p->pose_dev);
     cudaFreeHost(p->pose_pin); cudaFreeHost(p->ring_pin); cudaFree(p->partials); cudaFree(p->ticket);
+    cudaFree(p->group_partials); cudaFree(p->fuse_tables); cudaFree(p->fuse_items); cudaFree(p->fuse_item_count);
     cudaFree(p->n_upd_dev); cudaFreeHost(p->n_upd_pin);
     cudaFree(p->dbgJ); cudaFree(p->dbgPsi); cudaFree(p->dbgFlag); cudaFree(p->mailbox);
     cudaFree(p->flush_buf); cudaFree(p->scratch_d);

@@ -93,7 +93,9 @@ TSDF_HD void matvec3(const double* M, double x, double y, double z, double& ox, 
     oz = dot3_seq(M[6], M[7], M[8], x, y, z);
 }
 TSDF_HD void matmul3(const double* A, const double* B, double* C) {
+#pragma unroll
     for (int r = 0; r < 3; r++)
+#pragma unroll
         for (int c = 0; c < 3; c++)
             C[3 * r + c] = (A[3 * r + 0] * B[0 + c] + A[3 * r + 1] * B[3 + c]) + A[3 * r + 2] * B[6 + c];
 }
@@ -116,7 +118,9 @@ TSDF_HD void inverse3(const double* M, double* inv) {
 }
 /* camera_tracking.cpp:59-65 */
 TSDF_HD void pose_set(PoseState& p, const double* R, const double* t) {
+#pragma unroll
     for (int q = 0; q < 9; q++) p.R[q] = R[q];
+#pragma unroll
     for (int q = 0; q < 3; q++) p.t[q] = t[q];
     inverse3(p.R, p.Rinv);
     double x, y, z;
@@ -164,36 +168,36 @@ TSDF_HD bool normal_px(const K1Params& p, int u, int v, float zc, float zl, floa
 }
 
 /* ---- SDF::interpolate_distance, sdf.cpp:127-163 -----------------------------------------
- * fetch(ci,cj,ck,D,W) -> true when the voxel is inside the grid (sdf.h:113-119).  The loop
- * keeps the reference's neighbour order (i outer, j, k inner) and its early return. */
-template <class Fetch>
-TSDF_HD float interpolate_distance(double vx, double vy, double vz, Fetch&& fetch, bool& is_interpolated) {
-    const float i = (float)vx, j = (float)vy, k = (float)vz;
-    const int bi = trunc_f2i(i), bj = trunc_f2i(j), bk = trunc_f2i(k);
+ * The Fetch object gives access to the voxel store:
+ *   fetch(ci,cj,ck,D,W) -> true when the voxel is inside the grid (sdf.h:113-119)
+ *   fetch.interior(bi,bj,bk) -> all 8 cells bi..bi+1 x bj..bj+1 x bk..bk+1 are inside (and held)
+ *   fetch.load8(bi,bj,bk,d,w) -> their D,W in the reference's neighbour order (i outer, j, k inner)
+ * Semantics kept exactly: neighbour order, fp32 L1 "volume" = (|di|+|dj|)+|dk|, w = 1/volume,
+ * sequential fp32 sums, the early return when a W>0 neighbour has volume < 1e-5, and
+ * is_interpolated = any neighbour with W>0.  The six |c - x| terms are computed once (they are
+ * the same fp32 values the reference recomputes per neighbour).  The interior case first issues
+ * all eight loads, then does the arithmetic; the early-return test is hoisted: it can only
+ * fire when one candidate distance per axis is <= 1e-5. */
+template <bool CHECK_EXACT>
+TSDF_HD float interp_accumulate(const float* d, const float* w, const bool* inb,
+                                const float* fx, const float* fy, const float* fz, bool& is_interpolated) {
     float w_sum = 0.0f, sum_d = 0.0f;
     bool any = false, exact = false;
     float exact_val = 0.0f;
 #pragma unroll
-    for (int io = 0; io < 2; io++) {
-#pragma unroll
-        for (int jo = 0; jo < 2; jo++) {
-#pragma unroll
-            for (int ko = 0; ko < 2; ko++) {
-                const int ci = bi + io, cj = bj + jo, ck = bk + ko;
-                const float volume = fabsf((float)ci - i) + fabsf((float)cj - j) + fabsf((float)ck - k);
-                float d, w;
-                const bool inb = fetch(ci, cj, ck, d, w);
-                if (inb && w > 0.0f && !exact) {
-                    any = true;
-                    if (volume <= TSDF_VOL_EXACT_F) {
-                        exact = true;
-                        exact_val = d;
-                    } else {
-                        const float wt = 1.0f / volume;       /* == (float)(1.0 / (double)volume) */
-                        w_sum = w_sum + wt;
-                        sum_d = sum_d + wt * d;
-                    }
-                }
+    for (int n = 0; n < 8; n++) {
+        const float volume = (fx[n >> 2] + fy[(n >> 1) & 1]) + fz[n & 1];
+        bool use = inb[n] && w[n] > 0.0f;
+        if (CHECK_EXACT) use = use && !exact;
+        if (use) {
+            any = true;
+            if (CHECK_EXACT && volume <= TSDF_VOL_EXACT_F) {
+                exact = true;
+                exact_val = d[n];
+            } else {
+                const float wt = 1.0f / volume;       /* == (float)(1.0 / (double)volume), sdf.cpp:154 */
+                w_sum = w_sum + wt;
+                sum_d = sum_d + wt * d[n];
             }
         }
     }
@@ -201,8 +205,54 @@ TSDF_HD float interpolate_distance(double vx, double vy, double vz, Fetch&& fetc
     return exact ? exact_val : sum_d / w_sum;
 }
 
+template <class Fetch>
+TSDF_HD float interpolate_distance(double vx, double vy, double vz, Fetch&& fetch, bool& is_interpolated) {
+    const float i = (float)vx, j = (float)vy, k = (float)vz;
+    const int bi = trunc_f2i(i), bj = trunc_f2i(j), bk = trunc_f2i(k);
+    float fx[2], fy[2], fz[2];
+    fx[0] = fabsf((float)bi - i); fx[1] = fabsf((float)(bi + 1) - i);
+    fy[0] = fabsf((float)bj - j); fy[1] = fabsf((float)(bj + 1) - j);
+    fz[0] = fabsf((float)bk - k); fz[1] = fabsf((float)(bk + 1) - k);
+    float d[8], w[8];
+    bool inb[8];
+    if (fetch.interior(bi, bj, bk)) {
+        fetch.load8(bi, bj, bk, d, w);
+#pragma unroll
+        for (int n = 0; n < 8; n++) inb[n] = true;
+        const bool maybe_exact = (fminf(fx[0], fx[1]) <= TSDF_VOL_EXACT_F) && (fminf(fy[0], fy[1]) <= TSDF_VOL_EXACT_F) &&
+                                 (fminf(fz[0], fz[1]) <= TSDF_VOL_EXACT_F);
+        if (!maybe_exact) return interp_accumulate<false>(d, w, inb, fx, fy, fz, is_interpolated);
+        return interp_accumulate<true>(d, w, inb, fx, fy, fz, is_interpolated);
+    }
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+        d[n] = 0.0f; w[n] = 0.0f;
+        inb[n] = fetch(bi + (n >> 2), bj + ((n >> 1) & 1), bk + (n & 1), d[n], w[n]);
+    }
+    return interp_accumulate<true>(d, w, inb, fx, fy, fz, is_interpolated);
+}
+
 /* ---- fusion, per voxel: sdf.cpp:245-292 ---------------------------------------------------
  * Stage 1 (projection): camera-space voxel centre -> pixel, or reject. */
+/* reciprocal good to ~1e-12 relative: device = MUFU.RCP64H + one Newton step, host = 1/y */
+TSDF_HD double rcp_fast(double y) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    const double e = fma(-y, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / y;
+#endif
+}
+/* the reference's arithmetic, verbatim: two IEEE double divisions and (int) truncation */
+TSDF_HD bool project_exact(const GridParams& g, double ij0, double ij1, double ij2, int& iu, int& iv) {
+    const double u = ij0 / ij2, v = ij1 / ij2;                  /* camera_tracking.cpp:45-46 */
+    /* (int) truncation then 0 <= i < width  <=>  -1 < u < width (false for NaN/inf);  sdf.cpp:251-254 */
+    if (!(u > -1.0 && u < (double)g.img_w && v > -1.0 && v < (double)g.img_h)) return false;
+    iu = (int)u; iv = (int)v;
+    return true;
+}
 TSDF_HD bool fuse_project(const GridParams& g, double cx, double cy, double cz, int& iu, int& iv) {
     if (cz < 0) return false;                                   /* sdf.cpp:247 */
     double ij0, ij1, ij2;
@@ -215,11 +265,29 @@ TSDF_HD bool fuse_project(const GridParams& g, double cx, double cy, double cz, 
         ij1 = dot3_seq(g.K[3], g.K[4], g.K[5], cx, cy, cz);
         ij2 = dot3_seq(g.K[6], g.K[7], g.K[8], cx, cy, cz);
     }
-    const double u = ij0 / ij2, v = ij1 / ij2;                  /* camera_tracking.cpp:45-46 */
-    /* (int) truncation then 0 <= i < width  <=>  -1 < u < width (false for NaN/inf);  sdf.cpp:251-254 */
-    if (!(u > -1.0 && u < (double)g.img_w && v > -1.0 && v < (double)g.img_h)) return false;
-    iu = (int)u; iv = (int)v;
-    return true;
+    /* Only trunc(fl(ij0/ij2)) and trunc(fl(ij1/ij2)) are consumed (sdf.cpp:251-252).  With an
+     * approximate quotient q (|q - ij/ij2| <= ~1e-12 |q|, and fl() adds 1.1e-16 relative) the
+     * truncated value is certain unless q lies within TOL of an integer; those (and any
+     * non-finite q) take the exact divisions.  Results are identical to the exact path. */
+    const double TOL = 1e-7;
+    const double r = rcp_fast(ij2);
+    const double qu = ij0 * r, qv = ij1 * r;
+    const double Wd = (double)g.img_w, Hd = (double)g.img_h;
+    if (qu > -1.5 && qu < Wd + 0.5 && qv > -1.5 && qv < Hd + 0.5) {
+        const double fu = floor(qu), fv = floor(qv);
+        const double du = qu - fu, dv = qv - fv;
+        if (du > TOL && du < 1.0 - TOL && dv > TOL && dv < 1.0 - TOL) {
+            /* floor -> truncation toward zero: (-1,0) maps to 0; fu = -2 or fu = W is outside */
+            const int a = (int)fu, b = (int)fv;
+            if (a < -1 || a >= g.img_w || b < -1 || b >= g.img_h) return false;
+            iu = a < 0 ? 0 : a; iv = b < 0 ? 0 : b;
+            return true;
+        }
+        return project_exact(g, ij0, ij1, ij2, iu, iv);
+    }
+    /* finite and clearly outside the image: rejected.  NaN/inf (ij2 = 0 or denormal): exact path */
+    if (fabs(qu) <= 1e300 && fabs(qv) <= 1e300) return false;
+    return project_exact(g, ij0, ij1, ij2, iu, iv);
 }
 
 /* exp(x) for the weight of sdf.cpp:278.  For x in [-0.04, 0] a degree-9 Taylor polynomial in
@@ -228,15 +296,15 @@ TSDF_HD bool fuse_project(const GridParams& g, double cx, double cy, double cz, 
 TSDF_HD double weight_exp(double x) {
     if (x >= -0.04) {
         double p = 1.0 / 362880.0;
-        p = p * x + 1.0 / 40320.0;
-        p = p * x + 1.0 / 5040.0;
-        p = p * x + 1.0 / 720.0;
-        p = p * x + 1.0 / 120.0;
-        p = p * x + 1.0 / 24.0;
-        p = p * x + 1.0 / 6.0;
-        p = p * x + 0.5;
-        p = p * x + 1.0;
-        p = p * x + 1.0;
+        p = fma(p, x, 1.0 / 40320.0);
+        p = fma(p, x, 1.0 / 5040.0);
+        p = fma(p, x, 1.0 / 720.0);
+        p = fma(p, x, 1.0 / 120.0);
+        p = fma(p, x, 1.0 / 24.0);
+        p = fma(p, x, 1.0 / 6.0);
+        p = fma(p, x, 0.5);
+        p = fma(p, x, 1.0);
+        p = fma(p, x, 1.0);
         return p;
     }
     return exp(x);
@@ -355,35 +423,72 @@ TSDF_HD void perturbed_rot(const GridParams& g, const double* rot, int q, double
 enum { SLOT_A = 0, SLOT_B = 21, SLOT_RES = 27, SLOT_NVALID = 28, SLOT_NOOB = 29, N_SLOTS = 30 };
 
 /* ---- 6x6 partial-pivot LU solve, stands in for Eigen's A.inverse()*b (camera_tracking.cpp:191) */
-TSDF_HD int solve6(const double* Ain, const double* bin, double* x) {
-    double A[36], b[6];
-    for (int q = 0; q < 36; q++) A[q] = Ain[q];
-    for (int q = 0; q < 6; q++) b[q] = bin[q];
-    int singular = 0;
-    for (int c = 0; c < 6; c++) {
-        int piv = c;
-        double best = fabs(A[6 * c + c]);
-        for (int r = c + 1; r < 6; r++) {
-            double v = fabs(A[6 * r + c]);
+/* one elimination column; C is a template parameter so that every array index below is a
+ * compile-time constant and A, b stay in registers on the device (the pivot row is applied with
+ * conditional swaps instead of a dynamic index) */
+template <int C>
+struct Solve6Col {
+    static TSDF_HD void run(double (&A)[6][6], double (&b)[6], int& singular) {
+        int piv = C;
+        double best = fabs(A[C][C]);
+#pragma unroll
+        for (int r = C + 1; r < 6; r++) {
+            const double v = fabs(A[r][C]);
             if (v > best) { best = v; piv = r; }
         }
-        if (!(best > 0.0)) { singular = 1; continue; }
-        if (piv != c) {
-            for (int q = 0; q < 6; q++) { double tt = A[6 * c + q]; A[6 * c + q] = A[6 * piv + q]; A[6 * piv + q] = tt; }
-            double tt = b[c]; b[c] = b[piv]; b[piv] = tt;
+        const bool good = (best > 0.0);
+        if (!good) singular = 1;
+#pragma unroll
+        for (int r = C + 1; r < 6; r++) {
+            const bool sw = good && (piv == r);
+#pragma unroll
+            for (int q = C; q < 6; q++) {
+                const double u = A[C][q], v = A[r][q];
+                A[C][q] = sw ? v : u; A[r][q] = sw ? u : v;
+            }
+            const double u = b[C], v = b[r];
+            b[C] = sw ? v : u; b[r] = sw ? u : v;
         }
-        for (int r = c + 1; r < 6; r++) {
-            double f = A[6 * r + c] / A[6 * c + c];
-            A[6 * r + c] = f;
-            for (int q = c + 1; q < 6; q++) A[6 * r + q] = A[6 * r + q] - f * A[6 * c + q];
-            b[r] = b[r] - f * b[c];
+#pragma unroll
+        for (int r = C + 1; r < 6; r++) {
+            const double f = A[r][C] / A[C][C];
+#pragma unroll
+            for (int q = C + 1; q < 6; q++) A[r][q] = good ? (A[r][q] - f * A[C][q]) : A[r][q];
+            b[r] = good ? (b[r] - f * b[C]) : b[r];
         }
+        Solve6Col<C + 1>::run(A, b, singular);
     }
-    for (int r = 5; r >= 0; r--) {
-        double s = b[r];
-        for (int q = r + 1; q < 6; q++) s = s - A[6 * r + q] * x[q];
-        x[r] = s / A[6 * r + r];
+};
+template <>
+struct Solve6Col<6> {
+    static TSDF_HD void run(double (&)[6][6], double (&)[6], int&) {}
+};
+template <int R>
+struct Solve6Back {
+    static TSDF_HD void run(const double (&A)[6][6], const double (&b)[6], double* x) {
+        double sacc = b[R];
+#pragma unroll
+        for (int q = R + 1; q < 6; q++) sacc = sacc - A[R][q] * x[q];
+        x[R] = sacc / A[R][R];
+        Solve6Back<R - 1>::run(A, b, x);
     }
+};
+template <>
+struct Solve6Back<-1> {
+    static TSDF_HD void run(const double (&)[6][6], const double (&)[6], double*) {}
+};
+TSDF_HD int solve6(const double* Ain, const double* bin, double* x) {
+    double A[6][6], b[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) A[r][c] = Ain[6 * r + c];
+        b[r] = bin[r];
+    }
+    int singular = 0;
+    Solve6Col<0>::run(A, b, singular);
+    Solve6Back<5>::run(A, b, x);
+#pragma unroll
     for (int q = 0; q < 6; q++) if (!(fabs(x[q]) <= 1.7976931348623157e308)) singular = 1;
     return singular;
 }
@@ -393,7 +498,8 @@ TSDF_HD void exp_map(const double* v, double* rd, double* dt) {
     const double ang_min_sinc = 1.0e-8, ang_min_mc = 2.5e-4;
     const double u0 = v[3], u1 = v[4], u2 = v[5];
     const double theta = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
-    const double si = sin(theta), co = cos(theta);
+    double si, co;
+    sincos(theta, &si, &co);
     const double sinc = (fabs(theta) < ang_min_sinc) ? 1.0 : (si / theta);
     const double mcosc = (fabs(theta) < ang_min_mc) ? 0.5 : ((1.0 - co) / theta / theta);
     const double msinc = (fabs(theta) < ang_min_mc) ? (1. / 6.0) : ((1.0 - si / theta) / theta / theta);
@@ -415,15 +521,21 @@ TSDF_HD void exp_map(const double* v, double* rd, double* dt) {
  * camera_tracking.cpp:191-192, 216-224, 237-239.  sums = the 30 reduced slots. */
 TSDF_HD void gn_update(const GridParams& g, PoseState& p, const double* sums) {
     double A[36], b[6];
-    int q = 0;
+#pragma unroll
     for (int r = 0; r < 6; r++)
-        for (int c = r; c < 6; c++) { A[6 * r + c] = sums[SLOT_A + q]; A[6 * c + r] = sums[SLOT_A + q]; q++; }
+#pragma unroll
+        for (int c = r; c < 6; c++) {
+            const int q = r * 6 - (r * (r - 1)) / 2 + (c - r);       /* index in the row-major upper triangle */
+            A[6 * r + c] = sums[SLOT_A + q]; A[6 * c + r] = sums[SLOT_A + q];
+        }
+#pragma unroll
     for (int r = 0; r < 6; r++) b[r] = sums[SLOT_B + r];
     for (int s = 0; s < N_SLOTS; s++) p.sums[s] = sums[s];
     double tw[6];
     const int singular = solve6(A, b, tw);
     p.iterations = p.iterations + 1;
     if (singular) { p.singular = 1; p.stopped = 1; return; }    /* keep the previous pose, report */
+#pragma unroll
     for (int s = 0; s < 6; s++) p.twist[s] = tw[s];
     double rd[9], td[3];
     exp_map(tw, rd, td);

@@ -9,8 +9,9 @@ namespace tsdf {
 constexpr int LIN_THREADS = 256;          /* 8 warps, 16 pixels per sweep */
 constexpr int LIN_PARTIAL_STRIDE = 32;    /* doubles per block partial (30 used) */
 constexpr int MAX_WORLD = 16;
-constexpr int FUSE_ROWS = 8;              /* rows (j) per warp task */
+constexpr int LIN_GROUP = 16;             /* blocks per first-level reduction group */
 constexpr int FUSE_THREADS = 128;
+constexpr int FUSE_LAUNCHES = 3;          /* tables, plan, items */
 
 /* cross-shard exchange of the reduced normal equations (one slot per rank, double-buffered
  * by sequence parity so a fast rank cannot overwrite a slot a slow rank still reads) */
@@ -31,6 +32,8 @@ struct LinearizeArgs {
     PoseState* pose;
     double* partials;                      /* nblk * LIN_PARTIAL_STRIDE */
     unsigned int* ticket;
+    unsigned int* group_ticket;            /* one per LIN_GROUP blocks */
+    double* group_partials;                /* ngroups * LIN_PARTIAL_STRIDE */
     float* dbgJ; float* dbgPsi; uint8_t* dbgFlag;   /* optional per-pixel records */
     int32_t do_update;                     /* 1: solve + pose update in the last block */
     int32_t px_per_block;
@@ -43,8 +46,18 @@ void launch_prep(const GridParams& g, const float* depth, PixRec* pix, PoseState
  * launch_gn_combine sums in rank order).  seqno labels the exchange. */
 void launch_linearize(const LinearizeArgs& a, int nblk, int exchange_mode, unsigned long long seqno, cudaStream_t s);
 void launch_gn_combine(const LinearizeArgs& a, unsigned long long seqno, cudaStream_t s);
-void launch_fuse(const GridParams& g, float2* grid, const PixRec* pix, const PoseState* pose,
-                 unsigned long long* n_updated, int nblk, cudaStream_t s);
+struct FuseArgs {
+    GridParams g;
+    float2* grid;
+    const PixRec* pix;
+    const PoseState* pose;
+    double* tables;                        /* 9*m + 3 doubles */
+    unsigned long long* items;             /* capacity rows * (m/128 + 1) */
+    unsigned int* item_count;
+    unsigned long long* n_updated;         /* [0] this launch, [1] running total */
+    int nblk;
+};
+void launch_fuse(const FuseArgs& f, cudaStream_t s);
 void launch_fill(float2* grid, int64_t n, float d0, cudaStream_t s);
 void launch_sample(const GridParams& g, const float2* grid, int64_t n, const double* pts, float* out, uint8_t* ok, cudaStream_t s);
 void launch_export(const GridParams& g, const float2* grid, float* D, float* W, int layout, cudaStream_t s);

@@ -78,6 +78,18 @@ struct GridFetch {
         d = dw.x; w = dw.y;
         return true;
     }
+    __device__ __forceinline__ bool interior(int bi, int bj, int bk) const {
+        return bi >= 0 && bj >= 0 && bi < m - 1 && bj < m - 1 && bk >= ks0 && bk < ks1 - 1;
+    }
+    /* eight independent 8-byte loads, issued back to back (n = io*4 + jo*2 + ko) */
+    __device__ __forceinline__ void load8(int bi, int bj, int bk, float* d, float* w) const {
+        const float2* p = grid + (((size_t)(bk - ks0) * m + bj) * m + bi);
+        const size_t sj = (size_t)m, sk = (size_t)m * m;
+        const float2 v0 = __ldg(p), v1 = __ldg(p + sk), v2 = __ldg(p + sj), v3 = __ldg(p + sj + sk);
+        const float2 v4 = __ldg(p + 1), v5 = __ldg(p + 1 + sk), v6 = __ldg(p + 1 + sj), v7 = __ldg(p + 1 + sj + sk);
+        d[0] = v0.x; w[0] = v0.y; d[1] = v1.x; w[1] = v1.y; d[2] = v2.x; w[2] = v2.y; d[3] = v3.x; w[3] = v3.y;
+        d[4] = v4.x; w[4] = v4.y; d[5] = v5.x; w[5] = v5.y; d[6] = v6.x; w[6] = v6.y; d[7] = v7.x; w[7] = v7.y;
+    }
 };
 
 __global__ void k_sample(GridParams g, const float2* __restrict__ grid, int64_t n, const double* __restrict__ pts,
@@ -108,19 +120,11 @@ void launch_sample(const GridParams& g, const float2* grid, int64_t n, const dou
  * lane registers over the block's pixels -> half-warps -> warps -> blocks (last block, via a
  * ticket) -> ranks (mailboxes, rank order).
  * ------------------------------------------------------------------------------------------ */
-__device__ __forceinline__ void slot_operands(int slot, int& a, int& b, int& kind) {
-    /* kind 0: x[a]*x[b] with x = (J0..J5, psi); 1: n_valid; 2: n_oob; 3: unused */
-    kind = 0; a = 0; b = 0;
-    if (slot < SLOT_B) {
-        int q = 0;
-        for (int r = 0; r < 6; r++)
-            for (int c = r; c < 6; c++) { if (q == slot) { a = r; b = c; } q++; }
-    } else if (slot < SLOT_RES) { a = 6; b = slot - SLOT_B; }
-    else if (slot == SLOT_RES) { a = 6; b = 6; }
-    else if (slot == SLOT_NVALID) kind = 1;
-    else if (slot == SLOT_NOOB) kind = 2;
-    else kind = 3;
-}
+/* operands of the 32 reduction slots: slot < 21: J_a * J_b (upper triangle, row-major);
+ * 21..26: psi * J_b; 27: psi^2; 28: n_valid; 29: n_oob; 30,31 unused.  x = (J0..J5, psi). */
+__constant__ unsigned char c_slot_a[32] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5, 6, 6, 6, 6, 6, 6, 6, 0, 0, 0, 0};
+__constant__ unsigned char c_slot_b[32] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5, 0, 1, 2, 3, 4, 5, 6, 0, 0, 0, 0};
+__constant__ unsigned char c_slot_k[32] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 2, 3, 3};
 
 __device__ __forceinline__ double ld_volatile_f64(const double* p) { return *reinterpret_cast<const volatile double*>(p); }
 
@@ -150,7 +154,7 @@ __device__ void exchange_sums(const ShardLinks& L, unsigned long long seqno, dou
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinearizeArgs a, int exchange_mode, unsigned long long seqno) {
+__global__ void __launch_bounds__(LIN_THREADS, 3) k_linearize(LinearizeArgs a, int exchange_mode, unsigned long long seqno) {
     __shared__ double sM[7][9];
     __shared__ double sT[3];
     __shared__ double sRed[LIN_THREADS / 32][32];
@@ -166,18 +170,23 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinearizeArgs a, int 
     if (tid < 9) sM[0][tid] = pose->R[tid];
     if (tid < 3) sT[tid] = pose->t[tid];
     if (tid == 0) sMiss = 0;
-    if (tid >= 32 && tid < 38) {                          /* camera_tracking.cpp:92-145 */
-        double R[9], out[9];
-        for (int q = 0; q < 9; q++) R[q] = pose->R[q];
-        perturbed_rot(g, R, tid - 32, out);
-        for (int q = 0; q < 9; q++) sM[1 + tid - 32][q] = out[q];
+    if (tid >= 32 && tid < 32 + 54) {                     /* camera_tracking.cpp:92-145: (I +- w_h [e_k]x) * rot */
+        const int q = (tid - 32) / 9, e = (tid - 32) % 9, r = e / 3, c = e % 3;
+        const double w_h = (double)g.w_h;
+        /* row r of the perturbation matrix q; same values and product order as perturbed_rot() */
+        double d0 = (r == 0) ? 1.0 : 0.0, d1 = (r == 1) ? 1.0 : 0.0, d2 = (r == 2) ? 1.0 : 0.0;
+        const double sgn = (q & 1) ? -1.0 : 1.0;
+        const int axis = q >> 1;
+        if (axis == 0) { if (r == 1) d2 = -sgn * w_h; if (r == 2) d1 = sgn * w_h; }
+        if (axis == 1) { if (r == 0) d2 = sgn * w_h; if (r == 2) d0 = -sgn * w_h; }
+        if (axis == 2) { if (r == 0) d1 = -sgn * w_h; if (r == 1) d0 = sgn * w_h; }
+        sM[1 + q][e] = (d0 * pose->R[c] + d1 * pose->R[3 + c]) + d2 * pose->R[6 + c];
     }
     __syncthreads();
 
     const int grp = lane >> 4, s = lane & 15, base = grp << 4;
-    int a0, b0, k0, a1, b1, k1;
-    slot_operands(s, a0, b0, k0);
-    slot_operands(s + 16, a1, b1, k1);
+    const int a0 = c_slot_a[s], b0 = c_slot_b[s];
+    const int a1 = c_slot_a[s + 16], b1 = c_slot_b[s + 16], k1 = c_slot_k[s + 16];
     const K1Params kp = k1_params(g.K);
     const float step = (s == 0) ? g.v_h2_width : (s == 1) ? g.v_h2_height : (s == 2) ? g.v_h2_depth : g.two_w_h;
     const double* M = sM[(s < 7) ? 0 : (s - 6)];
@@ -186,6 +195,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinearizeArgs a, int 
 
     const bool sharded = (g.ko0 > 0 || g.ko1 < g.m);
     const int P = g.ni * g.nj;
+    const float inv_nj = 1.0f / (float)g.nj;
     const int p_begin = blockIdx.x * a.px_per_block;
     const int p_end = min(P, p_begin + a.px_per_block);
     double acc0 = 0.0, acc1 = 0.0;
@@ -196,8 +206,10 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinearizeArgs a, int 
         float z = __int_as_float(0x7fc00000);
         int u = 0, v = 0;
         if (have) {
-            const int ii = p / g.nj, jj = p - ii * g.nj;                     /* camera_tracking.cpp:162-163 */
-            u = ii * g.stride; v = jj * g.stride;
+            int ii = __float2int_rz(((float)p + 0.5f) * inv_nj);            /* p / nj for p < 2^22 */
+            int jj = p - ii * g.nj;
+            if (jj < 0) { ii--; jj += g.nj; } else if (jj >= g.nj) { ii++; jj -= g.nj; }
+            u = ii * g.stride; v = jj * g.stride;                            /* camera_tracking.cpp:162-163 */
             z = __ldg(&a.pix[(size_t)v * g.img_w + u].z);
         }
         const bool valid_pt = have && (z == z);                              /* camera_tracking.cpp:168 */
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinearizeArgs a, int 
         const double xa1 = (double)__shfl_sync(0xffffffffu, xv, base + a1);
         const double xb1 = (double)__shfl_sync(0xffffffffu, xv, base + b1);
         if (flag == 1) {                                                     /* camera_tracking.cpp:178-182 */
-            if (k0 == 0) acc0 = acc0 + xa0 * xb0;
+            acc0 = acc0 + xa0 * xb0;
             if (k1 == 0) acc1 = acc1 + xa1 * xb1; else if (k1 == 1) acc1 = acc1 + 1.0;
         } else if (flag == 2) {
             if (k1 == 2) acc1 = acc1 + 1.0;
@@ -258,47 +270,69 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinearizeArgs a, int 
     }
     if (miss) sMiss = 1;
 
-    /* half-warps -> warp */
+    /* half-warps -> warp -> block partial (fixed order) */
     acc0 = acc0 + __shfl_xor_sync(0xffffffffu, acc0, 16);
     acc1 = acc1 + __shfl_xor_sync(0xffffffffu, acc1, 16);
     if (lane < 16) { sRed[warp][lane] = acc0; sRed[warp][lane + 16] = acc1; }
     __syncthreads();
-    /* warps -> block partial */
-    if (tid < N_SLOTS) {
+    if (tid < 32) {
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < LIN_THREADS / 32; w++) v = v + sRed[w][tid];
         a.partials[(size_t)blockIdx.x * LIN_PARTIAL_STRIDE + tid] = v;
     }
     if (tid == 0 && sMiss) atomicAdd(&pose->halo_miss, 1);
+
+    /* ---- level 1: the last block of each group of LIN_GROUP blocks sums the group (fixed order) */
+    const int nb = gridDim.x;
+    const int ngroups = (nb + LIN_GROUP - 1) / LIN_GROUP;
+    const int grp_id = blockIdx.x / LIN_GROUP;
+    const int gsize = min(LIN_GROUP, nb - grp_id * LIN_GROUP);
     __threadfence();
     __syncthreads();
-    if (tid == 0) {
-        const unsigned t = atomicAdd(a.ticket, 1u);
-        sLast = (t == gridDim.x - 1);
-    }
+    if (tid == 0) sLast = (atomicAdd(&a.group_ticket[grp_id], 1u) == (unsigned)(gsize - 1));
     __syncthreads();
     if (!sLast) return;
-
-    /* ---- last block: blocks -> device sums, fixed order (8 chunks per slot, then chunk order) */
     __threadfence();
     {
-        const int slot = tid >> 3, chunk = tid & 7;
-        const int nb = gridDim.x;
-        const int per = (nb + 7) / 8;
+        const int slot = tid & 31, sub = tid >> 5;           /* 8 subs x 2 blocks = LIN_GROUP */
         double v = 0.0;
-        if (slot < N_SLOTS) {
-            const int b0_ = chunk * per, b1_ = min(nb, b0_ + per);
-            for (int b = b0_; b < b1_; b++) v = v + __ldcg(&a.partials[(size_t)b * LIN_PARTIAL_STRIDE + slot]);
-        }
-        /* combine the 8 chunk sums in chunk order on the chunk-0 lane */
-        double tot = v;
 #pragma unroll
-        for (int c = 1; c < 8; c++) {
-            const double o = __shfl_sync(0xffffffffu, v, (lane & ~7) + c);
-            tot = tot + o;
+        for (int q = 0; q < LIN_GROUP / 8; q++) {
+            const int bq = sub + 8 * q;
+            if (bq < gsize) v = v + __ldcg(&a.partials[(size_t)(grp_id * LIN_GROUP + bq) * LIN_PARTIAL_STRIDE + slot]);
         }
-        if (slot < N_SLOTS && chunk == 0) sSums[slot] = tot;
+        __syncthreads();
+        sRed[sub][slot] = v;
+        __syncthreads();
+        if (tid < 32) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) t = t + sRed[w][tid];
+            a.group_partials[(size_t)grp_id * LIN_PARTIAL_STRIDE + tid] = t;
+        }
+        if (tid == 0) a.group_ticket[grp_id] = 0u;
+    }
+    /* ---- level 2: the last group sums the groups */
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sLast = (atomicAdd(a.ticket, 1u) == (unsigned)(ngroups - 1));
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
+    {
+        const int slot = tid & 31, sub = tid >> 5;
+        double v = 0.0;
+        for (int q = sub; q < ngroups; q += 8) v = v + __ldcg(&a.group_partials[(size_t)q * LIN_PARTIAL_STRIDE + slot]);
+        __syncthreads();
+        sRed[sub][slot] = v;
+        __syncthreads();
+        if (tid < 32) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) t = t + sRed[w][tid];
+            sSums[tid] = t;
+        }
     }
     __syncthreads();
     if (exchange_mode == 1 && a.links.world > 1) exchange_sums(a.links, seqno, sSums, tid);
@@ -348,114 +382,140 @@ int linearize_blocks_per_sm() {
 }
 
 /* ------------------------------------------------------------------------------------------
- * K3: TSDF fusion (sdf.cpp:232-292).
+ * K3: TSDF fusion (sdf.cpp:232-292), three launches per frame:
  *
- * Layout: float2 {D,W} per voxel, x fastest; a lane owns 4 consecutive x voxels = one 32-byte
- * sector = two 16-byte vector loads/stores.  A warp task is FUSE_ROWS rows (same k, consecutive
- * j); lane r first clips row r against the view frustum (the projection is affine along a
- * row, so the in-image voxels form one interval; the clip is conservative by a voxel and the
- * exact double-precision test still decides every voxel).  Rows and 128-voxel chunks outside
- * the interval cost no memory traffic and almost no instructions.
- *
- * Exactness: the camera-space centre is ((Rinv_r0*gx + Rinv_r1*gy) + Rinv_r2*gz) + tinv_r in
- * double, identical rounding sequence to the reference's Eigen product; the three products
- * are hoisted (x per chunk, y per row, z per task), the three additions are per voxel.
+ *  k_fuse_tables  T[0..2][i] = Rinv(r,0)*gx(i), T[3..5][j] = Rinv(r,1)*gy(j), T[6..8][k] =
+ *                 Rinv(r,2)*gz(k), T[9][0..2] = tinv: the three products of the reference's
+ *                 rot_inv*g, hoisted out of the voxel loop (the three ADDITIONS stay per voxel, in
+ *                 the reference's order, so the camera-space centre is bit-identical).
+ *  k_fuse_plan    one thread per grid row (j,k): conservative scan-line clip of the row against
+ *                 the view frustum (row_clip), rows cut into items of 128 voxels, appended to a
+ *                 compact work list (one atomic per warp).  Rows outside the frustum cost nothing
+ *                 afterwards, and the item list is what balances the load across SMs.
+ *  k_fuse_items   persistent warps take items round-robin; a lane owns 4 consecutive voxels = one
+ *                 32-byte sector of the {D,W} store = two 16-byte loads + stores.  The D/W loads and
+ *                 the table loads are issued first, the exact double-precision geometry runs under
+ *                 their latency, stores are predicated on "any of my 4 voxels updated".
  * ------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(FUSE_THREADS) k_fuse(GridParams g, float2* __restrict__ grid,
-                                                       const PixRec* __restrict__ pix,
-                                                       const PoseState* __restrict__ pose,
-                                                       unsigned long long* n_updated /* [0] this launch, [1] running total */) {
-    const int lane = threadIdx.x & 31;
-    const int warps_per_block = FUSE_THREADS / 32;
-    const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    const int total_warps = gridDim.x * warps_per_block;
+__global__ void k_fuse_tables(GridParams g, const PoseState* __restrict__ pose, double* __restrict__ T,
+                              unsigned long long* n_updated, unsigned int* item_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = g.m;
-    const int jgroups = (m + FUSE_ROWS - 1) / FUSE_ROWS;
-    const int ntasks = (g.ks1 - g.ks0) * jgroups;
-    const int nchunks = (m + 127) / 128;
+    if (i == 0) { n_updated[0] = 0ull; *item_count = 0u; }
+    if (i < 3) T[9 * (size_t)m + i] = pose->tinv[i];
+    if (i >= m) return;
+    const double gx = voxel_centre(g.vs_x, i, g.origin[0]);
+    const double gy = voxel_centre(g.vs_y, i, g.origin[1]);
+    const double gz = voxel_centre(g.vs_z, i, g.origin[2]);
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        T[(size_t)(0 + r) * m + i] = pose->Rinv[3 * r + 0] * gx;
+        T[(size_t)(3 + r) * m + i] = pose->Rinv[3 * r + 1] * gy;
+        T[(size_t)(6 + r) * m + i] = pose->Rinv[3 * r + 2] * gz;
+    }
+}
 
-    double Ri[9], ti[3];
+/* item: k (12 bits) | j (12) | x_start (12) | ilo (12) | ihi (13) */
+__device__ __forceinline__ unsigned long long pack_item(int k, int j, int xs, int ilo, int ihi) {
+    return (unsigned long long)k | ((unsigned long long)j << 12) | ((unsigned long long)xs << 24) |
+           ((unsigned long long)ilo << 36) | ((unsigned long long)ihi << 48);
+}
+
+__global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, const PoseState* __restrict__ pose,
+                                                   const double* __restrict__ T, unsigned long long* __restrict__ items,
+                                                   unsigned int* item_count) {
+    const int m = g.m;
+    const int nrows = (g.ks1 - g.ks0) * m;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int cnt = 0, ilo = 0, ihi = 0, xs = 0, k = 0, j = 0;
+    if (row < nrows) {
+        k = g.ks0 + row / m; j = row - (row / m) * m;
+        double Ri[9], ti[3];
 #pragma unroll
-    for (int q = 0; q < 9; q++) Ri[q] = pose->Rinv[q];
+        for (int q = 0; q < 9; q++) Ri[q] = pose->Rinv[q];
 #pragma unroll
-    for (int q = 0; q < 3; q++) ti[q] = pose->tinv[q];
+        for (int q = 0; q < 3; q++) ti[q] = pose->tinv[q];
+        row_clip(g, Ri, ti, T[(size_t)3 * m + j], T[(size_t)4 * m + j], T[(size_t)5 * m + j],
+                 T[(size_t)6 * m + k], T[(size_t)7 * m + k], T[(size_t)8 * m + k], ilo, ihi);
+        if (ihi > ilo) { xs = ilo & ~3; cnt = (ihi - xs + 127) >> 7; }
+    }
+    /* warp-inclusive scan of cnt, one reservation per warp */
+    int scan = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, scan, o);
+        if (lane >= o) scan += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, scan, 31);
+    unsigned int basei = 0;
+    if (lane == 31 && total > 0) basei = atomicAdd(item_count, (unsigned int)total);
+    basei = __shfl_sync(0xffffffffu, basei, 31);
+    unsigned int o = basei + (unsigned int)(scan - cnt);
+    for (int c = 0; c < cnt; c++) items[o + c] = pack_item(k, j, xs + 128 * c, ilo, ihi);
+}
+
+__device__ __forceinline__ float4 ld_f4(const float4* p) { return *p; }
+
+__global__ void __launch_bounds__(FUSE_THREADS, 5) k_fuse_items(GridParams g, float2* __restrict__ grid,
+                                                                const PixRec* __restrict__ pix,
+                                                                const double* __restrict__ T,
+                                                                const unsigned long long* __restrict__ items,
+                                                                const unsigned int* __restrict__ item_count,
+                                                                unsigned long long* n_updated /* [0] this launch, [1] running total */) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (FUSE_THREADS / 32) + (threadIdx.x >> 5);
+    const int total_warps = gridDim.x * (FUSE_THREADS / 32);
+    const int m = g.m;
+    const unsigned int n_items = *item_count;
     const K1Params kp = k1_params(g.K);
+    const double ti0 = T[9 * (size_t)m + 0], ti1 = T[9 * (size_t)m + 1], ti2 = T[9 * (size_t)m + 2];
     unsigned int my_updates = 0;
 
-    for (int task = gw; task < ntasks; task += total_warps) {
-        const int k = g.ks0 + task / jgroups;
-        const int j0 = (task % jgroups) * FUSE_ROWS;
-        const double gz = voxel_centre(g.vs_z, k, g.origin[2]);
-        const double pz0 = Ri[2] * gz, pz1 = Ri[5] * gz, pz2 = Ri[8] * gz;
-
-        /* ---- per-row setup on lane r: y products and the conservative clip interval */
-        const int jrow = j0 + (lane & (FUSE_ROWS - 1));
-        const double gy = voxel_centre(g.vs_y, jrow, g.origin[1]);
-        const double py0 = Ri[1] * gy, py1 = Ri[4] * gy, py2 = Ri[7] * gy;
-        int ilo = 0, ihi = 0;
-        if (lane < FUSE_ROWS && jrow < m) row_clip(g, Ri, ti, py0, py1, py2, pz0, pz1, pz2, ilo, ihi);
-        /* union of the rows' intervals decides which chunks the warp visits at all */
-        int umin = ilo < ihi ? ilo : m, umax = ilo < ihi ? ihi : 0;
+    for (unsigned int it = gw; it < n_items; it += total_warps) {
+        const unsigned long long item = __ldg(&items[it]);
+        const int k = (int)(item & 0xfff), j = (int)((item >> 12) & 0xfff), xs = (int)((item >> 24) & 0xfff);
+        const int ilo = (int)((item >> 36) & 0xfff), ihi = (int)((item >> 48) & 0x1fff);
+        const int x0 = xs + 4 * lane;
+        if (x0 >= ihi || x0 >= m) continue;               /* lanes past the row's interval are idle */
+        float4* ptr = reinterpret_cast<float4*>(&grid[((size_t)(k - g.ks0) * m + j) * m + x0]);
+        /* issue every load up front: voxel store, then the hoisted products */
+        float4 q0 = ld_f4(ptr), q1 = ld_f4(ptr + 1);
+        const double2* tx0 = reinterpret_cast<const double2*>(T + (size_t)0 * m + x0);
+        const double2* tx1 = reinterpret_cast<const double2*>(T + (size_t)1 * m + x0);
+        const double2* tx2 = reinterpret_cast<const double2*>(T + (size_t)2 * m + x0);
+        const double2 a0 = __ldg(tx0), a1 = __ldg(tx0 + 1), b0 = __ldg(tx1), b1 = __ldg(tx1 + 1), c0 = __ldg(tx2), c1 = __ldg(tx2 + 1);
+        const double qy0 = __ldg(T + (size_t)3 * m + j), qy1 = __ldg(T + (size_t)4 * m + j), qy2 = __ldg(T + (size_t)5 * m + j);
+        const double pz0 = __ldg(T + (size_t)6 * m + k), pz1 = __ldg(T + (size_t)7 * m + k), pz2 = __ldg(T + (size_t)8 * m + k);
+        const double px0[4] = {a0.x, a0.y, a1.x, a1.y}, px1[4] = {b0.x, b0.y, b1.x, b1.y}, px2[4] = {c0.x, c0.y, c1.x, c1.y};
+        float dnew[4], wnew[4];
+        bool upd[4];
 #pragma unroll
-        for (int o = FUSE_ROWS / 2; o > 0; o >>= 1) {
-            umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-            umax = max(umax, __shfl_xor_sync(0xffffffffu, umax, o));
-        }
-        umin = __shfl_sync(0xffffffffu, umin, 0);
-        umax = __shfl_sync(0xffffffffu, umax, 0);
-        if (umin >= umax) continue;
-
-        for (int c = umin / 128; c < nchunks && c * 128 < umax; c++) {
-            const int x0 = c * 128 + lane * 4;
-            double px0[4], px1[4], px2[4];
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-                const double gx = voxel_centre(g.vs_x, x0 + v, g.origin[0]);
-                px0[v] = Ri[0] * gx; px1[v] = Ri[3] * gx; px2[v] = Ri[6] * gx;
-            }
-            for (int r = 0; r < FUSE_ROWS; r++) {
-                const int rlo = __shfl_sync(0xffffffffu, ilo, r), rhi = __shfl_sync(0xffffffffu, ihi, r);
-                if (rlo >= rhi || rhi <= c * 128 || rlo >= c * 128 + 128) continue;     /* warp-uniform */
-                const double qy0 = __shfl_sync(0xffffffffu, py0, r);
-                const double qy1 = __shfl_sync(0xffffffffu, py1, r);
-                const double qy2 = __shfl_sync(0xffffffffu, py2, r);
-                const int j = j0 + r;
-                float dnew[4], wnew[4];
-                bool upd[4];
-                bool any = false;
-#pragma unroll
-                for (int v = 0; v < 4; v++) {
-                    upd[v] = false;
-                    const int x = x0 + v;
-                    if (x >= rlo && x < rhi && x < m) {
-                        /* camera_tracking.cpp:51-54 : rot_inv * g + rot_inv_trans */
-                        const double cx = ((px0[v] + qy0) + pz0) + ti[0];
-                        const double cy = ((px1[v] + qy1) + pz1) + ti[1];
-                        const double cz = ((px2[v] + qy2) + pz2) + ti[2];
-                        int iu, iv;
-                        if (fuse_project(g, cx, cy, cz, iu, iv)) {
-                            const float4 rr = __ldg(reinterpret_cast<const float4*>(&pix[(size_t)iv * g.img_w + iu]));
-                            PixRec rec; rec.z = rr.x; rec.nx = rr.y; rec.ny = rr.z; rec.nz = rr.w;
-                            float fx_, fy_;
-                            backproject_px(kp, iu, iv, rec.z, fx_, fy_);
-                            upd[v] = fuse_distance(g, cx, cy, cz, fx_, fy_, rec, dnew[v], wnew[v]);
-                        }
-                    }
-                    any = any || upd[v];
-                }
-                if (any) {
-                    const bool owned = (k >= g.ko0 && k < g.ko1);    /* halo layers are fused redundantly, counted once */
-                    float4* ptr = reinterpret_cast<float4*>(&grid[((size_t)(k - g.ks0) * m + j) * m + x0]);
-                    float4 q0 = ptr[0], q1 = ptr[1];
-                    if (upd[0]) { fuse_apply(q0.x, q0.y, dnew[0], wnew[0]); my_updates += owned; }
-                    if (upd[1]) { fuse_apply(q0.z, q0.w, dnew[1], wnew[1]); my_updates += owned; }
-                    if (upd[2]) { fuse_apply(q1.x, q1.y, dnew[2], wnew[2]); my_updates += owned; }
-                    if (upd[3]) { fuse_apply(q1.z, q1.w, dnew[3], wnew[3]); my_updates += owned; }
-                    if (upd[0] || upd[1]) ptr[0] = q0;
-                    if (upd[2] || upd[3]) ptr[1] = q1;
+        for (int v = 0; v < 4; v++) {
+            upd[v] = false;
+            const int x = x0 + v;
+            if (x >= ilo && x < ihi) {
+                /* camera_tracking.cpp:51-54 : rot_inv * g + rot_inv_trans, reference rounding order */
+                const double cx = ((px0[v] + qy0) + pz0) + ti0;
+                const double cy = ((px1[v] + qy1) + pz1) + ti1;
+                const double cz = ((px2[v] + qy2) + pz2) + ti2;
+                int iu, iv;
+                if (fuse_project(g, cx, cy, cz, iu, iv)) {
+                    const float4 rr = __ldg(reinterpret_cast<const float4*>(&pix[(size_t)iv * g.img_w + iu]));
+                    PixRec rec; rec.z = rr.x; rec.nx = rr.y; rec.ny = rr.z; rec.nz = rr.w;
+                    float fx_, fy_;
+                    backproject_px(kp, iu, iv, rec.z, fx_, fy_);
+                    upd[v] = fuse_distance(g, cx, cy, cz, fx_, fy_, rec, dnew[v], wnew[v]);
                 }
             }
         }
+        const unsigned int owned = (k >= g.ko0 && k < g.ko1) ? 1u : 0u;    /* halo layers are fused redundantly, counted once */
+        if (upd[0]) { fuse_apply(q0.x, q0.y, dnew[0], wnew[0]); my_updates += owned; }
+        if (upd[1]) { fuse_apply(q0.z, q0.w, dnew[1], wnew[1]); my_updates += owned; }
+        if (upd[2]) { fuse_apply(q1.x, q1.y, dnew[2], wnew[2]); my_updates += owned; }
+        if (upd[3]) { fuse_apply(q1.z, q1.w, dnew[3], wnew[3]); my_updates += owned; }
+        if (upd[0] || upd[1]) ptr[0] = q0;
+        if (upd[2] || upd[3]) ptr[1] = q1;
     }
     /* one atomic per warp */
     unsigned int tot = my_updates;
@@ -464,13 +524,16 @@ __global__ void __launch_bounds__(FUSE_THREADS) k_fuse(GridParams g, float2* __r
     if (lane == 0 && tot) { atomicAdd(&n_updated[0], (unsigned long long)tot); atomicAdd(&n_updated[1], (unsigned long long)tot); }
 }
 
-void launch_fuse(const GridParams& g, float2* grid, const PixRec* pix, const PoseState* pose,
-                 unsigned long long* n_updated, int nblk, cudaStream_t s) {
-    k_fuse<<<nblk, FUSE_THREADS, 0, s>>>(g, grid, pix, pose, n_updated);
+void launch_fuse(const FuseArgs& f, cudaStream_t s) {
+    const GridParams& g = f.g;
+    k_fuse_tables<<<(g.m + 127) / 128, 128, 0, s>>>(g, f.pose, f.tables, f.n_updated, f.item_count);
+    const int nrows = (g.ks1 - g.ks0) * g.m;
+    k_fuse_plan<<<(nrows + 255) / 256, 256, 0, s>>>(g, f.pose, f.tables, f.items, f.item_count);
+    k_fuse_items<<<f.nblk, FUSE_THREADS, 0, s>>>(g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
 }
 int fuse_blocks_per_sm() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fuse, FUSE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fuse_items, FUSE_THREADS, 0);
     return n;
 }
 
