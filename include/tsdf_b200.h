@@ -196,6 +196,8 @@ int64_t     tsdf_kernel_launch_count(tsdf_handle h);            /* kernels launc
  * following frame records into them, end() syncs and returns ms[n][3] = {prep, track, fuse} */
 tsdf_status tsdf_stage_timing_begin(tsdf_handle h, int32_t n_frames);
 tsdf_status tsdf_stage_timing_end(tsdf_handle h, int32_t* n_frames, float* ms);
+/* debugging aid: globaltimer stamps (ns) of the phases of one linearise+update launch */
+tsdf_status tsdf_debug_phase_times(tsdf_handle h, const float* depth, int32_t mem, int64_t out[5]);
 /* running total of voxels updated by fusion since the last reset (for GB/s accounting) */
 tsdf_status tsdf_total_updates(tsdf_handle h, int32_t reset, int64_t* total);
 tsdf_status tsdf_flush_l2(tsdf_handle h);                       /* overwrite a >L2-sized scratch buffer */

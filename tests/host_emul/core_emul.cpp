@@ -125,12 +125,23 @@ int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const Pos
                 const double cy = ((px1 + py1) + pz1) + ti[1];
                 const double cz = ((px2 + py2) + pz2) + ti[2];
                 int iu, iv;
-                if (!fuse_project(g, cx, cy, cz, iu, iv)) continue;
-                const float* rr = pix + 4 * ((size_t)iv * g.img_w + iu);
+                bool ok, need_exact;
+                fuse_project_flags(g, cx, cy, cz, iu, iv, ok, need_exact);
+                if (need_exact) {
+                    double ij0, ij1, ij2;
+                    project_ij(g, cx, cy, cz, ij0, ij1, ij2);
+                    int eu_ = 0, ev_ = 0;
+                    ok = project_exact(g, ij0, ij1, ij2, eu_, ev_);
+                    if (ok) { iu = eu_; iv = ev_; }
+                }
+                const float* rr = pix + 4 * ((size_t)iv * g.img_w + iu);      /* unconditional, clamped */
                 PixRec rec; rec.z = rr[0]; rec.nx = rr[1]; rec.ny = rr[2]; rec.nz = rr[3];
-                float fx_, fy_, dn, wn;
+                float fx_, fy_, dn, eb;
+                bool band;
                 backproject_px(kp, iu, iv, rec.z, fx_, fy_);
-                if (!fuse_distance(g, cx, cy, cz, fx_, fy_, rec, dn, wn)) continue;
+                const bool upd = fuse_distance_flags(g, cx, cy, cz, fx_, fy_, rec, dn, eb, band) & ok;
+                if (!upd) continue;
+                const float wn = fuse_weight(band, eb);
                 const size_t o = (((size_t)(k - g.ks0) * m + j) * m + x) * 2;
                 fuse_apply(grid[o], grid[o + 1], dn, wn);
                 n_updated++;

@@ -102,6 +102,7 @@ PROTOTYPES = [
     ("tsdf_stage_timing_begin", _I32, [_VP, _I32]),
     ("tsdf_stage_timing_end", _I32, [_VP, c_i32p, c_fp]),
     ("tsdf_total_updates", _I32, [_VP, _I32, c_i64p]),
+    ("tsdf_debug_phase_times", _I32, [_VP, _VP, _I32, c_i64p]),
     ("tsdf_slab_plan", _I32, [_CFGP, c_i32p]),
     ("tsdf_shard_ipc_export", _I32, [_VP, c_u8p]),
     ("tsdf_shard_ipc_attach", _I32, [_VP, _I32, c_u8p]),
@@ -124,7 +125,7 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    path = library_path()
+    path = os.environ.get("TSDF_B200_LIB", library_path())      # override: kernel tuning experiments only
     if not os.path.exists(path):
         raise TsdfError(3, "libtsdf_b200.so not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                            "tracking_sdf_b200 has no CPU fallback")
@@ -382,6 +383,12 @@ class Tsdf:
         v = ctypes.c_int64()
         self._ck(self.L.tsdf_total_updates(self.h, int(reset), ctypes.byref(v)))
         return v.value
+
+    def debug_phase_times(self, depth):
+        p, mem, keep = _depth_arg(depth)
+        out = (ctypes.c_int64 * 5)()
+        self._ck(self.L.tsdf_debug_phase_times(self.h, p, mem, out))
+        return [int(x) for x in out]
 
     def flush_l2(self):
         self._ck(self.L.tsdf_flush_l2(self.h))

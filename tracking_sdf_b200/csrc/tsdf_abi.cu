@@ -43,6 +43,7 @@ struct Impl {
     unsigned long long* n_upd_dev = nullptr;
     unsigned long long* n_upd_pin = nullptr;
     float* dbgJ = nullptr; float* dbgPsi = nullptr; uint8_t* dbgFlag = nullptr;
+    unsigned long long* dbg_times = nullptr;   /* set by tsdf_debug_phase_times */
     Mailbox* mailbox = nullptr;
     ShardLinks links;
     int exchange_mode = 0;
@@ -147,6 +148,7 @@ LinearizeArgs lin_args(Impl* p, int do_update, bool debug) {
     a.partials = p->partials; a.ticket = p->ticket;
     a.group_ticket = p->ticket + 1; a.group_partials = p->group_partials;
     a.dbgJ = debug ? p->dbgJ : nullptr; a.dbgPsi = debug ? p->dbgPsi : nullptr; a.dbgFlag = debug ? p->dbgFlag : nullptr;
+    a.dbg_times = p->dbg_times;
     a.do_update = do_update;
     a.px_per_block = p->px_per_block;
     a.links = p->links;
@@ -783,6 +785,35 @@ tsdf_status tsdf_stage_timing_end(tsdf_handle h, int32_t* n_frames, float* ms /*
     p->ring_ev.clear(); p->ring_frames = 0; p->ring_pos = 0;
     return TSDF_OK;
 }
+/* debugging aid: globaltimer stamps (ns) of one linearise+update launch at the current pose:
+ * out[0] first block start, [1] last block's pixel loop end, [2] final-block start, [3] sums
+ * ready, [4] pose updated.  The pose IS updated (one GN step). */
+tsdf_status tsdf_debug_phase_times(tsdf_handle h, const float* depth, int32_t mem, int64_t out[5]) {
+    if (!h || !out) return bad("null argument");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    if (!p->have_K) { g_err = "camera matrix not set"; return TSDF_ERR_NO_INTRINSICS; }
+    const float* dptr;
+    tsdf_status st = stage_depth(p, depth, mem, &dptr);
+    if (st != TSDF_OK) return st;
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
+    unsigned long long init[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpyAsync(d, init, sizeof init, cudaMemcpyHostToDevice, p->stream));
+    enqueue_prep(p, dptr, 1);
+    enqueue_linearize(p, 1, false);      /* warm */
+    enqueue_prep(p, dptr, 1);
+    p->dbg_times = d;
+    enqueue_linearize(p, 1, false);
+    p->dbg_times = nullptr;
+    unsigned long long res[8];
+    CK(cudaMemcpyAsync(res, d, sizeof res, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    for (int q = 0; q < 5; q++) out[q] = (int64_t)res[q];
+    cudaFree(d);
+    return TSDF_OK;
+}
+
 tsdf_status tsdf_total_updates(tsdf_handle h, int32_t reset, int64_t* total) {
     if (!h) return bad("null handle");
     Impl* p = I(h);

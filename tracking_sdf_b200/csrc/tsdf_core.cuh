@@ -14,6 +14,7 @@
 #include <stdint.h>
 #include <limits.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define TSDF_HD __host__ __device__ __forceinline__
@@ -58,6 +59,30 @@ struct PoseState {
 };
 
 struct PixRec { float z, nx, ny, nz; };     /* per-pixel record written by K1 (16 B) */
+
+/* ---- bit access to doubles (device: register moves; host: memcpy) */
+TSDF_HD int dbl_hi(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    long long b; memcpy(&b, &x, 8); return (int)(b >> 32);
+#endif
+}
+TSDF_HD int dbl_lo(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2loint(x);
+#else
+    long long b; memcpy(&b, &x, 8); return (int)(b & 0xffffffffll);
+#endif
+}
+/* correctly rounded fp32 reciprocal: identical bits to 1.0f / x, fewer instructions on the device */
+TSDF_HD float rcp_rn(float x) {
+#if defined(__CUDA_ARCH__)
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+}
 
 /* ---- the reference's (int) casts: x86 cvttss2si — truncation toward zero, NaN and
  * out-of-range give INT_MIN.  sdf.cpp:143-145 ---- */
@@ -195,7 +220,7 @@ TSDF_HD float interp_accumulate(const float* d, const float* w, const bool* inb,
                 exact = true;
                 exact_val = d[n];
             } else {
-                const float wt = 1.0f / volume;       /* == (float)(1.0 / (double)volume), sdf.cpp:154 */
+                const float wt = rcp_rn(volume);      /* == (float)(1.0 / (double)volume), sdf.cpp:154 */
                 w_sum = w_sum + wt;
                 sum_d = sum_d + wt * d[n];
             }
@@ -253,41 +278,55 @@ TSDF_HD bool project_exact(const GridParams& g, double ij0, double ij1, double i
     iu = (int)u; iv = (int)v;
     return true;
 }
-TSDF_HD bool fuse_project(const GridParams& g, double cx, double cy, double cz, int& iu, int& iv) {
-    if (cz < 0) return false;                                   /* sdf.cpp:247 */
-    double ij0, ij1, ij2;
+/* camera-space centre -> (ij0, ij1, ij2) = K * cam  (camera_tracking.cpp:44) */
+TSDF_HD void project_ij(const GridParams& g, double cx, double cy, double cz, double& ij0, double& ij1, double& ij2) {
     if (g.k_simple) {       /* 0*x and +0 are exact no-ops for finite operands */
         ij0 = g.K[0] * cx + g.K[2] * cz;
         ij1 = g.K[4] * cy + g.K[5] * cz;
         ij2 = cz;
-    } else {                /* camera_tracking.cpp:44 */
+    } else {
         ij0 = dot3_seq(g.K[0], g.K[1], g.K[2], cx, cy, cz);
         ij1 = dot3_seq(g.K[3], g.K[4], g.K[5], cx, cy, cz);
         ij2 = dot3_seq(g.K[6], g.K[7], g.K[8], cx, cy, cz);
     }
-    /* Only trunc(fl(ij0/ij2)) and trunc(fl(ij1/ij2)) are consumed (sdf.cpp:251-252).  With an
-     * approximate quotient q (|q - ij/ij2| <= ~1e-12 |q|, and fl() adds 1.1e-16 relative) the
-     * truncated value is certain unless q lies within TOL of an integer; those (and any
-     * non-finite q) take the exact divisions.  Results are identical to the exact path. */
-    const double TOL = 1e-7;
+}
+/* Branch-free projection.  Only trunc(fl(ij0/ij2)) and trunc(fl(ij1/ij2)) are consumed
+ * (sdf.cpp:251-252).  With an approximate quotient q (relative error <= ~1e-12; fl() adds
+ * 1.1e-16) the truncated value is certain unless q lies within TOL of an integer; those, and
+ * |q| >= 2^30 or non-finite q (voxel practically in the camera plane) set need_exact and the
+ * caller runs project_exact: results are identical to the reference's two IEEE divisions.
+ * Round-to-nearest via the 2^52+2^51 constant: the low word of q + MAGIC is the integer,
+ * d = q - rint(q) is exact, floor(q) = rint(q) - (d < 0).
+ * iu, iv always come back clamped into the image so the pixel fetch is unconditional. */
+TSDF_HD void fuse_project_flags(const GridParams& g, double cx, double cy, double cz,
+                                int& iu, int& iv, bool& ok, bool& need_exact) {
+    double ij0, ij1, ij2;
+    project_ij(g, cx, cy, cz, ij0, ij1, ij2);
+    const double TOL = 1e-7, MAGIC = 6755399441055744.0;
     const double r = rcp_fast(ij2);
     const double qu = ij0 * r, qv = ij1 * r;
-    const double Wd = (double)g.img_w, Hd = (double)g.img_h;
-    if (qu > -1.5 && qu < Wd + 0.5 && qv > -1.5 && qv < Hd + 0.5) {
-        const double fu = floor(qu), fv = floor(qv);
-        const double du = qu - fu, dv = qv - fv;
-        if (du > TOL && du < 1.0 - TOL && dv > TOL && dv < 1.0 - TOL) {
-            /* floor -> truncation toward zero: (-1,0) maps to 0; fu = -2 or fu = W is outside */
-            const int a = (int)fu, b = (int)fv;
-            if (a < -1 || a >= g.img_w || b < -1 || b >= g.img_h) return false;
-            iu = a < 0 ? 0 : a; iv = b < 0 ? 0 : b;
-            return true;
-        }
+    const int eu = dbl_hi(qu) & 0x7ff00000, ev = dbl_hi(qv) & 0x7ff00000;
+    const double tu = qu + MAGIC, tv = qv + MAGIC;
+    const double du = qu - (tu - MAGIC), dv = qv - (tv - MAGIC);
+    const bool safe = (eu < 0x41d00000) & (ev < 0x41d00000) & (fabs(du) > TOL) & (fabs(dv) > TOL);
+    const int fu = dbl_lo(tu) + (dbl_hi(du) >> 31), fv = dbl_lo(tv) + (dbl_hi(dv) >> 31);
+    /* floor in [-1, W-1] <=> truncation toward zero in [0, W-1]; (-1,0) maps to 0 */
+    const bool inimg = ((unsigned)(fu + 1) <= (unsigned)g.img_w) & ((unsigned)(fv + 1) <= (unsigned)g.img_h);
+    const bool zpos = !(cz < 0);                                /* sdf.cpp:247 */
+    ok = zpos & safe & inimg;
+    need_exact = zpos & !safe;
+    iu = fu < 0 ? 0 : (fu > g.img_w - 1 ? g.img_w - 1 : fu);
+    iv = fv < 0 ? 0 : (fv > g.img_h - 1 ? g.img_h - 1 : fv);
+}
+TSDF_HD bool fuse_project(const GridParams& g, double cx, double cy, double cz, int& iu, int& iv) {
+    bool ok, need_exact;
+    fuse_project_flags(g, cx, cy, cz, iu, iv, ok, need_exact);
+    if (need_exact) {
+        double ij0, ij1, ij2;
+        project_ij(g, cx, cy, cz, ij0, ij1, ij2);
         return project_exact(g, ij0, ij1, ij2, iu, iv);
     }
-    /* finite and clearly outside the image: rejected.  NaN/inf (ij2 = 0 or denormal): exact path */
-    if (fabs(qu) <= 1e300 && fabs(qv) <= 1e300) return false;
-    return project_exact(g, ij0, ij1, ij2, iu, iv);
+    return ok;
 }
 
 /* exp(x) for the weight of sdf.cpp:278.  For x in [-0.04, 0] a degree-9 Taylor polynomial in
@@ -310,31 +349,41 @@ TSDF_HD double weight_exp(double x) {
     return exp(x);
 }
 
-/* Stage 2 (distance + weight): false = voxel skipped.  rec = the pixel's {z,n}; px,py =
- * the pixel's back-projected x,y (recomputed with backproject_px, bit-identical to K1). */
-TSDF_HD bool fuse_distance(const GridParams& g, double cx, double cy, double cz,
-                           float px, float py, const PixRec& rec, float& d_out, float& w_out) {
+/* Stage 2 (distance), branch-free: returns false when the voxel is skipped.  rec = the pixel's
+ * {z,n}; px,py = the pixel's back-projected x,y (backproject_px, bit-identical to K1).  d_out is
+ * already truncated (Eq. 28); band says the exponential weight applies, with e_band = d - eps. */
+TSDF_HD bool fuse_distance_flags(const GridParams& g, double cx, double cy, double cz,
+                                 float px, float py, const PixRec& rec, float& d_out, float& e_band, bool& band) {
     float d_new;
+    bool valid;
     if (g.metric == 0) {
         /* sdf.cpp:260: isnan(point.x)|isnan(point.y)|isnan(normal.*) — z NaN makes x,y NaN */
-        if (!(rec.z == rec.z) || !(rec.nx == rec.nx)) return false;
+        valid = (rec.z == rec.z) & (rec.nx == rec.nx);
         /* sdf.h:177-181, Eigen dot = c0 + (c1 + c2) */
         const double dx = (double)px - cx, dy = (double)py - cy, dz = (double)rec.z - cz;
         const double pp = dx * (double)rec.nx + (dy * (double)rec.ny + dz * (double)rec.nz);
         d_new = (float)pp;                                      /* sdf.cpp:274 */
     } else {
-        if (!(rec.z == rec.z)) return false;
+        valid = (rec.z == rec.z);
         const double pp = cz - (double)rec.z;                   /* sdf.h:169-172 */
         d_new = (float)pp;
     }
-    float w_new = 1.0f;                                         /* sdf.cpp:276 */
-    if (d_new >= g.eps && d_new <= g.delta) {
-        const float e = d_new - g.eps;
-        w_new = (float)weight_exp(-0.5 * (double)e * (double)e);   /* sdf.cpp:278 */
-    }
-    if (d_new > g.delta) return false;                          /* sdf.cpp:280-283 */
-    if (d_new < -g.delta) d_new = -g.delta;                     /* sdf.cpp:285-287 */
-    d_out = d_new; w_out = w_new;
+    band = (d_new >= g.eps) & (d_new <= g.delta);               /* sdf.cpp:277 */
+    e_band = d_new - g.eps;
+    valid = valid & !(d_new > g.delta);                         /* sdf.cpp:280-283 */
+    d_out = (d_new < -g.delta) ? -g.delta : d_new;              /* sdf.cpp:285-287 */
+    return valid;
+}
+/* weight of sdf.cpp:276-279 */
+TSDF_HD float fuse_weight(bool band, float e_band) {
+    return band ? (float)weight_exp(-0.5 * (double)e_band * (double)e_band) : 1.0f;
+}
+TSDF_HD bool fuse_distance(const GridParams& g, double cx, double cy, double cz,
+                           float px, float py, const PixRec& rec, float& d_out, float& w_out) {
+    float e; bool band;
+    const bool valid = fuse_distance_flags(g, cx, cy, cz, px, py, rec, d_out, e, band);
+    if (!valid) return false;
+    w_out = fuse_weight(band, e);
     return true;
 }
 /* Stage 3 (running weighted mean): sdf.cpp:289-292 */
@@ -383,8 +432,9 @@ TSDF_HD void row_clip(const GridParams& g, const double* Ri, const double* ti,
     }
     if (!empty && lo <= hi) {
         int l = (int)floor(lo) - 1, h = (int)ceil(hi) + 2;
-        ilo = l < 0 ? 0 : l;
-        ihi = h > m ? m : h;
+        l = l < 0 ? 0 : l; h = h > m ? m : h;
+        ilo = l & ~3;                       /* whole 32-byte sectors (m is a multiple of 4) */
+        ihi = (h + 3) & ~3;
     }
 }
 
@@ -399,10 +449,11 @@ TSDF_HD void sample_coords(const GridParams& g, const double* M, const double* t
     matvec3(M, px, py, pz, wx, wy, wz);
     wx = wx + t[0]; wy = wy + t[1]; wz = wz + t[2];
     world_to_voxel(g, wx, wy, wz, vx, vy, vz);
+    /* +-v_h on one axis for s = 1..6 (x + (-v_h) == x - v_h; x + 0.0 == x) */
     const double vh = (double)g.v_h;
-    if (s == 1) vx += vh; else if (s == 2) vx -= vh;
-    else if (s == 3) vy += vh; else if (s == 4) vy -= vh;
-    else if (s == 5) vz += vh; else if (s == 6) vz -= vh;
+    vx = vx + ((s == 1) ? vh : (s == 2) ? -vh : 0.0);
+    vy = vy + ((s == 3) ? vh : (s == 4) ? -vh : 0.0);
+    vz = vz + ((s == 5) ? vh : (s == 6) ? -vh : 0.0);
 }
 /* camera_tracking.cpp:92-145: perturbed rotation q (0..5) = (I +- w_h [e_k]x) * rot */
 TSDF_HD void perturbed_rot(const GridParams& g, const double* rot, int q, double* out) {

@@ -11,6 +11,12 @@ constexpr int LIN_PARTIAL_STRIDE = 32;    /* doubles per block partial (30 used)
 constexpr int MAX_WORLD = 16;
 constexpr int LIN_GROUP = 16;             /* blocks per first-level reduction group */
 constexpr int FUSE_THREADS = 128;
+#ifndef FUSE_MIN_BLOCKS
+#define FUSE_MIN_BLOCKS 5               /* resident blocks per SM the fusion kernel is compiled for */
+#endif
+#ifndef LIN_MIN_BLOCKS
+#define LIN_MIN_BLOCKS 3
+#endif
 constexpr int FUSE_LAUNCHES = 3;          /* tables, plan, items */
 
 /* cross-shard exchange of the reduced normal equations (one slot per rank, double-buffered
@@ -35,6 +41,7 @@ struct LinearizeArgs {
     unsigned int* group_ticket;            /* one per LIN_GROUP blocks */
     double* group_partials;                /* ngroups * LIN_PARTIAL_STRIDE */
     float* dbgJ; float* dbgPsi; uint8_t* dbgFlag;   /* optional per-pixel records */
+    unsigned long long* dbg_times;         /* optional: globaltimer stamps of the kernel's phases */
     int32_t do_update;                     /* 1: solve + pose update in the last block */
     int32_t px_per_block;
     ShardLinks links;                      /* world = 1: no exchange */

@@ -126,6 +126,11 @@ __constant__ unsigned char c_slot_a[32] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2
 __constant__ unsigned char c_slot_b[32] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5, 0, 1, 2, 3, 4, 5, 6, 0, 0, 0, 0};
 __constant__ unsigned char c_slot_k[32] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 2, 3, 3};
 
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ double ld_volatile_f64(const double* p) { return *reinterpret_cast<const volatile double*>(p); }
 
 /* sum of the 30 slots over all ranks, rank order; runs in the last block after its local sums
@@ -154,7 +159,7 @@ __device__ void exchange_sums(const ShardLinks& L, unsigned long long seqno, dou
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(LIN_THREADS, 3) k_linearize(LinearizeArgs a, int exchange_mode, unsigned long long seqno) {
+__global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(LinearizeArgs a, int exchange_mode, unsigned long long seqno) {
     __shared__ double sM[7][9];
     __shared__ double sT[3];
     __shared__ double sRed[LIN_THREADS / 32][32];
@@ -167,6 +172,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) k_linearize(LinearizeArgs a, i
     if (a.do_update && pose->stopped) return;             /* loop condition of camera_tracking.cpp:79 */
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (a.dbg_times && tid == 0) atomicMin(&a.dbg_times[0], gtime());
     if (tid < 9) sM[0][tid] = pose->R[tid];
     if (tid < 3) sT[tid] = pose->t[tid];
     if (tid == 0) sMiss = 0;
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) k_linearize(LinearizeArgs a, i
                 sample_coords(g, M, sT, s, (double)x, (double)y, (double)z, vx, vy, vz);
                 if (s == 0) {                                                /* camera_tracking.cpp:261-268 */
                     const double dm = (double)g.m;
-                    oob = (vx < 0 || vy < 0 || vz < 0 || vx >= dm || vy >= dm || vz >= dm);
+                    oob = (vx < 0) | (vy < 0) | (vz < 0) | (vx >= dm) | (vy >= dm) | (vz >= dm);
                 }
                 bool is_interp;
                 val = interpolate_distance(vx, vy, vz, fetch, is_interp);
@@ -269,6 +275,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) k_linearize(LinearizeArgs a, i
         }
     }
     if (miss) sMiss = 1;
+    if (a.dbg_times && tid == 0) atomicMax(&a.dbg_times[1], gtime());
 
     /* half-warps -> warp -> block partial (fixed order) */
     acc0 = acc0 + __shfl_xor_sync(0xffffffffu, acc0, 16);
@@ -319,6 +326,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) k_linearize(LinearizeArgs a, i
     if (tid == 0) sLast = (atomicAdd(a.ticket, 1u) == (unsigned)(ngroups - 1));
     __syncthreads();
     if (!sLast) return;
+    if (a.dbg_times && tid == 0) a.dbg_times[2] = gtime();
     __threadfence();
     {
         const int slot = tid & 31, sub = tid >> 5;
@@ -335,6 +343,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) k_linearize(LinearizeArgs a, i
         }
     }
     __syncthreads();
+    if (a.dbg_times && tid == 0) a.dbg_times[3] = gtime();
     if (exchange_mode == 1 && a.links.world > 1) exchange_sums(a.links, seqno, sSums, tid);
     if (exchange_mode == 2 && a.links.world > 1) {
         /* deferred (single-process emulation): publish our sums into every mailbox; a separate
@@ -347,6 +356,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 3) k_linearize(LinearizeArgs a, i
         else for (int q = 0; q < N_SLOTS; q++) pose->sums[q] = sSums[q];
     }
     if (tid == 0) *a.ticket = 0u;
+    if (a.dbg_times && tid == 0) a.dbg_times[4] = gtime();
 }
 
 /* deferred combine for in-process shards (exchange_mode 2) */
@@ -438,7 +448,7 @@ __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, const PoseState
         for (int q = 0; q < 3; q++) ti[q] = pose->tinv[q];
         row_clip(g, Ri, ti, T[(size_t)3 * m + j], T[(size_t)4 * m + j], T[(size_t)5 * m + j],
                  T[(size_t)6 * m + k], T[(size_t)7 * m + k], T[(size_t)8 * m + k], ilo, ihi);
-        if (ihi > ilo) { xs = ilo & ~3; cnt = (ihi - xs + 127) >> 7; }
+        if (ihi > ilo) { xs = ilo; cnt = (ihi - xs + 127) >> 7; }
     }
     /* warp-inclusive scan of cnt, one reservation per warp */
     int scan = cnt;
@@ -457,7 +467,7 @@ __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, const PoseState
 
 __device__ __forceinline__ float4 ld_f4(const float4* p) { return *p; }
 
-__global__ void __launch_bounds__(FUSE_THREADS, 5) k_fuse_items(GridParams g, float2* __restrict__ grid,
+__global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_items(GridParams g, float2* __restrict__ grid,
                                                                 const PixRec* __restrict__ pix,
                                                                 const double* __restrict__ T,
                                                                 const unsigned long long* __restrict__ items,
@@ -475,47 +485,70 @@ __global__ void __launch_bounds__(FUSE_THREADS, 5) k_fuse_items(GridParams g, fl
     for (unsigned int it = gw; it < n_items; it += total_warps) {
         const unsigned long long item = __ldg(&items[it]);
         const int k = (int)(item & 0xfff), j = (int)((item >> 12) & 0xfff), xs = (int)((item >> 24) & 0xfff);
-        const int ilo = (int)((item >> 36) & 0xfff), ihi = (int)((item >> 48) & 0x1fff);
-        const int x0 = xs + 4 * lane;
-        if (x0 >= ihi || x0 >= m) continue;               /* lanes past the row's interval are idle */
-        float4* ptr = reinterpret_cast<float4*>(&grid[((size_t)(k - g.ks0) * m + j) * m + x0]);
+        const int ihi = (int)((item >> 48) & 0x1fff);
+        /* lane owns voxel pairs A = xs + 2*lane + {0,1} and B = A + 64: each 16-byte access of the
+         * warp is one contiguous 512-byte run */
+        const int xa = xs + 2 * lane, xb = xa + 64;
+        const bool actA = xa < ihi, actB = xb < ihi;      /* interval ends are multiples of 4 */
+        if (!actA) continue;
+        float4* ptr = reinterpret_cast<float4*>(&grid[((size_t)(k - g.ks0) * m + j) * m + xa]);
         /* issue every load up front: voxel store, then the hoisted products */
-        float4 q0 = ld_f4(ptr), q1 = ld_f4(ptr + 1);
-        const double2* tx0 = reinterpret_cast<const double2*>(T + (size_t)0 * m + x0);
-        const double2* tx1 = reinterpret_cast<const double2*>(T + (size_t)1 * m + x0);
-        const double2* tx2 = reinterpret_cast<const double2*>(T + (size_t)2 * m + x0);
-        const double2 a0 = __ldg(tx0), a1 = __ldg(tx0 + 1), b0 = __ldg(tx1), b1 = __ldg(tx1 + 1), c0 = __ldg(tx2), c1 = __ldg(tx2 + 1);
+        float4 q0 = ld_f4(ptr), q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (actB) q1 = ld_f4(ptr + 32);
+        const int xbl = actB ? xb : xa;
+        const double2 a0 = __ldg(reinterpret_cast<const double2*>(T + (size_t)0 * m + xa)), a1 = __ldg(reinterpret_cast<const double2*>(T + (size_t)0 * m + xbl));
+        const double2 b0 = __ldg(reinterpret_cast<const double2*>(T + (size_t)1 * m + xa)), b1 = __ldg(reinterpret_cast<const double2*>(T + (size_t)1 * m + xbl));
+        const double2 c0 = __ldg(reinterpret_cast<const double2*>(T + (size_t)2 * m + xa)), c1 = __ldg(reinterpret_cast<const double2*>(T + (size_t)2 * m + xbl));
         const double qy0 = __ldg(T + (size_t)3 * m + j), qy1 = __ldg(T + (size_t)4 * m + j), qy2 = __ldg(T + (size_t)5 * m + j);
         const double pz0 = __ldg(T + (size_t)6 * m + k), pz1 = __ldg(T + (size_t)7 * m + k), pz2 = __ldg(T + (size_t)8 * m + k);
         const double px0[4] = {a0.x, a0.y, a1.x, a1.y}, px1[4] = {b0.x, b0.y, b1.x, b1.y}, px2[4] = {c0.x, c0.y, c1.x, c1.y};
-        float dnew[4], wnew[4];
-        bool upd[4];
+        /* straight-line, branch-free stages over the lane's four voxels so their dependency
+         * chains interleave; the rare exact-division and exponential-weight cases branch last */
+        double cx[4], cy[4], cz[4];
+        int iu[4], iv[4];
+        bool ok[4], need_exact[4];
 #pragma unroll
         for (int v = 0; v < 4; v++) {
-            upd[v] = false;
-            const int x = x0 + v;
-            if (x >= ilo && x < ihi) {
-                /* camera_tracking.cpp:51-54 : rot_inv * g + rot_inv_trans, reference rounding order */
-                const double cx = ((px0[v] + qy0) + pz0) + ti0;
-                const double cy = ((px1[v] + qy1) + pz1) + ti1;
-                const double cz = ((px2[v] + qy2) + pz2) + ti2;
-                int iu, iv;
-                if (fuse_project(g, cx, cy, cz, iu, iv)) {
-                    const float4 rr = __ldg(reinterpret_cast<const float4*>(&pix[(size_t)iv * g.img_w + iu]));
-                    PixRec rec; rec.z = rr.x; rec.nx = rr.y; rec.ny = rr.z; rec.nz = rr.w;
-                    float fx_, fy_;
-                    backproject_px(kp, iu, iv, rec.z, fx_, fy_);
-                    upd[v] = fuse_distance(g, cx, cy, cz, fx_, fy_, rec, dnew[v], wnew[v]);
-                }
-            }
+            /* camera_tracking.cpp:51-54 : rot_inv * g + rot_inv_trans, reference rounding order */
+            cx[v] = ((px0[v] + qy0) + pz0) + ti0;
+            cy[v] = ((px1[v] + qy1) + pz1) + ti1;
+            cz[v] = ((px2[v] + qy2) + pz2) + ti2;
+            fuse_project_flags(g, cx[v], cy[v], cz[v], iu[v], iv[v], ok[v], need_exact[v]);
         }
+        if (need_exact[0] | need_exact[1] | need_exact[2] | need_exact[3]) {
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+                if (need_exact[v]) {
+                    double ij0, ij1, ij2;
+                    project_ij(g, cx[v], cy[v], cz[v], ij0, ij1, ij2);
+                    int eu_ = 0, ev_ = 0;
+                    ok[v] = project_exact(g, ij0, ij1, ij2, eu_, ev_);
+                    if (ok[v]) { iu[v] = eu_; iv[v] = ev_; }
+                }
+        }
+        float4 rr[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) rr[v] = __ldg(reinterpret_cast<const float4*>(&pix[(size_t)iv[v] * g.img_w + iu[v]]));
+        float dnew[4], wnew[4], eband[4];
+        bool upd[4], band[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            PixRec rec; rec.z = rr[v].x; rec.nx = rr[v].y; rec.ny = rr[v].z; rec.nz = rr[v].w;
+            float fx_, fy_;
+            backproject_px(kp, iu[v], iv[v], rec.z, fx_, fy_);
+            upd[v] = fuse_distance_flags(g, cx[v], cy[v], cz[v], fx_, fy_, rec, dnew[v], eband[v], band[v]) & ok[v] & (v < 2 || actB);
+            wnew[v] = 1.0f;
+        }
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+            if (upd[v] & band[v]) wnew[v] = fuse_weight(true, eband[v]);     /* sdf.cpp:276-279 */
         const unsigned int owned = (k >= g.ko0 && k < g.ko1) ? 1u : 0u;    /* halo layers are fused redundantly, counted once */
         if (upd[0]) { fuse_apply(q0.x, q0.y, dnew[0], wnew[0]); my_updates += owned; }
         if (upd[1]) { fuse_apply(q0.z, q0.w, dnew[1], wnew[1]); my_updates += owned; }
         if (upd[2]) { fuse_apply(q1.x, q1.y, dnew[2], wnew[2]); my_updates += owned; }
         if (upd[3]) { fuse_apply(q1.z, q1.w, dnew[3], wnew[3]); my_updates += owned; }
         if (upd[0] || upd[1]) ptr[0] = q0;
-        if (upd[2] || upd[3]) ptr[1] = q1;
+        if (upd[2] || upd[3]) ptr[32] = q1;
     }
     /* one atomic per warp */
     unsigned int tot = my_updates;
