@@ -17,7 +17,7 @@ GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 NVCC = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc"
 
 # No fast-math, no FMA contraction, no -march: the fp32/fp64 rounding sequence is the spec.
-HOST_FLAGS = ["-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fPIC", "-Wall"]
+HOST_FLAGS = ["-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fPIC", "-Wall", "-Wno-unknown-pragmas"]
 # -fmad=false: device arithmetic must round exactly like the reference's non-contracted x86 code.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-Xcompiler", "-fno-strict-aliasing"]

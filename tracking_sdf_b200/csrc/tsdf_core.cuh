@@ -259,11 +259,14 @@ TSDF_HD float interpolate_distance(double vx, double vy, double vz, Fetch&& fetc
 
 /* ---- fusion, per voxel: sdf.cpp:245-292 ---------------------------------------------------
  * Stage 1 (projection): camera-space voxel centre -> pixel, or reject. */
-/* reciprocal good to ~1e-12 relative: device = MUFU.RCP64H + one Newton step, host = 1/y */
+/* reciprocal good to ~2e-14 relative for y in the float range: device = fp32 MUFU.RCP of the
+ * rounded operand (2^-23) + one Newton step in double (squares it); y beyond the float range
+ * gives 0/inf and the caller's exponent guard sends the voxel to the exact path.  host = 1/y */
 TSDF_HD double rcp_fast(double y) {
 #if defined(__CUDA_ARCH__)
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(__double2float_rn(y)));
+    const double r = (double)rf;
     const double e = fma(-y, r, 1.0);
     return fma(r, e, r);
 #else
@@ -278,6 +281,8 @@ TSDF_HD bool project_exact(const GridParams& g, double ij0, double ij1, double i
     iu = (int)u; iv = (int)v;
     return true;
 }
+TSDF_HD int imin(int a, int b) { return a < b ? a : b; }
+TSDF_HD int imax(int a, int b) { return a > b ? a : b; }
 /* camera-space centre -> (ij0, ij1, ij2) = K * cam  (camera_tracking.cpp:44) */
 TSDF_HD void project_ij(const GridParams& g, double cx, double cy, double cz, double& ij0, double& ij1, double& ij2) {
     if (g.k_simple) {       /* 0*x and +0 are exact no-ops for finite operands */
@@ -315,8 +320,8 @@ TSDF_HD void fuse_project_flags(const GridParams& g, double cx, double cy, doubl
     const bool zpos = !(cz < 0);                                /* sdf.cpp:247 */
     ok = zpos & safe & inimg;
     need_exact = zpos & !safe;
-    iu = fu < 0 ? 0 : (fu > g.img_w - 1 ? g.img_w - 1 : fu);
-    iv = fv < 0 ? 0 : (fv > g.img_h - 1 ? g.img_h - 1 : fv);
+    iu = imin(imax(fu, 0), g.img_w - 1);
+    iv = imin(imax(fv, 0), g.img_h - 1);
 }
 TSDF_HD bool fuse_project(const GridParams& g, double cx, double cy, double cz, int& iu, int& iv) {
     bool ok, need_exact;
@@ -391,6 +396,14 @@ TSDF_HD void fuse_apply(float& D, float& W, float d_new, float w_new) {
     const float w_old = W;
     W = w_old + w_new;
     D = (w_old * D + w_new * d_new) / W;
+}
+/* same, predicated without a branch (w_new must be > 0 even when !upd so the quotient is benign) */
+TSDF_HD void fuse_apply_sel(float& D, float& W, float d_new, float w_new, bool upd) {
+    const float w_old = W;
+    const float Wn = w_old + w_new;
+    const float Dn = (w_old * D + w_new * d_new) / Wn;
+    W = upd ? Wn : w_old;
+    D = upd ? Dn : D;
 }
 
 /* ---- scan-line clipping for the fusion kernel ------------------------------------------------

@@ -14,12 +14,33 @@
 
 namespace tsdf {
 
+/* Programmatic dependent launch (sm_90+): every kernel of the per-frame sequence is launched
+ * with cudaLaunchAttributeProgrammaticStreamSerialization, waits for its predecessor's memory
+ * at the top (griddepcontrol.wait) and releases its successor's launch right away, so the
+ * launch latency of kernel n+1 overlaps the tail of kernel n (the Gauss-Newton chain is ten
+ * dependent launches per frame). */
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 /* ------------------------------------------------------------------------------------------
  * K1: back-projection + normals.  One thread per pixel; 5 depth reads (L1/L2 resident),
  * one 16-byte record out.  Thread 0 also re-arms the tracker state for the coming frame.
  * ------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restrict__ depth,
                                               PixRec* __restrict__ pix, PoseState* pose, int reset_track) {
+    pdl_wait();
+    pdl_release();
     const int u = blockIdx.x * 32 + (threadIdx.x & 31);
     const int v = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (reset_track && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -44,7 +65,7 @@ __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restr
 
 void launch_prep(const GridParams& g, const float* depth, PixRec* pix, PoseState* pose, int reset_track, cudaStream_t s) {
     dim3 grid((g.img_w + 31) / 32, (g.img_h + 7) / 8);
-    k_prep<<<grid, 256, 0, s>>>(g, depth, pix, pose, reset_track);
+    launch_pdl(k_prep, grid, dim3(256), s, g, depth, pix, pose, reset_track);
 }
 
 /* organised cloud + normals for the accessor / tests */
@@ -159,6 +180,113 @@ __device__ void exchange_sums(const ShardLinks& L, unsigned long long seqno, dou
     __syncthreads();
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Gauss-Newton step by ONE WARP (camera_tracking.cpp:191-192, 216-224, 237-239): the same
+ * arithmetic as tsdf_core.cuh:gn_update / solve6 / exp_map / pose_set, element for element, but
+ * the 6x6 elimination runs one lane per matrix element in shared memory (the serial version
+ * needs ~170 registers and is a ~4 us dependent chain).  sc: >= 128 doubles of shared scratch.
+ * ------------------------------------------------------------------------------------------ */
+__device__ void gn_update_warp(const GridParams& g, PoseState* pose, const double* sums, double* sc, int lane) {
+    double (*sA)[8] = reinterpret_cast<double (*)[8]>(sc);        /* 6 x 8: [A | b] */
+    double* sRd = sc + 48;                                        /* 9  */
+    double* sTd = sc + 57;                                        /* 3  */
+    double* sR = sc + 60;                                         /* 9  current rot */
+    double* sT = sc + 69;                                         /* 3  current trans */
+    double* sNR = sc + 72;                                        /* 9  new rot */
+    double* sNT = sc + 81;                                        /* 3  new trans */
+    if (lane < N_SLOTS) pose->sums[lane] = sums[lane];
+    if (lane < 9) sR[lane] = pose->R[lane];
+    if (lane < 3) sT[lane] = pose->t[lane];
+    for (int e = lane; e < 42; e += 32) {
+        const int r = e / 7, c = e - 7 * r;
+        if (c < 6) {
+            const int lo = r < c ? r : c, hi = r < c ? c : r;
+            sA[r][c] = sums[SLOT_A + lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo)];
+        } else sA[r][6] = sums[SLOT_B + r];
+    }
+    __syncwarp();
+    int singular = 0;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        int piv = c;
+        double best = fabs(sA[c][c]);
+#pragma unroll
+        for (int r = c + 1; r < 6; r++) {
+            const double v = fabs(sA[r][c]);
+            if (v > best) { best = v; piv = r; }
+        }
+        const bool good = (best > 0.0);
+        if (!good) singular = 1;
+        __syncwarp();
+        if (good && piv != c && lane >= c && lane < 7) {
+            const double u = sA[c][lane], v = sA[piv][lane];
+            sA[c][lane] = v; sA[piv][lane] = u;
+        }
+        __syncwarp();
+        const int nq = 6 - c, nr = 5 - c;
+        const bool act = good && lane < nr * nq;
+        double val = 0.0;
+        int r = 0, q = 0;
+        if (act) {
+            r = c + 1 + lane / nq; q = c + 1 + lane % nq;
+            const double f = sA[r][c] / sA[c][c];
+            val = sA[r][q] - f * sA[c][q];
+        }
+        __syncwarp();
+        if (act) sA[r][q] = val;
+        __syncwarp();
+    }
+    double x[6];
+#pragma unroll
+    for (int r = 5; r >= 0; r--) {
+        double sacc = sA[r][6];
+#pragma unroll
+        for (int q = r + 1; q < 6; q++) sacc = sacc - sA[r][q] * x[q];
+        x[r] = sacc / sA[r][r];
+    }
+#pragma unroll
+    for (int q = 0; q < 6; q++) if (!(fabs(x[q]) <= 1.7976931348623157e308)) singular = 1;
+    if (lane == 0) pose->iterations = pose->iterations + 1;
+    if (singular) {                                  /* keep the previous pose, report (TRAP 12) */
+        if (lane == 0) { pose->singular = 1; pose->stopped = 1; }
+        return;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) pose->twist[q] = x[q];
+        double rd[9], td[3];
+        exp_map(x, rd, td);                          /* eigen_utils.cpp:85-128 */
+#pragma unroll
+        for (int q = 0; q < 9; q++) sRd[q] = rd[q];
+#pragma unroll
+        for (int q = 0; q < 3; q++) sTd[q] = td[q];
+    }
+    __syncwarp();
+    if (lane < 9) {                                  /* rot = Rd^T * rot            (:237) */
+        const int r = lane / 3, c = lane - 3 * r;
+        sNR[lane] = (sRd[r] * sR[c] + sRd[3 + r] * sR[3 + c]) + sRd[6 + r] * sR[6 + c];
+    } else if (lane < 12) {                          /* trans = trans - Rd^T * td   (:238) */
+        const int q = lane - 9;
+        const double v = (sRd[q] * sTd[0] + sRd[3 + q] * sTd[1]) + sRd[6 + q] * sTd[2];
+        sNT[q] = sT[q] - v;
+    }
+    __syncwarp();
+    if (lane == 0) {                                 /* set_camera_transformation   (:239, :59-65) */
+        double M[9], inv[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) M[q] = sNR[q];
+        inverse3(M, inv);
+        double tx, ty, tz;
+        matvec3(inv, sNT[0], sNT[1], sNT[2], tx, ty, tz);
+#pragma unroll
+        for (int q = 0; q < 9; q++) { pose->R[q] = M[q]; pose->Rinv[q] = inv[q]; }
+        pose->t[0] = sNT[0]; pose->t[1] = sNT[1]; pose->t[2] = sNT[2];
+        pose->tinv[0] = -1 * tx; pose->tinv[1] = -1 * ty; pose->tinv[2] = -1 * tz;
+        const double mtd = (double)g.max_twist_diff;               /* signed test, :216-224 */
+        if (x[0] < mtd && x[1] < mtd && x[2] < mtd && x[3] < mtd && x[4] < mtd && x[5] < mtd) pose->stopped = 1;
+    }
+}
+
 __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(LinearizeArgs a, int exchange_mode, unsigned long long seqno) {
     __shared__ double sM[7][9];
     __shared__ double sT[3];
@@ -169,6 +297,8 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
 
     const GridParams& g = a.g;
     PoseState* pose = a.pose;
+    pdl_wait();
+    pdl_release();
     if (a.do_update && pose->stopped) return;             /* loop condition of camera_tracking.cpp:79 */
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -351,9 +481,9 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
         const int par = (int)(seqno & 1ull);
         for (int r = 0; r < a.links.world; r++)
             if (tid < N_SLOTS) a.links.box[r]->sums[par][a.links.rank][tid] = sSums[tid];
-    } else if (tid == 0) {
-        if (a.do_update) gn_update(g, *pose, sSums);
-        else for (int q = 0; q < N_SLOTS; q++) pose->sums[q] = sSums[q];
+    } else if (tid < 32) {
+        if (a.do_update) gn_update_warp(g, pose, sSums, &sRed[0][0], tid);
+        else if (tid < N_SLOTS) pose->sums[tid] = sSums[tid];
     }
     if (tid == 0) *a.ticket = 0u;
     if (a.dbg_times && tid == 0) a.dbg_times[4] = gtime();
@@ -362,7 +492,10 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
 /* deferred combine for in-process shards (exchange_mode 2) */
 __global__ void k_gn_combine(LinearizeArgs a, unsigned long long seqno) {
     __shared__ double sSums[32];
+    __shared__ double sScratch[128];
     PoseState* pose = a.pose;
+    pdl_wait();
+    pdl_release();
     if (a.do_update && pose->stopped) return;
     const int tid = threadIdx.x;
     const int par = (int)(seqno & 1ull);
@@ -372,17 +505,15 @@ __global__ void k_gn_combine(LinearizeArgs a, unsigned long long seqno) {
         sSums[tid] = acc;
     }
     __syncthreads();
-    if (tid == 0) {
-        if (a.do_update) gn_update(a.g, *pose, sSums);
-        else for (int q = 0; q < N_SLOTS; q++) pose->sums[q] = sSums[q];
-    }
+    if (a.do_update) gn_update_warp(a.g, pose, sSums, sScratch, tid);
+    else if (tid < N_SLOTS) pose->sums[tid] = sSums[tid];
 }
 
 void launch_linearize(const LinearizeArgs& a, int nblk, int exchange_mode, unsigned long long seqno, cudaStream_t s) {
-    k_linearize<<<nblk, LIN_THREADS, 0, s>>>(a, exchange_mode, seqno);
+    launch_pdl(k_linearize, dim3(nblk), dim3(LIN_THREADS), s, a, exchange_mode, seqno);
 }
 void launch_gn_combine(const LinearizeArgs& a, unsigned long long seqno, cudaStream_t s) {
-    k_gn_combine<<<1, 32, 0, s>>>(a, seqno);
+    launch_pdl(k_gn_combine, dim3(1), dim3(32), s, a, seqno);
 }
 
 int linearize_blocks_per_sm() {
@@ -409,6 +540,8 @@ int linearize_blocks_per_sm() {
  * ------------------------------------------------------------------------------------------ */
 __global__ void k_fuse_tables(GridParams g, const PoseState* __restrict__ pose, double* __restrict__ T,
                               unsigned long long* n_updated, unsigned int* item_count) {
+    pdl_wait();
+    pdl_release();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = g.m;
     if (i == 0) { n_updated[0] = 0ull; *item_count = 0u; }
@@ -434,6 +567,8 @@ __device__ __forceinline__ unsigned long long pack_item(int k, int j, int xs, in
 __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, const PoseState* __restrict__ pose,
                                                    const double* __restrict__ T, unsigned long long* __restrict__ items,
                                                    unsigned int* item_count) {
+    pdl_wait();
+    pdl_release();
     const int m = g.m;
     const int nrows = (g.ks1 - g.ks0) * m;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -467,12 +602,17 @@ __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, const PoseState
 
 __device__ __forceinline__ float4 ld_f4(const float4* p) { return *p; }
 
-__global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_items(GridParams g, float2* __restrict__ grid,
+template <int METRIC, int KSIMPLE>
+__global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_items(GridParams g_in, float2* __restrict__ grid,
                                                                 const PixRec* __restrict__ pix,
                                                                 const double* __restrict__ T,
                                                                 const unsigned long long* __restrict__ items,
                                                                 const unsigned int* __restrict__ item_count,
                                                                 unsigned long long* n_updated /* [0] this launch, [1] running total */) {
+    pdl_wait();
+    pdl_release();
+    GridParams g = g_in;
+    g.metric = METRIC; g.k_simple = KSIMPLE;      /* compile-time: the unused metric / projection is not emitted */
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (FUSE_THREADS / 32) + (threadIdx.x >> 5);
     const int total_warps = gridDim.x * (FUSE_THREADS / 32);
@@ -495,12 +635,12 @@ __global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_items(Gr
         /* issue every load up front: voxel store, then the hoisted products */
         float4 q0 = ld_f4(ptr), q1 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (actB) q1 = ld_f4(ptr + 32);
-        const int xbl = actB ? xb : xa;
-        const double2 a0 = __ldg(reinterpret_cast<const double2*>(T + (size_t)0 * m + xa)), a1 = __ldg(reinterpret_cast<const double2*>(T + (size_t)0 * m + xbl));
-        const double2 b0 = __ldg(reinterpret_cast<const double2*>(T + (size_t)1 * m + xa)), b1 = __ldg(reinterpret_cast<const double2*>(T + (size_t)1 * m + xbl));
-        const double2 c0 = __ldg(reinterpret_cast<const double2*>(T + (size_t)2 * m + xa)), c1 = __ldg(reinterpret_cast<const double2*>(T + (size_t)2 * m + xbl));
-        const double qy0 = __ldg(T + (size_t)3 * m + j), qy1 = __ldg(T + (size_t)4 * m + j), qy2 = __ldg(T + (size_t)5 * m + j);
-        const double pz0 = __ldg(T + (size_t)6 * m + k), pz1 = __ldg(T + (size_t)7 * m + k), pz2 = __ldg(T + (size_t)8 * m + k);
+        const unsigned int xbl = actB ? xb : xa, um = (unsigned int)m;   /* tables are tiny: 32-bit offsets */
+        const double2 a0 = __ldg(reinterpret_cast<const double2*>(T + (unsigned int)xa)), a1 = __ldg(reinterpret_cast<const double2*>(T + xbl));
+        const double2 b0 = __ldg(reinterpret_cast<const double2*>(T + (um + xa))), b1 = __ldg(reinterpret_cast<const double2*>(T + (um + xbl)));
+        const double2 c0 = __ldg(reinterpret_cast<const double2*>(T + (2u * um + xa))), c1 = __ldg(reinterpret_cast<const double2*>(T + (2u * um + xbl)));
+        const double qy0 = __ldg(T + (3u * um + j)), qy1 = __ldg(T + (4u * um + j)), qy2 = __ldg(T + (5u * um + j));
+        const double pz0 = __ldg(T + (6u * um + k)), pz1 = __ldg(T + (7u * um + k)), pz2 = __ldg(T + (8u * um + k));
         const double px0[4] = {a0.x, a0.y, a1.x, a1.y}, px1[4] = {b0.x, b0.y, b1.x, b1.y}, px2[4] = {c0.x, c0.y, c1.x, c1.y};
         /* straight-line, branch-free stages over the lane's four voxels so their dependency
          * chains interleave; the rare exact-division and exponential-weight cases branch last */
@@ -528,7 +668,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_items(Gr
         }
         float4 rr[4];
 #pragma unroll
-        for (int v = 0; v < 4; v++) rr[v] = __ldg(reinterpret_cast<const float4*>(&pix[(size_t)iv[v] * g.img_w + iu[v]]));
+        for (int v = 0; v < 4; v++) rr[v] = __ldg(reinterpret_cast<const float4*>(&pix[(unsigned int)(iv[v] * g.img_w + iu[v])]));
         float dnew[4], wnew[4], eband[4];
         bool upd[4], band[4];
 #pragma unroll
@@ -539,16 +679,21 @@ __global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_items(Gr
             upd[v] = fuse_distance_flags(g, cx[v], cy[v], cz[v], fx_, fy_, rec, dnew[v], eband[v], band[v]) & ok[v] & (v < 2 || actB);
             wnew[v] = 1.0f;
         }
+        if ((upd[0] & band[0]) | (upd[1] & band[1]) | (upd[2] & band[2]) | (upd[3] & band[3])) {
 #pragma unroll
-        for (int v = 0; v < 4; v++)
-            if (upd[v] & band[v]) wnew[v] = fuse_weight(true, eband[v]);     /* sdf.cpp:276-279 */
-        const unsigned int owned = (k >= g.ko0 && k < g.ko1) ? 1u : 0u;    /* halo layers are fused redundantly, counted once */
-        if (upd[0]) { fuse_apply(q0.x, q0.y, dnew[0], wnew[0]); my_updates += owned; }
-        if (upd[1]) { fuse_apply(q0.z, q0.w, dnew[1], wnew[1]); my_updates += owned; }
-        if (upd[2]) { fuse_apply(q1.x, q1.y, dnew[2], wnew[2]); my_updates += owned; }
-        if (upd[3]) { fuse_apply(q1.z, q1.w, dnew[3], wnew[3]); my_updates += owned; }
-        if (upd[0] || upd[1]) ptr[0] = q0;
-        if (upd[2] || upd[3]) ptr[32] = q1;
+            for (int v = 0; v < 4; v++)
+                if (upd[v] & band[v]) wnew[v] = fuse_weight(true, eband[v]);     /* sdf.cpp:276-279 */
+        }
+        if (upd[0] | upd[1] | upd[2] | upd[3]) {
+            fuse_apply_sel(q0.x, q0.y, dnew[0], wnew[0], upd[0]);
+            fuse_apply_sel(q0.z, q0.w, dnew[1], wnew[1], upd[1]);
+            fuse_apply_sel(q1.x, q1.y, dnew[2], wnew[2], upd[2]);
+            fuse_apply_sel(q1.z, q1.w, dnew[3], wnew[3], upd[3]);
+            if (upd[0] | upd[1]) ptr[0] = q0;
+            if (upd[2] | upd[3]) ptr[32] = q1;
+            /* halo layers are fused redundantly, counted once */
+            if (k >= g.ko0 && k < g.ko1) my_updates += (unsigned)upd[0] + (unsigned)upd[1] + (unsigned)upd[2] + (unsigned)upd[3];
+        }
     }
     /* one atomic per warp */
     unsigned int tot = my_updates;
@@ -559,15 +704,22 @@ __global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_items(Gr
 
 void launch_fuse(const FuseArgs& f, cudaStream_t s) {
     const GridParams& g = f.g;
-    k_fuse_tables<<<(g.m + 127) / 128, 128, 0, s>>>(g, f.pose, f.tables, f.n_updated, f.item_count);
+    launch_pdl(k_fuse_tables, dim3((g.m + 127) / 128), dim3(128), s, g, f.pose, f.tables, f.n_updated, f.item_count);
     const int nrows = (g.ks1 - g.ks0) * g.m;
-    k_fuse_plan<<<(nrows + 255) / 256, 256, 0, s>>>(g, f.pose, f.tables, f.items, f.item_count);
-    k_fuse_items<<<f.nblk, FUSE_THREADS, 0, s>>>(g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
+    launch_pdl(k_fuse_plan, dim3((nrows + 255) / 256), dim3(256), s, g, f.pose, f.tables, f.items, f.item_count);
+    if (g.metric == 0) {
+        if (g.k_simple) launch_pdl(k_fuse_items<0, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
+        else launch_pdl(k_fuse_items<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
+    } else {
+        if (g.k_simple) launch_pdl(k_fuse_items<1, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
+        else launch_pdl(k_fuse_items<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
+    }
 }
 int fuse_blocks_per_sm() {
-    int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fuse_items, FUSE_THREADS, 0);
-    return n;
+    int n = 0, q = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fuse_items<0, 1>, FUSE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_fuse_items<0, 0>, FUSE_THREADS, 0);
+    return n < q ? n : q;
 }
 
 /* ------------------------------------------------------------------------------------------
