@@ -198,6 +198,9 @@ tsdf_status tsdf_stage_timing_begin(tsdf_handle h, int32_t n_frames);
 tsdf_status tsdf_stage_timing_end(tsdf_handle h, int32_t* n_frames, float* ms);
 /* debugging aid: globaltimer stamps (ns) of the phases of one linearise+update launch */
 tsdf_status tsdf_debug_phase_times(tsdf_handle h, const float* depth, int32_t mem, int64_t out[5]);
+/* debugging aid: exhaustive device check of the tracker's short fp32 reciprocal against IEEE
+ * 1.0f/x for every float in [x_lo, x_hi]; *n_bad = mismatches (must be 0 on [2^-17, 4]) */
+tsdf_status tsdf_debug_check_rcp(tsdf_handle h, float x_lo, float x_hi, int64_t* n_bad);
 /* running total of voxels updated by fusion since the last reset (for GB/s accounting) */
 tsdf_status tsdf_total_updates(tsdf_handle h, int32_t reset, int64_t* total);
 tsdf_status tsdf_flush_l2(tsdf_handle h);                       /* overwrite a >L2-sized scratch buffer */

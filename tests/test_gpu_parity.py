@@ -282,3 +282,11 @@ def test_reference_class_mirror(gpu_lib, frames, K):
     assert np.allclose(cam.rot_inv @ cam.rot, np.eye(3), atol=1e-12)
     assert sdf.get_number_of_voxels() == 64 ** 3 and sdf.get_array_index((1, 2, 3)) == 64 * 64 + 128 + 3
     o.close()
+
+
+def test_fast_reciprocal_is_exact_on_its_range(gpu_lib):
+    """The tracker computes w = 1/volume (sdf.cpp:154) with MUFU.RCP + one FMA Newton step.  Every
+    float in [2^-17, 4] (volume lies in (1e-5, 3]) is checked against IEEE 1.0f/x on the device."""
+    g = T.Tsdf(T.default_config(m=32))
+    assert g.debug_check_rcp(2.0 ** -17, 4.0) == 0
+    g.close()

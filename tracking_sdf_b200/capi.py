@@ -103,6 +103,7 @@ PROTOTYPES = [
     ("tsdf_stage_timing_end", _I32, [_VP, c_i32p, c_fp]),
     ("tsdf_total_updates", _I32, [_VP, _I32, c_i64p]),
     ("tsdf_debug_phase_times", _I32, [_VP, _VP, _I32, c_i64p]),
+    ("tsdf_debug_check_rcp", _I32, [_VP, ctypes.c_float, ctypes.c_float, c_i64p]),
     ("tsdf_slab_plan", _I32, [_CFGP, c_i32p]),
     ("tsdf_shard_ipc_export", _I32, [_VP, c_u8p]),
     ("tsdf_shard_ipc_attach", _I32, [_VP, _I32, c_u8p]),
@@ -383,6 +384,11 @@ class Tsdf:
         v = ctypes.c_int64()
         self._ck(self.L.tsdf_total_updates(self.h, int(reset), ctypes.byref(v)))
         return v.value
+
+    def debug_check_rcp(self, x_lo, x_hi):
+        n = ctypes.c_int64()
+        self._ck(self.L.tsdf_debug_check_rcp(self.h, x_lo, x_hi, ctypes.byref(n)))
+        return n.value
 
     def debug_phase_times(self, depth):
         p, mem, keep = _depth_arg(depth)

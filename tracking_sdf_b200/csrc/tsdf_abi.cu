@@ -814,6 +814,25 @@ tsdf_status tsdf_debug_phase_times(tsdf_handle h, const float* depth, int32_t me
     return TSDF_OK;
 }
 
+/* debugging aid: exhaustively compare the kernels' short reciprocal with IEEE 1.0f/x for every
+ * float in [x_lo, x_hi] (positive normals); *n_bad = number of mismatching operands */
+tsdf_status tsdf_debug_check_rcp(tsdf_handle h, float x_lo, float x_hi, int64_t* n_bad) {
+    if (!h || !n_bad || !(x_lo > 0.0f) || !(x_hi >= x_lo)) return bad("bad argument");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    unsigned int lo, hi;
+    memcpy(&lo, &x_lo, 4); memcpy(&hi, &x_hi, 4);
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(p->scratch_d);
+    CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), p->stream));
+    launch_check_rcp(lo, hi + 1u, d, p->stream);
+    p->launches++;
+    unsigned long long r = 0;
+    CK(cudaMemcpyAsync(&r, d, sizeof r, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    *n_bad = (int64_t)r;
+    return TSDF_OK;
+}
+
 tsdf_status tsdf_total_updates(tsdf_handle h, int32_t reset, int64_t* total) {
     if (!h) return bad("null handle");
     Impl* p = I(h);

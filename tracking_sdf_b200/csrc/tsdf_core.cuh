@@ -83,6 +83,20 @@ TSDF_HD float rcp_rn(float x) {
     return 1.0f / x;
 #endif
 }
+/* The same for operands known to be normal and in [2^-17, 4] (the L1 "volume" of sdf.cpp:146
+ * lies in (1e-5, 3]): hardware reciprocal + one FMA Newton step, without __frcp_rn's range
+ * checks.  Verified EXHAUSTIVELY against 1.0f/x over every float of that range on the device
+ * (tests/test_gpu_parity.py::test_fast_reciprocal_is_exact_on_its_range). */
+TSDF_HD float rcp_rn_small(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    const float e = fmaf(-x, r, 1.0f);
+    return fmaf(r, e, r);
+#else
+    return 1.0f / x;
+#endif
+}
 
 /* ---- the reference's (int) casts: x86 cvttss2si — truncation toward zero, NaN and
  * out-of-range give INT_MIN.  sdf.cpp:143-145 ---- */
@@ -203,6 +217,9 @@ TSDF_HD bool normal_px(const K1Params& p, int u, int v, float zc, float zl, floa
  * the same fp32 values the reference recomputes per neighbour).  The interior case first issues
  * all eight loads, then does the arithmetic; the early-return test is hoisted: it can only
  * fire when one candidate distance per axis is <= 1e-5. */
+#ifndef RCP_VOLUME
+#define RCP_VOLUME rcp_rn_small
+#endif
 template <bool CHECK_EXACT>
 TSDF_HD float interp_accumulate(const float* d, const float* w, const bool* inb,
                                 const float* fx, const float* fy, const float* fz, bool& is_interpolated) {
@@ -220,7 +237,7 @@ TSDF_HD float interp_accumulate(const float* d, const float* w, const bool* inb,
                 exact = true;
                 exact_val = d[n];
             } else {
-                const float wt = rcp_rn(volume);      /* == (float)(1.0 / (double)volume), sdf.cpp:154 */
+                const float wt = RCP_VOLUME(volume);  /* == (float)(1.0 / (double)volume), sdf.cpp:154 */
                 w_sum = w_sum + wt;
                 sum_d = sum_d + wt * d[n];
             }
@@ -455,18 +472,27 @@ TSDF_HD void row_clip(const GridParams& g, const double* Ri, const double* ti,
  * s = 0 centre; 1..6 = +x,-x,+y,-y,+z,-z voxel steps; 7..12 = r1p,r1m,r2p,r2m,r3p,r3m.
  * M = rot for s < 7, the perturbed rotation otherwise.  cvx.. returns the UN-stepped voxel
  * coordinate (the centre for s < 7) for the bounds test of :261-268. */
-TSDF_HD void sample_coords(const GridParams& g, const double* M, const double* t, int s,
-                           double px, double py, double pz,
-                           double& vx, double& vy, double& vz) {
+TSDF_HD void sample_offsets(const GridParams& g, int s, double& ox, double& oy, double& oz) {
+    /* +-v_h on one axis for s = 1..6 (x + (-v_h) == x - v_h; x + 0.0 == x) */
+    const double vh = (double)g.v_h;
+    ox = (s == 1) ? vh : (s == 2) ? -vh : 0.0;
+    oy = (s == 3) ? vh : (s == 4) ? -vh : 0.0;
+    oz = (s == 5) ? vh : (s == 6) ? -vh : 0.0;
+}
+TSDF_HD void sample_coords_off(const GridParams& g, const double* M, const double* t, double ox, double oy, double oz,
+                               double px, double py, double pz, double& vx, double& vy, double& vz) {
     double wx, wy, wz;
     matvec3(M, px, py, pz, wx, wy, wz);
     wx = wx + t[0]; wy = wy + t[1]; wz = wz + t[2];
     world_to_voxel(g, wx, wy, wz, vx, vy, vz);
-    /* +-v_h on one axis for s = 1..6 (x + (-v_h) == x - v_h; x + 0.0 == x) */
-    const double vh = (double)g.v_h;
-    vx = vx + ((s == 1) ? vh : (s == 2) ? -vh : 0.0);
-    vy = vy + ((s == 3) ? vh : (s == 4) ? -vh : 0.0);
-    vz = vz + ((s == 5) ? vh : (s == 6) ? -vh : 0.0);
+    vx = vx + ox; vy = vy + oy; vz = vz + oz;
+}
+TSDF_HD void sample_coords(const GridParams& g, const double* M, const double* t, int s,
+                           double px, double py, double pz,
+                           double& vx, double& vy, double& vz) {
+    double ox, oy, oz;
+    sample_offsets(g, s, ox, oy, oz);
+    sample_coords_off(g, M, t, ox, oy, oz, px, py, pz, vx, vy, vz);
 }
 /* camera_tracking.cpp:92-145: perturbed rotation q (0..5) = (I +- w_h [e_k]x) * rot */
 TSDF_HD void perturbed_rot(const GridParams& g, const double* rot, int q, double* out) {

@@ -6,10 +6,16 @@
 
 namespace tsdf {
 
-constexpr int LIN_THREADS = 256;          /* 8 warps, 16 pixels per sweep */
+#ifndef LIN_THREADS_DEF
+#define LIN_THREADS_DEF 256
+#endif
+constexpr int LIN_THREADS = LIN_THREADS_DEF;   /* 8 warps, 16 pixels per sweep */
 constexpr int LIN_PARTIAL_STRIDE = 32;    /* doubles per block partial (30 used) */
 constexpr int MAX_WORLD = 16;
-constexpr int LIN_GROUP = 16;             /* blocks per first-level reduction group */
+#ifndef LIN_GROUP_DEF
+#define LIN_GROUP_DEF 16
+#endif
+constexpr int LIN_GROUP = LIN_GROUP_DEF;  /* blocks per first-level reduction group */
 constexpr int FUSE_THREADS = 128;
 #ifndef FUSE_MIN_BLOCKS
 #define FUSE_MIN_BLOCKS 5               /* resident blocks per SM the fusion kernel is compiled for */
@@ -72,6 +78,7 @@ void launch_import(const GridParams& g, float2* grid, const float* D, const floa
 void launch_cloud(const GridParams& g, const PixRec* pix, float* cloud, float* normals, cudaStream_t s);
 void launch_exp_map(const double* twist, double* out12, cudaStream_t s);
 void launch_flush(float* buf, int64_t n, cudaStream_t s);
+void launch_check_rcp(unsigned int lo, unsigned int hi, unsigned long long* n_bad, cudaStream_t s);
 int  fuse_blocks_per_sm();
 int  linearize_blocks_per_sm();
 

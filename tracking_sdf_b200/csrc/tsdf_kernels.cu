@@ -290,7 +290,7 @@ __device__ void gn_update_warp(const GridParams& g, PoseState* pose, const doubl
 __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(LinearizeArgs a, int exchange_mode, unsigned long long seqno) {
     __shared__ double sM[7][9];
     __shared__ double sT[3];
-    __shared__ double sRed[LIN_THREADS / 32][32];
+    __shared__ double sRed[(LIN_THREADS / 32) < 4 ? 4 : (LIN_THREADS / 32)][32];   /* also the GN step's scratch (>= 128 doubles) */
     __shared__ double sSums[32];
     __shared__ int sLast;
     __shared__ int sMiss;
@@ -330,6 +330,9 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     GridFetch fetch{a.grid, g.m, g.ks0, g.ks1, &miss};
 
     const bool sharded = (g.ko0 > 0 || g.ko1 < g.m);
+    const double dm = (double)g.m;
+    double off_x, off_y, off_z;
+    sample_offsets(g, s, off_x, off_y, off_z);
     const int P = g.ni * g.nj;
     const float inv_nj = 1.0f / (float)g.nj;
     const int p_begin = blockIdx.x * a.px_per_block;
@@ -365,18 +368,16 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
             ok = false;
             if (valid_pt && mine) {
                 double vx, vy, vz;
-                sample_coords(g, M, sT, s, (double)x, (double)y, (double)z, vx, vy, vz);
-                if (s == 0) {                                                /* camera_tracking.cpp:261-268 */
-                    const double dm = (double)g.m;
-                    oob = (vx < 0) | (vy < 0) | (vz < 0) | (vx >= dm) | (vy >= dm) | (vz >= dm);
-                }
+                sample_coords_off(g, M, sT, off_x, off_y, off_z, (double)x, (double)y, (double)z, vx, vy, vz);
+                /* camera_tracking.cpp:261-268: only the centre sample's (s = 0) verdict is used */
+                oob = (fmin(fmin(vx, vy), vz) < 0.0) | (fmax(fmax(vx, vy), vz) >= dm);
                 bool is_interp;
                 val = interpolate_distance(vx, vy, vz, fetch, is_interp);
                 ok = is_interp;
             }
         }
         const unsigned okb = __ballot_sync(0xffffffffu, ok);
-        const unsigned oobb = __ballot_sync(0xffffffffu, oob);
+        const unsigned oobb = __ballot_sync(0xffffffffu, oob && s == 0);
         const bool allok = ((okb >> base) & 0xffffu) == 0xffffu;
         const bool is_oob = ((oobb >> base) & 1u) != 0u;
         const int flag = !valid_pt ? 0 : (!mine ? 4 : (is_oob ? 2 : (allok ? 1 : 3)));
@@ -425,35 +426,36 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     const int ngroups = (nb + LIN_GROUP - 1) / LIN_GROUP;
     const int grp_id = blockIdx.x / LIN_GROUP;
     const int gsize = min(LIN_GROUP, nb - grp_id * LIN_GROUP);
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) sLast = (atomicAdd(&a.group_ticket[grp_id], 1u) == (unsigned)(gsize - 1));
+    if (tid < 32) {                                     /* the warp that wrote the partial publishes it */
+        __threadfence();
+        __syncwarp();
+        if (tid == 0) sLast = (atomicAdd(&a.group_ticket[grp_id], 1u) == (unsigned)(gsize - 1));
+    }
     __syncthreads();
     if (!sLast) return;
     __threadfence();
     {
-        const int slot = tid & 31, sub = tid >> 5;           /* 8 subs x 2 blocks = LIN_GROUP */
+        const int slot = tid & 31, sub = tid >> 5;           /* one warp per stripe of the group's blocks */
         double v = 0.0;
-#pragma unroll
-        for (int q = 0; q < LIN_GROUP / 8; q++) {
-            const int bq = sub + 8 * q;
-            if (bq < gsize) v = v + __ldcg(&a.partials[(size_t)(grp_id * LIN_GROUP + bq) * LIN_PARTIAL_STRIDE + slot]);
-        }
+        for (int bq = sub; bq < gsize; bq += LIN_THREADS / 32)
+            v = v + __ldcg(&a.partials[(size_t)(grp_id * LIN_GROUP + bq) * LIN_PARTIAL_STRIDE + slot]);
         __syncthreads();
         sRed[sub][slot] = v;
         __syncthreads();
         if (tid < 32) {
             double t = 0.0;
 #pragma unroll
-            for (int w = 0; w < 8; w++) t = t + sRed[w][tid];
+            for (int w = 0; w < LIN_THREADS / 32; w++) t = t + sRed[w][tid];
             a.group_partials[(size_t)grp_id * LIN_PARTIAL_STRIDE + tid] = t;
         }
         if (tid == 0) a.group_ticket[grp_id] = 0u;
     }
     /* ---- level 2: the last group sums the groups */
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) sLast = (atomicAdd(a.ticket, 1u) == (unsigned)(ngroups - 1));
+    if (tid < 32) {
+        __threadfence();
+        __syncwarp();
+        if (tid == 0) sLast = (ngroups == 1) || (atomicAdd(a.ticket, 1u) == (unsigned)(ngroups - 1));
+    }
     __syncthreads();
     if (!sLast) return;
     if (a.dbg_times && tid == 0) a.dbg_times[2] = gtime();
@@ -461,14 +463,14 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     {
         const int slot = tid & 31, sub = tid >> 5;
         double v = 0.0;
-        for (int q = sub; q < ngroups; q += 8) v = v + __ldcg(&a.group_partials[(size_t)q * LIN_PARTIAL_STRIDE + slot]);
+        for (int q = sub; q < ngroups; q += LIN_THREADS / 32) v = v + __ldcg(&a.group_partials[(size_t)q * LIN_PARTIAL_STRIDE + slot]);
         __syncthreads();
         sRed[sub][slot] = v;
         __syncthreads();
         if (tid < 32) {
             double t = 0.0;
 #pragma unroll
-            for (int w = 0; w < 8; w++) t = t + sRed[w][tid];
+            for (int w = 0; w < LIN_THREADS / 32; w++) t = t + sRed[w][tid];
             sSums[tid] = t;
         }
     }
@@ -810,6 +812,20 @@ __global__ void k_exp_map(const double* twist, double* out12) {
     for (int q = 0; q < 3; q++) out12[9 + q] = dt[q];
 }
 void launch_exp_map(const double* twist, double* out12, cudaStream_t s) { k_exp_map<<<1, 1, 0, s>>>(twist, out12); }
+
+/* exhaustive check of rcp_rn_small against IEEE 1.0f/x over all floats with bit patterns [lo, hi) */
+__global__ void k_check_rcp(unsigned int lo, unsigned int hi, unsigned long long* n_bad) {
+    unsigned long long bad = 0;
+    for (unsigned long long b = (unsigned long long)lo + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; b < hi;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned int)b);
+        if (__float_as_uint(rcp_rn_small(x)) != __float_as_uint(__fdiv_rn(1.0f, x))) bad++;
+    }
+    if (bad) atomicAdd(n_bad, bad);
+}
+void launch_check_rcp(unsigned int lo, unsigned int hi, unsigned long long* n_bad, cudaStream_t s) {
+    k_check_rcp<<<148 * 16, 256, 0, s>>>(lo, hi, n_bad);
+}
 
 __global__ void k_flush(float4* buf, int64_t n4) {
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x)
