@@ -310,7 +310,27 @@ def main_cuda(args):
     share = {k: v / tot for k, v in share.items()}
     g.dev_free(dev)
 
-    # ---------------- e2e: host buffers through the public call --------------------------------
+    # ---------------- e2e: host buffers through the public calls -------------------------------
+    # (a) streaming: tsdf_submit_frame — every step does the H2D copy of its frame (pinned host
+    #     memory -> device ring, on a copy stream) and the D2H of its pose record; frames are
+    #     pipelined, results read after the final sync.  (b) synchronous: tsdf_track_and_fuse.
+    g.reset(); g.set_intrinsics(K)
+    g.set_pose(Rs[0], ts[0])
+    g.submit_frame(depth[0], track=0, slot=0)
+    for f in range(1, W):
+        g.submit_frame(depth[f], track=1, slot=f % ring)
+    g.sync()
+    if dist is not None:
+        import torch
+        dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for f in range(W, n_frames):
+        g.submit_frame(depth[f], track=1, slot=f % ring)
+    g.sync()
+    R_s, t_s, st_s = g.read_pose_ring((n_frames - 1) % ring)
+    e2e_stream_s = time.perf_counter() - t0
+    e2e_stream_s = barrier_max(dist, e2e_stream_s, tdev)
+
     g.reset(); g.set_intrinsics(K)
     g.fuse(depth[0], Rs[0], ts[0])
     for f in range(1, W):
@@ -323,9 +343,14 @@ def main_cuda(args):
         R_e, t_e, st_e, nu_e = g.track_and_fuse(depth[f])
     e2e_s = time.perf_counter() - t0
     e2e_s = barrier_max(dist, e2e_s, tdev)
-    e2e = {"value": n_gpus * Ksteps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(frame_bytes),
-           "d2h_bytes_per_step": 496 + 8,      # sizeof(PoseState) (pose, twist, normal equations, counters) + n_updated
-           "ms_per_step": 1e3 * e2e_s / Ksteps, "timing": "host wall clock around K synchronous tsdf_track_and_fuse(HOST depth) calls"}
+    e2e = {"value": n_gpus * Ksteps / e2e_stream_s, "unit": "frames/s", "h2d_bytes_per_step": int(frame_bytes),
+           "d2h_bytes_per_step": 496,          # sizeof(PoseState): pose, twist, normal equations, counters
+           "ms_per_step": 1e3 * e2e_stream_s / Ksteps,
+           "timing": "host wall clock around K tsdf_submit_frame(HOST pinned depth) calls + final tsdf_sync and pose read; "
+                     "H2D of frame n+1 overlaps track+fuse of frame n",
+           "sync_value": n_gpus * Ksteps / e2e_s, "sync_ms_per_step": 1e3 * e2e_s / Ksteps,
+           "sync_note": "K synchronous tsdf_track_and_fuse(HOST depth) calls: H2D, compute and D2H (504 B) serialised per frame",
+           "stream_vs_sync_pose_diff_m": float(np.linalg.norm(t_s - t_e))}
     pose_agree = float(np.linalg.norm(t_e - last_t))
     track_err = float(np.linalg.norm(last_t - ts[n_frames - 1]))
     g.close()
@@ -355,13 +380,114 @@ def main_cuda(args):
     return 0
 
 
+def main_sharded(args):
+    """BASELINE.json configs[2,3]: ONE large volume cut into z-slabs, one slab per GPU (strong scaling:
+    the frame sequence and the total voxel count are fixed as N grows).  Fusion needs no exchange
+    (halos are fused redundantly); tracking exchanges 30 doubles per Gauss-Newton iteration
+    in-kernel over NVLink peer stores."""
+    rank, world, local = dist_env()
+    n_gpus = max(world, 1)
+    import tracking_sdf_b200 as T
+    from tracking_sdf_b200 import sharding
+    from tools import synth
+    L = T.load_library()
+    if L.tsdf_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device visible (the product has no CPU path)")
+    device = local % L.tsdf_device_count()
+    dist = init_dist(world, local, "nccl")
+    tdev = None
+    if dist is not None:
+        import torch
+        tdev = torch.device("cuda", device)
+    hbm, peak_src = peaks()
+    K = synth.K_DEFAULT
+    m = args.m
+    W, Ksteps = args.warmup, args.steps
+    n_frames = W + Ksteps
+    depth, Rs, ts = render_frames(n_frames, start=0, pinned=True)
+    frame_bytes = depth[0].nbytes
+    kw = dict(m=m, gauss_newton_max_iteration=GN_ITERS, maximum_twist_diff=float("-inf"))
+    g = sharding.ShardedTsdf(dist, device, **kw) if dist is not None else T.Tsdf(T.default_config(device=device, **kw))
+    g.set_intrinsics(K)
+    ring = g.pose_ring_capacity()
+    ks0, ks1, ko0, ko1 = g.stored_range()
+    dev = g.dev_alloc(depth.nbytes); g.dev_upload(dev, depth)
+    g.set_pose(Rs[0], ts[0])
+    g.enqueue_frame(dev, track=0, slot=0)
+    for f in range(1, W):
+        g.enqueue_frame(dev + f * frame_bytes, track=1, slot=f % ring)
+    g.sync(); g.total_updates(reset=True)
+    launches0 = g.kernel_launch_count()
+    sampler = ClockSampler(device); sampler.start()
+    if dist is not None:
+        import torch
+        dist.barrier(); torch.cuda.synchronize()
+    g.stage_timing_begin(Ksteps)
+    g.timer_begin()
+    for f in range(W, n_frames):
+        g.enqueue_frame(dev + f * frame_bytes, track=1, slot=f % ring)
+    ms_total = g.timer_end()
+    g.sync()
+    ms_total = barrier_max(dist, ms_total, tdev)
+    clocks = sampler.stop()
+    launches = g.kernel_launch_count() - launches0
+    stage = g.stage_timing_end()
+    n_upd_local = g.total_updates()
+    R_l, t_l, st_l = g.read_pose_ring((n_frames - 1) % ring)
+    t_prep, t_track, t_fuse = [float(x) * 1e-3 for x in stage.mean(axis=0)]
+    t_fuse_max = barrier_max(dist, t_fuse, tdev)
+    t_track_max = barrier_max(dist, t_track, tdev)
+    n_upd = n_upd_local
+    if dist is not None:
+        import torch
+        tt = torch.tensor([float(n_upd_local)], dtype=torch.float64, device=tdev)
+        dist.all_reduce(tt); n_upd = float(tt.item())
+    # e2e: host buffers, synchronous per frame, every rank feeds the same frame
+    g.reset(); g.set_intrinsics(K); g.fuse(depth[0], Rs[0], ts[0])
+    for f in range(1, W):
+        g.track_and_fuse(depth[f])
+    if dist is not None:
+        import torch
+        dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for f in range(W, n_frames):
+        R_e, t_e, st_e, nu_e = g.track_and_fuse(depth[f])
+    e2e_s = barrier_max(dist, time.perf_counter() - t0, tdev)
+    upd_per_frame = n_upd / Ksteps
+    ach = 16.0 * upd_per_frame / t_fuse_max / 1e9
+    out = {"metric": METRIC.replace("512", str(m)) + " z-slab sharded", "value": Ksteps / (ms_total * 1e-3), "unit": "frames/s",
+           "n_gpus": n_gpus, "steps": Ksteps, "warmup": W, "ms_per_step": ms_total / Ksteps, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32 values / f64 geometry", "data": "synthetic",
+           "config": {"workload": "%d^3 grid z-slab sharded over %d GPU(s), 640x480 synthetic depth along fr1/plant GT path, %d GN iterations/frame "
+                                  "(BASELINE.json configs[2]/[3])" % (m, n_gpus, GN_ITERS),
+                      "slab_rank0": {"own": [ko0, ko1], "stored": [ks0, ks1]}, "grid_bytes_total": 8 * m ** 3,
+                      "l2": "inputs larger than L2; no flush", "exchange": "30 doubles per GN iteration, in-kernel NVLink peer stores, rank-order sum"},
+           "roofline": {"bound": "hbm", "kernel": "k_fuse_items", "achieved": ach, "peak": hbm * n_gpus, "unit": "GB/s", "frac": ach / (hbm * n_gpus),
+                        "traffic": None, "peak_source": peak_src + " x n_gpus", "ms_per_launch": t_fuse_max * 1e3,
+                        "voxels_updated_per_launch": upd_per_frame},
+           "stage_ms": {"prep": t_prep * 1e3, "track_max_over_ranks": t_track_max * 1e3, "fuse_max_over_ranks": t_fuse_max * 1e3},
+           "e2e": {"value": Ksteps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(frame_bytes) * n_gpus, "d2h_bytes_per_step": 504 * n_gpus,
+                   "ms_per_step": 1e3 * e2e_s / Ksteps, "timing": "host wall clock, synchronous tsdf_track_and_fuse(HOST depth) on every rank"},
+           "gpu_launches": int(launches), "clocks": clocks,
+           "tracking": {"final_pos_err_vs_gt_m": float(np.linalg.norm(t_l - ts[n_frames - 1])), "n_valid_last": int(st_l["n_valid"])}}
+    g.dev_free(dev)
+    g.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--m", type=int, default=512)
+    ap.add_argument("--m", type=int, default=None)
+    ap.add_argument("--workload", default="sequence", choices=["sequence", "sharded"],
+                    help="sequence: 512^3 per GPU, one independent sequence per GPU (default); sharded: one m^3 volume z-slab sharded over the GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense fusion micro-benchmark")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
@@ -369,8 +495,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.m is None:
+        args.m = 1024 if args.workload == "sharded" else 512
     if args.impl == "reference":
         return main_reference(args)
+    if args.workload == "sharded":
+        return main_sharded(args)
     return main_cuda(args)
 
 

@@ -136,6 +136,10 @@ tsdf_status tsdf_track_and_fuse(tsdf_handle h, const float* depth, int32_t mem,
  * pose of frame `slot` lands in an internal pinned ring (capacity tsdf_pose_ring_capacity)
  * and is read back after tsdf_sync with tsdf_read_pose_ring.  track = 0: fuse only. */
 tsdf_status tsdf_enqueue_frame(tsdf_handle h, const float* depth_dev, int32_t track, int32_t slot);
+/* The same with a HOST (preferably pinned) depth buffer: the H2D copy goes through a copy stream
+ * into a small ring of device frames, so the copy of frame n+1 overlaps track+fuse of frame n.
+ * The host buffer must stay valid until tsdf_sync (or until 4 later submissions returned). */
+tsdf_status tsdf_submit_frame(tsdf_handle h, const float* depth_host, int32_t track, int32_t slot);
 tsdf_status tsdf_sync(tsdf_handle h);
 int32_t     tsdf_pose_ring_capacity(void);
 tsdf_status tsdf_read_pose_ring(tsdf_handle h, int32_t slot, double R[9], double t[3], tsdf_track_stats* stats);

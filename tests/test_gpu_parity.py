@@ -170,6 +170,32 @@ def test_async_stream_path_equals_sync_path(gpu_lib, frames, K):
     a.close(); b.close()
 
 
+def test_host_streaming_path_equals_sync_path(gpu_lib, frames, K):
+    """tsdf_submit_frame (copy stream + device frame ring, H2D of frame n+1 under compute of frame n)
+    gives the same poses and grid as the synchronous host-buffer call."""
+    from tracking_sdf_b200 import capi
+    depth, Rs, ts = frames
+    kw = dict(gauss_newton_max_iteration=10, maximum_twist_diff=float("-inf"))
+    a = T.Tsdf(T.default_config(m=64, **kw)); b = T.Tsdf(T.default_config(m=64, **kw))
+    for x in (a, b):
+        x.set_intrinsics(K); x.set_pose(Rs[0], ts[0])
+    n = 10                                           # more frames than the 4-deep stage ring
+    pinned = capi.pinned_empty((n, 480, 640), np.float32)
+    pinned[:] = depth[:n]
+    a.submit_frame(pinned[0], track=0, slot=0)
+    for f in range(1, n):
+        a.submit_frame(pinned[f], track=1, slot=f)
+    a.sync()
+    b.fuse(depth[0])
+    for f in range(1, n):
+        Rb, tb, sb, _ = b.track_and_fuse(depth[f])
+        Ra, ta, sa = a.read_pose_ring(f)
+        assert np.array_equal(Ra, Rb) and np.array_equal(ta, tb)
+    Da, Wa = a.download(); Db, Wb = b.download()
+    assert np.array_equal(Da, Db) and np.array_equal(Wa, Wb)
+    a.close(); b.close()
+
+
 def test_against_committed_golden(gpu_lib, frames):
     gold = np.load(GOLD)
     depth, Rs, ts = frames

@@ -71,6 +71,7 @@ PROTOTYPES = [
     ("tsdf_fuse", _I32, [_VP, _VP, _I32, c_dp, c_dp, c_i64p]),
     ("tsdf_track_and_fuse", _I32, [_VP, _VP, _I32, c_dp, c_dp, _STP, c_i64p]),
     ("tsdf_enqueue_frame", _I32, [_VP, _VP, _I32, _I32]),
+    ("tsdf_submit_frame", _I32, [_VP, _VP, _I32, _I32]),
     ("tsdf_sync", _I32, [_VP]),
     ("tsdf_pose_ring_capacity", _I32, []),
     ("tsdf_read_pose_ring", _I32, [_VP, _I32, c_dp, c_dp, _STP]),
@@ -253,6 +254,11 @@ class Tsdf:
 
     def enqueue_frame(self, depth_dev, track, slot):
         self._ck(self.L.tsdf_enqueue_frame(self.h, ctypes.c_void_p(int(depth_dev)), int(track), int(slot)))
+
+    def submit_frame(self, depth_host, track, slot):
+        a = depth_host
+        assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+        self._ck(self.L.tsdf_submit_frame(self.h, ctypes.c_void_p(a.ctypes.data), int(track), int(slot)))
 
     def sync(self):
         self._ck(self.L.tsdf_sync(self.h))

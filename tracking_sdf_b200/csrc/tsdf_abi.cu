@@ -58,6 +58,13 @@ struct Impl {
     int lin_blocks = 0, px_per_block = 0, fuse_blocks = 0;
     int64_t launches = 0;
     float* flush_buf = nullptr;
+    /* host-buffer streaming (tsdf_submit_frame): a ring of device frames fed by a copy stream */
+    static constexpr int NSTAGE = 4;
+    cudaStream_t copy_stream = nullptr;
+    float* stage[NSTAGE] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t copied[NSTAGE] = {nullptr, nullptr, nullptr, nullptr};    /* H2D of stage b finished   */
+    cudaEvent_t consumed[NSTAGE] = {nullptr, nullptr, nullptr, nullptr};  /* compute done with stage b */
+    unsigned long long submit_seq = 0;
     double* scratch_d = nullptr;            /* 32 doubles */
 };
 
@@ -213,6 +220,7 @@ tsdf_status track_result(Impl* p, double R_out[9], double t_out[3], tsdf_track_s
     if (R_out) memcpy(R_out, ps.R, sizeof ps.R);
     if (t_out) memcpy(t_out, ps.t, sizeof ps.t);
     fill_stats(ps, stats);
+    if (ps.halo_miss & 0x40000000) { g_err = "sharded tracking: a peer rank did not deliver its normal equations within 2 s"; return TSDF_ERR_CUDA; }
     if (ps.halo_miss) { g_err = "a tracking sample needed a voxel outside this shard's slab+halo (increase tsdf_config.halo)"; return TSDF_ERR_HALO; }
     if (ps.singular) { g_err = "tracking lost: singular normal equations or non-finite twist"; return TSDF_ERR_TRACKING_LOST; }
     return TSDF_OK;
@@ -296,6 +304,12 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     A(cudaMalloc(&p->dbgFlag, (size_t)P));
     A(cudaMalloc(&p->mailbox, sizeof(Mailbox)));
     A(cudaMalloc(&p->scratch_d, 64 * sizeof(double)));
+    A(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    for (int q = 0; q < Impl::NSTAGE; q++) {
+        A(cudaMalloc(&p->stage[q], npx * sizeof(float)));
+        A(cudaEventCreateWithFlags(&p->copied[q], cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&p->consumed[q], cudaEventDisableTiming));
+    }
     for (int q = 0; q < 4; q++) A(cudaEventCreate(&p->ev[q]));
     for (int q = 0; q < 2; q++) A(cudaEventCreate(&p->tmr[q]));
     if (e != cudaSuccess) {
@@ -347,6 +361,12 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     cudaFree(p->dbgJ); cudaFree(p->dbgPsi); cudaFree(p->dbgFlag); cudaFree(p->mailbox);
     cudaFree(p->flush_buf); cudaFree(p->scratch_d);
     for (cudaEvent_t e : p->ring_ev) cudaEventDestroy(e);
+    if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
+    for (int q = 0; q < Impl::NSTAGE; q++) {
+        cudaFree(p->stage[q]);
+        if (p->copied[q]) cudaEventDestroy(p->copied[q]);
+        if (p->consumed[q]) cudaEventDestroy(p->consumed[q]);
+    }
     for (int q = 0; q < 4; q++) if (p->ev[q]) cudaEventDestroy(p->ev[q]);
     for (int q = 0; q < 2; q++) if (p->tmr[q]) cudaEventDestroy(p->tmr[q]);
     if (p->stream && p->own_stream) cudaStreamDestroy(p->stream);
@@ -480,6 +500,28 @@ tsdf_status tsdf_enqueue_frame(tsdf_handle h, const float* depth_dev, int32_t tr
     CK(cudaMemcpyAsync(&p->ring_pin[slot], p->pose_dev, sizeof(PoseState), cudaMemcpyDeviceToHost, p->stream));
     return TSDF_OK;
 }
+/* Streaming with HOST buffers: the H2D copy of frame n+1 runs on a copy stream while frame n is
+ * being tracked and fused; poses come back through the pinned ring like tsdf_enqueue_frame. */
+tsdf_status tsdf_submit_frame(tsdf_handle h, const float* depth_host, int32_t track, int32_t slot) {
+    if (!h || !depth_host) return bad("null argument");
+    if (slot < 0 || slot >= POSE_RING) return bad("slot out of range");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    if (!p->have_K) { g_err = "camera matrix not set (tsdf_set_intrinsics)"; return TSDF_ERR_NO_INTRINSICS; }
+    const int b = (int)(p->submit_seq % Impl::NSTAGE);
+    const size_t bytes = (size_t)p->g.img_w * p->g.img_h * sizeof(float);
+    if (p->submit_seq >= (unsigned long long)Impl::NSTAGE) CK(cudaStreamWaitEvent(p->copy_stream, p->consumed[b], 0));
+    CK(cudaMemcpyAsync(p->stage[b], depth_host, bytes, cudaMemcpyHostToDevice, p->copy_stream));
+    CK(cudaEventRecord(p->copied[b], p->copy_stream));
+    CK(cudaStreamWaitEvent(p->stream, p->copied[b], 0));
+    tsdf_status st = enqueue_frame(p, p->stage[b], track != 0, true);
+    if (st != TSDF_OK) return st;
+    CK(cudaEventRecord(p->consumed[b], p->stream));
+    CK(cudaMemcpyAsync(&p->ring_pin[slot], p->pose_dev, sizeof(PoseState), cudaMemcpyDeviceToHost, p->stream));
+    p->submit_seq++;
+    return TSDF_OK;
+}
+
 tsdf_status tsdf_sync(tsdf_handle h) {
     if (!h) return bad("null handle");
     Impl* p = I(h);

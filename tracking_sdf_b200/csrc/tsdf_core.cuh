@@ -226,18 +226,33 @@ TSDF_HD float interp_accumulate(const float* d, const float* w, const bool* inb,
     float w_sum = 0.0f, sum_d = 0.0f;
     bool any = false, exact = false;
     float exact_val = 0.0f;
+    if (!CHECK_EXACT) {
+        /* no neighbour can take the early return: straight-line, select instead of branch.
+         * Skipping a neighbour leaves both sums untouched, exactly like the reference's `if`. */
+#pragma unroll
+        for (int n = 0; n < 8; n++) {
+            const float volume = (fx[n >> 2] + fy[(n >> 1) & 1]) + fz[n & 1];
+            const bool use = inb[n] & (w[n] > 0.0f);
+            const float wt = RCP_VOLUME(volume);  /* == (float)(1.0 / (double)volume), sdf.cpp:154 */
+            const float ws = w_sum + wt, sd = sum_d + wt * d[n];
+            w_sum = use ? ws : w_sum;
+            sum_d = use ? sd : sum_d;
+            any = any | use;
+        }
+        is_interpolated = any;
+        return sum_d / w_sum;
+    }
 #pragma unroll
     for (int n = 0; n < 8; n++) {
         const float volume = (fx[n >> 2] + fy[(n >> 1) & 1]) + fz[n & 1];
-        bool use = inb[n] && w[n] > 0.0f;
-        if (CHECK_EXACT) use = use && !exact;
+        const bool use = inb[n] && w[n] > 0.0f && !exact;
         if (use) {
             any = true;
-            if (CHECK_EXACT && volume <= TSDF_VOL_EXACT_F) {
+            if (volume <= TSDF_VOL_EXACT_F) {
                 exact = true;
                 exact_val = d[n];
             } else {
-                const float wt = RCP_VOLUME(volume);  /* == (float)(1.0 / (double)volume), sdf.cpp:154 */
+                const float wt = rcp_rn(volume);      /* == (float)(1.0 / (double)volume), sdf.cpp:154 */
                 w_sum = w_sum + wt;
                 sum_d = sum_d + wt * d[n];
             }
