@@ -196,7 +196,7 @@ def main_reference(args):
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": time.time() - t0}
-    print(json.dumps(out), flush=True)
+    emit(out)
     return 0
 
 
@@ -376,7 +376,7 @@ def main_cuda(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     return 0
 
 
@@ -475,17 +475,35 @@ def main_sharded(args):
     if dist is not None:
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Libraries (NCCL's version banner) write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for the whole run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--m", type=int, default=None)
+    ap.add_argument("--grid", dest="m", type=int, default=None, help="voxels per axis (default 512; 1024 for --workload sharded)")
     ap.add_argument("--workload", default="sequence", choices=["sequence", "sharded"],
                     help="sequence: 512^3 per GPU, one independent sequence per GPU (default); sharded: one m^3 volume z-slab sharded over the GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

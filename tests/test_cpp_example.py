@@ -1,0 +1,48 @@
+"""The C++ host side: include/tracking_sdf_b200.hpp + examples/sdf_reconstruction_loop.cpp (the
+reference node's per-frame loop on the library).  CPU: it compiles, links, and fails loudly
+without a GPU.  GPU: it runs the loop and writes a TUM-format trajectory (sdf_reconstruction.cpp:4-17)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "_build", "sdf_loop")
+
+
+def build_exe():
+    import tracking_sdf_b200 as T
+    T.load_library()
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    lib_dir = os.path.join(ROOT, "tracking_sdf_b200", "_lib")
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "sdf_reconstruction_loop.cpp"), os.path.join(ROOT, "tools", "synth.cpp"),
+           "-L" + lib_dir, "-ltsdf_b200", "-Wl,-rpath," + lib_dir, "-fopenmp", "-o", EXE]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_cpp_example_builds_and_has_no_fallback(tmp_path):
+    import tracking_sdf_b200 as T
+    build_exe()
+    if T.load_library().tsdf_device_count() > 0:
+        pytest.skip("a GPU is present")
+    r = subprocess.run([EXE, os.path.join(ROOT, "data", "fr1_plant_gt_every4.txt"), "3", "64", str(tmp_path / "t.txt")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_example_runs_the_node_loop(tmp_path, gpu_lib):
+    build_exe()
+    out = tmp_path / "trajectory.txt"
+    r = subprocess.run([EXE, os.path.join(ROOT, "data", "fr1_plant_gt_every4.txt"), "8", "128", str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = np.loadtxt(out)
+    assert rows.shape == (7, 8)                       # frame 1 is not tracked (sdf_reconstruction.cpp:69)
+    gt = np.loadtxt(os.path.join(ROOT, "data", "fr1_plant_gt_every4.txt"))[1:8]
+    assert np.allclose(rows[:, 0], gt[:, 0], atol=1e-3)
+    assert np.linalg.norm(rows[:, 1:4] - gt[:, 1:4], axis=1).max() < 0.06
+    assert np.allclose(np.linalg.norm(rows[:, 4:8], axis=1), 1.0, atol=1e-3)

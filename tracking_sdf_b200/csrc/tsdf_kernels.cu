@@ -157,32 +157,32 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) { return *rei
 /* sum of the 30 slots over all ranks, rank order; runs in the last block after its local sums
  * are in s_sums.  mode 1: in-kernel exchange over peer-mapped mailboxes. */
 __device__ void exchange_sums(const ShardLinks& L, unsigned long long seqno, double* s_sums, int tid, PoseState* pose) {
+    /* executed by warp 0 of the final block only (tid = lane).  Data stores by lanes < 30, then one
+     * system-scope fence per publishing lane (cumulative over the warp's stores via __syncwarp),
+     * then the sequence flag; the reader side mirrors it. */
     const int par = (int)(seqno & 1ull);
     for (int r = 0; r < L.world; r++) {
         if (tid < N_SLOTS) L.box[r]->sums[par][L.rank][tid] = s_sums[tid];      /* peer stores over NVLink */
     }
-    __threadfence_system();
-    __syncthreads();
+    __syncwarp();
     if (tid < L.world) {
+        __threadfence_system();
         *reinterpret_cast<volatile unsigned long long*>(&L.box[tid]->seq[par][L.rank]) = seqno;
-    }
-    if (tid < L.world) {
         /* wait for rank `tid`'s contribution; bounded (2 s) so a dead peer cannot hang the GPU */
         const volatile unsigned long long* flag = &L.box[L.rank]->seq[par][tid];
         const unsigned long long t0 = gtime();
         while (*flag != seqno) {
-            __nanosleep(20);
             if (gtime() - t0 > 2000000000ull) { atomicOr(&pose->halo_miss, 0x40000000); break; }
         }
+        __threadfence_system();
     }
-    __threadfence_system();
-    __syncthreads();
+    __syncwarp();
     if (tid < N_SLOTS) {
         double acc = 0.0;
         for (int r = 0; r < L.world; r++) acc = acc + ld_volatile_f64(&L.box[L.rank]->sums[par][r][tid]);   /* rank order */
         s_sums[tid] = acc;
     }
-    __syncthreads();
+    __syncwarp();
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     }
     __syncthreads();
     if (a.dbg_times && tid == 0) a.dbg_times[3] = gtime();
-    if (exchange_mode == 1 && a.links.world > 1) exchange_sums(a.links, seqno, sSums, tid, pose);
+    if (exchange_mode == 1 && a.links.world > 1 && tid < 32) exchange_sums(a.links, seqno, sSums, tid, pose);
     if (exchange_mode == 2 && a.links.world > 1) {
         /* deferred (single-process emulation): publish our sums into every mailbox; a separate
          * k_gn_combine launch sums them in rank order and updates the pose */
