@@ -44,7 +44,7 @@ except capi.TsdfError as e:
 assert ok
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank%d-ok\n" % rank); sys.stdout.flush()
 '''
 
 
@@ -61,7 +61,7 @@ def test_two_rank_gloo_plumbing(tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert "rank0-ok" in r.stdout and "rank1-ok" in r.stdout
 
 
 def test_halo_covers_the_tracking_stencil():
