@@ -205,6 +205,10 @@ tsdf_status tsdf_debug_phase_times(tsdf_handle h, const float* depth, int32_t me
 /* debugging aid: exhaustive device check of the tracker's short fp32 reciprocal against IEEE
  * 1.0f/x for every float in [x_lo, x_hi]; *n_bad = mismatches (must be 0 on [2^-17, 4]) */
 tsdf_status tsdf_debug_check_rcp(tsdf_handle h, float x_lo, float x_hi, int64_t* n_bad);
+/* debugging aid: fusion self-check at the current pose, no voxel written: out[0] = voxels decided
+ * by the certified fp32 fast path, out[1] = of those, verdicts that disagree with the exact fp64
+ * path (must be 0), out[2] = work items */
+tsdf_status tsdf_debug_fuse_check(tsdf_handle h, const float* depth, int32_t mem, int64_t out[3]);
 /* running total of voxels updated by fusion since the last reset (for GB/s accounting) */
 tsdf_status tsdf_total_updates(tsdf_handle h, int32_t reset, int64_t* total);
 tsdf_status tsdf_flush_l2(tsdf_handle h);                       /* overwrite a >L2-sized scratch buffer */

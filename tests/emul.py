@@ -16,6 +16,7 @@ def lib():
     if _lib is None:
         _lib = ctypes.CDLL(build.build_emul())
         _lib.emul_fuse.restype = ctypes.c_int64
+        _lib.emul_last_fast_count.restype = ctypes.c_int64
         _lib.emul_weight_exp.restype = ctypes.c_double
         _lib.emul_weight_exp.argtypes = [ctypes.c_double]
         _lib.emul_trunc_f2i.argtypes = [ctypes.c_float]
@@ -69,8 +70,10 @@ class Emul:
         self.L.emul_cloud(self.g, _f(self.pix), _f(c), _f(n))
         return c, n
 
-    def fuse(self, use_clip=1):
-        return self.L.emul_fuse(self.g, _f(self.grid), _f(self.pix), self.pose, use_clip)
+    def fuse(self, use_clip=1, use_fast=1):
+        n = self.L.emul_fuse(self.g, _f(self.grid), _f(self.pix), self.pose, use_clip, use_fast)
+        self.last_fast = self.L.emul_last_fast_count()
+        return n
 
     def interpolate(self, pts):
         pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)

@@ -101,15 +101,39 @@ void emul_interpolate(const GridParams* g, const float* grid, int64_t n, const d
     }
 }
 
-/* K3, mirroring k_fuse: rows clipped, products hoisted exactly like the kernel.
- * use_clip = 0 visits every voxel (checks that clipping never drops an accepted voxel). */
-int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const PoseState* pose, int use_clip) {
+/* K3, mirroring the fusion kernels: rows clipped (k_fuse_plan), lane units of four voxels certified
+ * against the pyramid (k_prep level 0 + k_pyramid + k_fuse_cert), the rest through the exact path
+ * (k_fuse_exact), products hoisted exactly like the kernels.
+ * use_clip = 0 visits every voxel; use_cert = 0 sends every unit through the exact path. */
+static int64_t g_last_fast = 0;
+int64_t emul_last_fast_count() { return g_last_fast; }
+int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const PoseState* pose, int use_clip, int use_cert) {
     const GridParams& g = *gp;
     const int m = g.m;
     const double* Ri = pose->Rinv; const double* ti = pose->tinv;
     const K1Params kp = k1_params(g.K);
-    int64_t n_updated = 0;
-#pragma omp parallel for reduction(+ : n_updated) schedule(dynamic, 1)
+    /* certificate pyramid */
+    CertPyramid P;
+    std::vector<std::vector<float>> zf(CERT_LEVELS), zb(CERT_LEVELS);
+    for (int l = 0; l < CERT_LEVELS; l++) {
+        P.w[l] = (g.img_w + (1 << l) - 1) >> l; P.h[l] = (g.img_h + (1 << l) - 1) >> l; P.off[l] = 0;
+        zf[l].assign((size_t)P.w[l] * P.h[l], 3.402823466e+38f); zb[l].assign((size_t)P.w[l] * P.h[l], -3.402823466e+38f);
+    }
+    for (int v = 0; v < g.img_h; v++)
+        for (int u = 0; u < g.img_w; u++) {
+            const float* q = pix + 4 * ((size_t)v * g.img_w + u);
+            PixRec r; r.z = q[0]; r.nx = q[1]; r.ny = q[2]; r.nz = q[3];
+            cert_pixel(g, kp, u, v, r, zf[0][(size_t)v * P.w[0] + u], zb[0][(size_t)v * P.w[0] + u]);
+        }
+    for (int l = 1; l < CERT_LEVELS; l++)
+        for (int y = 0; y < P.h[l - 1]; y++)
+            for (int x = 0; x < P.w[l - 1]; x++) {
+                const size_t o = (size_t)(y >> 1) * P.w[l] + (x >> 1), i = (size_t)y * P.w[l - 1] + x;
+                zf[l][o] = fminf(zf[l][o], zf[l - 1][i]); zb[l][o] = fmaxf(zb[l][o], zb[l - 1][i]);
+            }
+    auto fetch = [&](int level, int x, int y, float& f, float& b) { f = zf[level][(size_t)y * P.w[level] + x]; b = zb[level][(size_t)y * P.w[level] + x]; };
+    int64_t n_updated = 0, n_fast = 0;
+#pragma omp parallel for reduction(+ : n_updated, n_fast) schedule(dynamic, 1)
     for (int k = g.ks0; k < g.ks1; k++) {
         const double gz = voxel_centre(g.vs_z, k, g.origin[2]);
         const double pz0 = Ri[2] * gz, pz1 = Ri[5] * gz, pz2 = Ri[8] * gz;
@@ -118,36 +142,48 @@ int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const Pos
             const double py0 = Ri[1] * gy, py1 = Ri[4] * gy, py2 = Ri[7] * gy;
             int ilo = 0, ihi = m;
             if (use_clip) row_clip(g, Ri, ti, py0, py1, py2, pz0, pz1, pz2, ilo, ihi);
-            for (int x = ilo; x < ihi; x++) {
-                const double gx = voxel_centre(g.vs_x, x, g.origin[0]);
-                const double px0 = Ri[0] * gx, px1 = Ri[3] * gx, px2 = Ri[6] * gx;
-                const double cx = ((px0 + py0) + pz0) + ti[0];
-                const double cy = ((px1 + py1) + pz1) + ti[1];
-                const double cz = ((px2 + py2) + pz2) + ti[2];
-                int iu, iv;
-                bool ok, need_exact;
-                fuse_project_flags(g, cx, cy, cz, iu, iv, ok, need_exact);
-                if (need_exact) {
-                    double ij0, ij1, ij2;
-                    project_ij(g, cx, cy, cz, ij0, ij1, ij2);
-                    int eu_ = 0, ev_ = 0;
-                    ok = project_exact(g, ij0, ij1, ij2, eu_, ev_);
-                    if (ok) { iu = eu_; iv = ev_; }
+            for (int x0 = ilo; x0 < ihi; x0 += 4) {
+                double cx[4], cy[4], cz[4];
+                for (int v = 0; v < 4; v++) {
+                    const double gx = voxel_centre(g.vs_x, x0 + v, g.origin[0]);
+                    cx[v] = ((Ri[0] * gx + py0) + pz0) + ti[0];
+                    cy[v] = ((Ri[3] * gx + py1) + pz1) + ti[1];
+                    cz[v] = ((Ri[6] * gx + py2) + pz2) + ti[2];
                 }
-                const float* rr = pix + 4 * ((size_t)iv * g.img_w + iu);      /* unconditional, clamped */
-                PixRec rec; rec.z = rr[0]; rec.nx = rr[1]; rec.ny = rr[2]; rec.nz = rr[3];
-                float fx_, fy_, dn, eb;
-                bool band;
-                backproject_px(kp, iu, iv, rec.z, fx_, fy_);
-                const bool upd = fuse_distance_flags(g, cx, cy, cz, fx_, fy_, rec, dn, eb, band) & ok;
-                if (!upd) continue;
-                const float wn = fuse_weight(band, eb);
-                const size_t o = (((size_t)(k - g.ks0) * m + j) * m + x) * 2;
-                fuse_apply(grid[o], grid[o + 1], dn, wn);
-                n_updated++;
+                const int verdict = use_cert ? unit_certificate(g, P, cx[0], cy[0], cz[0], cx[3], cy[3], cz[3], fetch) : UNIT_UNKNOWN;
+                if (verdict == UNIT_SKIP) { n_fast += 4; continue; }
+                for (int v = 0; v < 4; v++) {
+                    const size_t o = (((size_t)(k - g.ks0) * m + j) * m + x0 + v) * 2;
+                    if (verdict == UNIT_FRONT) {
+                        fuse_apply(grid[o], grid[o + 1], -g.delta, 1.0f);
+                        n_updated++; n_fast++;
+                        continue;
+                    }
+                    int iu, iv;
+                    bool ok, need_exact;
+                    fuse_project_flags(g, cx[v], cy[v], cz[v], iu, iv, ok, need_exact);
+                    if (need_exact) {
+                        double ij0, ij1, ij2;
+                        project_ij(g, cx[v], cy[v], cz[v], ij0, ij1, ij2);
+                        int eu_ = 0, ev_ = 0;
+                        ok = project_exact(g, ij0, ij1, ij2, eu_, ev_);
+                        if (ok) { iu = eu_; iv = ev_; }
+                    }
+                    const float* rr = pix + 4 * ((size_t)iv * g.img_w + iu);      /* unconditional, clamped */
+                    PixRec rec; rec.z = rr[0]; rec.nx = rr[1]; rec.ny = rr[2]; rec.nz = rr[3];
+                    float fx_, fy_, dn, eb;
+                    bool band;
+                    backproject_px(kp, iu, iv, rec.z, fx_, fy_);
+                    const bool upd = fuse_distance_flags(g, cx[v], cy[v], cz[v], fx_, fy_, rec, dn, eb, band) & ok;
+                    if (!upd) continue;
+                    const float wn = fuse_weight(band, eb);
+                    fuse_apply(grid[o], grid[o + 1], dn, wn);
+                    n_updated++;
+                }
             }
         }
     }
+    g_last_fast = n_fast;
     return n_updated;
 }
 

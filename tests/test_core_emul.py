@@ -65,6 +65,29 @@ def test_scanline_clip_never_drops_a_voxel(frames, K):
     assert (e.W == 1).all() and (e.D == np.float32(-0.3)).all()
 
 
+def test_certificates_match_exact_path(frames, K):
+    # the pyramid certificates (free space / skipped) must never change a result: fuse with and without them
+    depth, Rs, ts = frames
+    for metric in (0, 1):
+        for f, m in [(0, 64), (4, 96), (8, 48)]:
+            a = emul.Emul(K, m=m, metric=metric); b = emul.Emul(K, m=m, metric=metric)
+            for e in (a, b):
+                e.set_pose(Rs[f], ts[f]); e.prep(depth[f])
+            na = a.fuse(use_fast=1); nb = b.fuse(use_fast=0)
+            assert na == nb and np.array_equal(a.grid, b.grid)
+            assert a.last_fast > 0.3 * na                    # and they decide a good share of the in-view voxels
+            g = (f + 1) % len(depth)                         # second frame on a non-empty grid
+            for e in (a, b):
+                e.set_pose(Rs[g], ts[g]); e.prep(depth[g])
+            assert a.fuse(use_fast=1) == b.fuse(use_fast=0) and np.array_equal(a.grid, b.grid)
+    # ragged validity: invalid pixels must make units skip or fall back, never update
+    d = depth[2].copy(); d[100:300, 200:500] = np.nan; d[::7, ::5] = 0.0
+    a = emul.Emul(K, m=64); b = emul.Emul(K, m=64)
+    for e in (a, b):
+        e.set_pose(Rs[2], ts[2]); e.prep(d)
+    assert a.fuse(use_fast=1) == b.fuse(use_fast=0) and np.array_equal(a.grid, b.grid)
+
+
 def test_skewed_intrinsics_take_the_general_projection(frames):
     # K with skew: camera_tracking.cpp:44 keeps the full 3x3 product
     depth, Rs, ts = frames

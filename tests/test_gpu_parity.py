@@ -316,3 +316,27 @@ def test_fast_reciprocal_is_exact_on_its_range(gpu_lib):
     g = T.Tsdf(T.default_config(m=32))
     assert g.debug_check_rcp(2.0 ** -17, 4.0) == 0
     g.close()
+
+
+def test_certificates_are_certified(gpu_lib, frames, K):
+    """Fusion decides whole four-voxel units from the certificate pyramid (free space: updated with
+    d = -delta, w = 1; or skipped).  The self-check build runs the exact fp64 path on EVERY voxel of
+    every certified unit and compares: trajectory frames at 256^3 and the dense pose, both metrics."""
+    depth, Rs, ts = frames
+    for metric in (0, 1):
+        g = T.Tsdf(T.default_config(m=256, metric=metric)); g.set_intrinsics(K)
+        for f in (0, 3, 7, 11):
+            g.set_pose(Rs[f], ts[f])
+            r = g.debug_fuse_check(depth[f])
+            assert r["wrong"] == 0 and r["fast"] > 100000, r
+        d = depth[5].copy(); d[100:300, 200:500] = np.nan; d[::7, ::5] = 0.0      # ragged validity
+        g.set_pose(Rs[5], ts[5])
+        r = g.debug_fuse_check(d)
+        assert r["wrong"] == 0, r
+        R = np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0]], float)
+        g.set_pose(R, [0.0, -12.0, 1.25])
+        r = g.debug_fuse_check(np.full((480, 640), 40.0, np.float32))
+        assert r["wrong"] == 0 and r["fast"] >= 0.99 * 256 ** 3, r
+        D, W = g.download()
+        assert (W == 0).all()                      # the self-check never writes
+        g.close()

@@ -104,6 +104,7 @@ PROTOTYPES = [
     ("tsdf_stage_timing_end", _I32, [_VP, c_i32p, c_fp]),
     ("tsdf_total_updates", _I32, [_VP, _I32, c_i64p]),
     ("tsdf_debug_phase_times", _I32, [_VP, _VP, _I32, c_i64p]),
+    ("tsdf_debug_fuse_check", _I32, [_VP, _VP, _I32, c_i64p]),
     ("tsdf_debug_check_rcp", _I32, [_VP, ctypes.c_float, ctypes.c_float, c_i64p]),
     ("tsdf_slab_plan", _I32, [_CFGP, c_i32p]),
     ("tsdf_shard_ipc_export", _I32, [_VP, c_u8p]),
@@ -390,6 +391,12 @@ class Tsdf:
         v = ctypes.c_int64()
         self._ck(self.L.tsdf_total_updates(self.h, int(reset), ctypes.byref(v)))
         return v.value
+
+    def debug_fuse_check(self, depth):
+        p, mem, keep = _depth_arg(depth)
+        out = (ctypes.c_int64 * 3)()
+        self._ck(self.L.tsdf_debug_fuse_check(self.h, p, mem, out))
+        return {"fast": int(out[0]), "wrong": int(out[1]), "items": int(out[2])}
 
     def debug_check_rcp(self, x_lo, x_hi):
         n = ctypes.c_int64()

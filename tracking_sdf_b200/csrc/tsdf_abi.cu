@@ -39,7 +39,12 @@ struct Impl {
     unsigned int* ticket = nullptr;         /* [0] final ticket, [1..] group tickets */
     double* fuse_tables = nullptr;
     unsigned long long* fuse_items = nullptr;
-    unsigned int* fuse_item_count = nullptr;
+    unsigned int* fuse_item_count = nullptr;      /* [0] items, [1] units */
+    unsigned long long* fuse_units = nullptr;
+    float2* cert = nullptr;
+    CertPyramid pyr;
+    int fuse_cert_blocks = 0;
+    int fuse_check = 0;
     unsigned long long* n_upd_dev = nullptr;
     unsigned long long* n_upd_pin = nullptr;
     float* dbgJ = nullptr; float* dbgPsi = nullptr; uint8_t* dbgFlag = nullptr;
@@ -163,8 +168,9 @@ LinearizeArgs lin_args(Impl* p, int do_update, bool debug) {
 }
 
 void enqueue_prep(Impl* p, const float* dptr, int reset_track) {
-    launch_prep(p->g, dptr, p->pix, p->pose_dev, reset_track, p->stream);
-    p->launches++;
+    launch_prep(p->g, dptr, p->pix, p->cert + p->pyr.off[0], p->pose_dev, reset_track, p->stream);
+    launch_pyramid(p->pyr, p->cert, p->stream);
+    p->launches += 2;
 }
 void enqueue_linearize(Impl* p, int do_update, bool debug) {
     p->seqno++;
@@ -179,9 +185,9 @@ void enqueue_fuse(Impl* p) {
     FuseArgs f;
     f.g = p->g; f.grid = p->grid; f.pix = p->pix; f.pose = p->pose_dev;
     f.tables = p->fuse_tables; f.items = p->fuse_items; f.item_count = p->fuse_item_count;
-    f.n_updated = p->n_upd_dev; f.nblk = p->fuse_blocks;
-    launch_fuse(f, p->stream);
-    p->launches += FUSE_LAUNCHES;
+    f.n_updated = p->n_upd_dev; f.nblk = p->fuse_blocks; f.nblk_cert = p->fuse_cert_blocks; f.check = p->fuse_check;
+    f.pyr = p->pyr; f.cert = p->cert; f.units = p->fuse_units; f.unit_count = p->fuse_item_count + 1;
+    p->launches += launch_fuse(f, p->stream);
 }
 
 /* the per-frame sequence of sdf_reconstruction.cpp:69-74 on the stream, no host round trip */
@@ -296,8 +302,19 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     A(cudaMalloc(&p->ticket, 1024 * sizeof(unsigned int)));
     A(cudaMalloc(&p->fuse_tables, ((size_t)9 * cfg->m + 8) * sizeof(double)));
     A(cudaMalloc(&p->fuse_items, (size_t)(p->g.ks1 - p->g.ks0) * cfg->m * ((cfg->m + 127) / 128 + 1) * sizeof(unsigned long long)));
-    A(cudaMalloc(&p->fuse_item_count, sizeof(unsigned int)));
-    A(cudaMalloc(&p->n_upd_dev, 2 * sizeof(unsigned long long)));
+    A(cudaMalloc(&p->fuse_item_count, 2 * sizeof(unsigned int)));
+    A(cudaMalloc(&p->fuse_units, (size_t)(p->n_stored / 4 + 64) * sizeof(unsigned long long)));
+    {
+        int64_t off = 0;
+        for (int l = 0; l < CERT_LEVELS; l++) {
+            p->pyr.w[l] = (cfg->image_width + (1 << l) - 1) >> l;
+            p->pyr.h[l] = (cfg->image_height + (1 << l) - 1) >> l;
+            p->pyr.off[l] = off;
+            off += (int64_t)p->pyr.w[l] * p->pyr.h[l];
+        }
+        A(cudaMalloc(&p->cert, (size_t)off * sizeof(float2)));
+    }
+    A(cudaMalloc(&p->n_upd_dev, 4 * sizeof(unsigned long long)));
     A(cudaMallocHost(&p->n_upd_pin, sizeof(unsigned long long)));
     A(cudaMalloc(&p->dbgJ, (size_t)P * 6 * sizeof(float)));
     A(cudaMalloc(&p->dbgPsi, (size_t)P * sizeof(float)));
@@ -318,7 +335,7 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
         return e == cudaErrorMemoryAllocation ? TSDF_ERR_NOMEM : TSDF_ERR_CUDA;
     }
     cudaMemset(p->ticket, 0, 1024 * sizeof(unsigned int));
-    cudaMemset(p->n_upd_dev, 0, 2 * sizeof(unsigned long long));
+    cudaMemset(p->n_upd_dev, 0, 4 * sizeof(unsigned long long));
     cudaMemset(p->mailbox, 0, sizeof(Mailbox));
     p->links.box[0] = p->mailbox;
 
@@ -340,6 +357,9 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     int fb = fuse_blocks_per_sm();
     if (fb < 1) fb = 1;
     p->fuse_blocks = sms * fb;
+    int cb = fuse_cert_blocks_per_sm();
+    if (cb < 1) cb = 1;
+    p->fuse_cert_blocks = sms * cb;
     if (e != cudaSuccess) { g_err = "allocation failed"; tsdf_destroy(reinterpret_cast<tsdf_handle>(p)); return TSDF_ERR_NOMEM; }
 
     *out = reinterpret_cast<tsdf_handle>(p);
@@ -357,6 +377,7 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     cudaFree(p->grid); cudaFree(p->pix); cudaFree(p->depth_stage); cudaFree(p->pose_dev);
     cudaFreeHost(p->pose_pin); cudaFreeHost(p->ring_pin); cudaFree(p->partials); cudaFree(p->ticket);
     cudaFree(p->group_partials); cudaFree(p->fuse_tables); cudaFree(p->fuse_items); cudaFree(p->fuse_item_count);
+    cudaFree(p->fuse_units); cudaFree(p->cert);
     cudaFree(p->n_upd_dev); cudaFreeHost(p->n_upd_pin);
     cudaFree(p->dbgJ); cudaFree(p->dbgPsi); cudaFree(p->dbgFlag); cudaFree(p->mailbox);
     cudaFree(p->flush_buf); cudaFree(p->scratch_d);
@@ -872,6 +893,31 @@ tsdf_status tsdf_debug_check_rcp(tsdf_handle h, float x_lo, float x_hi, int64_t*
     CK(cudaMemcpyAsync(&r, d, sizeof r, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     *n_bad = (int64_t)r;
+    return TSDF_OK;
+}
+
+/* debugging aid: run fusion's self-check build for `depth` at the current pose (no voxel is
+ * written): every voxel of every unit certified by the pyramid is compared with the exact fp64 path.
+ * out[0] = voxels in certified units, out[1] = of those, wrong (must be 0), out[2] = work items */
+tsdf_status tsdf_debug_fuse_check(tsdf_handle h, const float* depth, int32_t mem, int64_t out[3]) {
+    if (!h || !out) return bad("null argument");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    if (!p->have_K) { g_err = "camera matrix not set"; return TSDF_ERR_NO_INTRINSICS; }
+    const float* dptr;
+    tsdf_status st = stage_depth(p, depth, mem, &dptr);
+    if (st != TSDF_OK) return st;
+    CK(cudaMemsetAsync(p->n_upd_dev + 2, 0, 2 * sizeof(unsigned long long), p->stream));
+    enqueue_prep(p, dptr, 0);
+    p->fuse_check = 1;
+    enqueue_fuse(p);
+    p->fuse_check = 0;
+    unsigned long long v[4];
+    unsigned int items = 0;
+    CK(cudaMemcpyAsync(v, p->n_upd_dev, sizeof v, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(&items, p->fuse_item_count, sizeof items, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    out[0] = (int64_t)v[2]; out[1] = (int64_t)v[3]; out[2] = (int64_t)items;
     return TSDF_OK;
 }
 

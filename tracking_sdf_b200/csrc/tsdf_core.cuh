@@ -438,6 +438,105 @@ TSDF_HD void fuse_apply_sel(float& D, float& W, float d_new, float w_new, bool u
     D = upd ? Dn : D;
 }
 
+/* ---- constants of the certified fp32 evaluations below */
+#define FAST_ZMIN 0.05f                     /* closer to the camera plane than this: exact path */
+#define FAST_DMARG 1e-4f                    /* margin on signed distances, metres (fp32 error <= ~1.1e-5) */
+TSDF_HD float rcp_approx32(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
+/* ---- hierarchical certificates for fusion ------------------------------------------------------
+ * Per pixel p (with the point P = z*ray and, for the plane metric, the unit normal n facing the
+ * camera, g0 = ray.n <= 0) the signed distance of ANY camera-space point c that the reference maps
+ * to p (its projection truncates to p) is  d = P.n - c_z * (g0 + e),  |e| <= ea = |nx|/fx + |ny|/fy,
+ * so with a = |g0|:
+ *      c_z <  zfree(p)   = (a*z - delta - M) / (a + ea)   =>  d < -delta - M   (updated with d = -delta, w = 1)
+ *      c_z >  zbehind(p) = (a*z + delta + M) / (a - ea)   =>  d >  delta + M   (skipped)
+ * (M = FAST_DMARG absorbs the rounding of the exact path's own d; the fp32 evaluation of the two
+ * bounds is padded by 1e-5 relative + 1e-4 m).  An invalid pixel is skipped whatever c_z is:
+ * zfree = -inf, zbehind = -inf.  Point metric: zfree = z - delta - M, zbehind = z + delta + M.
+ * A min-pyramid of zfree and a max-pyramid of zbehind then certify a whole group of voxels whose
+ * pixels lie in a bounding box: all updated-as-free-space, or all skipped.  Everything not
+ * certified takes the exact path; the device self-check compares every certified voxel with it. */
+#define CERT_LEVELS 7                       /* levels 0..6: texels of 1..64 pixels */
+struct CertPyramid {
+    int32_t w[CERT_LEVELS], h[CERT_LEVELS];
+    int64_t off[CERT_LEVELS];               /* element offsets (float2) of each level in one buffer */
+};
+TSDF_HD void cert_pixel(const GridParams& g, const K1Params& kp, int u, int v, const PixRec& rec, float& zfree, float& zbehind) {
+    const float NINF = -3.402823466e+38f, PINF = 3.402823466e+38f;
+    zfree = NINF; zbehind = NINF;
+    if (!(rec.z == rec.z)) return;
+    if (g.metric != 0) {
+        zfree = (rec.z - g.delta - FAST_DMARG) * (1.0f - 1e-5f) - 1e-4f;
+        zbehind = (rec.z + g.delta + FAST_DMARG) * (1.0f + 1e-5f) + 1e-4f;
+        return;
+    }
+    if (!(rec.nx == rec.nx)) return;
+    const float rx = ((float)u - kp.cx) * kp.inv_fx, ry = ((float)v - kp.cy) * kp.inv_fy;
+    const float a = -(rx * rec.nx + ry * rec.ny + rec.nz);            /* |ray.n| */
+    const float ea = (fabsf(rec.nx) * kp.inv_fx + fabsf(rec.ny) * kp.inv_fy) * 1.001f;   /* cell of +-1 pixel */
+    zbehind = PINF;
+    if (!(a > 1e-4f)) return;                                         /* grazing: no certificate, never skipped */
+    const float num = a * rec.z - g.delta - FAST_DMARG;
+    if (num > 0.0f) zfree = (num / (a + ea)) * (1.0f - 1e-5f) - 1e-4f;
+    const float den = a - ea;
+    if (den > 1e-4f) zbehind = ((a * rec.z + g.delta + FAST_DMARG) / den) * (1.0f + 1e-5f) + 1e-4f;
+}
+
+enum { UNIT_UNKNOWN = 0, UNIT_FRONT = 1, UNIT_SKIP = 2 };
+TSDF_HD int bit_length(int x) {             /* number of bits needed for x >= 0 */
+#if defined(__CUDA_ARCH__)
+    return 32 - __clz(x);
+#else
+    int n = 0;
+    while ((x >> n) > 0) n++;
+    return n;
+#endif
+}
+
+/* Verdict for a group of voxels whose camera-space centres lie on the segment between cA and cB
+ * (the lane's four consecutive x voxels): project both ends in fp32 (error < 3e-4 px), take the
+ * pixel bounding box dilated by one pixel, query the pyramid at the level where the box spans at
+ * most 2x2 texels.  fetch(level, x, y) -> (min zfree, max zbehind) of that texel. */
+template <class TexFetch>
+TSDF_HD int unit_certificate(const GridParams& g, const CertPyramid& P, double ax, double ay, double az,
+                             double bx, double by, double bz, TexFetch&& fetch) {
+    if (!g.k_simple) return UNIT_UNKNOWN;
+    const float XA = (float)ax, YA = (float)ay, ZA = (float)az, XB = (float)bx, YB = (float)by, ZB = (float)bz;
+    const float zmin = fminf(ZA, ZB), zmax = fmaxf(ZA, ZB);
+    if (zmax < -FAST_ZMIN) return UNIT_SKIP;                          /* all behind the camera, sdf.cpp:247 */
+    if (!(zmin >= FAST_ZMIN)) return UNIT_UNKNOWN;
+    const float ra = rcp_approx32(ZA), rb = rcp_approx32(ZB);
+    const float fxf = (float)g.K[0], fyf = (float)g.K[4], cxf = (float)g.K[2], cyf = (float)g.K[5];
+    const float ua = fmaf(fxf, XA * ra, cxf), va = fmaf(fyf, YA * ra, cyf);
+    const float ub = fmaf(fxf, XB * rb, cxf), vb = fmaf(fyf, YB * rb, cyf);
+    if (!(fabsf(ua) < 1e6f && fabsf(ub) < 1e6f && fabsf(va) < 1e6f && fabsf(vb) < 1e6f)) return UNIT_UNKNOWN;
+    int u0 = (int)floorf(fminf(ua, ub)) - 1, u1 = (int)floorf(fmaxf(ua, ub)) + 1;
+    int v0 = (int)floorf(fminf(va, vb)) - 1, v1 = (int)floorf(fmaxf(va, vb)) + 1;
+    if (u1 < -1 || v1 < -1 || u0 > g.img_w || v0 > g.img_h) return UNIT_SKIP;   /* certainly outside the image, sdf.cpp:254 */
+    const bool inside = (u0 >= 0) & (v0 >= 0) & (u1 <= g.img_w - 1) & (v1 <= g.img_h - 1);
+    u0 = imax(u0, 0); v0 = imax(v0, 0); u1 = imin(u1, g.img_w - 1); v1 = imin(v1, g.img_h - 1);
+    const int ext = imax(u1 - u0, v1 - v0);                           /* extent - 1 */
+    const int level = bit_length(ext);                                /* 2^level >= extent: the box spans <= 2 texels */
+    if (level >= CERT_LEVELS) return UNIT_UNKNOWN;
+    const int x0 = u0 >> level, x1 = u1 >> level, y0 = v0 >> level, y1 = v1 >> level;
+    float f00, b00, f10, b10, f01, b01, f11, b11;
+    fetch(level, x0, y0, f00, b00); fetch(level, x1, y0, f10, b10);
+    fetch(level, x0, y1, f01, b01); fetch(level, x1, y1, f11, b11);
+    const float zfree = fminf(fminf(f00, f10), fminf(f01, f11));
+    const float zbehind = fmaxf(fmaxf(b00, b10), fmaxf(b01, b11));
+    if (inside && zmax * (1.0f + 1e-6f) < zfree) return UNIT_FRONT;
+    if (zmin * (1.0f - 1e-6f) > zbehind) return UNIT_SKIP;           /* pixels outside the image skip anyway */
+    return UNIT_UNKNOWN;
+}
+
 /* ---- scan-line clipping for the fusion kernel ------------------------------------------------
  * Along a grid row (fixed j,k; i = 0..m-1) the camera-space centre is affine in i, so each of
  * the five acceptance tests of sdf.cpp:247-254 (z >= 0, -1 < u < width, -1 < v < height, the

@@ -20,10 +20,12 @@ constexpr int FUSE_THREADS = 128;
 #ifndef FUSE_MIN_BLOCKS
 #define FUSE_MIN_BLOCKS 5               /* resident blocks per SM the fusion kernel is compiled for */
 #endif
+#ifndef CERT_MIN_BLOCKS
+#define CERT_MIN_BLOCKS 8
+#endif
 #ifndef LIN_MIN_BLOCKS
 #define LIN_MIN_BLOCKS 3
 #endif
-constexpr int FUSE_LAUNCHES = 3;          /* tables, plan, items */
 
 /* cross-shard exchange of the reduced normal equations (one slot per rank, double-buffered
  * by sequence parity so a fast rank cannot overwrite a slot a slow rank still reads) */
@@ -53,7 +55,8 @@ struct LinearizeArgs {
     ShardLinks links;                      /* world = 1: no exchange */
 };
 
-void launch_prep(const GridParams& g, const float* depth, PixRec* pix, PoseState* pose, int reset_track, cudaStream_t s);
+void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, PoseState* pose, int reset_track, cudaStream_t s);
+void launch_pyramid(const CertPyramid& P, float2* cert, cudaStream_t s);
 /* exchange_mode: 0 none, 1 in-kernel mailbox all-reduce over peer memory (one kernel per
  * device, all running concurrently), 2 deferred (same-device shards: publish, then
  * launch_gn_combine sums in rank order).  seqno labels the exchange. */
@@ -67,10 +70,16 @@ struct FuseArgs {
     double* tables;                        /* 9*m + 3 doubles */
     unsigned long long* items;             /* capacity rows * (m/128 + 1) */
     unsigned int* item_count;
-    unsigned long long* n_updated;         /* [0] this launch, [1] running total */
-    int nblk;
+    unsigned long long* n_updated;         /* [0] this launch, [1] running total, [2..3] self-check counters */
+    CertPyramid pyr;                       /* certificate pyramid (levels 0..6) */
+    const float2* cert;
+    unsigned long long* units;             /* queue of uncertified lane units (capacity: stored voxels / 4) */
+    unsigned int* unit_count;
+    int nblk, nblk_cert;
+    int check;                             /* 1: run the self-check build (no stores) */
 };
-void launch_fuse(const FuseArgs& f, cudaStream_t s);
+int launch_fuse(const FuseArgs& f, cudaStream_t s);    /* returns the number of kernels launched */
+int fuse_cert_blocks_per_sm();
 void launch_fill(float2* grid, int64_t n, float d0, cudaStream_t s);
 void launch_sample(const GridParams& g, const float2* grid, int64_t n, const double* pts, float* out, uint8_t* ok, cudaStream_t s);
 void launch_export(const GridParams& g, const float2* grid, float* D, float* W, int layout, cudaStream_t s);

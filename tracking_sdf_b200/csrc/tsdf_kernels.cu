@@ -38,7 +38,7 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
  * one 16-byte record out.  Thread 0 also re-arms the tracker state for the coming frame.
  * ------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restrict__ depth,
-                                              PixRec* __restrict__ pix, PoseState* pose, int reset_track) {
+                                              PixRec* __restrict__ pix, float2* __restrict__ cert0, PoseState* pose, int reset_track) {
     pdl_wait();
     pdl_release();
     const int u = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -61,11 +61,14 @@ __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restr
         }
     }
     *reinterpret_cast<float4*>(&pix[o]) = make_float4(r.z, r.nx, r.ny, r.nz);
+    float zf, zb;
+    cert_pixel(g, kp, u, v, r, zf, zb);               /* level 0 of the fusion certificates */
+    cert0[o] = make_float2(zf, zb);
 }
 
-void launch_prep(const GridParams& g, const float* depth, PixRec* pix, PoseState* pose, int reset_track, cudaStream_t s) {
+void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, PoseState* pose, int reset_track, cudaStream_t s) {
     dim3 grid((g.img_w + 31) / 32, (g.img_h + 7) / 8);
-    launch_pdl(k_prep, grid, dim3(256), s, g, depth, pix, pose, reset_track);
+    launch_pdl(k_prep, grid, dim3(256), s, g, depth, pix, cert0, pose, reset_track);
 }
 
 /* organised cloud + normals for the accessor / tests */
@@ -546,12 +549,12 @@ int linearize_blocks_per_sm() {
  *                 their latency, stores are predicated on "any of my 4 voxels updated".
  * ------------------------------------------------------------------------------------------ */
 __global__ void k_fuse_tables(GridParams g, const PoseState* __restrict__ pose, double* __restrict__ T,
-                              unsigned long long* n_updated, unsigned int* item_count) {
+                              unsigned long long* n_updated, unsigned int* item_count, unsigned int* unit_count) {
     pdl_wait();
     pdl_release();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = g.m;
-    if (i == 0) { n_updated[0] = 0ull; *item_count = 0u; }
+    if (i == 0) { n_updated[0] = 0ull; *item_count = 0u; *unit_count = 0u; }
     if (i < 3) T[9 * (size_t)m + i] = pose->tinv[i];
     if (i >= m) return;
     const double gx = voxel_centre(g.vs_x, i, g.origin[0]);
@@ -609,13 +612,93 @@ __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, const PoseState
 
 __device__ __forceinline__ float4 ld_f4(const float4* p) { return *p; }
 
+/* The exact per-voxel path for a lane's four voxels (sdf.cpp:245-287), straight-line and
+ * branch-free so the four dependency chains interleave; the rare exact-division and
+ * exponential-weight cases branch last.  cx,cy,cz = camera-space centres (reference rounding). */
+__device__ __forceinline__ void exact_four(const GridParams& g, const K1Params& kp, const PixRec* __restrict__ pix,
+                                           const double* cx, const double* cy, const double* cz,
+                                           bool* upd, float* dnew, float* wnew) {
+    int iu[4], iv[4];
+    bool ok[4], need_exact[4];
+#pragma unroll
+    for (int v = 0; v < 4; v++) fuse_project_flags(g, cx[v], cy[v], cz[v], iu[v], iv[v], ok[v], need_exact[v]);
+    if (need_exact[0] | need_exact[1] | need_exact[2] | need_exact[3]) {
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+            if (need_exact[v]) {
+                double ij0, ij1, ij2;
+                project_ij(g, cx[v], cy[v], cz[v], ij0, ij1, ij2);
+                int eu_ = 0, ev_ = 0;
+                ok[v] = project_exact(g, ij0, ij1, ij2, eu_, ev_);
+                if (ok[v]) { iu[v] = eu_; iv[v] = ev_; }
+            }
+    }
+    float4 rr[4];
+#pragma unroll
+    for (int v = 0; v < 4; v++) rr[v] = __ldg(reinterpret_cast<const float4*>(&pix[(unsigned int)(iv[v] * g.img_w + iu[v])]));
+    float eband[4];
+    bool band[4];
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        PixRec rec; rec.z = rr[v].x; rec.nx = rr[v].y; rec.ny = rr[v].z; rec.nz = rr[v].w;
+        float fx_, fy_;
+        backproject_px(kp, iu[v], iv[v], rec.z, fx_, fy_);
+        upd[v] = fuse_distance_flags(g, cx[v], cy[v], cz[v], fx_, fy_, rec, dnew[v], eband[v], band[v]) & ok[v];
+        wnew[v] = 1.0f;
+    }
+    if ((upd[0] & band[0]) | (upd[1] & band[1]) | (upd[2] & band[2]) | (upd[3] & band[3])) {
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+            if (upd[v] & band[v]) wnew[v] = fuse_weight(true, eband[v]);     /* sdf.cpp:276-279 */
+    }
+}
+
+/* camera-space centres of the four voxels x0..x0+3 of row (j,k): camera_tracking.cpp:51-54 with
+ * the three products hoisted into the tables, the three additions in the reference's order */
+__device__ __forceinline__ void cam_four(const double* __restrict__ T, unsigned int um, int x0, int j, int k,
+                                         double ti0, double ti1, double ti2, double* cx, double* cy, double* cz) {
+    const double2 a0 = __ldg(reinterpret_cast<const double2*>(T + (unsigned int)x0)), a1 = __ldg(reinterpret_cast<const double2*>(T + (unsigned int)x0 + 2));
+    const double2 b0 = __ldg(reinterpret_cast<const double2*>(T + (um + x0))), b1 = __ldg(reinterpret_cast<const double2*>(T + (um + x0 + 2)));
+    const double2 c0 = __ldg(reinterpret_cast<const double2*>(T + (2u * um + x0))), c1 = __ldg(reinterpret_cast<const double2*>(T + (2u * um + x0 + 2)));
+    const double qy0 = __ldg(T + (3u * um + j)), qy1 = __ldg(T + (4u * um + j)), qy2 = __ldg(T + (5u * um + j));
+    const double pz0 = __ldg(T + (6u * um + k)), pz1 = __ldg(T + (7u * um + k)), pz2 = __ldg(T + (8u * um + k));
+    const double px0[4] = {a0.x, a0.y, a1.x, a1.y}, px1[4] = {b0.x, b0.y, b1.x, b1.y}, px2[4] = {c0.x, c0.y, c1.x, c1.y};
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        cx[v] = ((px0[v] + qy0) + pz0) + ti0;
+        cy[v] = ((px1[v] + qy1) + pz1) + ti1;
+        cz[v] = ((px2[v] + qy2) + pz2) + ti2;
+    }
+}
+
+__device__ __forceinline__ unsigned int apply_four(const GridParams& g, float4* ptr, float4 q0, float4 q1, int k,
+                                                   const bool* upd, const float* dnew, const float* wnew) {
+    if (!(upd[0] | upd[1] | upd[2] | upd[3])) return 0u;
+    fuse_apply_sel(q0.x, q0.y, dnew[0], wnew[0], upd[0]);
+    fuse_apply_sel(q0.z, q0.w, dnew[1], wnew[1], upd[1]);
+    fuse_apply_sel(q1.x, q1.y, dnew[2], wnew[2], upd[2]);
+    fuse_apply_sel(q1.z, q1.w, dnew[3], wnew[3], upd[3]);
+    if (upd[0] | upd[1]) ptr[0] = q0;
+    if (upd[2] | upd[3]) ptr[1] = q1;
+    /* halo layers are fused redundantly, counted once */
+    return (k >= g.ko0 && k < g.ko1) ? (unsigned)upd[0] + (unsigned)upd[1] + (unsigned)upd[2] + (unsigned)upd[3] : 0u;
+}
+
+__device__ __forceinline__ void count_updates(unsigned int my_updates, int lane, unsigned long long* n_updated) {
+    unsigned int tot = my_updates;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0 && tot) { atomicAdd(&n_updated[0], (unsigned long long)tot); atomicAdd(&n_updated[1], (unsigned long long)tot); }
+}
+
+/* ---- item kernel: exact path for every voxel of every item (used when K has skew: no certificates) */
 template <int METRIC, int KSIMPLE>
 __global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_items(GridParams g_in, float2* __restrict__ grid,
                                                                 const PixRec* __restrict__ pix,
                                                                 const double* __restrict__ T,
                                                                 const unsigned long long* __restrict__ items,
                                                                 const unsigned int* __restrict__ item_count,
-                                                                unsigned long long* n_updated /* [0] this launch, [1] running total */) {
+                                                                unsigned long long* n_updated) {
     pdl_wait();
     pdl_release();
     GridParams g = g_in;
@@ -628,105 +711,257 @@ __global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_items(Gr
     const K1Params kp = k1_params(g.K);
     const double ti0 = T[9 * (size_t)m + 0], ti1 = T[9 * (size_t)m + 1], ti2 = T[9 * (size_t)m + 2];
     unsigned int my_updates = 0;
-
     for (unsigned int it = gw; it < n_items; it += total_warps) {
         const unsigned long long item = __ldg(&items[it]);
         const int k = (int)(item & 0xfff), j = (int)((item >> 12) & 0xfff), xs = (int)((item >> 24) & 0xfff);
         const int ihi = (int)((item >> 48) & 0x1fff);
-        /* lane owns voxel pairs A = xs + 2*lane + {0,1} and B = A + 64: each 16-byte access of the
-         * warp is one contiguous 512-byte run */
-        const int xa = xs + 2 * lane, xb = xa + 64;
-        const bool actA = xa < ihi, actB = xb < ihi;      /* interval ends are multiples of 4 */
-        if (!actA) continue;
-        float4* ptr = reinterpret_cast<float4*>(&grid[((size_t)(k - g.ks0) * m + j) * m + xa]);
-        /* issue every load up front: voxel store, then the hoisted products */
-        float4 q0 = ld_f4(ptr), q1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (actB) q1 = ld_f4(ptr + 32);
-        const unsigned int xbl = actB ? xb : xa, um = (unsigned int)m;   /* tables are tiny: 32-bit offsets */
-        const double2 a0 = __ldg(reinterpret_cast<const double2*>(T + (unsigned int)xa)), a1 = __ldg(reinterpret_cast<const double2*>(T + xbl));
-        const double2 b0 = __ldg(reinterpret_cast<const double2*>(T + (um + xa))), b1 = __ldg(reinterpret_cast<const double2*>(T + (um + xbl)));
-        const double2 c0 = __ldg(reinterpret_cast<const double2*>(T + (2u * um + xa))), c1 = __ldg(reinterpret_cast<const double2*>(T + (2u * um + xbl)));
-        const double qy0 = __ldg(T + (3u * um + j)), qy1 = __ldg(T + (4u * um + j)), qy2 = __ldg(T + (5u * um + j));
-        const double pz0 = __ldg(T + (6u * um + k)), pz1 = __ldg(T + (7u * um + k)), pz2 = __ldg(T + (8u * um + k));
-        const double px0[4] = {a0.x, a0.y, a1.x, a1.y}, px1[4] = {b0.x, b0.y, b1.x, b1.y}, px2[4] = {c0.x, c0.y, c1.x, c1.y};
-        /* straight-line, branch-free stages over the lane's four voxels so their dependency
-         * chains interleave; the rare exact-division and exponential-weight cases branch last */
+        const int x0 = xs + 4 * lane;                     /* four consecutive voxels = one 32-byte sector */
+        if (x0 >= ihi) continue;                          /* interval ends are multiples of 4 */
+        float4* ptr = reinterpret_cast<float4*>(&grid[((size_t)(k - g.ks0) * m + j) * m + x0]);
+        const float4 q0 = ld_f4(ptr), q1 = ld_f4(ptr + 1);
         double cx[4], cy[4], cz[4];
-        int iu[4], iv[4];
-        bool ok[4], need_exact[4];
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-            /* camera_tracking.cpp:51-54 : rot_inv * g + rot_inv_trans, reference rounding order */
-            cx[v] = ((px0[v] + qy0) + pz0) + ti0;
-            cy[v] = ((px1[v] + qy1) + pz1) + ti1;
-            cz[v] = ((px2[v] + qy2) + pz2) + ti2;
-            fuse_project_flags(g, cx[v], cy[v], cz[v], iu[v], iv[v], ok[v], need_exact[v]);
-        }
-        if (need_exact[0] | need_exact[1] | need_exact[2] | need_exact[3]) {
-#pragma unroll
-            for (int v = 0; v < 4; v++)
-                if (need_exact[v]) {
-                    double ij0, ij1, ij2;
-                    project_ij(g, cx[v], cy[v], cz[v], ij0, ij1, ij2);
-                    int eu_ = 0, ev_ = 0;
-                    ok[v] = project_exact(g, ij0, ij1, ij2, eu_, ev_);
-                    if (ok[v]) { iu[v] = eu_; iv[v] = ev_; }
-                }
-        }
-        float4 rr[4];
-#pragma unroll
-        for (int v = 0; v < 4; v++) rr[v] = __ldg(reinterpret_cast<const float4*>(&pix[(unsigned int)(iv[v] * g.img_w + iu[v])]));
-        float dnew[4], wnew[4], eband[4];
-        bool upd[4], band[4];
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-            PixRec rec; rec.z = rr[v].x; rec.nx = rr[v].y; rec.ny = rr[v].z; rec.nz = rr[v].w;
-            float fx_, fy_;
-            backproject_px(kp, iu[v], iv[v], rec.z, fx_, fy_);
-            upd[v] = fuse_distance_flags(g, cx[v], cy[v], cz[v], fx_, fy_, rec, dnew[v], eband[v], band[v]) & ok[v] & (v < 2 || actB);
-            wnew[v] = 1.0f;
-        }
-        if ((upd[0] & band[0]) | (upd[1] & band[1]) | (upd[2] & band[2]) | (upd[3] & band[3])) {
-#pragma unroll
-            for (int v = 0; v < 4; v++)
-                if (upd[v] & band[v]) wnew[v] = fuse_weight(true, eband[v]);     /* sdf.cpp:276-279 */
-        }
-        if (upd[0] | upd[1] | upd[2] | upd[3]) {
-            fuse_apply_sel(q0.x, q0.y, dnew[0], wnew[0], upd[0]);
-            fuse_apply_sel(q0.z, q0.w, dnew[1], wnew[1], upd[1]);
-            fuse_apply_sel(q1.x, q1.y, dnew[2], wnew[2], upd[2]);
-            fuse_apply_sel(q1.z, q1.w, dnew[3], wnew[3], upd[3]);
-            if (upd[0] | upd[1]) ptr[0] = q0;
-            if (upd[2] | upd[3]) ptr[32] = q1;
-            /* halo layers are fused redundantly, counted once */
-            if (k >= g.ko0 && k < g.ko1) my_updates += (unsigned)upd[0] + (unsigned)upd[1] + (unsigned)upd[2] + (unsigned)upd[3];
-        }
+        cam_four(T, (unsigned int)m, x0, j, k, ti0, ti1, ti2, cx, cy, cz);
+        float dnew[4], wnew[4];
+        bool upd[4];
+        exact_four(g, kp, pix, cx, cy, cz, upd, dnew, wnew);
+        my_updates += apply_four(g, ptr, q0, q1, k, upd, dnew, wnew);
     }
-    /* one atomic per warp */
-    unsigned int tot = my_updates;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0 && tot) { atomicAdd(&n_updated[0], (unsigned long long)tot); atomicAdd(&n_updated[1], (unsigned long long)tot); }
+    count_updates(my_updates, lane, n_updated);
 }
 
-void launch_fuse(const FuseArgs& f, cudaStream_t s) {
+/* ---- certificate pyramid: level 0 is written by k_prep; this builds levels 1..6 (min zfree, max zbehind) */
+__global__ void __launch_bounds__(256) k_pyramid(CertPyramid P, float2* __restrict__ cert) {
+    pdl_wait();
+    pdl_release();
+    __shared__ float2 s1[32][32];
+    __shared__ float2 s2[16][16];
+    __shared__ float2 s3[8][8];
+    __shared__ float2 s4[4][4];
+    __shared__ float2 s5[2][2];
+    const float PINF = 3.402823466e+38f, NINF = -3.402823466e+38f;
+    const int tid = threadIdx.x;
+    const int bx = blockIdx.x, by = blockIdx.y;           /* 64x64 pixel tile */
+    const float2* L0 = cert + P.off[0];
+    for (int t = tid; t < 1024; t += 256) {
+        const int tx = t & 31, ty = t >> 5;
+        float zf = PINF, zb = NINF;
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 2; dx++) {
+                const int x = bx * 64 + tx * 2 + dx, y = by * 64 + ty * 2 + dy;
+                if (x < P.w[0] && y < P.h[0]) { const float2 c = L0[(size_t)y * P.w[0] + x]; zf = fminf(zf, c.x); zb = fmaxf(zb, c.y); }
+            }
+        s1[ty][tx] = make_float2(zf, zb);
+        const int X = bx * 32 + tx, Y = by * 32 + ty;
+        if (X < P.w[1] && Y < P.h[1]) cert[P.off[1] + (size_t)Y * P.w[1] + X] = make_float2(zf, zb);
+    }
+    __syncthreads();
+#define PYR_STEP(SRC, DST, N, LVL)                                                                         \
+    if (tid < (N) * (N)) {                                                                                 \
+        const int tx = tid % (N), ty = tid / (N);                                                          \
+        const float2 a = SRC[2 * ty][2 * tx], b = SRC[2 * ty][2 * tx + 1], c = SRC[2 * ty + 1][2 * tx], d = SRC[2 * ty + 1][2 * tx + 1]; \
+        const float2 r = make_float2(fminf(fminf(a.x, b.x), fminf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)));              \
+        DST[ty][tx] = r;                                                                                   \
+        const int X = bx * (N) + tx, Y = by * (N) + ty;                                                    \
+        if (X < P.w[LVL] && Y < P.h[LVL]) cert[P.off[LVL] + (size_t)Y * P.w[LVL] + X] = r;                 \
+    }                                                                                                      \
+    __syncthreads();
+    PYR_STEP(s1, s2, 16, 2)
+    PYR_STEP(s2, s3, 8, 3)
+    PYR_STEP(s3, s4, 4, 4)
+    PYR_STEP(s4, s5, 2, 5)
+    if (tid == 0) {
+        const float2 a = s5[0][0], b = s5[0][1], c = s5[1][0], d = s5[1][1];
+        if (bx < P.w[6] && by < P.h[6])
+            cert[P.off[6] + (size_t)by * P.w[6] + bx] = make_float2(fminf(fminf(a.x, b.x), fminf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)));
+    }
+#undef PYR_STEP
+}
+
+/* unit = a lane's four consecutive voxels: k (12 bits) | j (12) | x0/4 (10) | verdict (2) */
+__device__ __forceinline__ unsigned long long pack_unit(int k, int j, int x0, int verdict) {
+    return (unsigned long long)k | ((unsigned long long)j << 12) | ((unsigned long long)(x0 >> 2) << 24) | ((unsigned long long)verdict << 34);
+}
+
+/* ---- pass 1: certify lane units against the pyramid.  Free-space units are updated right here
+ * (32 bytes in, 32 bytes out, four fp32 divisions); skipped units cost nothing; the rest is queued.
+ * Software pipeline over the warp's items: item descriptors are fetched two items ahead and the
+ * (speculative) voxel loads one item ahead, so HBM latency overlaps the certificate arithmetic of
+ * the previous item (loads for units that end up skipped or queued are wasted bandwidth, which
+ * only the HBM-bound dense case would notice, and there every unit is free space). */
+template <int CHECK>
+__global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(GridParams g, CertPyramid P, float2* __restrict__ grid,
+                                                               const float2* __restrict__ cert, const double* __restrict__ T,
+                                                               const unsigned long long* __restrict__ items,
+                                                               const unsigned int* __restrict__ item_count,
+                                                               unsigned long long* __restrict__ units, unsigned int* unit_count,
+                                                               unsigned long long* n_updated) {
+    pdl_wait();
+    pdl_release();
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (FUSE_THREADS / 32) + (threadIdx.x >> 5);
+    const int total_warps = gridDim.x * (FUSE_THREADS / 32);
+    const int m = g.m;
+    const unsigned int um = (unsigned int)m;
+    const unsigned int n_items = *item_count;
+    const double ti0 = T[9 * (size_t)m + 0], ti1 = T[9 * (size_t)m + 1], ti2 = T[9 * (size_t)m + 2];
+    const float neg_delta = -g.delta;
+    unsigned int my_updates = 0;
+    auto fetch = [&](int level, int x, int y, float& zf, float& zb) {
+        const float2 c = __ldg(&cert[P.off[level] + (size_t)y * P.w[level] + x]);
+        zf = c.x; zb = c.y;
+    };
+    auto decode_ptr = [&](unsigned long long item, int& k, int& j, int& x0, bool& act) -> float4* {
+        k = (int)(item & 0xfff); j = (int)((item >> 12) & 0xfff);
+        const int xs = (int)((item >> 24) & 0xfff), ihi = (int)((item >> 48) & 0x1fff);
+        x0 = xs + 4 * lane;
+        act = x0 < ihi;                                   /* interval ends are multiples of 4 */
+        return reinterpret_cast<float4*>(&grid[((size_t)(k - g.ks0) * m + j) * m + (act ? x0 : xs)]);
+    };
+    /* pipeline prologue */
+    unsigned int it = gw;
+    unsigned long long item_cur = it < n_items ? __ldg(&items[it]) : 0ull;
+    unsigned long long item_nxt = it + total_warps < n_items ? __ldg(&items[it + total_warps]) : 0ull;
+    int k, j, x0; bool act;
+    float4* ptr = decode_ptr(item_cur, k, j, x0, act);
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+    if (it < n_items && act && !CHECK) { q0 = ld_f4(ptr); q1 = ld_f4(ptr + 1); }
+    for (; it < n_items; it += total_warps) {
+        /* stage A: descriptor two items ahead, voxel loads one item ahead */
+        const unsigned int it2 = it + 2 * total_warps;
+        const unsigned long long item_nn = it2 < n_items ? __ldg(&items[it2]) : 0ull;
+        int kn = 0, jn = 0, x0n = 0; bool actn = false;
+        float4* ptrn = decode_ptr(item_nxt, kn, jn, x0n, actn);
+        float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0;
+        const bool have_n = it + total_warps < n_items;
+        if (have_n && actn && !CHECK) { n0 = ld_f4(ptrn); n1 = ld_f4(ptrn + 1); }
+        /* stage B: certificate of the current unit */
+        int verdict = UNIT_SKIP;
+        if (act) {
+            const double qy0 = __ldg(T + (3u * um + j)), qy1 = __ldg(T + (4u * um + j)), qy2 = __ldg(T + (5u * um + j));
+            const double pz0 = __ldg(T + (6u * um + k)), pz1 = __ldg(T + (7u * um + k)), pz2 = __ldg(T + (8u * um + k));
+            const double ax = ((__ldg(T + (unsigned int)x0) + qy0) + pz0) + ti0, bx = ((__ldg(T + (unsigned int)x0 + 3) + qy0) + pz0) + ti0;
+            const double ay = ((__ldg(T + (um + x0)) + qy1) + pz1) + ti1, by = ((__ldg(T + (um + x0 + 3)) + qy1) + pz1) + ti1;
+            const double az = ((__ldg(T + (2u * um + x0)) + qy2) + pz2) + ti2, bz = ((__ldg(T + (2u * um + x0 + 3)) + qy2) + pz2) + ti2;
+            verdict = unit_certificate(g, P, ax, ay, az, bx, by, bz, fetch);
+        }
+        if (CHECK) {
+            /* self-check build: queue EVERY unit with its verdict; pass 2 compares, nothing is written */
+            const unsigned int mask = __ballot_sync(0xffffffffu, act);
+            unsigned int base = 0;
+            if (lane == 0 && mask) base = atomicAdd(unit_count, (unsigned int)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (act) units[base + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, verdict);
+        } else {
+            if (verdict == UNIT_FRONT) {
+                /* free space: d < -delta => d_new = -delta, w_new = 1  (sdf.cpp:276, 285-292) */
+                fuse_apply(q0.x, q0.y, neg_delta, 1.0f);
+                fuse_apply(q0.z, q0.w, neg_delta, 1.0f);
+                fuse_apply(q1.x, q1.y, neg_delta, 1.0f);
+                fuse_apply(q1.z, q1.w, neg_delta, 1.0f);
+                ptr[0] = q0; ptr[1] = q1;
+                if (k >= g.ko0 && k < g.ko1) my_updates += 4u;
+            }
+            const unsigned int mask = __ballot_sync(0xffffffffu, verdict == UNIT_UNKNOWN);
+            if (mask) {
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(unit_count, (unsigned int)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (verdict == UNIT_UNKNOWN) units[base + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, UNIT_UNKNOWN);
+            }
+        }
+        /* rotate the pipeline */
+        item_nxt = item_nn;
+        k = kn; j = jn; x0 = x0n; act = actn; ptr = ptrn; q0 = n0; q1 = n1;
+    }
+    count_updates(my_updates, lane, n_updated);
+}
+
+/* ---- pass 2: the exact path on the queued units, one unit (four voxels) per thread */
+template <int METRIC, int CHECK>
+__global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_exact(GridParams g_in, float2* __restrict__ grid,
+                                                                              const PixRec* __restrict__ pix, const double* __restrict__ T,
+                                                                              const unsigned long long* __restrict__ units,
+                                                                              const unsigned int* __restrict__ unit_count,
+                                                                              unsigned long long* n_updated) {
+    pdl_wait();
+    pdl_release();
+    GridParams g = g_in;
+    g.metric = METRIC; g.k_simple = 1;
+    const int lane = threadIdx.x & 31;
+    const int m = g.m;
+    const unsigned int n_units = *unit_count;
+    const K1Params kp = k1_params(g.K);
+    const double ti0 = T[9 * (size_t)m + 0], ti1 = T[9 * (size_t)m + 1], ti2 = T[9 * (size_t)m + 2];
+    unsigned int my_updates = 0, chk_n = 0, chk_bad = 0;
+    for (unsigned int q = blockIdx.x * FUSE_THREADS + threadIdx.x; q < n_units; q += gridDim.x * FUSE_THREADS) {
+        const unsigned long long unit = __ldg(&units[q]);
+        const int k = (int)(unit & 0xfff), j = (int)((unit >> 12) & 0xfff), x0 = (int)((unit >> 24) & 0x3ff) << 2;
+        const int verdict = (int)((unit >> 34) & 3);
+        float4* ptr = reinterpret_cast<float4*>(&grid[((size_t)(k - g.ks0) * m + j) * m + x0]);
+        const float4 q0 = ld_f4(ptr), q1 = ld_f4(ptr + 1);
+        double cx[4], cy[4], cz[4];
+        cam_four(T, (unsigned int)m, x0, j, k, ti0, ti1, ti2, cx, cy, cz);
+        float dnew[4], wnew[4];
+        bool upd[4];
+        exact_four(g, kp, pix, cx, cy, cz, upd, dnew, wnew);
+        if (CHECK) {
+            if (verdict != UNIT_UNKNOWN) {
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    chk_n++;
+                    const bool good = (verdict == UNIT_FRONT) ? (upd[v] && dnew[v] == -g.delta && wnew[v] == 1.0f) : !upd[v];
+                    if (!good) chk_bad++;
+                }
+            }
+            continue;
+        }
+        my_updates += apply_four(g, ptr, q0, q1, k, upd, dnew, wnew);
+    }
+    if (CHECK) {
+        if (chk_n) atomicAdd(&n_updated[2], (unsigned long long)chk_n);
+        if (chk_bad) atomicAdd(&n_updated[3], (unsigned long long)chk_bad);
+        return;
+    }
+    count_updates(my_updates, lane, n_updated);
+}
+
+void launch_pyramid(const CertPyramid& P, float2* cert, cudaStream_t s) {
+    launch_pdl(k_pyramid, dim3((P.w[0] + 63) / 64, (P.h[0] + 63) / 64), dim3(256), s, P, cert);
+}
+
+int launch_fuse(const FuseArgs& f, cudaStream_t s) {
     const GridParams& g = f.g;
-    launch_pdl(k_fuse_tables, dim3((g.m + 127) / 128), dim3(128), s, g, f.pose, f.tables, f.n_updated, f.item_count);
+    launch_pdl(k_fuse_tables, dim3((g.m + 127) / 128), dim3(128), s, g, f.pose, f.tables, f.n_updated, f.item_count, f.unit_count);
     const int nrows = (g.ks1 - g.ks0) * g.m;
     launch_pdl(k_fuse_plan, dim3((nrows + 255) / 256), dim3(256), s, g, f.pose, f.tables, f.items, f.item_count);
-    if (g.metric == 0) {
-        if (g.k_simple) launch_pdl(k_fuse_items<0, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
-        else launch_pdl(k_fuse_items<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
-    } else {
-        if (g.k_simple) launch_pdl(k_fuse_items<1, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
+    if (!g.k_simple) {          /* skewed intrinsics: the exact path for every in-view voxel */
+        if (g.metric == 0) launch_pdl(k_fuse_items<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
         else launch_pdl(k_fuse_items<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
+        return 3;
     }
+    if (f.check) {
+        launch_pdl(k_fuse_cert<1>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_count, f.units, f.unit_count, f.n_updated);
+        if (g.metric == 0) launch_pdl(k_fuse_exact<0, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated);
+        else launch_pdl(k_fuse_exact<1, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated);
+        return 4;
+    }
+    launch_pdl(k_fuse_cert<0>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_count, f.units, f.unit_count, f.n_updated);
+    if (g.metric == 0) launch_pdl(k_fuse_exact<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated);
+    else launch_pdl(k_fuse_exact<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated);
+    return 4;
 }
 int fuse_blocks_per_sm() {
     int n = 0, q = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fuse_items<0, 1>, FUSE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fuse_exact<0, 0>, FUSE_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_fuse_items<0, 0>, FUSE_THREADS, 0);
     return n < q ? n : q;
+}
+int fuse_cert_blocks_per_sm() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fuse_cert<0>, FUSE_THREADS, 0);
+    return n;
 }
 
 /* ------------------------------------------------------------------------------------------
