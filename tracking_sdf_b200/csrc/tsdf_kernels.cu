@@ -808,6 +808,30 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
     const double ti0 = T[9 * (size_t)m + 0], ti1 = T[9 * (size_t)m + 1], ti2 = T[9 * (size_t)m + 2];
     const float neg_delta = -g.delta;
     unsigned int my_updates = 0;
+    /* queue appends are staged per warp in shared memory and flushed 32+ at a time, so the
+     * atomicAdd round trip is paid once per several items and is off the per-item critical path */
+    __shared__ unsigned long long s_stage[FUSE_THREADS / 32][96];
+    unsigned long long* stage = s_stage[threadIdx.x >> 5];
+    int staged = 0;                                       /* warp-uniform */
+    auto flush = [&](int keep_below) {
+        while (staged > keep_below) {
+            const int n = staged < 32 ? staged : 32;      /* flush the oldest n entries */
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(unit_count, (unsigned int)n);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lane < n) units[base + lane] = stage[lane];
+            __syncwarp();
+            const int rem = staged - n;                   /* warp-uniform: shift the remainder down */
+            for (int b0 = 0; b0 < rem; b0 += 32) {
+                const int q = b0 + lane;
+                const unsigned long long v = q < rem ? stage[n + q] : 0ull;
+                __syncwarp();
+                if (q < rem) stage[q] = v;
+                __syncwarp();
+            }
+            staged = rem;
+        }
+    };
     auto fetch = [&](int level, int x, int y, float& zf, float& zb) {
         const float2 c = __ldg(&cert[P.off[level] + (size_t)y * P.w[level] + x]);
         zf = c.x; zb = c.y;
@@ -849,10 +873,10 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
         if (CHECK) {
             /* self-check build: queue EVERY unit with its verdict; pass 2 compares, nothing is written */
             const unsigned int mask = __ballot_sync(0xffffffffu, act);
-            unsigned int base = 0;
-            if (lane == 0 && mask) base = atomicAdd(unit_count, (unsigned int)__popc(mask));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (act) units[base + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, verdict);
+            if (act) stage[staged + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, verdict);
+            __syncwarp();
+            staged += __popc(mask);
+            flush(63);
         } else {
             if (verdict == UNIT_FRONT) {
                 /* free space: d < -delta => d_new = -delta, w_new = 1  (sdf.cpp:276, 285-292) */
@@ -865,16 +889,17 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
             }
             const unsigned int mask = __ballot_sync(0xffffffffu, verdict == UNIT_UNKNOWN);
             if (mask) {
-                unsigned int base = 0;
-                if (lane == 0) base = atomicAdd(unit_count, (unsigned int)__popc(mask));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (verdict == UNIT_UNKNOWN) units[base + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, UNIT_UNKNOWN);
+                if (verdict == UNIT_UNKNOWN) stage[staged + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, UNIT_UNKNOWN);
+                __syncwarp();
+                staged += __popc(mask);
+                flush(63);
             }
         }
         /* rotate the pipeline */
         item_nxt = item_nn;
         k = kn; j = jn; x0 = x0n; act = actn; ptr = ptrn; q0 = n0; q1 = n1;
     }
+    flush(0);
     count_updates(my_updates, lane, n_updated);
 }
 
