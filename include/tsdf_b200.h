@@ -209,6 +209,9 @@ tsdf_status tsdf_debug_check_rcp(tsdf_handle h, float x_lo, float x_hi, int64_t*
  * by the certified fp32 fast path, out[1] = of those, verdicts that disagree with the exact fp64
  * path (must be 0), out[2] = work items */
 tsdf_status tsdf_debug_fuse_check(tsdf_handle h, const float* depth, int32_t mem, int64_t out[3]);
+/* roofline ceiling probe: mean milliseconds of a plain read-modify-write stream over the whole
+ * store (the free-space update on every voxel, no geometry).  MODIFIES the grid. */
+tsdf_status tsdf_debug_stream_rmw(tsdf_handle h, int32_t reps, float* ms);
 /* running total of voxels updated by fusion since the last reset (for GB/s accounting) */
 tsdf_status tsdf_total_updates(tsdf_handle h, int32_t reset, int64_t* total);
 tsdf_status tsdf_flush_l2(tsdf_handle h);                       /* overwrite a >L2-sized scratch buffer */

@@ -104,6 +104,7 @@ PROTOTYPES = [
     ("tsdf_stage_timing_end", _I32, [_VP, c_i32p, c_fp]),
     ("tsdf_total_updates", _I32, [_VP, _I32, c_i64p]),
     ("tsdf_debug_phase_times", _I32, [_VP, _VP, _I32, c_i64p]),
+    ("tsdf_debug_stream_rmw", _I32, [_VP, _I32, c_fp]),
     ("tsdf_debug_fuse_check", _I32, [_VP, _VP, _I32, c_i64p]),
     ("tsdf_debug_check_rcp", _I32, [_VP, ctypes.c_float, ctypes.c_float, c_i64p]),
     ("tsdf_slab_plan", _I32, [_CFGP, c_i32p]),
@@ -391,6 +392,11 @@ class Tsdf:
         v = ctypes.c_int64()
         self._ck(self.L.tsdf_total_updates(self.h, int(reset), ctypes.byref(v)))
         return v.value
+
+    def debug_stream_rmw(self, reps=10):
+        ms = ctypes.c_float()
+        self._ck(self.L.tsdf_debug_stream_rmw(self.h, reps, ctypes.byref(ms)))
+        return ms.value
 
     def debug_fuse_check(self, depth):
         p, mem, keep = _depth_arg(depth)

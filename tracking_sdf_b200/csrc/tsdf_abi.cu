@@ -921,6 +921,24 @@ tsdf_status tsdf_debug_fuse_check(tsdf_handle h, const float* depth, int32_t mem
     return TSDF_OK;
 }
 
+/* debugging aid / roofline ceiling: time `reps` plain read-modify-write streams over the whole store
+ * (the free-space update on every voxel, no geometry).  MODIFIES the grid.  ms = mean per pass. */
+tsdf_status tsdf_debug_stream_rmw(tsdf_handle h, int32_t reps, float* ms) {
+    if (!h || !ms || reps < 1) return bad("bad argument");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    launch_stream_rmw(p->grid, p->n_stored, -p->g.delta, p->stream);
+    CK(cudaEventRecord(p->tmr[0], p->stream));
+    for (int r = 0; r < reps; r++) launch_stream_rmw(p->grid, p->n_stored, -p->g.delta, p->stream);
+    CK(cudaEventRecord(p->tmr[1], p->stream));
+    CK(cudaEventSynchronize(p->tmr[1]));
+    p->launches += reps + 1;
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, p->tmr[0], p->tmr[1]));
+    *ms = t / reps;
+    return TSDF_OK;
+}
+
 tsdf_status tsdf_total_updates(tsdf_handle h, int32_t reset, int64_t* total) {
     if (!h) return bad("null handle");
     Impl* p = I(h);

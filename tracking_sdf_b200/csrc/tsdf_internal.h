@@ -87,6 +87,7 @@ void launch_import(const GridParams& g, float2* grid, const float* D, const floa
 void launch_cloud(const GridParams& g, const PixRec* pix, float* cloud, float* normals, cudaStream_t s);
 void launch_exp_map(const double* twist, double* out12, cudaStream_t s);
 void launch_flush(float* buf, int64_t n, cudaStream_t s);
+void launch_stream_rmw(float2* grid, int64_t n, float neg_delta, cudaStream_t s);
 void launch_check_rcp(unsigned int lo, unsigned int hi, unsigned long long* n_bad, cudaStream_t s);
 int  fuse_blocks_per_sm();
 int  linearize_blocks_per_sm();

@@ -1092,6 +1092,20 @@ void launch_check_rcp(unsigned int lo, unsigned int hi, unsigned long long* n_ba
     k_check_rcp<<<148 * 16, 256, 0, s>>>(lo, hi, n_bad);
 }
 
+/* ceiling probe: the free-space update applied to EVERY stored voxel by a plain grid-stride stream
+ * (no geometry, no certificate): what a pure read-modify-write of the store costs on this GPU */
+__global__ void __launch_bounds__(256) k_stream_rmw(float4* __restrict__ grid, int64_t n4, float neg_delta) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = grid[q];
+        fuse_apply(v.x, v.y, neg_delta, 1.0f);
+        fuse_apply(v.z, v.w, neg_delta, 1.0f);
+        grid[q] = v;
+    }
+}
+void launch_stream_rmw(float2* grid, int64_t n, float neg_delta, cudaStream_t s) {
+    k_stream_rmw<<<148 * 8, 256, 0, s>>>(reinterpret_cast<float4*>(grid), n / 2, neg_delta);
+}
+
 __global__ void k_flush(float4* buf, int64_t n4) {
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x)
         buf[q] = make_float4(0.f, 0.f, 0.f, 0.f);
