@@ -169,7 +169,7 @@ LinearizeArgs lin_args(Impl* p, int do_update, bool debug) {
 
 void enqueue_prep(Impl* p, const float* dptr, int reset_track) {
     launch_prep(p->g, dptr, p->pix, p->cert + p->pyr.off[0], p->pose_dev, reset_track, p->stream);
-    launch_pyramid(p->pyr, p->cert, p->stream);
+    launch_pyramid(p->pyr, p->cert, p->ticket + 1000, p->stream);
     p->launches += 2;
 }
 void enqueue_linearize(Impl* p, int do_update, bool debug) {

@@ -464,7 +464,7 @@ TSDF_HD float rcp_approx32(float x) {
  * A min-pyramid of zfree and a max-pyramid of zbehind then certify a whole group of voxels whose
  * pixels lie in a bounding box: all updated-as-free-space, or all skipped.  Everything not
  * certified takes the exact path; the device self-check compares every certified voxel with it. */
-#define CERT_LEVELS 7                       /* levels 0..6: texels of 1..64 pixels */
+#define CERT_LEVELS 11                      /* levels 0..10: texels of 1..1024 pixels */
 struct CertPyramid {
     int32_t w[CERT_LEVELS], h[CERT_LEVELS];
     int64_t off[CERT_LEVELS];               /* element offsets (float2) of each level in one buffer */

@@ -56,7 +56,7 @@ struct LinearizeArgs {
 };
 
 void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, PoseState* pose, int reset_track, cudaStream_t s);
-void launch_pyramid(const CertPyramid& P, float2* cert, cudaStream_t s);
+void launch_pyramid(const CertPyramid& P, float2* cert, unsigned int* ticket, cudaStream_t s);
 /* exchange_mode: 0 none, 1 in-kernel mailbox all-reduce over peer memory (one kernel per
  * device, all running concurrently), 2 deferred (same-device shards: publish, then
  * launch_gn_combine sums in rank order).  seqno labels the exchange. */

@@ -574,7 +574,8 @@ __device__ __forceinline__ unsigned long long pack_item(int k, int j, int xs, in
            ((unsigned long long)ilo << 36) | ((unsigned long long)ihi << 48);
 }
 
-__global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, const PoseState* __restrict__ pose,
+__global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, CertPyramid P, const float2* __restrict__ cert, int check,
+                                                   const PoseState* __restrict__ pose,
                                                    const double* __restrict__ T, unsigned long long* __restrict__ items,
                                                    unsigned int* item_count) {
     pdl_wait();
@@ -583,7 +584,7 @@ __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, const PoseState
     const int nrows = (g.ks1 - g.ks0) * m;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    int cnt = 0, ilo = 0, ihi = 0, xs = 0, k = 0, j = 0;
+    int cnt = 0, ilo = 0, ihi = 0, xs = 0, k = 0, j = 0, rowv = UNIT_UNKNOWN;
     if (row < nrows) {
         k = g.ks0 + row / m; j = row - (row / m) * m;
         double Ri[9], ti[3];
@@ -593,7 +594,21 @@ __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, const PoseState
         for (int q = 0; q < 3; q++) ti[q] = pose->tinv[q];
         row_clip(g, Ri, ti, T[(size_t)3 * m + j], T[(size_t)4 * m + j], T[(size_t)5 * m + j],
                  T[(size_t)6 * m + k], T[(size_t)7 * m + k], T[(size_t)8 * m + k], ilo, ihi);
-        if (ihi > ilo) { xs = ilo; cnt = (ihi - xs + 127) >> 7; }
+        if (ihi > ilo) {
+            xs = ilo; cnt = (ihi - xs + 127) >> 7;
+            /* row-level certificate: the whole clipped row against the pyramid.  A row certainly
+             * skipped emits no work at all; a row certainly in free space is flagged so pass 1 streams
+             * it without per-unit certificates; anything else is judged per unit. */
+            const unsigned int um = (unsigned int)m;
+            const double ax = ((T[ilo] + T[3u * um + j]) + T[6u * um + k]) + ti[0], bx = ((T[ihi - 1] + T[3u * um + j]) + T[6u * um + k]) + ti[0];
+            const double ay = ((T[um + ilo] + T[4u * um + j]) + T[7u * um + k]) + ti[1], by = ((T[um + ihi - 1] + T[4u * um + j]) + T[7u * um + k]) + ti[1];
+            const double az = ((T[2u * um + ilo] + T[5u * um + j]) + T[8u * um + k]) + ti[2], bz = ((T[2u * um + ihi - 1] + T[5u * um + j]) + T[8u * um + k]) + ti[2];
+            rowv = unit_certificate(g, P, ax, ay, az, bx, by, bz, [&](int level, int x, int y, float& zf, float& zb) {
+                const float2 c = __ldg(&cert[P.off[level] + (size_t)y * P.w[level] + x]);
+                zf = c.x; zb = c.y;
+            });
+            if (rowv == UNIT_SKIP && !check) cnt = 0;
+        }
     }
     /* warp-inclusive scan of cnt, one reservation per warp */
     int scan = cnt;
@@ -607,7 +622,7 @@ __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, const PoseState
     if (lane == 31 && total > 0) basei = atomicAdd(item_count, (unsigned int)total);
     basei = __shfl_sync(0xffffffffu, basei, 31);
     unsigned int o = basei + (unsigned int)(scan - cnt);
-    for (int c = 0; c < cnt; c++) items[o + c] = pack_item(k, j, xs + 128 * c, ilo, ihi);
+    for (int c = 0; c < cnt; c++) items[o + c] = pack_item(k, j, xs + 128 * c, ilo, ihi) | ((unsigned long long)rowv << 61);
 }
 
 __device__ __forceinline__ float4 ld_f4(const float4* p) { return *p; }
@@ -730,9 +745,10 @@ __global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_items(Gr
 }
 
 /* ---- certificate pyramid: level 0 is written by k_prep; this builds levels 1..6 (min zfree, max zbehind) */
-__global__ void __launch_bounds__(256) k_pyramid(CertPyramid P, float2* __restrict__ cert) {
+__global__ void __launch_bounds__(256) k_pyramid(CertPyramid P, float2* __restrict__ cert, unsigned int* ticket) {
     pdl_wait();
     pdl_release();
+    __shared__ int s_last;
     __shared__ float2 s1[32][32];
     __shared__ float2 s2[16][16];
     __shared__ float2 s3[8][8];
@@ -777,6 +793,31 @@ __global__ void __launch_bounds__(256) k_pyramid(CertPyramid P, float2* __restri
             cert[P.off[6] + (size_t)by * P.w[6] + bx] = make_float2(fminf(fminf(a.x, b.x), fminf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)));
     }
 #undef PYR_STEP
+    /* levels 7..10 (a handful of texels, for row-level certificates) by the last block to finish */
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int l = 7; l < CERT_LEVELS; l++) {
+        for (int t = tid; t < P.w[l] * P.h[l]; t += 256) {
+            const int X = t % P.w[l], Y = t / P.w[l];
+            float zf = PINF, zb = NINF;
+            for (int dy = 0; dy < 2; dy++)
+                for (int dx = 0; dx < 2; dx++) {
+                    const int x = 2 * X + dx, y = 2 * Y + dy;
+                    if (x < P.w[l - 1] && y < P.h[l - 1]) {
+                        const float2 c = __ldcg(&cert[P.off[l - 1] + (size_t)y * P.w[l - 1] + x]);
+                        zf = fminf(zf, c.x); zb = fmaxf(zb, c.y);
+                    }
+                }
+            cert[P.off[l] + (size_t)Y * P.w[l] + X] = make_float2(zf, zb);
+        }
+        __threadfence();
+        __syncthreads();
+    }
+    if (tid == 0) *ticket = 0u;
 }
 
 /* unit = a lane's four consecutive voxels: k (12 bits) | j (12) | x0/4 (10) | verdict (2) */
@@ -860,9 +901,11 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
         float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0;
         const bool have_n = it + total_warps < n_items;
         if (have_n && actn && !CHECK) { n0 = ld_f4(ptrn); n1 = ld_f4(ptrn + 1); }
-        /* stage B: certificate of the current unit */
+        /* stage B: certificate of the current unit (unless the whole row was already judged) */
         int verdict = UNIT_SKIP;
-        if (act) {
+        const int rowv = (int)(item_cur >> 61) & 3;
+        if (act && rowv != UNIT_UNKNOWN) verdict = rowv;
+        else if (act) {
             const double qy0 = __ldg(T + (3u * um + j)), qy1 = __ldg(T + (4u * um + j)), qy2 = __ldg(T + (5u * um + j));
             const double pz0 = __ldg(T + (6u * um + k)), pz1 = __ldg(T + (7u * um + k)), pz2 = __ldg(T + (8u * um + k));
             const double ax = ((__ldg(T + (unsigned int)x0) + qy0) + pz0) + ti0, bx = ((__ldg(T + (unsigned int)x0 + 3) + qy0) + pz0) + ti0;
@@ -896,6 +939,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
             }
         }
         /* rotate the pipeline */
+        item_cur = item_nxt;
         item_nxt = item_nn;
         k = kn; j = jn; x0 = x0n; act = actn; ptr = ptrn; q0 = n0; q1 = n1;
     }
@@ -952,15 +996,15 @@ __global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_exact(Gr
     count_updates(my_updates, lane, n_updated);
 }
 
-void launch_pyramid(const CertPyramid& P, float2* cert, cudaStream_t s) {
-    launch_pdl(k_pyramid, dim3((P.w[0] + 63) / 64, (P.h[0] + 63) / 64), dim3(256), s, P, cert);
+void launch_pyramid(const CertPyramid& P, float2* cert, unsigned int* ticket, cudaStream_t s) {
+    launch_pdl(k_pyramid, dim3((P.w[0] + 63) / 64, (P.h[0] + 63) / 64), dim3(256), s, P, cert, ticket);
 }
 
 int launch_fuse(const FuseArgs& f, cudaStream_t s) {
     const GridParams& g = f.g;
     launch_pdl(k_fuse_tables, dim3((g.m + 127) / 128), dim3(128), s, g, f.pose, f.tables, f.n_updated, f.item_count, f.unit_count);
     const int nrows = (g.ks1 - g.ks0) * g.m;
-    launch_pdl(k_fuse_plan, dim3((nrows + 255) / 256), dim3(256), s, g, f.pose, f.tables, f.items, f.item_count);
+    launch_pdl(k_fuse_plan, dim3((nrows + 255) / 256), dim3(256), s, g, f.pyr, f.cert, f.check, f.pose, f.tables, f.items, f.item_count);
     if (!g.k_simple) {          /* skewed intrinsics: the exact path for every in-view voxel */
         if (g.metric == 0) launch_pdl(k_fuse_items<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
         else launch_pdl(k_fuse_items<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
