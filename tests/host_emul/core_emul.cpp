@@ -105,7 +105,8 @@ void emul_interpolate(const GridParams* g, const float* grid, int64_t n, const d
  * against the pyramid (k_prep level 0 + k_pyramid + k_fuse_cert), the rest through the exact path
  * (k_fuse_exact), products hoisted exactly like the kernels.
  * use_clip = 0 visits every voxel; use_cert = 0 sends every unit through the exact path. */
-static int64_t g_last_fast = 0;
+static int64_t g_last_fast = 0, g_rows_front = 0, g_rows_skip = 0, g_rows_unknown = 0;
+void emul_row_stats(int64_t out[3]) { out[0] = g_rows_front; out[1] = g_rows_skip; out[2] = g_rows_unknown; }
 int64_t emul_last_fast_count() { return g_last_fast; }
 int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const PoseState* pose, int use_clip, int use_cert) {
     const GridParams& g = *gp;
@@ -133,6 +134,7 @@ int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const Pos
             }
     auto fetch = [&](int level, int x, int y, float& f, float& b) { f = zf[level][(size_t)y * P.w[level] + x]; b = zb[level][(size_t)y * P.w[level] + x]; };
     int64_t n_updated = 0, n_fast = 0;
+    g_rows_front = g_rows_skip = g_rows_unknown = 0;
 #pragma omp parallel for reduction(+ : n_updated, n_fast) schedule(dynamic, 1)
     for (int k = g.ks0; k < g.ks1; k++) {
         const double gz = voxel_centre(g.vs_z, k, g.origin[2]);
@@ -147,6 +149,8 @@ int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const Pos
                 const double gxa = voxel_centre(g.vs_x, ilo, g.origin[0]), gxb = voxel_centre(g.vs_x, ihi - 1, g.origin[0]);
                 rowv = unit_certificate(g, P, ((Ri[0] * gxa + py0) + pz0) + ti[0], ((Ri[3] * gxa + py1) + pz1) + ti[1], ((Ri[6] * gxa + py2) + pz2) + ti[2],
                                         ((Ri[0] * gxb + py0) + pz0) + ti[0], ((Ri[3] * gxb + py1) + pz1) + ti[1], ((Ri[6] * gxb + py2) + pz2) + ti[2], fetch);
+#pragma omp critical
+                { if (rowv == UNIT_FRONT) g_rows_front++; else if (rowv == UNIT_SKIP) g_rows_skip++; else g_rows_unknown++; }
                 if (rowv == UNIT_SKIP) { n_fast += ihi - ilo; continue; }
             }
             for (int x0 = ilo; x0 < ihi; x0 += 4) {

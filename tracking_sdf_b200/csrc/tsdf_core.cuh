@@ -472,20 +472,24 @@ struct CertPyramid {
 TSDF_HD void cert_pixel(const GridParams& g, const K1Params& kp, int u, int v, const PixRec& rec, float& zfree, float& zbehind) {
     const float NINF = -3.402823466e+38f, PINF = 3.402823466e+38f;
     zfree = NINF; zbehind = NINF;
-    if (!(rec.z == rec.z)) return;
+    /* The outermost pixel ring never takes part in a free-space certificate (unit_certificate asks for
+     * a footprint strictly inside it), so it is neutral for the min-pyramid; otherwise its missing
+     * normals would poison every coarse texel that touches the image border. */
+    const bool border = (u == 0) | (v == 0) | (u == g.img_w - 1) | (v == g.img_h - 1);
+    if (!(rec.z == rec.z)) { if (border) zfree = PINF; return; }
     if (g.metric != 0) {
-        zfree = (rec.z - g.delta - FAST_DMARG) * (1.0f - 1e-5f) - 1e-4f;
+        zfree = border ? PINF : (rec.z - g.delta - FAST_DMARG) * (1.0f - 1e-5f) - 1e-4f;
         zbehind = (rec.z + g.delta + FAST_DMARG) * (1.0f + 1e-5f) + 1e-4f;
         return;
     }
-    if (!(rec.nx == rec.nx)) return;
+    if (!(rec.nx == rec.nx)) { if (border) zfree = PINF; return; }
     const float rx = ((float)u - kp.cx) * kp.inv_fx, ry = ((float)v - kp.cy) * kp.inv_fy;
     const float a = -(rx * rec.nx + ry * rec.ny + rec.nz);            /* |ray.n| */
     const float ea = (fabsf(rec.nx) * kp.inv_fx + fabsf(rec.ny) * kp.inv_fy) * 1.001f;   /* cell of +-1 pixel */
     zbehind = PINF;
     if (!(a > 1e-4f)) return;                                         /* grazing: no certificate, never skipped */
     const float num = a * rec.z - g.delta - FAST_DMARG;
-    if (num > 0.0f) zfree = (num / (a + ea)) * (1.0f - 1e-5f) - 1e-4f;
+    if (border) zfree = PINF; else if (num > 0.0f) zfree = (num / (a + ea)) * (1.0f - 1e-5f) - 1e-4f;
     const float den = a - ea;
     if (den > 1e-4f) zbehind = ((a * rec.z + g.delta + FAST_DMARG) / den) * (1.0f + 1e-5f) + 1e-4f;
 }
@@ -521,7 +525,7 @@ TSDF_HD int unit_certificate(const GridParams& g, const CertPyramid& P, double a
     int u0 = (int)floorf(fminf(ua, ub)) - 1, u1 = (int)floorf(fmaxf(ua, ub)) + 1;
     int v0 = (int)floorf(fminf(va, vb)) - 1, v1 = (int)floorf(fmaxf(va, vb)) + 1;
     if (u1 < -1 || v1 < -1 || u0 > g.img_w || v0 > g.img_h) return UNIT_SKIP;   /* certainly outside the image, sdf.cpp:254 */
-    const bool inside = (u0 >= 0) & (v0 >= 0) & (u1 <= g.img_w - 1) & (v1 <= g.img_h - 1);
+    const bool inside = (u0 >= 1) & (v0 >= 1) & (u1 <= g.img_w - 2) & (v1 <= g.img_h - 2);   /* strictly inside the border ring */
     u0 = imax(u0, 0); v0 = imax(v0, 0); u1 = imin(u1, g.img_w - 1); v1 = imin(v1, g.img_h - 1);
     const int ext = imax(u1 - u0, v1 - v0);                           /* extent - 1 */
     const int level = bit_length(ext);                                /* 2^level >= extent: the box spans <= 2 texels */
