@@ -144,7 +144,7 @@ int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const Pos
             const double py0 = Ri[1] * gy, py1 = Ri[4] * gy, py2 = Ri[7] * gy;
             int ilo = 0, ihi = m;
             if (use_clip) row_clip(g, Ri, ti, py0, py1, py2, pz0, pz1, pz2, ilo, ihi);
-            int rowv = UNIT_UNKNOWN;
+            int rowv = UNIT_UNKNOWN, itemv = UNIT_UNKNOWN;
             if (use_cert && ihi > ilo) {
                 const double gxa = voxel_centre(g.vs_x, ilo, g.origin[0]), gxb = voxel_centre(g.vs_x, ihi - 1, g.origin[0]);
                 rowv = unit_certificate(g, P, ((Ri[0] * gxa + py0) + pz0) + ti[0], ((Ri[3] * gxa + py1) + pz1) + ti[1], ((Ri[6] * gxa + py2) + pz2) + ti[2],
@@ -154,6 +154,13 @@ int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const Pos
                 if (rowv == UNIT_SKIP) { n_fast += ihi - ilo; continue; }
             }
             for (int x0 = ilo; x0 < ihi; x0 += 4) {
+                /* item-level certificate (128 voxels), like k_fuse_plan */
+                if (use_cert && rowv == UNIT_UNKNOWN && ((x0 - ilo) & 127) == 0) {
+                    const int xa = x0, xb = (xa + 127 < ihi - 1) ? xa + 127 : ihi - 1;
+                    const double gxa = voxel_centre(g.vs_x, xa, g.origin[0]), gxb = voxel_centre(g.vs_x, xb, g.origin[0]);
+                    itemv = unit_certificate(g, P, ((Ri[0] * gxa + py0) + pz0) + ti[0], ((Ri[3] * gxa + py1) + pz1) + ti[1], ((Ri[6] * gxa + py2) + pz2) + ti[2],
+                                             ((Ri[0] * gxb + py0) + pz0) + ti[0], ((Ri[3] * gxb + py1) + pz1) + ti[1], ((Ri[6] * gxb + py2) + pz2) + ti[2], fetch);
+                }
                 double cx[4], cy[4], cz[4];
                 for (int v = 0; v < 4; v++) {
                     const double gx = voxel_centre(g.vs_x, x0 + v, g.origin[0]);
@@ -161,7 +168,7 @@ int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const Pos
                     cy[v] = ((Ri[3] * gx + py1) + pz1) + ti[1];
                     cz[v] = ((Ri[6] * gx + py2) + pz2) + ti[2];
                 }
-                const int verdict = !use_cert ? UNIT_UNKNOWN : (rowv != UNIT_UNKNOWN ? rowv : unit_certificate(g, P, cx[0], cy[0], cz[0], cx[3], cy[3], cz[3], fetch));
+                const int verdict = !use_cert ? UNIT_UNKNOWN : (rowv != UNIT_UNKNOWN ? rowv : itemv != UNIT_UNKNOWN ? itemv : unit_certificate(g, P, cx[0], cy[0], cz[0], cx[3], cy[3], cz[3], fetch));
                 if (verdict == UNIT_SKIP) { n_fast += 4; continue; }
                 for (int v = 0; v < 4; v++) {
                     const size_t o = (((size_t)(k - g.ks0) * m + j) * m + x0 + v) * 2;

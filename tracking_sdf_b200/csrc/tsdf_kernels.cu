@@ -585,6 +585,8 @@ __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, CertPyramid P, 
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int cnt = 0, ilo = 0, ihi = 0, xs = 0, k = 0, j = 0, rowv = UNIT_UNKNOWN;
+    unsigned long long itemv = 0ull;                      /* per-item verdicts of a row judged item by item */
+    bool per_item = false;
     if (row < nrows) {
         k = g.ks0 + row / m; j = row - (row / m) * m;
         double Ri[9], ti[3];
@@ -603,11 +605,27 @@ __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, CertPyramid P, 
             const double ax = ((T[ilo] + T[3u * um + j]) + T[6u * um + k]) + ti[0], bx = ((T[ihi - 1] + T[3u * um + j]) + T[6u * um + k]) + ti[0];
             const double ay = ((T[um + ilo] + T[4u * um + j]) + T[7u * um + k]) + ti[1], by = ((T[um + ihi - 1] + T[4u * um + j]) + T[7u * um + k]) + ti[1];
             const double az = ((T[2u * um + ilo] + T[5u * um + j]) + T[8u * um + k]) + ti[2], bz = ((T[2u * um + ihi - 1] + T[5u * um + j]) + T[8u * um + k]) + ti[2];
-            rowv = unit_certificate(g, P, ax, ay, az, bx, by, bz, [&](int level, int x, int y, float& zf, float& zb) {
+            auto fetch = [&](int level, int x, int y, float& zf, float& zb) {
                 const float2 c = __ldg(&cert[P.off[level] + (size_t)y * P.w[level] + x]);
                 zf = c.x; zb = c.y;
-            });
+            };
+            rowv = unit_certificate(g, P, ax, ay, az, bx, by, bz, fetch);
             if (rowv == UNIT_SKIP && !check) cnt = 0;
+            if (rowv == UNIT_UNKNOWN) {
+                /* item-level certificates (128 voxels each): 2 bits per item; skipped items are not emitted */
+                const int n_items_row = cnt;
+                cnt = 0;
+                for (int c = 0; c < n_items_row; c++) {
+                    const int xa = xs + 128 * c, xb = min(xa + 127, ihi - 1);
+                    const double cax = ((T[xa] + T[3u * um + j]) + T[6u * um + k]) + ti[0], cbx = ((T[xb] + T[3u * um + j]) + T[6u * um + k]) + ti[0];
+                    const double cay = ((T[um + xa] + T[4u * um + j]) + T[7u * um + k]) + ti[1], cby = ((T[um + xb] + T[4u * um + j]) + T[7u * um + k]) + ti[1];
+                    const double caz = ((T[2u * um + xa] + T[5u * um + j]) + T[8u * um + k]) + ti[2], cbz = ((T[2u * um + xb] + T[5u * um + j]) + T[8u * um + k]) + ti[2];
+                    const int iv = unit_certificate(g, P, cax, cay, caz, cbx, cby, cbz, fetch);
+                    itemv |= (unsigned long long)iv << (2 * c);
+                    if (iv != UNIT_SKIP || check) cnt++;
+                }
+                per_item = true;
+            }
         }
     }
     /* warp-inclusive scan of cnt, one reservation per warp */
@@ -622,7 +640,15 @@ __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, CertPyramid P, 
     if (lane == 31 && total > 0) basei = atomicAdd(item_count, (unsigned int)total);
     basei = __shfl_sync(0xffffffffu, basei, 31);
     unsigned int o = basei + (unsigned int)(scan - cnt);
-    for (int c = 0; c < cnt; c++) items[o + c] = pack_item(k, j, xs + 128 * c, ilo, ihi) | ((unsigned long long)rowv << 61);
+    if (!per_item) {
+        for (int c = 0; c < cnt; c++) items[o + c] = pack_item(k, j, xs + 128 * c, ilo, ihi) | ((unsigned long long)rowv << 61);
+    } else {
+        const int n_items_row = (ihi - xs + 127) >> 7;
+        for (int c = 0; c < n_items_row; c++) {
+            const int iv = (int)(itemv >> (2 * c)) & 3;
+            if (iv != UNIT_SKIP || check) items[o++] = pack_item(k, j, xs + 128 * c, ilo, ihi) | ((unsigned long long)iv << 61);
+        }
+    }
 }
 
 __device__ __forceinline__ float4 ld_f4(const float4* p) { return *p; }
@@ -800,22 +826,49 @@ __global__ void __launch_bounds__(256) k_pyramid(CertPyramid P, float2* __restri
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int l = 7; l < CERT_LEVELS; l++) {
-        for (int t = tid; t < P.w[l] * P.h[l]; t += 256) {
-            const int X = t % P.w[l], Y = t / P.w[l];
-            float zf = PINF, zb = NINF;
-            for (int dy = 0; dy < 2; dy++)
-                for (int dx = 0; dx < 2; dx++) {
-                    const int x = 2 * X + dx, y = 2 * Y + dy;
-                    if (x < P.w[l - 1] && y < P.h[l - 1]) {
-                        const float2 c = __ldcg(&cert[P.off[l - 1] + (size_t)y * P.w[l - 1] + x]);
-                        zf = fminf(zf, c.x); zb = fmaxf(zb, c.y);
-                    }
-                }
-            cert[P.off[l] + (size_t)Y * P.w[l] + X] = make_float2(zf, zb);
-        }
-        __threadfence();
+    /* level 6 has at most a few hundred texels: stage it in shared memory (reusing s1) and reduce
+     * level by level there; only the results go to global memory */
+    float2* sbuf = &s1[0][0];                              /* 1024 float2: two ping-pong halves of 512 */
+    const int n6 = P.w[6] * P.h[6];
+    if (n6 <= 512) {
+        for (int t = tid; t < n6; t += 256) sbuf[t] = __ldcg(&cert[P.off[6] + t]);
         __syncthreads();
+        int src = 0;
+        for (int l = 7; l < CERT_LEVELS; l++) {
+            const float2* in = sbuf + src * 512;
+            float2* out = sbuf + (1 - src) * 512;
+            for (int t = tid; t < P.w[l] * P.h[l]; t += 256) {
+                const int X = t % P.w[l], Y = t / P.w[l];
+                float zf = PINF, zb = NINF;
+                for (int dy = 0; dy < 2; dy++)
+                    for (int dx = 0; dx < 2; dx++) {
+                        const int x = 2 * X + dx, y = 2 * Y + dy;
+                        if (x < P.w[l - 1] && y < P.h[l - 1]) { const float2 c = in[y * P.w[l - 1] + x]; zf = fminf(zf, c.x); zb = fmaxf(zb, c.y); }
+                    }
+                out[t] = make_float2(zf, zb);
+                cert[P.off[l] + t] = make_float2(zf, zb);
+            }
+            __syncthreads();
+            src = 1 - src;
+        }
+    } else {
+        for (int l = 7; l < CERT_LEVELS; l++) {
+            for (int t = tid; t < P.w[l] * P.h[l]; t += 256) {
+                const int X = t % P.w[l], Y = t / P.w[l];
+                float zf = PINF, zb = NINF;
+                for (int dy = 0; dy < 2; dy++)
+                    for (int dx = 0; dx < 2; dx++) {
+                        const int x = 2 * X + dx, y = 2 * Y + dy;
+                        if (x < P.w[l - 1] && y < P.h[l - 1]) {
+                            const float2 c = __ldcg(&cert[P.off[l - 1] + (size_t)y * P.w[l - 1] + x]);
+                            zf = fminf(zf, c.x); zb = fmaxf(zb, c.y);
+                        }
+                    }
+                cert[P.off[l] + (size_t)Y * P.w[l] + X] = make_float2(zf, zb);
+            }
+            __threadfence();
+            __syncthreads();
+        }
     }
     if (tid == 0) *ticket = 0u;
 }
