@@ -48,6 +48,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
+    capture summary (profiles/ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(key)
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -219,11 +229,14 @@ def dense_fuse_bench(T, m, K, reps, hbm):
         g.enqueue_frame(dev, track=0, slot=0)
     ms = g.stage_timing_end()
     upd = g.total_updates()
+    rmw_ms = g.debug_stream_rmw(10)           # plain RMW stream over the store: the practical ceiling
     g.dev_free(dev); g.close()
     t_fuse = float(ms[:, 2].mean()) * 1e-3
     per_launch = upd / reps
     ach = 16.0 * per_launch / t_fuse / 1e9
-    return {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+    return {"bound": "hbm", "kernel": "k_fuse_cert (row-certified free space: pure read-modify-write of the store)",
+            "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": ncu_traffic("fuse_dense"),
+            "rmw_stream_ceiling_ms": rmw_ms, "rmw_stream_ceiling_gbs": 16.0 * m ** 3 / (rmw_ms * 1e-3) / 1e9,
             "ms_per_launch": t_fuse * 1e3, "voxels_updated_per_launch": per_launch, "all_voxels_updated": bool(per_launch == m ** 3),
             "voxel_updates_per_s": per_launch / t_fuse}
 
@@ -296,11 +309,13 @@ def main_cuda(args):
     ach = 16.0 * upd_per_frame / t_fuse / 1e9
     n_valid = last_st["n_valid"]
     gather = 832.0 * n_valid * GN_ITERS / t_track / 1e9
-    roof_fuse = {"bound": "hbm", "kernel": "k_fuse", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                 "traffic": None, "peak_source": peak_src, "ms_per_launch": t_fuse * 1e3,
+    roof_fuse = {"bound": "hbm", "kernel": "fusion stage (k_fuse_tables + k_fuse_plan + k_fuse_cert + k_fuse_exact)", "achieved": ach, "peak": hbm,
+                 "unit": "GB/s", "frac": ach / hbm, "traffic": ncu_traffic("fuse_trajectory"), "peak_source": peak_src, "ms_per_launch": t_fuse * 1e3,
                  "voxels_updated_per_launch": upd_per_frame, "voxel_updates_per_s": upd_per_frame / t_fuse,
                  "voxels_visited_per_s": m ** 3 / t_fuse,
-                 "note": "algorithmic bytes = 16 B x voxels updated (read+write D,W); skipped voxels move no bytes"}
+                 "note": "algorithmic bytes = 16 B x voxels updated (read+write D,W); skipped voxels move no bytes. On this workload only ~5 % of the "
+                         "134 M voxels are in view, so the stage is bound by certificate/fp64 latency on in-view voxels, not by HBM: see dense_fuse for the "
+                         "HBM-bound case (every voxel updated), which is where north_star's >= 70 % target is defined"}
     roof_track = {"bound": "l2-gather-latency", "kernel": "k_linearize", "achieved": gather, "peak": hbm, "unit": "GB/s",
                   "frac": gather / hbm, "ms_per_launch": t_track * 1e3 / GN_ITERS, "launches_per_frame": GN_ITERS,
                   "note": "832 B gathered per valid pixel-iteration (13 samples x 8 neighbours x {D,W}); working set is L2-resident, "
@@ -462,7 +477,7 @@ def main_sharded(args):
                                   "(BASELINE.json configs[2]/[3])" % (m, n_gpus, GN_ITERS),
                       "slab_rank0": {"own": [ko0, ko1], "stored": [ks0, ks1]}, "grid_bytes_total": 8 * m ** 3,
                       "l2": "inputs larger than L2; no flush", "exchange": "30 doubles per GN iteration, in-kernel NVLink peer stores, rank-order sum"},
-           "roofline": {"bound": "hbm", "kernel": "k_fuse_items", "achieved": ach, "peak": hbm * n_gpus, "unit": "GB/s", "frac": ach / (hbm * n_gpus),
+           "roofline": {"bound": "hbm", "kernel": "fusion stage (k_fuse_tables + k_fuse_plan + k_fuse_cert + k_fuse_exact)", "achieved": ach, "peak": hbm * n_gpus, "unit": "GB/s", "frac": ach / (hbm * n_gpus),
                         "traffic": None, "peak_source": peak_src + " x n_gpus", "ms_per_launch": t_fuse_max * 1e3,
                         "voxels_updated_per_launch": upd_per_frame},
            "stage_ms": {"prep": t_prep * 1e3, "track_max_over_ranks": t_track_max * 1e3, "fuse_max_over_ranks": t_fuse_max * 1e3},
