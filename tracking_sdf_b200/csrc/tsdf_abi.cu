@@ -30,6 +30,7 @@ struct Impl {
     float2* grid = nullptr;
     int64_t n_stored = 0;
     PixRec* pix = nullptr;
+    float4* pts = nullptr;
     float* depth_stage = nullptr;
     PoseState* pose_dev = nullptr;
     PoseState* pose_pin = nullptr;          /* pinned: D2H landing zone for track results */
@@ -156,7 +157,7 @@ tsdf_status stage_depth(Impl* p, const float* depth, int mem, const float** dptr
 LinearizeArgs lin_args(Impl* p, int do_update, bool debug) {
     LinearizeArgs a;
     a.g = p->g;
-    a.grid = p->grid; a.pix = p->pix; a.pose = p->pose_dev;
+    a.grid = p->grid; a.pix = p->pix; a.pts = p->pts; a.pose = p->pose_dev;
     a.partials = p->partials; a.ticket = p->ticket;
     a.group_ticket = p->ticket + 1; a.group_partials = p->group_partials;
     a.dbgJ = debug ? p->dbgJ : nullptr; a.dbgPsi = debug ? p->dbgPsi : nullptr; a.dbgFlag = debug ? p->dbgFlag : nullptr;
@@ -168,7 +169,7 @@ LinearizeArgs lin_args(Impl* p, int do_update, bool debug) {
 }
 
 void enqueue_prep(Impl* p, const float* dptr, int reset_track) {
-    launch_prep(p->g, dptr, p->pix, p->cert + p->pyr.off[0], p->pose_dev, reset_track, p->stream);
+    launch_prep(p->g, dptr, p->pix, p->cert + p->pyr.off[0], p->pts, p->pose_dev, reset_track, p->stream);
     launch_pyramid(p->pyr, p->cert, p->ticket + 1000, p->stream);
     p->launches += 2;
 }
@@ -295,6 +296,7 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     A(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     A(cudaMalloc(&p->grid, (size_t)p->n_stored * sizeof(float2)));
     A(cudaMalloc(&p->pix, npx * sizeof(PixRec)));
+    A(cudaMalloc(&p->pts, (size_t)P * sizeof(float4)));
     A(cudaMalloc(&p->depth_stage, npx * sizeof(float)));
     A(cudaMalloc(&p->pose_dev, sizeof(PoseState)));
     A(cudaMallocHost(&p->pose_pin, sizeof(PoseState)));
@@ -342,13 +344,9 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     const int sms = prop.multiProcessorCount;
-    /* K2: one resident wave; every block a contiguous run of pixels (multiple of 16) */
-    int lb = linearize_blocks_per_sm();
-    if (lb < 1) lb = 1;
-    int nb = sms * lb;
-    int ppb = (P + nb - 1) / nb;
-    ppb = ((ppb + 15) / 16) * 16;
-    nb = (P + ppb - 1) / ppb;
+    /* K2: one block per LIN_TW x LIN_TH tile of the strided pixel grid */
+    const int ppb = LIN_TW * LIN_TH;
+    const int nb = ((p->g.ni + LIN_TW - 1) / LIN_TW) * ((p->g.nj + LIN_TH - 1) / LIN_TH);
     if ((nb + LIN_GROUP - 1) / LIN_GROUP > 1000) { g_err = "image too large for the reduction tree"; tsdf_destroy(reinterpret_cast<tsdf_handle>(p)); return TSDF_ERR_BAD_ARG; }
     p->px_per_block = ppb; p->lin_blocks = nb;
     A(cudaMalloc(&p->partials, (size_t)nb * LIN_PARTIAL_STRIDE * sizeof(double)));
@@ -374,7 +372,7 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     for (void* q : p->ipc_opened) cudaIpcCloseMemHandle(q);
-    cudaFree(p->grid); cudaFree(p->pix); cudaFree(p->depth_stage); cudaFree(p->pose_dev);
+    cudaFree(p->grid); cudaFree(p->pix); cudaFree(p->pts); cudaFree(p->depth_stage); cudaFree(p->pose_dev);
     cudaFreeHost(p->pose_pin); cudaFreeHost(p->ring_pin); cudaFree(p->partials); cudaFree(p->ticket);
     cudaFree(p->group_partials); cudaFree(p->fuse_tables); cudaFree(p->fuse_items); cudaFree(p->fuse_item_count);
     cudaFree(p->fuse_units); cudaFree(p->cert);

@@ -10,6 +10,7 @@ namespace tsdf {
 #define LIN_THREADS_DEF 256
 #endif
 constexpr int LIN_THREADS = LIN_THREADS_DEF;   /* 8 warps, 16 pixels per sweep */
+constexpr int LIN_TW = 8, LIN_TH = 10;      /* strided-pixel tile per block (columns x rows) = 80 pixels = 5 sweeps of 16 */
 constexpr int LIN_PARTIAL_STRIDE = 32;    /* doubles per block partial (30 used) */
 constexpr int MAX_WORLD = 16;
 #ifndef LIN_GROUP_DEF
@@ -43,6 +44,7 @@ struct LinearizeArgs {
     GridParams g;
     const float2* grid;
     const PixRec* pix;
+    const float4* pts;                     /* strided pixels back-projected by k_prep: x, y, z (NaN = invalid) */
     PoseState* pose;
     double* partials;                      /* nblk * LIN_PARTIAL_STRIDE */
     unsigned int* ticket;
@@ -55,7 +57,7 @@ struct LinearizeArgs {
     ShardLinks links;                      /* world = 1: no exchange */
 };
 
-void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, PoseState* pose, int reset_track, cudaStream_t s);
+void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, PoseState* pose, int reset_track, cudaStream_t s);
 void launch_pyramid(const CertPyramid& P, float2* cert, unsigned int* ticket, cudaStream_t s);
 /* exchange_mode: 0 none, 1 in-kernel mailbox all-reduce over peer memory (one kernel per
  * device, all running concurrently), 2 deferred (same-device shards: publish, then

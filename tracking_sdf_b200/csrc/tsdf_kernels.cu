@@ -38,7 +38,8 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
  * one 16-byte record out.  Thread 0 also re-arms the tracker state for the coming frame.
  * ------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restrict__ depth,
-                                              PixRec* __restrict__ pix, float2* __restrict__ cert0, PoseState* pose, int reset_track) {
+                                              PixRec* __restrict__ pix, float2* __restrict__ cert0, float4* __restrict__ pts,
+                                              PoseState* pose, int reset_track) {
     pdl_wait();
     pdl_release();
     const int u = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -64,11 +65,18 @@ __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restr
     float zf, zb;
     cert_pixel(g, kp, u, v, r, zf, zb);               /* level 0 of the fusion certificates */
     cert0[o] = make_float2(zf, zb);
+    /* the tracker's strided pixels (camera_tracking.cpp:162-163), back-projected once per frame,
+     * in the reference's loop order (column outer, row inner) */
+    if (u % g.stride == 0 && v % g.stride == 0) {
+        float x, y;
+        backproject_px(kp, u, v, r.z, x, y);
+        pts[(u / g.stride) * g.nj + v / g.stride] = make_float4(x, y, r.z, 0.0f);
+    }
 }
 
-void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, PoseState* pose, int reset_track, cudaStream_t s) {
+void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, PoseState* pose, int reset_track, cudaStream_t s) {
     dim3 grid((g.img_w + 31) / 32, (g.img_h + 7) / 8);
-    launch_pdl(k_prep, grid, dim3(256), s, g, depth, pix, cert0, pose, reset_track);
+    launch_pdl(k_prep, grid, dim3(256), s, g, depth, pix, cert0, pts, pose, reset_track);
 }
 
 /* organised cloud + normals for the accessor / tests */
@@ -341,29 +349,25 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     const double dm = (double)g.m;
     double off_x, off_y, off_z;
     sample_offsets(g, s, off_x, off_y, off_z);
-    const int P = g.ni * g.nj;
-    const float inv_nj = 1.0f / (float)g.nj;
-    const int p_begin = blockIdx.x * a.px_per_block;
-    const int p_end = min(P, p_begin + a.px_per_block);
+    /* each block owns a LIN_TW x LIN_TH tile of the strided pixel grid (columns x rows), so its
+     * samples touch a compact piece of the volume and share voxel lines in L1 */
+    const int tiles_y = (g.nj + LIN_TH - 1) / LIN_TH;
+    const int tile_x = blockIdx.x / tiles_y, tile_y = blockIdx.x - tile_x * tiles_y;
     double acc0 = 0.0, acc1 = 0.0;
 
-    for (int pb = p_begin; pb < p_end; pb += (LIN_THREADS / 32) * 2) {     /* warp-uniform trip count */
-        const int p = pb + warp * 2 + grp;
-        const bool have = p < p_end;
-        float z = __int_as_float(0x7fc00000);
-        int u = 0, v = 0;
+    for (int t0 = 0; t0 < LIN_TW * LIN_TH; t0 += (LIN_THREADS / 32) * 2) {  /* warp-uniform trip count */
+        const int t = t0 + warp * 2 + grp;
+        const int ii = tile_x * LIN_TW + t / LIN_TH, jj = tile_y * LIN_TH + t % LIN_TH;
+        const bool have = (t < LIN_TW * LIN_TH) & (ii < g.ni) & (jj < g.nj);
+        const int p = ii * g.nj + jj;                                        /* reference loop order, camera_tracking.cpp:162-163 */
+        float x = 0.0f, y = 0.0f, z = __int_as_float(0x7fc00000);
         if (have) {
-            int ii = __float2int_rz(((float)p + 0.5f) * inv_nj);            /* p / nj for p < 2^22 */
-            int jj = p - ii * g.nj;
-            if (jj < 0) { ii--; jj += g.nj; } else if (jj >= g.nj) { ii++; jj -= g.nj; }
-            u = ii * g.stride; v = jj * g.stride;                            /* camera_tracking.cpp:162-163 */
-            z = __ldg(&a.pix[(size_t)v * g.img_w + u].z);
+            const float4 pt = __ldg(&a.pts[p]);                              /* back-projected by k_prep; z = NaN when invalid */
+            x = pt.x; y = pt.y; z = pt.z;
         }
         const bool valid_pt = have && (z == z);                              /* camera_tracking.cpp:168 */
         float val = 0.0f;
         bool ok = true, oob = false, mine = true;
-        float x = 0.0f, y = 0.0f;
-        if (valid_pt) backproject_px(kp, u, v, z, x, y);
         if (sharded && valid_pt) {
             /* pixel owner = the slab holding the centre sample's base cell */
             const double wz = ((sM[0][6] * (double)x + sM[0][7] * (double)y) + sM[0][8] * (double)z) + sT[2];
