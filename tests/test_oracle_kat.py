@@ -347,3 +347,16 @@ def test_tracking_follows_ground_truth(frames, K):
         _, t = o.get_pose()
         assert np.linalg.norm(t - ts[f]) < 0.06
     o.close()
+
+
+def test_ate_tool_alignment():
+    # tools/evaluate_ate.py (TUM-style ATE for the trajectory the node writes, sdf_reconstruction.cpp:4-17)
+    from tools import evaluate_ate as E
+    rng = np.random.default_rng(0)
+    gt = rng.normal(size=(50, 3))
+    th = 0.3
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    est = (gt - 0.5) @ R.T
+    assert E.ate_rmse(est, gt)[0] < 1e-12 and E.ate_rmse(est, gt, do_align=False)[0] > 0.5
+    noisy = gt + 0.01
+    assert E.ate_rmse(noisy, gt, do_align=False)[0] == pytest.approx(0.01 * np.sqrt(3), rel=1e-9)
