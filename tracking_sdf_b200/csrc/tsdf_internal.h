@@ -6,9 +6,11 @@
 
 namespace tsdf {
 
-constexpr int LIN_WARPS = 13;               /* one warp per SDF sample of a pixel (camera_tracking.cpp:269-361) */
-constexpr int LIN_THREADS = LIN_WARPS * 32; /* lane = pixel, warp = sample */
-constexpr int LIN_TW = 8, LIN_TH = 8;       /* strided-pixel tile per block (columns x rows) = 64 pixels = 2 batches of 32 */
+#ifndef LIN_THREADS_DEF
+#define LIN_THREADS_DEF 256
+#endif
+constexpr int LIN_THREADS = LIN_THREADS_DEF;   /* 8 warps, 16 pixels per sweep */
+constexpr int LIN_TW = 8, LIN_TH = 10;      /* strided-pixel tile per block (columns x rows) = 80 pixels = 5 sweeps of 16 */
 constexpr int LIN_PARTIAL_STRIDE = 32;    /* doubles per block partial (30 used) */
 constexpr int MAX_WORLD = 16;
 #ifndef LIN_GROUP_DEF
@@ -23,7 +25,7 @@ constexpr int FUSE_THREADS = 128;
 #define CERT_MIN_BLOCKS 8
 #endif
 #ifndef LIN_MIN_BLOCKS
-#define LIN_MIN_BLOCKS 2
+#define LIN_MIN_BLOCKS 3
 #endif
 
 /* cross-shard exchange of the reduced normal equations (one slot per rank, double-buffered

@@ -308,10 +308,6 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     __shared__ double sT[3];
     __shared__ double sRed[(LIN_THREADS / 32) < 4 ? 4 : (LIN_THREADS / 32)][32];   /* also the GN step's scratch (>= 128 doubles) */
     __shared__ double sSums[32];
-    __shared__ float sVal[13][32];                         /* phase A: sample values of the batch */
-    __shared__ float sX[7][32];                            /* phase B: J0..J5, psi */
-    __shared__ unsigned sOk[13];
-    __shared__ unsigned sMask[3];
     __shared__ int sLast;
     __shared__ int sMiss;
 
@@ -340,34 +336,27 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     }
     __syncthreads();
 
-    /* ---- pixel loop.  Mapping: lane = pixel, warp = sample (13 warps: centre, +-x, +-y, +-z voxel
-     * steps, six perturbed rotations), so all 32 lanes of every warp do useful, uniform work and
-     * neighbouring lanes (neighbouring pixels) gather from neighbouring voxels.  A block owns a
-     * LIN_TW x LIN_TH tile of the strided pixel grid, processed in batches of 32 pixels:
-     *   phase A  warp s samples the SDF for the batch's 32 pixels (tsdf_core.cuh:interpolate_distance)
-     *   phase B  warps 0..5 form J_a = (plus - minus) / step in fp32, flags are combined
-     *   phase C  warp w accumulates its reduction slots {w, w+13, w+26} in double, lane = pixel
-     * and at the end each warp reduces its slots over its lanes with a fixed shuffle tree. */
-    const int s = warp;                                   /* sample index of this warp */
+    const int grp = lane >> 4, s = lane & 15, base = grp << 4;
+    const int a0 = c_slot_a[s], b0 = c_slot_b[s];
+    const int a1 = c_slot_a[s + 16], b1 = c_slot_b[s + 16], k1 = c_slot_k[s + 16];
+    const K1Params kp = k1_params(g.K);
+    const float step = (s == 0) ? g.v_h2_width : (s == 1) ? g.v_h2_height : (s == 2) ? g.v_h2_depth : g.two_w_h;
     const double* M = sM[(s < 7) ? 0 : (s - 6)];
     int miss = 0;
     GridFetch fetch{a.grid, g.m, g.ks0, g.ks1, &miss};
+
     const bool sharded = (g.ko0 > 0 || g.ko1 < g.m);
     const double dm = (double)g.m;
     double off_x, off_y, off_z;
     sample_offsets(g, s, off_x, off_y, off_z);
-    const float step = (warp == 0) ? g.v_h2_width : (warp == 1) ? g.v_h2_height : (warp == 2) ? g.v_h2_depth : g.two_w_h;
-    /* slots owned by this warp */
-    const int sl0 = warp, sl1 = warp + LIN_WARPS, sl2 = warp + 2 * LIN_WARPS;
-    const int a0 = c_slot_a[sl0], b0 = c_slot_b[sl0];
-    const int a1 = c_slot_a[sl1], b1 = c_slot_b[sl1];
-    const int a2 = sl2 < 32 ? c_slot_a[sl2] : 0, b2 = sl2 < 32 ? c_slot_b[sl2] : 0, k2 = sl2 < 32 ? c_slot_k[sl2] : 3;
+    /* each block owns a LIN_TW x LIN_TH tile of the strided pixel grid (columns x rows), so its
+     * samples touch a compact piece of the volume and share voxel lines in L1 */
     const int tiles_y = (g.nj + LIN_TH - 1) / LIN_TH;
     const int tile_x = blockIdx.x / tiles_y, tile_y = blockIdx.x - tile_x * tiles_y;
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    double acc0 = 0.0, acc1 = 0.0;
 
-    for (int t0 = 0; t0 < LIN_TW * LIN_TH; t0 += 32) {
-        const int t = t0 + lane;
+    for (int t0 = 0; t0 < LIN_TW * LIN_TH; t0 += (LIN_THREADS / 32) * 2) {  /* warp-uniform trip count */
+        const int t = t0 + warp * 2 + grp;
         const int ii = tile_x * LIN_TW + t / LIN_TH, jj = tile_y * LIN_TH + t % LIN_TH;
         const bool have = (t < LIN_TW * LIN_TH) & (ii < g.ni) & (jj < g.nj);
         const int p = ii * g.nj + jj;                                        /* reference loop order, camera_tracking.cpp:162-163 */
@@ -377,7 +366,8 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
             x = pt.x; y = pt.y; z = pt.z;
         }
         const bool valid_pt = have && (z == z);                              /* camera_tracking.cpp:168 */
-        bool mine = true;
+        float val = 0.0f;
+        bool ok = true, oob = false, mine = true;
         if (sharded && valid_pt) {
             /* pixel owner = the slab holding the centre sample's base cell */
             const double wz = ((sM[0][6] * (double)x + sM[0][7] * (double)y) + sM[0][8] * (double)z) + sT[2];
@@ -386,72 +376,61 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
             kc = kc < 0 ? 0 : (kc > g.m - 1 ? g.m - 1 : kc);
             mine = (kc >= g.ko0 && kc < g.ko1);
         }
-        /* ---- phase A */
-        float val = 0.0f;
-        bool ok = false, oob = false;
-        if (valid_pt && mine) {
-            double vx, vy, vz;
-            sample_coords_off(g, M, sT, off_x, off_y, off_z, (double)x, (double)y, (double)z, vx, vy, vz);
-            /* camera_tracking.cpp:261-268: only the centre sample's (s = 0) verdict is used */
-            oob = (fmin(fmin(vx, vy), vz) < 0.0) | (fmax(fmax(vx, vy), vz) >= dm);
-            bool is_interp;
-            val = interpolate_distance(vx, vy, vz, fetch, is_interp);
-            ok = is_interp;
+        if (s < 13) {
+            ok = false;
+            if (valid_pt && mine) {
+                double vx, vy, vz;
+                sample_coords_off(g, M, sT, off_x, off_y, off_z, (double)x, (double)y, (double)z, vx, vy, vz);
+                /* camera_tracking.cpp:261-268: only the centre sample's (s = 0) verdict is used */
+                oob = (fmin(fmin(vx, vy), vz) < 0.0) | (fmax(fmax(vx, vy), vz) >= dm);
+                bool is_interp;
+                val = interpolate_distance(vx, vy, vz, fetch, is_interp);
+                ok = is_interp;
+            }
         }
-        sVal[s][lane] = val;
         const unsigned okb = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) sOk[s] = okb;
-        if (s == 0) {
-            const unsigned vb = __ballot_sync(0xffffffffu, valid_pt), ob = __ballot_sync(0xffffffffu, oob), mb = __ballot_sync(0xffffffffu, mine);
-            if (lane == 0) { sMask[0] = vb; sMask[1] = ob; sMask[2] = mb; }
-        }
-        __syncthreads();
-        /* ---- phase B: J_a = (plus - minus) / step in fp32, camera_tracking.cpp:286,301,316,331,346,361 */
-        unsigned allok = 0xffffffffu;
-#pragma unroll
-        for (int q = 0; q < 13; q++) allok &= sOk[q];
-        const bool p_valid = (sMask[0] >> lane) & 1u, p_oob = (sMask[1] >> lane) & 1u, p_mine = (sMask[2] >> lane) & 1u;
-        const int flag = !p_valid ? 0 : (!p_mine ? 4 : (p_oob ? 2 : (((allok >> lane) & 1u) ? 1 : 3)));
-        if (warp < 6) {
-            const float Ja = (sVal[2 * warp + 1][lane] - sVal[2 * warp + 2][lane]) / step;
-            sX[warp][lane] = Ja;
-            if (a.dbgFlag && have) a.dbgJ[(size_t)p * 6 + warp] = (flag == 1) ? Ja : 0.0f;
-        } else if (warp == 6) {
-            const float psi = sVal[0][lane];
-            sX[6][lane] = psi;
-            if (a.dbgFlag && have) a.dbgPsi[p] = (flag == 1) ? psi : 0.0f;
-        } else if (warp == 7) {
-            if (a.dbgFlag && have) a.dbgFlag[p] = (uint8_t)flag;
-        }
-        __syncthreads();
-        /* ---- phase C: A += J J^T, b += psi J (camera_tracking.cpp:178-182), exact products, double sums */
-        if (flag == 1) {
-            acc0 = acc0 + (double)sX[a0][lane] * (double)sX[b0][lane];
-            acc1 = acc1 + (double)sX[a1][lane] * (double)sX[b1][lane];
-            if (k2 == 0) acc2 = acc2 + (double)sX[a2][lane] * (double)sX[b2][lane];
-            else if (k2 == 1) acc2 = acc2 + 1.0;
+        const unsigned oobb = __ballot_sync(0xffffffffu, oob && s == 0);
+        const bool allok = ((okb >> base) & 0xffffu) == 0xffffu;
+        const bool is_oob = ((oobb >> base) & 1u) != 0u;
+        const int flag = !valid_pt ? 0 : (!mine ? 4 : (is_oob ? 2 : (allok ? 1 : 3)));
+
+        /* J_a = (plus - minus) / step  in fp32, camera_tracking.cpp:286,301,316,331,346,361 */
+        const int sa = (s < 6) ? s : 0;
+        const float vplus = __shfl_sync(0xffffffffu, val, base + 2 * sa + 1);
+        const float vminus = __shfl_sync(0xffffffffu, val, base + 2 * sa + 2);
+        const float psi = __shfl_sync(0xffffffffu, val, base);
+        const float Ja = (vplus - vminus) / step;
+        const float xv = (s < 6) ? Ja : psi;                                 /* lane 6 (and up) holds psi */
+        const double xa0 = (double)__shfl_sync(0xffffffffu, xv, base + a0);
+        const double xb0 = (double)__shfl_sync(0xffffffffu, xv, base + b0);
+        const double xa1 = (double)__shfl_sync(0xffffffffu, xv, base + a1);
+        const double xb1 = (double)__shfl_sync(0xffffffffu, xv, base + b1);
+        if (flag == 1) {                                                     /* camera_tracking.cpp:178-182 */
+            acc0 = acc0 + xa0 * xb0;
+            if (k1 == 0) acc1 = acc1 + xa1 * xb1; else if (k1 == 1) acc1 = acc1 + 1.0;
         } else if (flag == 2) {
-            if (k2 == 2) acc2 = acc2 + 1.0;
+            if (k1 == 2) acc1 = acc1 + 1.0;
         }
-        /* the next batch's phase A writes sVal/sOk only after every warp passed this point's reads of
-         * sX (next __syncthreads is after phase A) — sVal/sOk/sMask were last read before the previous barrier */
+        if (a.dbgFlag && have) {
+            if (s < 6) a.dbgJ[(size_t)p * 6 + s] = (flag == 1) ? Ja : 0.0f;
+            else if (s == 6) a.dbgPsi[p] = (flag == 1) ? psi : 0.0f;
+            else if (s == 7) a.dbgFlag[p] = (uint8_t)flag;
+        }
     }
     if (miss) sMiss = 1;
     if (a.dbg_times && tid == 0) atomicMax(&a.dbg_times[1], gtime());
 
-    /* lanes (pixels) -> warp, fixed shuffle tree; every slot is owned by exactly one warp */
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        acc0 = acc0 + __shfl_xor_sync(0xffffffffu, acc0, o);
-        acc1 = acc1 + __shfl_xor_sync(0xffffffffu, acc1, o);
-        acc2 = acc2 + __shfl_xor_sync(0xffffffffu, acc2, o);
-    }
-    if (lane == 0) {
-        double* out = a.partials + (size_t)blockIdx.x * LIN_PARTIAL_STRIDE;
-        out[sl0] = acc0; out[sl1] = acc1;
-        if (sl2 < 32) out[sl2] = acc2;
-    }
+    /* half-warps -> warp -> block partial (fixed order) */
+    acc0 = acc0 + __shfl_xor_sync(0xffffffffu, acc0, 16);
+    acc1 = acc1 + __shfl_xor_sync(0xffffffffu, acc1, 16);
+    if (lane < 16) { sRed[warp][lane] = acc0; sRed[warp][lane + 16] = acc1; }
     __syncthreads();
+    if (tid < 32) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < LIN_THREADS / 32; w++) v = v + sRed[w][tid];
+        a.partials[(size_t)blockIdx.x * LIN_PARTIAL_STRIDE + tid] = v;
+    }
     if (tid == 0 && sMiss) atomicAdd(&pose->halo_miss, 1);
 
     /* ---- level 1: the last block of each group of LIN_GROUP blocks sums the group (fixed order) */
