@@ -10,7 +10,13 @@ namespace tsdf {
 #define LIN_THREADS_DEF 256
 #endif
 constexpr int LIN_THREADS = LIN_THREADS_DEF;   /* 8 warps, 16 pixels per sweep */
-constexpr int LIN_TW = 8, LIN_TH = 10;      /* strided-pixel tile per block (columns x rows) = 80 pixels = 5 sweeps of 16 */
+#ifndef LIN_TW_DEF
+#define LIN_TW_DEF 8
+#endif
+#ifndef LIN_TH_DEF
+#define LIN_TH_DEF 10
+#endif
+constexpr int LIN_TW = LIN_TW_DEF, LIN_TH = LIN_TH_DEF;      /* strided-pixel tile per block (columns x rows) = 80 pixels = 5 sweeps of 16 */
 constexpr int LIN_PARTIAL_STRIDE = 32;    /* doubles per block partial (30 used) */
 constexpr int MAX_WORLD = 16;
 #ifndef LIN_GROUP_DEF
