@@ -29,8 +29,20 @@ struct Impl {
     bool own_stream = true;
     float2* grid = nullptr;
     int64_t n_stored = 0;
+    /* per-frame records, double-buffered: frame n+1 is preprocessed on prep_stream while frame n
+     * is still being tracked and fused.  pix/pts/cert point at the current frame's buffers. */
     PixRec* pix = nullptr;
     float4* pts = nullptr;
+    PixRec* pix_buf[2] = {nullptr, nullptr};
+    float4* pts_buf[2] = {nullptr, nullptr};
+    float2* cert_buf[2] = {nullptr, nullptr};
+    cudaStream_t prep_stream = nullptr;
+    cudaEvent_t prepped[2] = {nullptr, nullptr};      /* records of buffer b are complete          */
+    cudaEvent_t rec_free[2] = {nullptr, nullptr};     /* every consumer of buffer b has finished   */
+    cudaEvent_t depth_copied = nullptr;               /* synchronous-API H2D of the depth image    */
+    cudaEvent_t depth_ready = nullptr, depth_done = nullptr;   /* optional events for the next enqueue_prep */
+    unsigned long long prep_seq = 0;
+    int lin_first = 0;
     float* depth_stage = nullptr;
     PoseState* pose_dev = nullptr;
     PoseState* pose_pin = nullptr;          /* pinned: D2H landing zone for track results */
@@ -150,6 +162,8 @@ tsdf_status stage_depth(Impl* p, const float* depth, int mem, const float** dptr
     if (mem == TSDF_DEVICE) { *dptr = depth; return TSDF_OK; }
     const size_t bytes = (size_t)p->g.img_w * p->g.img_h * sizeof(float);
     CK(cudaMemcpyAsync(p->depth_stage, depth, bytes, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaEventRecord(p->depth_copied, p->stream));
+    p->depth_ready = p->depth_copied;
     *dptr = p->depth_stage;
     return TSDF_OK;
 }
@@ -163,19 +177,38 @@ LinearizeArgs lin_args(Impl* p, int do_update, bool debug) {
     a.dbgJ = debug ? p->dbgJ : nullptr; a.dbgPsi = debug ? p->dbgPsi : nullptr; a.dbgFlag = debug ? p->dbgFlag : nullptr;
     a.dbg_times = p->dbg_times;
     a.do_update = do_update;
+    a.first = 0;
     a.px_per_block = p->px_per_block;
     a.links = p->links;
     return a;
 }
 
+/* K1 on prep_stream into the other record buffer.  It depends only on the depth image, so it
+ * overlaps the previous frame's tracking tail and fusion; the main stream joins on `prepped`.
+ * Buffer b is reused two frames later: rec_free[b] (recorded on the main stream one call later)
+ * covers every consumer of it. */
 void enqueue_prep(Impl* p, const float* dptr, int reset_track) {
-    launch_prep(p->g, dptr, p->pix, p->cert + p->pyr.off[0], p->pts, p->pose_dev, reset_track, p->stream);
-    launch_pyramid(p->pyr, p->cert, p->ticket + 1000, p->stream);
+    const int b = (int)(p->prep_seq & 1ull);
+    cudaEventRecord(p->rec_free[b ^ 1], p->stream);              /* all work on the previous frame's records is enqueued */
+    if (p->prep_seq >= 2) cudaStreamWaitEvent(p->prep_stream, p->rec_free[b], 0);
+    if (p->depth_ready) cudaStreamWaitEvent(p->prep_stream, p->depth_ready, 0);
+    p->pix = p->pix_buf[b]; p->pts = p->pts_buf[b]; p->cert = p->cert_buf[b];
+    launch_prep(p->g, dptr, p->pix, p->cert + p->pyr.off[0], p->pts, p->prep_stream);
+    launch_pyramid(p->pyr, p->cert, p->ticket + 1000, p->prep_stream);
+    if (p->depth_done) cudaEventRecord(p->depth_done, p->prep_stream);
+    cudaEventRecord(p->prepped[b], p->prep_stream);
+    cudaStreamWaitEvent(p->stream, p->prepped[b], 0);
+    p->depth_ready = nullptr; p->depth_done = nullptr;
+    p->prep_seq++;
+    p->lin_first = reset_track;
     p->launches += 2;
 }
 void enqueue_linearize(Impl* p, int do_update, bool debug) {
     p->seqno++;
-    launch_linearize(lin_args(p, do_update, debug), p->lin_blocks, p->exchange_mode, p->seqno, p->stream);
+    LinearizeArgs a = lin_args(p, do_update, debug);
+    a.first = p->lin_first;
+    p->lin_first = 0;
+    launch_linearize(a, p->lin_blocks, p->exchange_mode, p->seqno, p->stream);
     p->launches++;
 }
 void enqueue_combine(Impl* p, int do_update) {
@@ -295,8 +328,15 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     A(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     A(cudaMalloc(&p->grid, (size_t)p->n_stored * sizeof(float2)));
-    A(cudaMalloc(&p->pix, npx * sizeof(PixRec)));
-    A(cudaMalloc(&p->pts, (size_t)P * sizeof(float4)));
+    A(cudaStreamCreateWithFlags(&p->prep_stream, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; q++) {
+        A(cudaMalloc(&p->pix_buf[q], npx * sizeof(PixRec)));
+        A(cudaMalloc(&p->pts_buf[q], (size_t)P * sizeof(float4)));
+        A(cudaEventCreateWithFlags(&p->prepped[q], cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&p->rec_free[q], cudaEventDisableTiming));
+    }
+    A(cudaEventCreateWithFlags(&p->depth_copied, cudaEventDisableTiming));
+    p->pix = p->pix_buf[0]; p->pts = p->pts_buf[0];
     A(cudaMalloc(&p->depth_stage, npx * sizeof(float)));
     A(cudaMalloc(&p->pose_dev, sizeof(PoseState)));
     A(cudaMallocHost(&p->pose_pin, sizeof(PoseState)));
@@ -314,7 +354,8 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
             p->pyr.off[l] = off;
             off += (int64_t)p->pyr.w[l] * p->pyr.h[l];
         }
-        A(cudaMalloc(&p->cert, (size_t)off * sizeof(float2)));
+        for (int q = 0; q < 2; q++) A(cudaMalloc(&p->cert_buf[q], (size_t)off * sizeof(float2)));
+        p->cert = p->cert_buf[0];
     }
     A(cudaMalloc(&p->n_upd_dev, 4 * sizeof(unsigned long long)));
     A(cudaMallocHost(&p->n_upd_pin, sizeof(unsigned long long)));
@@ -370,12 +411,20 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     if (!h) return TSDF_OK;
     Impl* p = I(h);
     cudaSetDevice(p->device);
+    if (p->prep_stream) cudaStreamSynchronize(p->prep_stream);
     if (p->stream) cudaStreamSynchronize(p->stream);
     for (void* q : p->ipc_opened) cudaIpcCloseMemHandle(q);
-    cudaFree(p->grid); cudaFree(p->pix); cudaFree(p->pts); cudaFree(p->depth_stage); cudaFree(p->pose_dev);
+    for (int q = 0; q < 2; q++) {
+        cudaFree(p->pix_buf[q]); cudaFree(p->pts_buf[q]); cudaFree(p->cert_buf[q]);
+        if (p->prepped[q]) cudaEventDestroy(p->prepped[q]);
+        if (p->rec_free[q]) cudaEventDestroy(p->rec_free[q]);
+    }
+    if (p->depth_copied) cudaEventDestroy(p->depth_copied);
+    if (p->prep_stream) cudaStreamDestroy(p->prep_stream);
+    cudaFree(p->grid); cudaFree(p->depth_stage); cudaFree(p->pose_dev);
     cudaFreeHost(p->pose_pin); cudaFreeHost(p->ring_pin); cudaFree(p->partials); cudaFree(p->ticket);
     cudaFree(p->group_partials); cudaFree(p->fuse_tables); cudaFree(p->fuse_items); cudaFree(p->fuse_item_count);
-    cudaFree(p->fuse_units); cudaFree(p->cert);
+    cudaFree(p->fuse_units);
     cudaFree(p->n_upd_dev); cudaFreeHost(p->n_upd_pin);
     cudaFree(p->dbgJ); cudaFree(p->dbgPsi); cudaFree(p->dbgFlag); cudaFree(p->mailbox);
     cudaFree(p->flush_buf); cudaFree(p->scratch_d);
@@ -532,10 +581,10 @@ tsdf_status tsdf_submit_frame(tsdf_handle h, const float* depth_host, int32_t tr
     if (p->submit_seq >= (unsigned long long)Impl::NSTAGE) CK(cudaStreamWaitEvent(p->copy_stream, p->consumed[b], 0));
     CK(cudaMemcpyAsync(p->stage[b], depth_host, bytes, cudaMemcpyHostToDevice, p->copy_stream));
     CK(cudaEventRecord(p->copied[b], p->copy_stream));
-    CK(cudaStreamWaitEvent(p->stream, p->copied[b], 0));
+    p->depth_ready = p->copied[b];               /* K1 waits for the copy and releases the stage buffer itself */
+    p->depth_done = p->consumed[b];
     tsdf_status st = enqueue_frame(p, p->stage[b], track != 0, true);
     if (st != TSDF_OK) return st;
-    CK(cudaEventRecord(p->consumed[b], p->stream));
     CK(cudaMemcpyAsync(&p->ring_pin[slot], p->pose_dev, sizeof(PoseState), cudaMemcpyDeviceToHost, p->stream));
     p->submit_seq++;
     return TSDF_OK;

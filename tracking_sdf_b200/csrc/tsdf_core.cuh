@@ -526,7 +526,10 @@ TSDF_HD int unit_certificate(const GridParams& g, const CertPyramid& P, double a
     int v0 = (int)floorf(fminf(va, vb)) - 1, v1 = (int)floorf(fmaxf(va, vb)) + 1;
     if (u1 < -1 || v1 < -1 || u0 > g.img_w || v0 > g.img_h) return UNIT_SKIP;   /* certainly outside the image, sdf.cpp:254 */
     const bool inside = (u0 >= 1) & (v0 >= 1) & (u1 <= g.img_w - 2) & (v1 <= g.img_h - 2);   /* strictly inside the border ring */
-    u0 = imax(u0, 0); v0 = imax(v0, 0); u1 = imin(u1, g.img_w - 1); v1 = imin(v1, g.img_h - 1);
+    /* clamp BOTH ends into the image: u1 = -1 / u0 = img_w (box touching the image from outside)
+     * pass the test above and must not index outside the pyramid */
+    u0 = imin(imax(u0, 0), g.img_w - 1); v0 = imin(imax(v0, 0), g.img_h - 1);
+    u1 = imax(imin(u1, g.img_w - 1), 0); v1 = imax(imin(v1, g.img_h - 1), 0);
     const int ext = imax(u1 - u0, v1 - v0);                           /* extent - 1 */
     const int level = bit_length(ext);                                /* 2^level >= extent: the box spans <= 2 texels */
     if (level >= CERT_LEVELS) return UNIT_UNKNOWN;
@@ -628,7 +631,7 @@ TSDF_HD void perturbed_rot(const GridParams& g, const double* rot, int q, double
 }
 
 /* slot layout of the reduced normal equations */
-enum { SLOT_A = 0, SLOT_B = 21, SLOT_RES = 27, SLOT_NVALID = 28, SLOT_NOOB = 29, N_SLOTS = 30 };
+enum { SLOT_A = 0, SLOT_B = 21, SLOT_RES = 27, SLOT_NVALID = 28, SLOT_NOOB = 29, N_SLOTS = 30, SLOT_MISS = 30 /* local, not exchanged */ };
 
 /* ---- 6x6 partial-pivot LU solve, stands in for Eigen's A.inverse()*b (camera_tracking.cpp:191) */
 /* one elimination column; C is a template parameter so that every array index below is a

@@ -59,11 +59,12 @@ struct LinearizeArgs {
     float* dbgJ; float* dbgPsi; uint8_t* dbgFlag;   /* optional per-pixel records */
     unsigned long long* dbg_times;         /* optional: globaltimer stamps of the kernel's phases */
     int32_t do_update;                     /* 1: solve + pose update in the last block */
+    int32_t first;                         /* 1: first launch of a frame (resets the per-frame tracking state) */
     int32_t px_per_block;
     ShardLinks links;                      /* world = 1: no exchange */
 };
 
-void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, PoseState* pose, int reset_track, cudaStream_t s);
+void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, cudaStream_t s);
 void launch_pyramid(const CertPyramid& P, float2* cert, unsigned int* ticket, cudaStream_t s);
 /* exchange_mode: 0 none, 1 in-kernel mailbox all-reduce over peer memory (one kernel per
  * device, all running concurrently), 2 deferred (same-device shards: publish, then

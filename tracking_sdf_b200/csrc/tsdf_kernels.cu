@@ -38,15 +38,11 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
  * one 16-byte record out.  Thread 0 also re-arms the tracker state for the coming frame.
  * ------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restrict__ depth,
-                                              PixRec* __restrict__ pix, float2* __restrict__ cert0, float4* __restrict__ pts,
-                                              PoseState* pose, int reset_track) {
+                                              PixRec* __restrict__ pix, float2* __restrict__ cert0, float4* __restrict__ pts) {
     pdl_wait();
     pdl_release();
     const int u = blockIdx.x * 32 + (threadIdx.x & 31);
     const int v = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (reset_track && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-        pose->iterations = 0; pose->stopped = 0; pose->singular = 0; pose->halo_miss = 0;
-    }
     if (u >= g.img_w || v >= g.img_h) return;
     const K1Params kp = k1_params(g.K);
     const size_t o = (size_t)v * g.img_w + u;
@@ -74,9 +70,9 @@ __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restr
     }
 }
 
-void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, PoseState* pose, int reset_track, cudaStream_t s) {
+void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, cudaStream_t s) {
     dim3 grid((g.img_w + 31) / 32, (g.img_h + 7) / 8);
-    launch_pdl(k_prep, grid, dim3(256), s, g, depth, pix, cert0, pts, pose, reset_track);
+    launch_pdl(k_prep, grid, dim3(256), s, g, depth, pix, cert0, pts);
 }
 
 /* organised cloud + normals for the accessor / tests */
@@ -315,7 +311,10 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     PoseState* pose = a.pose;
     pdl_wait();
     pdl_release();
-    if (a.do_update && pose->stopped) return;             /* loop condition of camera_tracking.cpp:79 */
+    /* a.first: first launch of a frame; the per-frame state (iterations, stopped, singular,
+     * halo_miss) is reset by the final block below, so the frame's preprocessing can run on
+     * another stream and never touches the pose block */
+    if (a.do_update && !a.first && pose->stopped) return;  /* loop condition of camera_tracking.cpp:79 */
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (a.dbg_times && tid == 0) atomicMin(&a.dbg_times[0], gtime());
@@ -429,9 +428,9 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < LIN_THREADS / 32; w++) v = v + sRed[w][tid];
+        if (tid == SLOT_MISS) v = sMiss ? 1.0 : 0.0;      /* blocks that needed a voxel outside the slab */
         a.partials[(size_t)blockIdx.x * LIN_PARTIAL_STRIDE + tid] = v;
     }
-    if (tid == 0 && sMiss) atomicAdd(&pose->halo_miss, 1);
 
     /* ---- level 1: the last block of each group of LIN_GROUP blocks sums the group (fixed order) */
     const int nb = gridDim.x;
@@ -471,6 +470,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     __syncthreads();
     if (!sLast) return;
     if (a.dbg_times && tid == 0) a.dbg_times[2] = gtime();
+    if (a.first && tid == 0) { pose->iterations = 0; pose->stopped = 0; pose->singular = 0; pose->halo_miss = 0; }
     __threadfence();
     {
         const int slot = tid & 31, sub = tid >> 5;
@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     }
     __syncthreads();
     if (a.dbg_times && tid == 0) a.dbg_times[3] = gtime();
+    if (tid == 0 && sSums[SLOT_MISS] > 0.0) atomicAdd(&pose->halo_miss, (int)sSums[SLOT_MISS]);
     if (exchange_mode == 1 && a.links.world > 1 && tid < 32) exchange_sums(a.links, seqno, sSums, tid, pose);
     if (exchange_mode == 2 && a.links.world > 1) {
         /* deferred (single-process emulation): publish our sums into every mailbox; a separate
