@@ -227,6 +227,7 @@ def dense_fuse_bench(T, m, K, reps, hbm):
     g.stage_timing_begin(reps)
     for _ in range(reps):
         g.enqueue_frame(dev, track=0, slot=0)
+        g.sync()      # the fusion launch is timed alone: without this the NEXT call's preprocessing (second stream) overlaps it
     ms = g.stage_timing_end()
     upd = g.total_updates()
     rmw_ms = g.debug_stream_rmw(10)           # plain RMW stream over the store: the practical ceiling

@@ -14,6 +14,8 @@
  *   estimate_new_position(sdf, cloud)                           estimate_new_position(sdf, depth)   camera_tracking.cpp:66-245
  *   sdf->update(camera_tracking, cloud, normals)                update(camera_tracking, depth)      sdf.cpp:224-315
  *   interpolate_distance(voxel_pt, is_interpolated)             interpolate_distance(...)       sdf.cpp:127-163
+ *   sdf->update(...) colour part (cloud's r,g,b)                update(camera_tracking, depth, rgb) sdf.cpp:294-304
+ *   interpolate_color(global_coords, color)                     interpolate_color(global, rgba) sdf.cpp:164-217
  *   get_array_index / get_voxel_coordinates / get_global_coordinates / get_number_of_voxels     sdf.h:107-157
  *   public rot, trans, rot_inv, rot_inv_trans, K, isKFilled     rot(), trans(), ... accessors
  *
@@ -85,6 +87,24 @@ public:
 
     /* sdf.cpp:224-315: integrate `depth` (host, float32 metres, row-major) at the tracker's current pose */
     inline int64_t update(CameraTracking* camera_tracking, const float* depth);
+
+    /* the same with the colour running mean (sdf.cpp:294-304); rgb = height*width*3 bytes, the r,g,b of the
+     * organised XYZRGB cloud the reference receives */
+    inline int64_t update(CameraTracking* camera_tracking, const float* depth, const uint8_t* rgb);
+
+    /* sdf.cpp:164-217: colour at a WORLD point; rgba[3] = 1 */
+    void interpolate_color(const double global_coords[3], float rgba[4]) const {
+        check(tsdf_interpolate_color(handle(), 1, global_coords, rgba));
+    }
+    void interpolate_color(int64_t n, const double* global_pts, float* rgba) const {
+        check(tsdf_interpolate_color(handle(), n, global_pts, rgba));
+    }
+    /* Color_W, R, G, B (sdf.h:49-52), reference layout */
+    void download_color(std::vector<float>& CW, std::vector<float>& R, std::vector<float>& G, std::vector<float>& B) const {
+        const size_t n = (size_t)get_number_of_voxels();
+        CW.resize(n); R.resize(n); G.resize(n); B.resize(n);
+        check(tsdf_download_color(handle(), CW.data(), R.data(), G.data(), B.data(), TSDF_LAYOUT_REFERENCE));
+    }
 
     /* the raw arrays the reference hands to its mesher (sdf.cpp:47-48), reference (z-fastest) layout */
     void download(std::vector<float>& D, std::vector<float>& W) const {
@@ -170,6 +190,13 @@ inline int64_t SDF::update(CameraTracking* camera_tracking, const float* depth) 
     if (!camera_tracking->isKFilled) throw Error(TSDF_ERR_NO_INTRINSICS, "Camera Matrix not received");   /* sdf.cpp:227-229 */
     int64_t n = 0;
     check(tsdf_fuse(handle(), depth, TSDF_HOST, nullptr, nullptr, &n));
+    return n;
+}
+
+inline int64_t SDF::update(CameraTracking* camera_tracking, const float* depth, const uint8_t* rgb) {
+    if (!camera_tracking->isKFilled) throw Error(TSDF_ERR_NO_INTRINSICS, "Camera Matrix not received");   /* sdf.cpp:227-229 */
+    int64_t n = 0;
+    check(tsdf_fuse_rgb(handle(), depth, rgb, TSDF_HOST, nullptr, nullptr, &n));
     return n;
 }
 

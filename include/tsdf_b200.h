@@ -132,6 +132,25 @@ tsdf_status tsdf_track_and_fuse(tsdf_handle h, const float* depth, int32_t mem,
                                 double R_out[9], double t_out[3],
                                 tsdf_track_stats* stats, int64_t* n_updated);
 
+/* ---- colour (the second half of SDF::update, sdf.cpp:294-304, and SDF::interpolate_color,
+ * sdf.cpp:164-217).  The colour store (Color_W, R, G, B: 16 B per voxel, sdf.cpp:14-17, initial
+ * values 0 / 0.4 / 0.4 / 0.4, sdf.cpp:30-34) is allocated by tsdf_enable_color; the *_rgb calls
+ * enable it implicitly.  rgb: height*width*3 bytes (the r,g,b of pcl::PointXYZRGB at (col,row)),
+ * registered to the depth image, in the same memory space as `depth`.  Only the point-to-plane
+ * metric has a colour update in the reference (it needs the normal); TSDF_ERR_BAD_ARG otherwise. */
+tsdf_status tsdf_enable_color(tsdf_handle h);
+tsdf_status tsdf_fuse_rgb(tsdf_handle h, const float* depth, const uint8_t* rgb, int32_t mem,
+                          const double R[9], const double t[3], int64_t* n_updated);
+tsdf_status tsdf_track_and_fuse_rgb(tsdf_handle h, const float* depth, const uint8_t* rgb, int32_t mem,
+                                    double R_out[9], double t_out[3],
+                                    tsdf_track_stats* stats, int64_t* n_updated);
+/* n WORLD points (host, n x 3 doubles) -> n x (r,g,b,a) floats (host), exactly as
+ * SDF::interpolate_color: interpolated values are scaled by 1/255, an exact voxel hit is not
+ * (sdf.cpp:193-198), nothing in range gives NaN. */
+tsdf_status tsdf_interpolate_color(tsdf_handle h, int64_t n, const double* global_pts, float* rgba);
+/* the four colour arrays of this handle's stored z range, same layouts as tsdf_download */
+tsdf_status tsdf_download_color(tsdf_handle h, float* color_w, float* r, float* g, float* b, int32_t layout);
+
 /* Asynchronous variant for streaming: enqueue track+fuse of a DEVICE-resident frame; the
  * pose of frame `slot` lands in an internal pinned ring (capacity tsdf_pose_ring_capacity)
  * and is read back after tsdf_sync with tsdf_read_pose_ring.  track = 0: fuse only. */

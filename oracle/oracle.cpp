@@ -85,6 +85,7 @@ struct Oracle {
     float v_h2_width, v_h2_height, v_h2_depth;           /* camera_tracking.cpp:15-17 */
     double origin[3];
     std::vector<float> D, W;                              /* sdf.cpp:10,13 */
+    std::vector<float> CW, R, G, B;                       /* sdf.cpp:14-17 Color_W,R,G,B (allocated by orc_enable_color) */
     std::vector<V3> global_coords;                        /* sdf.cpp:11 (optional) */
     double K[9];
     bool isKFilled;
@@ -232,8 +233,9 @@ static void backproject(const Oracle* o, const float* depth, float* cloud, float
     }
 }
 
-/* sdf.cpp:224-305, D/W part only (colour :294-304 out of scope) */
-static int64_t fuse_cloud(Oracle* o, const float* cloud, const float* normals) {
+/* sdf.cpp:224-305; the colour part (:294-304) runs when an RGB image is given (rgb: h*w*3 bytes, the
+ * r,g,b of pcl::PointXYZRGB at (col,row)) */
+static int64_t fuse_cloud(Oracle* o, const float* cloud, const float* normals, const uint8_t* rgb = nullptr) {
     const int Wd = o->cfg.image_width, Hd = o->cfg.image_height;
     const float distance_epsilon = o->cfg.distance_epsilon, distance_delta = o->cfg.distance_delta;
     const int metric = o->cfg.metric;
@@ -286,6 +288,21 @@ static int64_t fuse_cloud(Oracle* o, const float* cloud, const float* normals) {
         o->W[idx] = w_old + w_new;                                        /* sdf.cpp:290 */
         o->D[idx] = (w_old * o->D[idx] + w_new * d_new) / o->W[idx];      /* sdf.cpp:292 */
         n_updated++;
+        if (rgb && metric == 0) {
+            /* sdf.cpp:294-304.  cam_vect = (0,0,1) (:235); Eigen 3-vector reductions are c0 + (c1 + c2) */
+            const float* nm = normals + 3 * ((size_t)j_image * Wd + i_image);
+            const double nx = (double)nm[0], ny = (double)nm[1], nz = (double)nm[2];
+            const double dotv = 0.0 * nx + (0.0 * ny + 1.0 * nz);
+            const double norm = std::sqrt(nx * nx + (ny * ny + nz * nz));
+            const double cosine = std::fabs(dotv) / norm;                 /* :294 */
+            const uint8_t* c = rgb + 3 * ((size_t)j_image * Wd + i_image);
+            w_old = o->CW[idx];                                           /* :298 */
+            w_new = (float)(w_new * cosine);                              /* :299 float = float * double */
+            o->CW[idx] = w_old + w_new;                                   /* :300 */
+            o->R[idx] = (w_old * o->R[idx] + w_new * c[0]) / o->CW[idx];  /* :302-304, uint8 promoted to int then float */
+            o->G[idx] = (w_old * o->G[idx] + w_new * c[1]) / o->CW[idx];
+            o->B[idx] = (w_old * o->B[idx] + w_new * c[2]) / o->CW[idx];
+        }
     }
     return n_updated;
 }
@@ -531,6 +548,59 @@ void orc_reset(void* h) {
     const float d0 = o->cfg.width + o->cfg.height + o->cfg.depth;         /* sdf.cpp:29 */
 #pragma omp parallel for
     for (int64_t i = 0; i < o->number_of_voxels; i++) { o->D[i] = d0; o->W[i] = 0; }
+    if (!o->CW.empty()) {
+#pragma omp parallel for
+        for (int64_t i = 0; i < o->number_of_voxels; i++) { o->CW[i] = 0; o->R[i] = 0.4; o->G[i] = 0.4; o->B[i] = 0.4; }   /* sdf.cpp:30,32-34 */
+    }
+}
+
+void orc_enable_color(void* h) {
+    Oracle* o = (Oracle*)h;
+    if (!o->CW.empty()) return;
+    o->CW.assign(o->number_of_voxels, 0.0f);                              /* sdf.cpp:14-17, 30-34 */
+    o->R.assign(o->number_of_voxels, 0.4);
+    o->G.assign(o->number_of_voxels, 0.4);
+    o->B.assign(o->number_of_voxels, 0.4);
+}
+float* orc_color(void* h, int which) {
+    Oracle* o = (Oracle*)h;
+    if (o->CW.empty()) return nullptr;
+    return which == 0 ? o->CW.data() : which == 1 ? o->R.data() : which == 2 ? o->G.data() : o->B.data();
+}
+
+/* sdf.cpp:164-217 — colour at WORLD coordinates; out = r,g,b,a floats (std_msgs::ColorRGBA).  Quirks kept:
+ * the exact-hit early return leaves the value unscaled (0..255) while the interpolated value is divided
+ * by 255; nothing qualifying gives 0/0 = NaN. */
+static void interpolate_color(const Oracle* o, const V3& global, float out[4]) {
+    V3 vc = get_voxel_coordinates(o, global);                             /* :170 */
+    float i = (float)vc.x, j = (float)vc.y, k = (float)vc.z;              /* :172-174 */
+    float w_sum = 0.0f, aux = 0;
+    float r = 0.0f, g = 0.0f, b = 0.0f;                                   /* color.r/g/b are float32 */
+    out[3] = 1.0f;
+    float w = 0, volume;
+    for (int io = 0; io < 2; io++)
+        for (int jo = 0; jo < 2; jo++)
+            for (int ko = 0; ko < 2; ko++) {
+                const int ci = cast_int(i) + io, cj = cast_int(j) + jo, ck = cast_int(k) + ko;   /* :186-188 */
+                volume = std::fabs((float)ci - i) + std::fabs((float)cj - j) + std::fabs((float)ck - k);   /* :189 */
+                const int64_t a_idx = get_array_index(o, ci, cj, ck);
+                if (a_idx != -1 && o->CW[a_idx] > 0) {
+                    if (volume < 0.00001) { out[0] = o->R[a_idx]; out[1] = o->G[a_idx]; out[2] = o->B[a_idx]; return; }   /* :193-198 */
+                    w = (float)(1.0 / volume);                            /* :200 */
+                    w_sum += w;
+                    r += w * o->R[a_idx]; g += w * o->G[a_idx]; b += w * o->B[a_idx];
+                }
+            }
+    aux = (float)(w_sum * 255.0);                                         /* :210 */
+    out[0] = r / aux; out[1] = g / aux; out[2] = b / aux;
+}
+void orc_interpolate_color(void* h, int64_t n, const double* global_pts, float* rgba) {
+    Oracle* o = (Oracle*)h;
+#pragma omp parallel for
+    for (int64_t q = 0; q < n; q++) {
+        V3 gp = {global_pts[3 * q], global_pts[3 * q + 1], global_pts[3 * q + 2]};
+        interpolate_color(o, gp, rgba + 4 * q);
+    }
 }
 
 void orc_set_intrinsics(void* h, const double K[9]) {
@@ -563,6 +633,13 @@ int64_t orc_fuse_cloud(void* h, const float* cloud, const float* normals) {
     Oracle* o = (Oracle*)h;
     if (!o->isKFilled) return -1;                                         /* sdf.cpp:227-229 */
     return fuse_cloud(o, cloud, normals);
+}
+int64_t orc_fuse_rgb(void* h, const float* depth, const uint8_t* rgb) {
+    Oracle* o = (Oracle*)h;
+    if (!o->isKFilled || o->cfg.metric != 0) return -1;
+    orc_enable_color(h);
+    ensure_cloud(o, depth, true);
+    return fuse_cloud(o, o->cloud.data(), o->normals.data(), rgb);
 }
 int64_t orc_fuse(void* h, const float* depth) {
     Oracle* o = (Oracle*)h;

@@ -58,6 +58,10 @@ def lib():
     L.orc_backproject.argtypes = [vp, c_fp, c_fp, c_fp]
     L.orc_fuse.argtypes = [vp, c_fp]; L.orc_fuse.restype = ctypes.c_int64
     L.orc_fuse_cloud.argtypes = [vp, c_fp, c_fp]; L.orc_fuse_cloud.restype = ctypes.c_int64
+    L.orc_fuse_rgb.argtypes = [vp, c_fp, c_u8p]; L.orc_fuse_rgb.restype = ctypes.c_int64
+    L.orc_enable_color.argtypes = [vp]
+    L.orc_color.argtypes = [vp, ctypes.c_int]; L.orc_color.restype = c_fp
+    L.orc_interpolate_color.argtypes = [vp, ctypes.c_int64, c_dp, c_fp]
     L.orc_track.argtypes = [vp, c_fp, ctypes.POINTER(TrackStats)]
     L.orc_linearize.argtypes = [vp, c_fp, c_dp, c_dp, ctypes.POINTER(TrackStats)]
     L.orc_linearize_pixels.argtypes = [vp, c_fp, c_fp, c_fp, c_u8p]; L.orc_linearize_pixels.restype = ctypes.c_int32
@@ -153,6 +157,27 @@ class Oracle:
     def fuse(self, depth):
         depth = np.ascontiguousarray(depth, np.float32)
         return self.L.orc_fuse(self.h, _f(depth))
+
+    # sdf.cpp:224-305 with the colour running mean (:294-304); rgb: (h, w, 3) uint8
+    def fuse_rgb(self, depth, rgb):
+        depth = np.ascontiguousarray(depth, np.float32)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        assert rgb.shape[-1] == 3 and rgb.size == depth.size * 3
+        return self.L.orc_fuse_rgb(self.h, _f(depth), rgb.ctypes.data_as(c_u8p))
+
+    def enable_color(self):
+        self.L.orc_enable_color(self.h)
+
+    def color(self):
+        """(Color_W, R, G, B) views, each [i, j, k] (reference layout)."""
+        return tuple(self._grid(lambda h, q=q: self.L.orc_color(h, q)) for q in range(4))
+
+    # sdf.cpp:164-217
+    def interpolate_color(self, global_pts):
+        pts = np.ascontiguousarray(global_pts, np.float64).reshape(-1, 3)
+        out = np.empty((len(pts), 4), np.float32)
+        self.L.orc_interpolate_color(self.h, len(pts), _d(pts), _f(out))
+        return out
 
     # camera_tracking.cpp:66-245
     def track(self, depth):

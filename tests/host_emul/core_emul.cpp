@@ -253,6 +253,99 @@ void emul_linearize(const GridParams* gp, const float* grid, const float* pix, c
     }
 }
 
+/* certificate statistics of one frame (no grid access): how the 128-voxel items of k_fuse_cert split
+ * into verdict classes.  out: [0] items total, [1] items in FRONT rows, [2] items FRONT at item level,
+ * [3] items SKIP at item level, [4] per-lane items (row+item UNKNOWN), [5] of those: every active unit UNKNOWN,
+ * [6] of those: no unit UNKNOWN, [7] units UNKNOWN, [8] units FRONT (lane level), [9] units SKIP (lane level),
+ * [10] per-lane items whose centre-pixel band test predicts "hopeless", [11] of those really all-UNKNOWN,
+ * [12] units certified inside predicted-hopeless items (the cost of a wrong prediction) */
+void emul_fuse_stats(const GridParams* gp, const float* pix, const PoseState* pose, float band_margin, int64_t out[16]) {
+    const GridParams& g = *gp;
+    const int m = g.m;
+    const double* Ri = pose->Rinv; const double* ti = pose->tinv;
+    const K1Params kp = k1_params(g.K);
+    CertPyramid P;
+    std::vector<std::vector<float>> zf(CERT_LEVELS), zb(CERT_LEVELS);
+    for (int l = 0; l < CERT_LEVELS; l++) {
+        P.w[l] = (g.img_w + (1 << l) - 1) >> l; P.h[l] = (g.img_h + (1 << l) - 1) >> l; P.off[l] = 0;
+        zf[l].assign((size_t)P.w[l] * P.h[l], 3.402823466e+38f); zb[l].assign((size_t)P.w[l] * P.h[l], -3.402823466e+38f);
+    }
+    for (int v = 0; v < g.img_h; v++)
+        for (int u = 0; u < g.img_w; u++) {
+            const float* q = pix + 4 * ((size_t)v * g.img_w + u);
+            PixRec r; r.z = q[0]; r.nx = q[1]; r.ny = q[2]; r.nz = q[3];
+            cert_pixel(g, kp, u, v, r, zf[0][(size_t)v * P.w[0] + u], zb[0][(size_t)v * P.w[0] + u]);
+        }
+    for (int l = 1; l < CERT_LEVELS; l++)
+        for (int y = 0; y < P.h[l - 1]; y++)
+            for (int x = 0; x < P.w[l - 1]; x++) {
+                const size_t o = (size_t)(y >> 1) * P.w[l] + (x >> 1), i = (size_t)y * P.w[l - 1] + x;
+                zf[l][o] = fminf(zf[l][o], zf[l - 1][i]); zb[l][o] = fmaxf(zb[l][o], zb[l - 1][i]);
+            }
+    auto fetch = [&](int level, int x, int y, float& f, float& b) { f = zf[level][(size_t)y * P.w[level] + x]; b = zb[level][(size_t)y * P.w[level] + x]; };
+    int64_t c[16] = {0};
+#pragma omp parallel
+    {
+        int64_t lc[16] = {0};
+#pragma omp for schedule(dynamic, 1)
+        for (int k = g.ks0; k < g.ks1; k++) {
+            const double gz = voxel_centre(g.vs_z, k, g.origin[2]);
+            const double pz0 = Ri[2] * gz, pz1 = Ri[5] * gz, pz2 = Ri[8] * gz;
+            for (int j = 0; j < m; j++) {
+                const double gy = voxel_centre(g.vs_y, j, g.origin[1]);
+                const double py0 = Ri[1] * gy, py1 = Ri[4] * gy, py2 = Ri[7] * gy;
+                int ilo = 0, ihi = m;
+                row_clip(g, Ri, ti, py0, py1, py2, pz0, pz1, pz2, ilo, ihi);
+                if (ihi <= ilo) continue;
+                auto cam = [&](int x, double& X, double& Y, double& Z) {
+                    const double gx = voxel_centre(g.vs_x, x, g.origin[0]);
+                    X = ((Ri[0] * gx + py0) + pz0) + ti[0]; Y = ((Ri[3] * gx + py1) + pz1) + ti[1]; Z = ((Ri[6] * gx + py2) + pz2) + ti[2];
+                };
+                double ax, ay, az, bx, by, bz;
+                cam(ilo, ax, ay, az); cam(ihi - 1, bx, by, bz);
+                const int rowv = unit_certificate(g, P, ax, ay, az, bx, by, bz, fetch);
+                if (rowv == UNIT_SKIP) continue;
+                for (int xs = ilo; xs < ihi; xs += 128) {
+                    lc[0]++;
+                    if (rowv == UNIT_FRONT) { lc[1]++; continue; }
+                    const int xb = (xs + 127 < ihi - 1) ? xs + 127 : ihi - 1;
+                    cam(xs, ax, ay, az); cam(xb, bx, by, bz);
+                    const int itemv = unit_certificate(g, P, ax, ay, az, bx, by, bz, fetch);
+                    if (itemv == UNIT_FRONT) { lc[2]++; continue; }
+                    if (itemv == UNIT_SKIP) { lc[3]++; continue; }
+                    lc[4]++;
+                    int nu = 0, nf = 0, ns = 0;
+                    for (int x0 = xs; x0 <= xb; x0 += 4) {
+                        cam(x0, ax, ay, az); cam(x0 + 3, bx, by, bz);
+                        const int v = unit_certificate(g, P, ax, ay, az, bx, by, bz, fetch);
+                        if (v == UNIT_UNKNOWN) nu++; else if (v == UNIT_FRONT) nf++; else ns++;
+                    }
+                    lc[7] += nu; lc[8] += nf; lc[9] += ns;
+                    if (nf + ns == 0) lc[5]++;
+                    if (nu == 0) lc[6]++;
+                    /* predictor: both ends and the middle of the item project to pixels whose band
+                     * [zfree, zbehind] contains the voxel depth with a margin */
+                    bool hopeless = true;
+                    const int probes[3] = {xs, (xs + xb) >> 1, xb};
+                    for (int q = 0; q < 3 && hopeless; q++) {
+                        cam(probes[q], ax, ay, az);
+                        if (!(az > 0.05)) { hopeless = false; break; }
+                        const float uu = (float)(g.K[0] * ax / az + g.K[2]), vv = (float)(g.K[4] * ay / az + g.K[5]);
+                        const int iu = (int)floorf(uu + 0.5f), iv = (int)floorf(vv + 0.5f);
+                        if (iu < 1 || iv < 1 || iu > g.img_w - 2 || iv > g.img_h - 2) { hopeless = false; break; }
+                        const float f = zf[0][(size_t)iv * P.w[0] + iu], b = zb[0][(size_t)iv * P.w[0] + iu];
+                        if (!((float)az > f + band_margin && (float)az < b - band_margin)) hopeless = false;
+                    }
+                    if (hopeless) { lc[10]++; if (nf + ns == 0) lc[11]++; lc[12] += nf + ns; }
+                }
+            }
+        }
+#pragma omp critical
+        for (int q = 0; q < 16; q++) c[q] += lc[q];
+    }
+    for (int q = 0; q < 16; q++) out[q] = c[q];
+}
+
 void emul_gn_update(const GridParams* g, PoseState* pose, const double* sums) { gn_update(*g, *pose, sums); }
 void emul_pose_stats(const PoseState* p, int32_t out[4], double twist[6]) {
     out[0] = p->iterations; out[1] = p->stopped; out[2] = p->singular; out[3] = p->halo_miss;

@@ -360,3 +360,67 @@ def test_ate_tool_alignment():
     assert E.ate_rmse(est, gt)[0] < 1e-12 and E.ate_rmse(est, gt, do_align=False)[0] > 0.5
     noisy = gt + 0.01
     assert E.ate_rmse(noisy, gt, do_align=False)[0] == pytest.approx(0.01 * np.sqrt(3), rel=1e-9)
+
+
+def test_color_fusion_by_hand():
+    # sdf.cpp:294-304: for a fronto-parallel plane n = (0,0,-1) the cosine is 1, so the colour weight is the
+    # D/W weight and one observation stores the pixel's colour exactly; a second one is the running mean.
+    o, depth = _single_voxel_case(0, 2.0)
+    o.enable_color()
+    CW, R, G, B = o.color()
+    assert (CW == 0).all() and (R == np.float32(0.4)).all() and (G == np.float32(0.4)).all() and (B == np.float32(0.4)).all()   # sdf.cpp:30-34
+    rgb = np.zeros((480, 640, 3), np.uint8); rgb[..., 0] = 200; rgb[..., 1] = 100; rgb[..., 2] = 50
+    o.fuse_rgb(depth, rgb)
+    CW, R, G, B = o.color()
+    W = o.W
+    upd = W > 0
+    assert upd.any() and np.array_equal(CW[upd], W[upd])                  # cosine == 1
+    assert (R[upd] == 200).all() and (G[upd] == 100).all() and (B[upd] == 50).all()
+    assert (R[~upd] == np.float32(0.4)).all() and (CW[~upd] == 0).all()   # untouched voxels keep the initial grey
+    rgb2 = np.zeros_like(rgb); rgb2[..., 0] = 100
+    W1 = W.copy()
+    o.fuse_rgb(depth, rgb2)
+    CW, R, G, B = o.color()
+    i = j = o.m // 2
+    k = int(np.argmax(W1[i, j]))
+    w1 = np.float32(W1[i, j, k]); w2 = np.float32(o.W[i, j, k] - w1)
+    assert CW[i, j, k] == np.float32(w1 + w2)
+    assert R[i, j, k] == np.float32(np.float32(np.float32(w1 * np.float32(200)) + np.float32(w2 * np.float32(100))) / np.float32(w1 + w2))
+    assert G[i, j, k] == np.float32(np.float32(np.float32(w1 * np.float32(100)) + np.float32(w2 * np.float32(0))) / np.float32(w1 + w2))
+    o.close()
+
+
+def test_color_weight_is_cosine_of_the_normal(frames, K):
+    # sdf.cpp:294,299: Color_W accumulates w * |n_z| / ||n||; with one observation Color_W / W = |n_z| of the pixel's
+    # (unit) normal, so it lies in (0, 1] and is < 1 on slanted surfaces
+    depth, Rs, ts = frames
+    o = po.Oracle(m=64, use_coord_table=0); o.set_intrinsics(K); o.set_pose(Rs[0], ts[0])
+    o.fuse_rgb(depth[0], np.full((480, 640, 3), 7, np.uint8))
+    CW, R, G, B = o.color(); W = o.W
+    upd = W > 0
+    ratio = CW[upd] / W[upd]
+    assert ratio.max() <= 1.0 + 1e-6 and ratio.min() >= 0.0 and (ratio < 0.9).any() and (ratio > 0.99).any()
+    ok = CW > 0
+    assert np.allclose(R[ok], 7, atol=1e-4) and np.allclose(B[ok], 7, atol=1e-4)    # a constant image stays constant
+    o.close()
+
+
+def test_interpolate_color_quirks():
+    # sdf.cpp:164-217: world coordinates in; an exact voxel hit returns the raw 0..255 value (:193-198),
+    # anything else is the inverse-L1 mean divided by 255 (:210-213); nothing in range -> 0/0 = NaN; alpha = 1
+    o, depth = _single_voxel_case(0, 2.0)
+    rgb = np.zeros((480, 640, 3), np.uint8); rgb[..., 0] = 200; rgb[..., 1] = 100; rgb[..., 2] = 50
+    o.fuse_rgb(depth, rgb)
+    CW = o.color()[0]
+    i = j = o.m // 2
+    k = int(np.argmax(CW[i, j]))
+    assert CW[i, j, k] > 0 and CW[i, j, k + 1] > 0
+    c = o.get_global_coordinates([i, j, k])
+    out = o.interpolate_color([c])[0]
+    assert tuple(out) == (200.0, 100.0, 50.0, 1.0)
+    c2 = np.array(o.get_global_coordinates([i, j, k + 1]))
+    mid = o.interpolate_color([(np.array(c) + c2) / 2 + [0.003, 0.002, 0.0]])[0]
+    assert mid[0] == pytest.approx(200 / 255, rel=1e-5) and mid[1] == pytest.approx(100 / 255, rel=1e-5) and mid[3] == 1.0
+    far = o.interpolate_color([[100.0, 100.0, 100.0]])[0]
+    assert np.isnan(far[:3]).all() and far[3] == 1.0
+    o.close()

@@ -79,3 +79,26 @@ def render_sequence(n_frames, start=0, K=K_DEFAULT, w=WIDTH, h=HEIGHT, out=None)
     for q, i in enumerate(idx):
         render_depth(Rs[i], ts[i], K, w, h, out[q])
     return out, Rs[idx].copy(), ts[idx].copy()
+
+
+def synth_rgb(depth, R, t, K=None):
+    """Procedural colour image registered to a depth frame: a 3-D checker/gradient texture evaluated at
+    the world position of every pixel (so the same surface point keeps its colour across frames).
+    Returns (h, w, 3) uint8; pixels with invalid depth are black."""
+    K = K_DEFAULT if K is None else np.asarray(K, float).reshape(9)
+    h, w = depth.shape
+    u, v = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    z = depth.astype(np.float64)
+    cam = np.stack([(u - K[2]) * z / K[0], (v - K[5]) * z / K[4], z], axis=-1)
+    world = cam @ np.asarray(R, float).T + np.asarray(t, float)
+    ok = np.isfinite(z) & (z > 0)
+    world = np.where(ok[..., None], world, 0.0)
+    cell = np.floor(world / 0.25).astype(np.int64)
+    check = ((cell[..., 0] + cell[..., 1] + cell[..., 2]) & 1).astype(np.float64)
+    rgb = np.empty((h, w, 3), np.float64)
+    rgb[..., 0] = 40 + 150 * check + 60 * (0.5 + 0.5 * np.sin(3.0 * world[..., 0]))
+    rgb[..., 1] = 30 + 200 * (0.5 + 0.5 * np.sin(2.0 * world[..., 1] + 1.0))
+    rgb[..., 2] = 255 * np.clip(world[..., 2] / 2.5, 0, 1) * (1.0 - 0.5 * check)
+    rgb = np.clip(np.rint(rgb), 0, 255).astype(np.uint8)
+    rgb[~ok] = 0
+    return rgb

@@ -70,6 +70,11 @@ PROTOTYPES = [
     ("tsdf_track", _I32, [_VP, _VP, _I32, c_dp, c_dp, _STP]),
     ("tsdf_fuse", _I32, [_VP, _VP, _I32, c_dp, c_dp, c_i64p]),
     ("tsdf_track_and_fuse", _I32, [_VP, _VP, _I32, c_dp, c_dp, _STP, c_i64p]),
+    ("tsdf_enable_color", _I32, [_VP]),
+    ("tsdf_fuse_rgb", _I32, [_VP, _VP, _VP, _I32, c_dp, c_dp, c_i64p]),
+    ("tsdf_track_and_fuse_rgb", _I32, [_VP, _VP, _VP, _I32, c_dp, c_dp, _STP, c_i64p]),
+    ("tsdf_interpolate_color", _I32, [_VP, _I64, c_dp, c_fp]),
+    ("tsdf_download_color", _I32, [_VP, c_fp, c_fp, c_fp, c_fp, _I32]),
     ("tsdf_enqueue_frame", _I32, [_VP, _VP, _I32, _I32]),
     ("tsdf_submit_frame", _I32, [_VP, _VP, _I32, _I32]),
     ("tsdf_sync", _I32, [_VP]),
@@ -253,6 +258,52 @@ class Tsdf:
         R = np.empty(9); t = np.empty(3); st = TrackStats(); n = ctypes.c_int64()
         self._ck(self.L.tsdf_track_and_fuse(self.h, p, mem, _d(R), _d(t), ctypes.byref(st), ctypes.byref(n)))
         return R.reshape(3, 3), t, st.as_dict(), n.value
+
+    # ---- colour (sdf.cpp:294-304, 164-217); rgb: (h, w, 3) uint8 host array
+    def enable_color(self):
+        self._ck(self.L.tsdf_enable_color(self.h))
+
+    @staticmethod
+    def _rgb_arg(rgb):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        assert rgb.ndim == 3 and rgb.shape[2] == 3
+        return ctypes.c_void_p(rgb.ctypes.data), rgb
+
+    def fuse_rgb(self, depth, rgb, R=None, t=None):
+        p, mem, keep = _depth_arg(depth)
+        assert mem == HOST
+        q, keep2 = self._rgb_arg(rgb)
+        n = ctypes.c_int64()
+        if R is None:
+            self._ck(self.L.tsdf_fuse_rgb(self.h, p, q, mem, None, None, ctypes.byref(n)))
+        else:
+            R = np.ascontiguousarray(R, np.float64).reshape(9)
+            t = np.ascontiguousarray(t, np.float64).reshape(3)
+            self._ck(self.L.tsdf_fuse_rgb(self.h, p, q, mem, _d(R), _d(t), ctypes.byref(n)))
+        return n.value
+
+    def track_and_fuse_rgb(self, depth, rgb):
+        p, mem, keep = _depth_arg(depth)
+        assert mem == HOST
+        q, keep2 = self._rgb_arg(rgb)
+        R = np.empty(9); t = np.empty(3); st = TrackStats(); n = ctypes.c_int64()
+        self._ck(self.L.tsdf_track_and_fuse_rgb(self.h, p, q, mem, _d(R), _d(t), ctypes.byref(st), ctypes.byref(n)))
+        return R.reshape(3, 3), t, st.as_dict(), n.value
+
+    def interpolate_color(self, global_pts):
+        pts = np.ascontiguousarray(global_pts, np.float64).reshape(-1, 3)
+        out = np.empty((len(pts), 4), np.float32)
+        self._ck(self.L.tsdf_interpolate_color(self.h, len(pts), _d(pts), _f(out)))
+        return out
+
+    def download_color(self, layout=LAYOUT_REFERENCE):
+        """-> Color_W, R, G, B, shaped like download()."""
+        ks0, ks1, _, _ = self.stored_range()
+        nk = ks1 - ks0
+        shape = (self.m, self.m, nk) if layout == LAYOUT_REFERENCE else (nk, self.m, self.m)
+        a = [np.empty(shape, np.float32) for _ in range(4)]
+        self._ck(self.L.tsdf_download_color(self.h, _f(a[0]), _f(a[1]), _f(a[2]), _f(a[3]), layout))
+        return tuple(a)
 
     def enqueue_frame(self, depth_dev, track, slot):
         self._ck(self.L.tsdf_enqueue_frame(self.h, ctypes.c_void_p(int(depth_dev)), int(track), int(slot)))

@@ -43,6 +43,15 @@ struct Impl {
     cudaEvent_t depth_ready = nullptr, depth_done = nullptr;   /* optional events for the next enqueue_prep */
     unsigned long long prep_seq = 0;
     int lin_first = 0;
+    /* colour (tsdf_enable_color): {Color_W, R, G, B} per voxel, the frame's packed colour image
+     * (double-buffered like the other records) and a staging buffer for host images */
+    float4* color = nullptr;
+    uchar4* rgb4_buf[2] = {nullptr, nullptr};
+    uchar4* rgb4 = nullptr;
+    uint8_t* rgb_stage = nullptr;
+    const uint8_t* frame_rgb = nullptr;           /* device pointer consumed by the next enqueue_prep (or NULL) */
+    bool frame_has_color = false;                 /* the current records carry a colour image */
+    int fuse_color_blocks = 0;
     float* depth_stage = nullptr;
     PoseState* pose_dev = nullptr;
     PoseState* pose_pin = nullptr;          /* pinned: D2H landing zone for track results */
@@ -168,6 +177,21 @@ tsdf_status stage_depth(Impl* p, const float* depth, int mem, const float** dptr
     return TSDF_OK;
 }
 
+/* colour image for the next frame: host images go through rgb_stage on the main stream (the
+ * same event as the depth copy orders K1 behind both) */
+tsdf_status stage_rgb(Impl* p, const uint8_t* rgb, int mem) {
+    if (!rgb) return bad("rgb is NULL");
+    if (p->g.metric != 0) return bad("colour fusion needs the point-to-plane metric (sdf.cpp:294 uses the normal)");
+    if (!p->color) return bad("colour store not allocated (tsdf_enable_color)");
+    if (mem == TSDF_DEVICE) { p->frame_rgb = rgb; return TSDF_OK; }
+    const size_t bytes = (size_t)p->g.img_w * p->g.img_h * 3;
+    CK(cudaMemcpyAsync(p->rgb_stage, rgb, bytes, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaEventRecord(p->depth_copied, p->stream));
+    p->depth_ready = p->depth_copied;
+    p->frame_rgb = p->rgb_stage;
+    return TSDF_OK;
+}
+
 LinearizeArgs lin_args(Impl* p, int do_update, bool debug) {
     LinearizeArgs a;
     a.g = p->g;
@@ -192,8 +216,10 @@ void enqueue_prep(Impl* p, const float* dptr, int reset_track) {
     cudaEventRecord(p->rec_free[b ^ 1], p->stream);              /* all work on the previous frame's records is enqueued */
     if (p->prep_seq >= 2) cudaStreamWaitEvent(p->prep_stream, p->rec_free[b], 0);
     if (p->depth_ready) cudaStreamWaitEvent(p->prep_stream, p->depth_ready, 0);
-    p->pix = p->pix_buf[b]; p->pts = p->pts_buf[b]; p->cert = p->cert_buf[b];
-    launch_prep(p->g, dptr, p->pix, p->cert + p->pyr.off[0], p->pts, p->prep_stream);
+    p->pix = p->pix_buf[b]; p->pts = p->pts_buf[b]; p->cert = p->cert_buf[b]; p->rgb4 = p->rgb4_buf[b];
+    p->frame_has_color = p->frame_rgb != nullptr;
+    launch_prep(p->g, dptr, p->pix, p->cert + p->pyr.off[0], p->pts, p->frame_rgb, p->rgb4, p->prep_stream);
+    p->frame_rgb = nullptr;
     launch_pyramid(p->pyr, p->cert, p->ticket + 1000, p->prep_stream);
     if (p->depth_done) cudaEventRecord(p->depth_done, p->prep_stream);
     cudaEventRecord(p->prepped[b], p->prep_stream);
@@ -221,6 +247,7 @@ void enqueue_fuse(Impl* p) {
     f.tables = p->fuse_tables; f.items = p->fuse_items; f.item_count = p->fuse_item_count;
     f.n_updated = p->n_upd_dev; f.nblk = p->fuse_blocks; f.nblk_cert = p->fuse_cert_blocks; f.check = p->fuse_check;
     f.pyr = p->pyr; f.cert = p->cert; f.units = p->fuse_units; f.unit_count = p->fuse_item_count + 1;
+    f.color = p->frame_has_color ? p->color : nullptr; f.rgb4 = p->rgb4; f.nblk_color = p->fuse_color_blocks;
     p->launches += launch_fuse(f, p->stream);
 }
 
@@ -421,6 +448,7 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     }
     if (p->depth_copied) cudaEventDestroy(p->depth_copied);
     if (p->prep_stream) cudaStreamDestroy(p->prep_stream);
+    cudaFree(p->color); cudaFree(p->rgb4_buf[0]); cudaFree(p->rgb4_buf[1]); cudaFree(p->rgb_stage);
     cudaFree(p->grid); cudaFree(p->depth_stage); cudaFree(p->pose_dev);
     cudaFreeHost(p->pose_pin); cudaFreeHost(p->ring_pin); cudaFree(p->partials); cudaFree(p->ticket);
     cudaFree(p->group_partials); cudaFree(p->fuse_tables); cudaFree(p->fuse_items); cudaFree(p->fuse_item_count);
@@ -450,6 +478,7 @@ tsdf_status tsdf_reset(tsdf_handle h) {
     const float d0 = p->cfg.width + p->cfg.height + p->cfg.depth;        /* sdf.cpp:29 */
     launch_fill(p->grid, p->n_stored, d0, p->stream);
     p->launches++;
+    if (p->color) { launch_fill_color(p->color, p->n_stored, p->stream); p->launches++; }   /* sdf.cpp:30-34 */
     CK(cudaGetLastError());
     /* camera_tracking.cpp:5-8 initial pose */
     const double R0[9] = {1, 0, 0, 0, 0, -1, 0, -1, 0};
@@ -554,6 +583,115 @@ tsdf_status tsdf_track_and_fuse(tsdf_handle h, const float* depth, int32_t mem, 
     if (st != TSDF_OK) return st;
     if (n_updated) *n_updated = (int64_t)*p->n_upd_pin;
     return track_result(p, R_out, t_out, stats);
+}
+
+tsdf_status tsdf_enable_color(tsdf_handle h) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    if (p->color) return TSDF_OK;
+    if (p->g.metric != 0) return bad("colour fusion needs the point-to-plane metric (sdf.cpp:294 uses the normal)");
+    const size_t npx = (size_t)p->g.img_w * p->g.img_h;
+    cudaError_t e = cudaMalloc(&p->color, (size_t)p->n_stored * sizeof(float4));
+    for (int q = 0; q < 2 && e == cudaSuccess; q++) e = cudaMalloc(&p->rgb4_buf[q], npx * sizeof(uchar4));
+    if (e == cudaSuccess) e = cudaMalloc(&p->rgb_stage, npx * 3);
+    if (e != cudaSuccess) {
+        cudaFree(p->color); p->color = nullptr;
+        for (int q = 0; q < 2; q++) { cudaFree(p->rgb4_buf[q]); p->rgb4_buf[q] = nullptr; }
+        cudaFree(p->rgb_stage); p->rgb_stage = nullptr;
+        cudaGetLastError();
+        g_err = std::string("colour store allocation failed: ") + cudaGetErrorString(e);
+        return TSDF_ERR_NOMEM;
+    }
+    int cb = fuse_color_blocks_per_sm();
+    if (cb < 1) cb = 1;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, p->device));
+    p->fuse_color_blocks = prop.multiProcessorCount * cb;
+    launch_fill_color(p->color, p->n_stored, p->stream);
+    p->launches++;
+    CK(cudaStreamSynchronize(p->stream));
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_fuse_rgb(tsdf_handle h, const float* depth, const uint8_t* rgb, int32_t mem,
+                          const double R[9], const double t[3], int64_t* n_updated) {
+    if (!h) return bad("null handle");
+    if ((R == nullptr) != (t == nullptr)) return bad("R and t must both be given or both be NULL");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    if (!p->have_K) { g_err = "camera matrix not set (tsdf_set_intrinsics)"; return TSDF_ERR_NO_INTRINSICS; }
+    tsdf_status st = tsdf_enable_color(h);
+    if (st != TSDF_OK) return st;
+    if (R) { st = tsdf_set_pose(h, R, t); if (st != TSDF_OK) return st; }
+    const float* dptr;
+    st = stage_depth(p, depth, mem, &dptr);
+    if (st != TSDF_OK) return st;
+    st = stage_rgb(p, rgb, mem);
+    if (st != TSDF_OK) return st;
+    st = enqueue_frame(p, dptr, false, true);
+    if (st != TSDF_OK) return st;
+    CK(cudaMemcpyAsync(p->n_upd_pin, p->n_upd_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (n_updated) *n_updated = (int64_t)*p->n_upd_pin;
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_track_and_fuse_rgb(tsdf_handle h, const float* depth, const uint8_t* rgb, int32_t mem,
+                                    double R_out[9], double t_out[3], tsdf_track_stats* stats, int64_t* n_updated) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    tsdf_status st = tsdf_enable_color(h);
+    if (st != TSDF_OK) return st;
+    const float* dptr;
+    st = stage_depth(p, depth, mem, &dptr);
+    if (st != TSDF_OK) return st;
+    st = stage_rgb(p, rgb, mem);
+    if (st != TSDF_OK) return st;
+    st = enqueue_frame(p, dptr, true, true);
+    if (st != TSDF_OK) return st;
+    CK(cudaMemcpyAsync(p->n_upd_pin, p->n_upd_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
+    st = fetch_pose(p);
+    if (st != TSDF_OK) return st;
+    if (n_updated) *n_updated = (int64_t)*p->n_upd_pin;
+    return track_result(p, R_out, t_out, stats);
+}
+
+tsdf_status tsdf_interpolate_color(tsdf_handle h, int64_t n, const double* global_pts, float* rgba) {
+    if (!h || !global_pts || !rgba || n < 0) return bad("bad argument");
+    Impl* p = I(h);
+    if (!p->color) return bad("colour store not allocated (tsdf_enable_color)");
+    if (n == 0) return TSDF_OK;
+    CK(cudaSetDevice(p->device));
+    double* dp = nullptr; float* dout = nullptr;
+    CK(cudaMalloc(&dp, (size_t)n * 3 * sizeof(double)));
+    CK(cudaMalloc(&dout, (size_t)n * 4 * sizeof(float)));
+    CK(cudaMemcpyAsync(dp, global_pts, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    launch_sample_color(p->g, p->color, n, dp, dout, p->stream);
+    p->launches++;
+    CK(cudaMemcpyAsync(rgba, dout, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    cudaFree(dp); cudaFree(dout);
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_download_color(tsdf_handle h, float* cw, float* r, float* g, float* b, int32_t layout) {
+    if (!h || !cw || !r || !g || !b) return bad("null argument");
+    if (layout != TSDF_LAYOUT_REFERENCE && layout != TSDF_LAYOUT_XFASTEST) return bad("bad layout");
+    Impl* p = I(h);
+    if (!p->color) return bad("colour store not allocated (tsdf_enable_color)");
+    CK(cudaSetDevice(p->device));
+    float* d[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* hst[4] = {cw, r, g, b};
+    for (int q = 0; q < 4; q++) CK(cudaMalloc(&d[q], (size_t)p->n_stored * sizeof(float)));
+    launch_export_color(p->g, p->color, d[0], d[1], d[2], d[3], layout == TSDF_LAYOUT_REFERENCE ? 1 : 0, p->stream);
+    p->launches++;
+    for (int q = 0; q < 4; q++) CK(cudaMemcpyAsync(hst[q], d[q], (size_t)p->n_stored * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    for (int q = 0; q < 4; q++) cudaFree(d[q]);
+    CK(cudaGetLastError());
+    return TSDF_OK;
 }
 
 int32_t tsdf_pose_ring_capacity(void) { return POSE_RING; }

@@ -438,6 +438,47 @@ TSDF_HD void fuse_apply_sel(float& D, float& W, float d_new, float w_new, bool u
     D = upd ? Dn : D;
 }
 
+/* ---- colour fusion, sdf.cpp:294-304 --------------------------------------------------------------
+ * cosine = |cam_vect . n| / ||n|| with cam_vect = (0,0,1) (sdf.cpp:235): the dot product is n_z
+ * exactly (the two zero products only add a signed zero); Eigen's norm is sqrt(c0 + (c1 + c2)).
+ * The colour weight is the D/W weight times the cosine: float = float * double (:299). */
+TSDF_HD float color_weight(float w_new, float nx, float ny, float nz) {
+    const double x = (double)nx, y = (double)ny, z = (double)nz;
+    const double norm = sqrt(x * x + (y * y + z * z));
+    const double cosine = fabs(z) / norm;
+    return (float)((double)w_new * cosine);
+}
+/* running mean of one voxel's colour: the uint8 channel is promoted to int, then to float (:302-304) */
+TSDF_HD void color_apply(float& CW, float& R, float& G, float& B, float w_c, int r, int g, int b) {
+    const float w_old = CW;
+    CW = w_old + w_c;
+    R = (w_old * R + w_c * (float)r) / CW;
+    G = (w_old * G + w_c * (float)g) / CW;
+    B = (w_old * B + w_c * (float)b) / CW;
+}
+/* SDF::interpolate_color, sdf.cpp:164-217, for continuous voxel coordinates (the caller applies
+ * get_voxel_coordinates, :170).  fetch(ci,cj,ck, cw,r,g,b) -> false when outside the grid. */
+template <class Fetch>
+TSDF_HD void interpolate_color(double vx, double vy, double vz, Fetch&& fetch, float out[4]) {
+    const float i = (float)vx, j = (float)vy, k = (float)vz;
+    const int bi = trunc_f2i(i), bj = trunc_f2i(j), bk = trunc_f2i(k);
+    float w_sum = 0.0f, r = 0.0f, g = 0.0f, b = 0.0f;
+    out[3] = 1.0f;
+    for (int n = 0; n < 8; n++) {
+        const int ci = bi + (n >> 2), cj = bj + ((n >> 1) & 1), ck = bk + (n & 1);
+        const float volume = (fabsf((float)ci - i) + fabsf((float)cj - j)) + fabsf((float)ck - k);
+        float cw, cr, cg, cb;
+        if (!fetch(ci, cj, ck, cw, cr, cg, cb)) continue;
+        if (!(cw > 0.0f)) continue;
+        if (volume <= TSDF_VOL_EXACT_F) { out[0] = cr; out[1] = cg; out[2] = cb; return; }   /* unscaled, :193-198 */
+        const float w = rcp_rn(volume);                              /* (float)(1.0 / volume), :200 */
+        w_sum = w_sum + w;
+        r = r + w * cr; g = g + w * cg; b = b + w * cb;
+    }
+    const float aux = (float)((double)w_sum * 255.0);                /* :210 */
+    out[0] = r / aux; out[1] = g / aux; out[2] = b / aux;
+}
+
 /* ---- constants of the certified fp32 evaluations below */
 #define FAST_ZMIN 0.05f                     /* closer to the camera plane than this: exact path */
 #define FAST_DMARG 1e-4f                    /* margin on signed distances, metres (fp32 error <= ~1.1e-5) */

@@ -64,7 +64,7 @@ struct LinearizeArgs {
     ShardLinks links;                      /* world = 1: no exchange */
 };
 
-void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, cudaStream_t s);
+void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, const uint8_t* rgb3, uchar4* rgb4, cudaStream_t s);
 void launch_pyramid(const CertPyramid& P, float2* cert, unsigned int* ticket, cudaStream_t s);
 /* exchange_mode: 0 none, 1 in-kernel mailbox all-reduce over peer memory (one kernel per
  * device, all running concurrently), 2 deferred (same-device shards: publish, then
@@ -84,11 +84,17 @@ struct FuseArgs {
     const float2* cert;
     unsigned long long* units;             /* queue of uncertified lane units (capacity: stored voxels / 4) */
     unsigned int* unit_count;
-    int nblk, nblk_cert;
+    int nblk, nblk_cert, nblk_color;
     int check;                             /* 1: run the self-check build (no stores) */
+    float4* color;                         /* {Color_W, R, G, B} per voxel, or NULL: no colour update this frame */
+    const uchar4* rgb4;                    /* the frame's colour image, packed by k_prep */
 };
 int launch_fuse(const FuseArgs& f, cudaStream_t s);    /* returns the number of kernels launched */
 int fuse_cert_blocks_per_sm();
+int fuse_color_blocks_per_sm();
+void launch_fill_color(float4* color, int64_t n, cudaStream_t s);
+void launch_export_color(const GridParams& g, const float4* color, float* cw, float* r, float* gg, float* b, int layout_ref, cudaStream_t s);
+void launch_sample_color(const GridParams& g, const float4* color, int64_t n, const double* gpts, float* rgba, cudaStream_t s);
 void launch_fill(float2* grid, int64_t n, float d0, cudaStream_t s);
 void launch_sample(const GridParams& g, const float2* grid, int64_t n, const double* pts, float* out, uint8_t* ok, cudaStream_t s);
 void launch_export(const GridParams& g, const float2* grid, float* D, float* W, int layout, cudaStream_t s);

@@ -38,7 +38,8 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
  * one 16-byte record out.  Thread 0 also re-arms the tracker state for the coming frame.
  * ------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restrict__ depth,
-                                              PixRec* __restrict__ pix, float2* __restrict__ cert0, float4* __restrict__ pts) {
+                                              PixRec* __restrict__ pix, float2* __restrict__ cert0, float4* __restrict__ pts,
+                                              const uint8_t* __restrict__ rgb3, uchar4* __restrict__ rgb4) {
     pdl_wait();
     pdl_release();
     const int u = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restr
     if (u >= g.img_w || v >= g.img_h) return;
     const K1Params kp = k1_params(g.K);
     const size_t o = (size_t)v * g.img_w + u;
+    if (rgb3) rgb4[o] = make_uchar4(rgb3[3 * o], rgb3[3 * o + 1], rgb3[3 * o + 2], 0);   /* colour fusion: one 4-byte fetch per voxel */
     const float zc = depth[o];
     const float qnan = __int_as_float(0x7fc00000);
     PixRec r;
@@ -70,9 +72,9 @@ __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restr
     }
 }
 
-void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, cudaStream_t s) {
+void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, const uint8_t* rgb3, uchar4* rgb4, cudaStream_t s) {
     dim3 grid((g.img_w + 31) / 32, (g.img_h + 7) / 8);
-    launch_pdl(k_prep, grid, dim3(256), s, g, depth, pix, cert0, pts);
+    launch_pdl(k_prep, grid, dim3(256), s, g, depth, pix, cert0, pts, rgb3, rgb4);
 }
 
 /* organised cloud + normals for the accessor / tests */
@@ -132,6 +134,30 @@ __global__ void k_sample(GridParams g, const float2* __restrict__ grid, int64_t 
 }
 void launch_sample(const GridParams& g, const float2* grid, int64_t n, const double* pts, float* out, uint8_t* ok, cudaStream_t s) {
     k_sample<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, grid, n, pts, out, ok);
+}
+
+/* SDF::interpolate_color (sdf.cpp:164-217) for n world points */
+__global__ void k_sample_color(GridParams g, const float4* __restrict__ color, int64_t n, const double* __restrict__ gpts, float* rgba) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    /* get_voxel_coordinates, sdf.h:143-147 */
+    const double vx = ((gpts[3 * q] - g.origin[0]) * (double)g.m_div_width - 0.5);
+    const double vy = ((gpts[3 * q + 1] - g.origin[1]) * (double)g.m_div_height - 0.5);
+    const double vz = ((gpts[3 * q + 2] - g.origin[2]) * (double)g.m_div_depth - 0.5);
+    const int m = g.m, ks0 = g.ks0, ks1 = g.ks1;
+    auto fetch = [&](int ci, int cj, int ck, float& cw, float& r, float& gg, float& b) {
+        if ((unsigned)ci >= (unsigned)m || (unsigned)cj >= (unsigned)m || (unsigned)ck >= (unsigned)m) return false;
+        if (ck < ks0 || ck >= ks1) { cw = 0.0f; r = gg = b = 0.0f; return true; }      /* not held by this shard: no weight */
+        const float4 c = __ldg(&color[((size_t)(ck - ks0) * m + cj) * m + ci]);
+        cw = c.x; r = c.y; gg = c.z; b = c.w;
+        return true;
+    };
+    float out[4];
+    interpolate_color(vx, vy, vz, fetch, out);
+    rgba[4 * q] = out[0]; rgba[4 * q + 1] = out[1]; rgba[4 * q + 2] = out[2]; rgba[4 * q + 3] = out[3];
+}
+void launch_sample_color(const GridParams& g, const float4* color, int64_t n, const double* gpts, float* rgba, cudaStream_t s) {
+    k_sample_color<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, color, n, gpts, rgba);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -661,9 +687,11 @@ __device__ __forceinline__ float4 ld_f4(const float4* p) { return *p; }
 /* The exact per-voxel path for a lane's four voxels (sdf.cpp:245-287), straight-line and
  * branch-free so the four dependency chains interleave; the rare exact-division and
  * exponential-weight cases branch last.  cx,cy,cz = camera-space centres (reference rounding). */
+template <bool COLOR = false>
 __device__ __forceinline__ void exact_four(const GridParams& g, const K1Params& kp, const PixRec* __restrict__ pix,
                                            const double* cx, const double* cy, const double* cz,
-                                           bool* upd, float* dnew, float* wnew) {
+                                           bool* upd, float* dnew, float* wnew,
+                                           unsigned int* pidx = nullptr, float* wcol = nullptr) {
     int iu[4], iv[4];
     bool ok[4], need_exact[4];
 #pragma unroll
@@ -697,6 +725,29 @@ __device__ __forceinline__ void exact_four(const GridParams& g, const K1Params& 
         for (int v = 0; v < 4; v++)
             if (upd[v] & band[v]) wnew[v] = fuse_weight(true, eband[v]);     /* sdf.cpp:276-279 */
     }
+    if (COLOR) {
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            pidx[v] = (unsigned int)(iv[v] * g.img_w + iu[v]);
+            wcol[v] = color_weight(wnew[v], rr[v].y, rr[v].z, rr[v].w);      /* sdf.cpp:294,299 */
+        }
+    }
+}
+
+/* colour running mean of the lane's four voxels (sdf.cpp:298-304): 64 bytes in, 64 bytes out */
+__device__ __forceinline__ void color_four(float4* cptr, const uchar4* __restrict__ rgb4, const bool* upd,
+                                           const unsigned int* pidx, const float* wcol) {
+    if (!(upd[0] | upd[1] | upd[2] | upd[3])) return;
+    float4 c[4];
+    uchar4 px[4];
+#pragma unroll
+    for (int v = 0; v < 4; v++) { c[v] = cptr[v]; px[v] = __ldg(&rgb4[pidx[v]]); }
+#pragma unroll
+    for (int v = 0; v < 4; v++)
+        if (upd[v]) {
+            color_apply(c[v].x, c[v].y, c[v].z, c[v].w, wcol[v], (int)px[v].x, (int)px[v].y, (int)px[v].z);
+            cptr[v] = c[v];
+        }
 }
 
 /* camera-space centres of the four voxels x0..x0+3 of row (j,k): camera_tracking.cpp:51-54 with
@@ -738,13 +789,14 @@ __device__ __forceinline__ void count_updates(unsigned int my_updates, int lane,
 }
 
 /* ---- item kernel: exact path for every voxel of every item (used when K has skew: no certificates) */
-template <int METRIC, int KSIMPLE>
-__global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_items(GridParams g_in, float2* __restrict__ grid,
+template <int METRIC, int KSIMPLE, bool COLOR = false>
+__global__ void __launch_bounds__(FUSE_THREADS, COLOR ? 4 : FUSE_MIN_BLOCKS) k_fuse_items(GridParams g_in, float2* __restrict__ grid,
                                                                 const PixRec* __restrict__ pix,
                                                                 const double* __restrict__ T,
                                                                 const unsigned long long* __restrict__ items,
                                                                 const unsigned int* __restrict__ item_count,
-                                                                unsigned long long* n_updated) {
+                                                                unsigned long long* n_updated,
+                                                                float4* __restrict__ color, const uchar4* __restrict__ rgb4) {
     pdl_wait();
     pdl_release();
     GridParams g = g_in;
@@ -769,7 +821,14 @@ __global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_items(Gr
         cam_four(T, (unsigned int)m, x0, j, k, ti0, ti1, ti2, cx, cy, cz);
         float dnew[4], wnew[4];
         bool upd[4];
-        exact_four(g, kp, pix, cx, cy, cz, upd, dnew, wnew);
+        if (COLOR) {
+            unsigned int pidx[4];
+            float wcol[4];
+            exact_four<true>(g, kp, pix, cx, cy, cz, upd, dnew, wnew, pidx, wcol);
+            color_four(reinterpret_cast<float4*>(color) + (((size_t)(k - g.ks0) * m + j) * m + x0), rgb4, upd, pidx, wcol);
+        } else {
+            exact_four(g, kp, pix, cx, cy, cz, upd, dnew, wnew);
+        }
         my_updates += apply_four(g, ptr, q0, q1, k, upd, dnew, wnew);
     }
     count_updates(my_updates, lane, n_updated);
@@ -895,7 +954,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
                                                                const unsigned long long* __restrict__ items,
                                                                const unsigned int* __restrict__ item_count,
                                                                unsigned long long* __restrict__ units, unsigned int* unit_count,
-                                                               unsigned long long* n_updated) {
+                                                               unsigned long long* n_updated, int queue_front) {
     pdl_wait();
     pdl_release();
     const int lane = threadIdx.x & 31;
@@ -958,7 +1017,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
         float4* ptrn = decode_ptr(item_nxt, kn, jn, x0n, actn);
         float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0;
         const bool have_n = it + total_warps < n_items;
-        if (have_n && actn && !CHECK) { n0 = ld_f4(ptrn); n1 = ld_f4(ptrn + 1); }
+        if (have_n && actn && !CHECK && !queue_front) { n0 = ld_f4(ptrn); n1 = ld_f4(ptrn + 1); }
         /* stage B: certificate of the current unit (unless the whole row was already judged) */
         int verdict = UNIT_SKIP;
         const int rowv = (int)(item_cur >> 61) & 3;
@@ -971,6 +1030,9 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
             const double az = ((__ldg(T + (2u * um + x0)) + qy2) + pz2) + ti2, bz = ((__ldg(T + (2u * um + x0 + 3)) + qy2) + pz2) + ti2;
             verdict = unit_certificate(g, P, ax, ay, az, bx, by, bz, fetch);
         }
+        /* colour fusion needs every updated voxel's pixel (normal, rgb): certified free space is
+         * queued for the exact pass too; only the skip certificate is used */
+        if (queue_front && verdict == UNIT_FRONT) verdict = UNIT_UNKNOWN;
         if (CHECK) {
             /* self-check build: queue EVERY unit with its verdict; pass 2 compares, nothing is written */
             const unsigned int mask = __ballot_sync(0xffffffffu, act);
@@ -1006,12 +1068,13 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
 }
 
 /* ---- pass 2: the exact path on the queued units, one unit (four voxels) per thread */
-template <int METRIC, int CHECK>
-__global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_exact(GridParams g_in, float2* __restrict__ grid,
+template <int METRIC, int CHECK, bool COLOR = false>
+__global__ void __launch_bounds__(FUSE_THREADS, COLOR ? 4 : FUSE_MIN_BLOCKS) k_fuse_exact(GridParams g_in, float2* __restrict__ grid,
                                                                               const PixRec* __restrict__ pix, const double* __restrict__ T,
                                                                               const unsigned long long* __restrict__ units,
                                                                               const unsigned int* __restrict__ unit_count,
-                                                                              unsigned long long* n_updated) {
+                                                                              unsigned long long* n_updated,
+                                                                              float4* __restrict__ color, const uchar4* __restrict__ rgb4) {
     pdl_wait();
     pdl_release();
     GridParams g = g_in;
@@ -1032,7 +1095,14 @@ __global__ void __launch_bounds__(FUSE_THREADS, FUSE_MIN_BLOCKS) k_fuse_exact(Gr
         cam_four(T, (unsigned int)m, x0, j, k, ti0, ti1, ti2, cx, cy, cz);
         float dnew[4], wnew[4];
         bool upd[4];
-        exact_four(g, kp, pix, cx, cy, cz, upd, dnew, wnew);
+        if (COLOR) {
+            unsigned int pidx[4];
+            float wcol[4];
+            exact_four<true>(g, kp, pix, cx, cy, cz, upd, dnew, wnew, pidx, wcol);
+            color_four(reinterpret_cast<float4*>(color) + (((size_t)(k - g.ks0) * m + j) * m + x0), rgb4, upd, pidx, wcol);
+        } else {
+            exact_four(g, kp, pix, cx, cy, cz, upd, dnew, wnew);
+        }
         if (CHECK) {
             if (verdict != UNIT_UNKNOWN) {
 #pragma unroll
@@ -1063,21 +1133,30 @@ int launch_fuse(const FuseArgs& f, cudaStream_t s) {
     launch_pdl(k_fuse_tables, dim3((g.m + 127) / 128), dim3(128), s, g, f.pose, f.tables, f.n_updated, f.item_count, f.unit_count);
     const int nrows = (g.ks1 - g.ks0) * g.m;
     launch_pdl(k_fuse_plan, dim3((nrows + 255) / 256), dim3(256), s, g, f.pyr, f.cert, f.check, f.pose, f.tables, f.items, f.item_count);
+    const bool color = f.color != nullptr;      /* plane metric only (checked by the caller) */
     if (!g.k_simple) {          /* skewed intrinsics: the exact path for every in-view voxel */
-        if (g.metric == 0) launch_pdl(k_fuse_items<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
-        else launch_pdl(k_fuse_items<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated);
+        if (color) launch_pdl(k_fuse_items<0, 0, true>, dim3(f.nblk_color), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated, f.color, f.rgb4);
+        else if (g.metric == 0) launch_pdl(k_fuse_items<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated, f.color, f.rgb4);
+        else launch_pdl(k_fuse_items<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated, f.color, f.rgb4);
         return 3;
     }
     if (f.check) {
-        launch_pdl(k_fuse_cert<1>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_count, f.units, f.unit_count, f.n_updated);
-        if (g.metric == 0) launch_pdl(k_fuse_exact<0, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated);
-        else launch_pdl(k_fuse_exact<1, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated);
+        launch_pdl(k_fuse_cert<1>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_count, f.units, f.unit_count, f.n_updated, 0);
+        if (g.metric == 0) launch_pdl(k_fuse_exact<0, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4);
+        else launch_pdl(k_fuse_exact<1, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4);
         return 4;
     }
-    launch_pdl(k_fuse_cert<0>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_count, f.units, f.unit_count, f.n_updated);
-    if (g.metric == 0) launch_pdl(k_fuse_exact<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated);
-    else launch_pdl(k_fuse_exact<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated);
+    launch_pdl(k_fuse_cert<0>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_count, f.units, f.unit_count, f.n_updated, color ? 1 : 0);
+    if (color) launch_pdl(k_fuse_exact<0, 0, true>, dim3(f.nblk_color), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4);
+    else if (g.metric == 0) launch_pdl(k_fuse_exact<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4);
+    else launch_pdl(k_fuse_exact<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4);
     return 4;
+}
+int fuse_color_blocks_per_sm() {
+    int n = 0, q = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fuse_exact<0, 0, true>, FUSE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_fuse_items<0, 0, true>, FUSE_THREADS, 0);
+    return n < q ? n : q;
 }
 int fuse_blocks_per_sm() {
     int n = 0, q = 0;
@@ -1098,6 +1177,28 @@ __global__ void k_fill(float4* grid, int64_t n4, float d0) {
     const float4 v = make_float4(d0, 0.0f, d0, 0.0f);
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) grid[q] = v;
 }
+/* colour store: Color_W = 0, R = G = B = 0.4 (sdf.cpp:30-34) */
+__global__ void k_fill_color(float4* color, int64_t n) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) color[q] = make_float4(0.0f, 0.4f, 0.4f, 0.4f);
+}
+void launch_fill_color(float4* color, int64_t n, cudaStream_t s) { k_fill_color<<<148 * 8, 256, 0, s>>>(color, n); }
+/* colour arrays for the accessor: split, in the reference (z fastest) or the native (x fastest) order */
+__global__ void k_export_color(GridParams g, const float4* __restrict__ color, float* cw, float* r, float* gg, float* b, int layout_ref) {
+    const int64_t n = (int64_t)(g.ks1 - g.ks0) * g.m * g.m;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const float4 c = color[q];
+        int64_t o = q;
+        if (layout_ref) {                                   /* q = ((k-ks0)*m + j)*m + i  ->  (i*m + j)*nk + (k-ks0) */
+            const int i = (int)(q % g.m), j = (int)((q / g.m) % g.m), kk = (int)(q / ((int64_t)g.m * g.m));
+            o = ((int64_t)i * g.m + j) * (g.ks1 - g.ks0) + kk;
+        }
+        cw[o] = c.x; r[o] = c.y; gg[o] = c.z; b[o] = c.w;
+    }
+}
+void launch_export_color(const GridParams& g, const float4* color, float* cw, float* r, float* gg, float* b, int layout_ref, cudaStream_t s) {
+    k_export_color<<<148 * 8, 256, 0, s>>>(g, color, cw, r, gg, b, layout_ref);
+}
+
 void launch_fill(float2* grid, int64_t n, float d0, cudaStream_t s) {
     k_fill<<<148 * 8, 256, 0, s>>>(reinterpret_cast<float4*>(grid), n / 2, d0);
 }
