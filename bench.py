@@ -242,6 +242,40 @@ def dense_fuse_bench(T, m, K, reps, hbm):
             "voxel_updates_per_s": per_launch / t_fuse}
 
 
+def color_fuse_bench(T, m, K, reps, hbm, depth_frame, R, t):
+    """Colour fusion (sdf.cpp:294-304): (a) the dense pose of dense_fuse_bench with a
+    constant image: every voxel gets D/W and Color_W/R/G/B updated = 48 B per voxel; (b) one trajectory
+    frame.  Timed per launch with the library's stage events (the fusion stage alone)."""
+    from tools import synth
+    g = T.Tsdf(T.default_config(m=m, gauss_newton_max_iteration=GN_ITERS, maximum_twist_diff=float("-inf")))
+    g.set_intrinsics(K)
+    g.enable_color()
+    Rd = np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0]], float); td = np.array([0.0, -12.0, 1.25])
+    depth = np.full((480, 640), 40.0, np.float32)
+    rgb = np.full((480, 640, 3), 128, np.uint8)
+    g.fuse_rgb(depth, rgb, Rd, td)
+    ts_ = []
+    n = 0
+    for _ in range(reps):
+        n = g.fuse_rgb(depth, rgb, Rd, td)
+        ts_.append(float(g.last_stage_ms()[2]))
+    t_dense = float(np.mean(ts_)) * 1e-3
+    g.reset(); g.set_intrinsics(K)
+    rgb_t = synth.synth_rgb(depth_frame, R, t)
+    g.fuse_rgb(depth_frame, rgb_t, R, t)
+    tt = []
+    nt = 0
+    for _ in range(reps):
+        nt = g.fuse_rgb(depth_frame, rgb_t, R, t)
+        tt.append(float(g.last_stage_ms()[2]))
+    g.close()
+    ach = 48.0 * n / t_dense / 1e9
+    return {"bound": "hbm", "kernel": "k_fuse_cert (skip certificates) + k_fuse_exact<colour> (every updated voxel needs its pixel: normal + rgb)",
+            "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "bytes_per_updated_voxel": 48,
+            "dense_ms_per_launch": t_dense * 1e3, "dense_voxels_updated": int(n),
+            "trajectory_ms_per_launch": float(np.mean(tt)), "trajectory_voxels_updated": int(nt)}
+
+
 def main_cuda(args):
     rank, world, local = dist_env()
     if world != args.gpus and world > 1:
@@ -330,6 +364,9 @@ def main_cuda(args):
     tot = sum(share.values())
     share = {k: v / tot for k, v in share.items()}
     g.dev_free(dev)
+    color = None
+    if rank == 0 and n_gpus == 1 and not args.no_color:
+        color = color_fuse_bench(T, m, K, 5, hbm, depth[W], Rs[W], ts[W])
 
     # ---------------- e2e: host buffers through the public calls -------------------------------
     # (a) streaming: tsdf_submit_frame — every step does the H2D copy of its frame (pinned host
@@ -393,6 +430,8 @@ def main_cuda(args):
 
     if rank == 0 and n_gpus == 1 and not args.no_dense:
         out["dense_fuse"] = dense_fuse_bench(T, m, K, reps=20, hbm=hbm)
+    if color is not None:
+        out["color_fuse"] = color
     if rank == 0 and n_gpus == 1 and not args.no_cpu:
         nb = min(n_frames, 40)
         out["cpu_baseline"] = run_cpu_baseline(depth[:nb], Rs[:nb], ts[:nb], m, budget_s=args.cpu_budget, max_frames=nb - 1)
@@ -532,6 +571,7 @@ def main():
                     help="sequence: 512^3 per GPU, one independent sequence per GPU (default); sharded: one m^3 volume z-slab sharded over the GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense fusion micro-benchmark")
+    ap.add_argument("--no-color", action="store_true", help="skip the colour fusion measurement")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-budget", type=float, default=90.0)
     args = ap.parse_args()
