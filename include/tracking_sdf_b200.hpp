@@ -16,6 +16,7 @@
  *   interpolate_distance(voxel_pt, is_interpolated)             interpolate_distance(...)       sdf.cpp:127-163
  *   sdf->update(...) colour part (cloud's r,g,b)                update(camera_tracking, depth, rgb) sdf.cpp:294-304
  *   interpolate_color(global_coords, color)                     interpolate_color(global, rgba) sdf.cpp:164-217
+ *   mc->performReconstruction(cloud) + marker fill              mesh(xyz[, world, rgba])        marching_cubes_sdf.cpp:243-287, sdf.cpp:327-385
  *   get_array_index / get_voxel_coordinates / get_global_coordinates / get_number_of_voxels     sdf.h:107-157
  *   public rot, trans, rot_inv, rot_inv_trans, K, isKFilled     rot(), trans(), ... accessors
  *
@@ -104,6 +105,19 @@ public:
         const size_t n = (size_t)get_number_of_voxels();
         CW.resize(n); R.resize(n); G.resize(n); B.resize(n);
         check(tsdf_download_color(handle(), CW.data(), R.data(), G.data(), B.data(), TSDF_LAYOUT_REFERENCE));
+    }
+
+    /* the visualisation thread's product (sdf.cpp:327-385) without the 1-64 GiB download: marching cubes on the
+     * device (iso level 0, sdf.cpp:44), triangle soup in the reference's order; world = marker points
+     * (+ sdf_origin), rgba = interpolate_color per vertex (needs colour fusion to have run) */
+    int64_t mesh(std::vector<float>& xyz, std::vector<double>* world = nullptr, std::vector<float>* rgba = nullptr, float iso_level = 0.0f) const {
+        int64_t n = 0;
+        check(tsdf_mesh_extract(handle(), iso_level, &n));
+        xyz.resize((size_t)n * 3);
+        if (world) world->resize((size_t)n * 3);
+        if (rgba) rgba->resize((size_t)n * 4);
+        check(tsdf_mesh_download(handle(), xyz.data(), world ? world->data() : nullptr, rgba ? rgba->data() : nullptr));
+        return n;
     }
 
     /* the raw arrays the reference hands to its mesher (sdf.cpp:47-48), reference (z-fastest) layout */

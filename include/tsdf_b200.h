@@ -151,6 +151,20 @@ tsdf_status tsdf_interpolate_color(tsdf_handle h, int64_t n, const double* globa
 /* the four colour arrays of this handle's stored z range, same layouts as tsdf_download */
 tsdf_status tsdf_download_color(tsdf_handle h, float* color_w, float* r, float* g, float* b, int32_t layout);
 
+/* ---- mesh (the visualisation thread's consumer of D/W: pcl::MarchingCubesSDF::performReconstruction,
+ * marching_cubes_sdf.cpp:243-287, called from SDF::visualize, sdf.cpp:327).  Marching cubes over the
+ * interior cells (m-2)^3 (sdf.cpp:36-39), a cell takes part only when all eight corners have W > 0
+ * (marching_cubes_sdf.cpp:221); output = unindexed triangle soup, three vertices per triangle, cells in
+ * the reference's index order, in the mesher's own frame: x,y,z in [0,width]x[0,height]x[0,depth] with
+ * vertex = extent * index / m (no half-voxel offset, :123-125).  iso_level outside [0,1) gives an empty
+ * mesh like the reference (:248-254).  The mesh stays on the device until the next extract / destroy.
+ * On a z-slab handle only the cells of the owned layers are meshed. */
+tsdf_status tsdf_mesh_extract(tsdf_handle h, float iso_level, int64_t* n_vertices);
+/* copy the last mesh to the host; any pointer may be NULL.  xyz: n*3 floats as above; world: n*3
+ * doubles = (double)xyz + sdf_origin, the marker points of sdf.cpp:354-356; rgba: n*4 floats =
+ * SDF::interpolate_color at those points (sdf.cpp:380-385; needs the colour store). */
+tsdf_status tsdf_mesh_download(tsdf_handle h, float* xyz, double* world, float* rgba);
+
 /* Asynchronous variant for streaming: enqueue track+fuse of a DEVICE-resident frame; the
  * pose of frame `slot` lands in an internal pinned ring (capacity tsdf_pose_ring_capacity)
  * and is read back after tsdf_sync with tsdf_read_pose_ring.  track = 0: fuse only. */

@@ -90,6 +90,7 @@ struct Oracle {
     double K[9];
     bool isKFilled;
     double rot[9], rot_inv[9], trans[3], rot_inv_trans[3];/* camera_tracking.h:42-49 */
+    std::vector<float> mesh;                              /* last orc_mesh result: xyz per vertex */
     /* scratch */
     std::vector<float> cloud, normals;
     std::vector<float> pxJ, pxPsi;
@@ -704,6 +705,106 @@ void orc_interpolate(void* h, int64_t n, const double* pts, float* out, uint8_t*
         bool is_interp;
         out[q] = interpolate_distance(o, v, is_interp);
         ok[q] = is_interp ? 1 : 0;
+    }
+}
+
+/* ---- pcl::MarchingCubesSDF (marching_cubes_sdf.cpp), the mesher of SDF::visualize (sdf.cpp:327) -------------
+ * The triangle table is the classic public-domain one (Bourke 1994 / Bloyd) that PCL ships and the reference
+ * vendors (marching_cubes_sdf.h:107-364); it is kept packed in tracking_sdf_b200/csrc/mc_tables.inc (generated
+ * by tools/gen_mc_tables.py, which also proves it consistent with the cube topology) and unpacked here.  The
+ * edge mask (marching_cubes_sdf.h:73-106) is derived from the topology. */
+static const unsigned long long mc_packed[256] = {
+#include "../tracking_sdf_b200/csrc/mc_tables.inc"
+};
+static int mc_triTable[256][16];
+static unsigned int mc_edgeTable[256];
+static bool mc_ready = false;
+static void mc_init_tables() {
+    if (mc_ready) return;
+    static const int ea[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3}, eb[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
+    for (int c = 0; c < 256; c++) {
+        for (int q = 0; q < 16; q++) {
+            const int v = (int)((mc_packed[c] >> (4 * q)) & 0xF);
+            mc_triTable[c][q] = (v == 0xF) ? -1 : v;
+        }
+        unsigned int mask = 0;
+        for (int e = 0; e < 12; e++)
+            if (((c >> ea[e]) & 1) != ((c >> eb[e]) & 1)) mask |= 1u << e;
+        mc_edgeTable[c] = mask;
+    }
+    mc_ready = true;
+}
+struct V3f { float v[3]; };
+/* marching_cubes_sdf.cpp:87-99 */
+static void mc_interpolateEdge(const V3f& p1, const V3f& p2, float val_p1, float val_p2, float iso_level, V3f& output) {
+    float mu = (iso_level - val_p1) / (val_p2 - val_p1);
+    for (int c = 0; c < 3; c++) output.v[c] = p1.v[c] + mu * (p2.v[c] - p1.v[c]);
+}
+/* marching_cubes_sdf.cpp:101-197 */
+static void mc_createSurface(const Oracle* o, float iso_level, const float leaf_node[8], const int index_3d[3], std::vector<float>& cloud) {
+    int cubeindex = 0;
+    V3f vertex_list[12];
+    for (int n = 0; n < 8; n++)
+        if (leaf_node[n] < iso_level) cubeindex |= 1 << n;                /* :107-115 */
+    if (mc_edgeTable[cubeindex] == 0) return;                             /* :118 */
+    const float min_p[3] = {0, 0, 0}, max_p[3] = {o->cfg.width, o->cfg.height, o->cfg.depth};   /* setBBox :52-63 */
+    const float res[3] = {float(o->m), float(o->m), float(o->m)};
+    V3f center;
+    for (int c = 0; c < 3; c++) center.v[c] = min_p[c] + (max_p[c] - min_p[c]) * float(index_3d[c]) / res[c];   /* :123-125 */
+    V3f p[8];
+    for (int i = 0; i < 8; i++) {                                         /* :127-140 */
+        V3f point = center;
+        if (i & 0x4) point.v[1] = static_cast<float>(center.v[1] + (max_p[1] - min_p[1]) / res[1]);
+        if (i & 0x2) point.v[2] = static_cast<float>(center.v[2] + (max_p[2] - min_p[2]) / res[2]);
+        if ((i & 0x1) ^ ((i >> 1) & 0x1)) point.v[0] = static_cast<float>(center.v[0] + (max_p[0] - min_p[0]) / res[0]);
+        p[i] = point;
+    }
+    static const int ea[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3}, eb[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};   /* :146-169 */
+    for (int e = 0; e < 12; e++)
+        if (mc_edgeTable[cubeindex] & (1u << e)) mc_interpolateEdge(p[ea[e]], p[eb[e]], leaf_node[ea[e]], leaf_node[eb[e]], iso_level, vertex_list[e]);
+    for (int i = 0; mc_triTable[cubeindex][i] != -1; i += 3)              /* :175-194 */
+        for (int q = 0; q < 3; q++) {
+            const V3f& v = vertex_list[mc_triTable[cubeindex][i + q]];
+            cloud.push_back(v.v[0]); cloud.push_back(v.v[1]); cloud.push_back(v.v[2]);
+        }
+}
+/* marching_cubes_sdf.cpp:203-241 */
+static void mc_getNeighborList1D(const Oracle* o, float leaf[8], const int pos[3]) {
+    const int64_t res_z = o->m, zy_index_offset = (int64_t)o->m * o->m;
+    int64_t g0 = pos[0] * zy_index_offset + pos[1] * res_z + pos[2];
+    int64_t g1 = g0 + zy_index_offset, g2 = g1 + 1, g3 = g0 + 1, g4 = g0 + res_z, g5 = g4 + zy_index_offset, g6 = g5 + 1, g7 = g4 + 1;
+    const int64_t gi[8] = {g0, g1, g2, g3, g4, g5, g6, g7};
+    bool all = true;
+    for (int n = 0; n < 8; n++) all = all && (o->W[gi[n]] > 0);
+    for (int n = 0; n < 8; n++) leaf[n] = all ? o->D[gi[n]] : o->D[g0];
+}
+/* marching_cubes_sdf.cpp:243-287 over the interior voxels (sdf.cpp:36-39), serial = the reference's concatenation
+ * of per-thread clouds in index order.  Returns the number of vertices (3 per triangle). */
+int64_t orc_mesh(void* h, float iso_level) {
+    Oracle* o = (Oracle*)h;
+    mc_init_tables();
+    o->mesh.clear();
+    if (!(iso_level >= 0 && iso_level < 1)) return 0;                     /* :248-254 */
+    for (int i = 1; i < o->m - 1; i++)
+        for (int j = 1; j < o->m - 1; j++)
+            for (int k = 1; k < o->m - 1; k++) {
+                float leaf_node[8];
+                const int index_3d[3] = {i, j, k};
+                mc_getNeighborList1D(o, leaf_node, index_3d);
+                mc_createSurface(o, iso_level, leaf_node, index_3d, o->mesh);
+            }
+    return (int64_t)(o->mesh.size() / 3);
+}
+/* the last mesh: xyz (n*3 floats, mesher frame), and optionally the marker points / colours of
+ * SDF::visualize (sdf.cpp:354-356, 380-385): world = (double)xyz + sdf_origin, rgba = interpolate_color(world) */
+void orc_mesh_copy(void* h, float* xyz, double* world, float* rgba) {
+    Oracle* o = (Oracle*)h;
+    const int64_t n = (int64_t)(o->mesh.size() / 3);
+    if (xyz) memcpy(xyz, o->mesh.data(), o->mesh.size() * sizeof(float));
+    for (int64_t q = 0; q < n; q++) {
+        V3 p = {o->mesh[3 * q] + o->origin[0], o->mesh[3 * q + 1] + o->origin[1], o->mesh[3 * q + 2] + o->origin[2]};
+        if (world) { world[3 * q] = p.x; world[3 * q + 1] = p.y; world[3 * q + 2] = p.z; }
+        if (rgba) interpolate_color(o, p, rgba + 4 * q);
     }
 }
 

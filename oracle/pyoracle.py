@@ -62,6 +62,8 @@ def lib():
     L.orc_enable_color.argtypes = [vp]
     L.orc_color.argtypes = [vp, ctypes.c_int]; L.orc_color.restype = c_fp
     L.orc_interpolate_color.argtypes = [vp, ctypes.c_int64, c_dp, c_fp]
+    L.orc_mesh.argtypes = [vp, ctypes.c_float]; L.orc_mesh.restype = ctypes.c_int64
+    L.orc_mesh_copy.argtypes = [vp, c_fp, c_dp, c_fp]
     L.orc_track.argtypes = [vp, c_fp, ctypes.POINTER(TrackStats)]
     L.orc_linearize.argtypes = [vp, c_fp, c_dp, c_dp, ctypes.POINTER(TrackStats)]
     L.orc_linearize_pixels.argtypes = [vp, c_fp, c_fp, c_fp, c_u8p]; L.orc_linearize_pixels.restype = ctypes.c_int32
@@ -178,6 +180,15 @@ class Oracle:
         out = np.empty((len(pts), 4), np.float32)
         self.L.orc_interpolate_color(self.h, len(pts), _d(pts), _f(out))
         return out
+
+    # marching_cubes_sdf.cpp:243-287 (+ sdf.cpp:354-356, 380-385 when world / colours are asked for)
+    def mesh(self, iso_level=0.0, world=False, colors=False):
+        n = self.L.orc_mesh(self.h, ctypes.c_float(iso_level))
+        xyz = np.empty((n, 3), np.float32)
+        wd = np.empty((n, 3), np.float64) if world else None
+        col = np.empty((n, 4), np.float32) if colors else None
+        self.L.orc_mesh_copy(self.h, _f(xyz), _d(wd) if world else None, _f(col) if colors else None)
+        return (xyz,) + ((wd,) if world else ()) + ((col,) if colors else ())
 
     # camera_tracking.cpp:66-245
     def track(self, depth):

@@ -424,3 +424,51 @@ def test_interpolate_color_quirks():
     far = o.interpolate_color([[100.0, 100.0, 100.0]])[0]
     assert np.isnan(far[:3]).all() and far[3] == 1.0
     o.close()
+
+
+def test_marching_cubes_sphere_is_closed_and_on_the_surface():
+    # pcl::MarchingCubesSDF on an analytic sphere (create_circle fixture, sdf.cpp:62-93): vertices sit on the iso
+    # surface (mesher frame: extent * index / m, i.e. world - origin - half a voxel, marching_cubes_sdf.cpp:123-125),
+    # every edge is shared by exactly two triangles and V - E + F = 2
+    m = 40
+    o = po.Oracle(m=m, use_coord_table=0)
+    o.create_circle(1.0, 0.0, 0.0, 1.25)
+    (xyz,) = o.mesh(0.0)
+    assert len(xyz) % 3 == 0 and len(xyz) > 900
+    p = xyz.astype(np.float64) + [-3.0, -3.0, -0.5] + np.array([6.0, 6.0, 3.5]) / m / 2
+    r = np.linalg.norm(p - [0.0, 0.0, 1.25], axis=1)
+    assert abs(r.mean() - 1.0) < 0.02 and np.abs(r - 1.0).max() < 0.05
+    # neighbouring cells compute a shared vertex from differently rounded corners (centre + step vs the next centre):
+    # weld at 1e-4 m (voxels are 0.15 m here)
+    uniq, inv = np.unique(np.rint(xyz.astype(np.float64) / 1e-4).astype(np.int64), axis=0, return_inverse=True)
+    tri = inv.reshape(-1, 3)
+    tri = tri[(tri[:, 0] != tri[:, 1]) & (tri[:, 1] != tri[:, 2]) & (tri[:, 0] != tri[:, 2])]        # drop degenerate slivers
+    e = np.sort(np.concatenate([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]]]), axis=1)
+    ue, cnt = np.unique(e, axis=0, return_counts=True)
+    assert (cnt == 2).all()
+    assert len(np.unique(tri)) - len(ue) + len(tri) == 2
+    # iso level outside [0, 1): empty (marching_cubes_sdf.cpp:248-254); unseen voxels: no surface (:221-241)
+    assert len(o.mesh(1.0)[0]) == 0 and len(o.mesh(-0.01)[0]) == 0
+    o.W[:, :, : m // 2] = 0
+    (half,) = o.mesh(0.0)
+    assert 0 < len(half) < len(xyz)
+    o.close()
+
+
+def test_marching_cubes_single_cell_by_hand():
+    # one corner below the iso level -> one triangle on the three edges that meet there, interpolated linearly
+    m = 8
+    o = po.Oracle(m=m, use_coord_table=0)
+    o.W[...] = 1.0; o.D[...] = 1.0
+    o.D[3, 3, 3] = -1.0                                       # corner 0 of cell (3,3,3), corner 1 of cell (2,3,3), ...
+    (xyz,) = o.mesh(0.0)
+    assert len(xyz) == 8 * 3                                  # the eight cells around the voxel, one triangle each
+    vs = np.float32(6.0) / np.float32(m); vz = np.float32(3.5) / np.float32(m)
+    c = np.array([np.float32(6.0) * np.float32(3) / np.float32(m)] * 2 + [np.float32(3.5) * np.float32(3) / np.float32(m)], np.float32)
+    # cell (3,3,3): configuration 1 -> edges 0 (x), 8 (y), 3 (z, from corner 3 to corner 0): mu = 0.5 on each
+    cell = xyz[-3:]
+    expect = {(float(c[0] + np.float32(0.5) * vs), float(c[1]), float(c[2])),
+              (float(c[0]), float(c[1] + np.float32(0.5) * vs), float(c[2])),
+              (float(c[0]), float(c[1]), float(np.float32(c[2] + vz) + np.float32(0.5) * np.float32(c[2] - np.float32(c[2] + vz))))}
+    assert {tuple(map(float, v)) for v in cell} == expect
+    o.close()

@@ -75,6 +75,8 @@ PROTOTYPES = [
     ("tsdf_track_and_fuse_rgb", _I32, [_VP, _VP, _VP, _I32, c_dp, c_dp, _STP, c_i64p]),
     ("tsdf_interpolate_color", _I32, [_VP, _I64, c_dp, c_fp]),
     ("tsdf_download_color", _I32, [_VP, c_fp, c_fp, c_fp, c_fp, _I32]),
+    ("tsdf_mesh_extract", _I32, [_VP, ctypes.c_float, c_i64p]),
+    ("tsdf_mesh_download", _I32, [_VP, c_fp, c_dp, c_fp]),
     ("tsdf_enqueue_frame", _I32, [_VP, _VP, _I32, _I32]),
     ("tsdf_submit_frame", _I32, [_VP, _VP, _I32, _I32]),
     ("tsdf_sync", _I32, [_VP]),
@@ -304,6 +306,18 @@ class Tsdf:
         a = [np.empty(shape, np.float32) for _ in range(4)]
         self._ck(self.L.tsdf_download_color(self.h, _f(a[0]), _f(a[1]), _f(a[2]), _f(a[3]), layout))
         return tuple(a)
+
+    # ---- mesh (marching_cubes_sdf.cpp:243-287; sdf.cpp:354-356, 380-385)
+    def mesh(self, iso_level=0.0, world=False, colors=False):
+        """-> (xyz [n,3] float32[, world [n,3] float64][, rgba [n,4] float32]); 3 vertices per triangle."""
+        n = ctypes.c_int64()
+        self._ck(self.L.tsdf_mesh_extract(self.h, ctypes.c_float(iso_level), ctypes.byref(n)))
+        n = n.value
+        xyz = np.empty((n, 3), np.float32)
+        wd = np.empty((n, 3), np.float64) if world else None
+        col = np.empty((n, 4), np.float32) if colors else None
+        self._ck(self.L.tsdf_mesh_download(self.h, _f(xyz), _d(wd) if world else None, _f(col) if colors else None))
+        return (xyz,) + ((wd,) if world else ()) + ((col,) if colors else ())
 
     def enqueue_frame(self, depth_dev, track, slot):
         self._ck(self.L.tsdf_enqueue_frame(self.h, ctypes.c_void_p(int(depth_dev)), int(track), int(slot)))

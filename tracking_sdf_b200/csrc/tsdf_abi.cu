@@ -52,6 +52,13 @@ struct Impl {
     const uint8_t* frame_rgb = nullptr;           /* device pointer consumed by the next enqueue_prep (or NULL) */
     bool frame_has_color = false;                 /* the current records carry a colour image */
     int fuse_color_blocks = 0;
+    /* mesher: per-row vertex counts / offsets (m*m + 1), scan scratch, the last mesh */
+    unsigned int* mc_count = nullptr;
+    unsigned int* mc_off = nullptr;
+    void* mc_tmp = nullptr;
+    size_t mc_tmp_bytes = 0;
+    float* mesh_xyz = nullptr;
+    int64_t mesh_n = 0;
     float* depth_stage = nullptr;
     PoseState* pose_dev = nullptr;
     PoseState* pose_pin = nullptr;          /* pinned: D2H landing zone for track results */
@@ -448,6 +455,7 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     }
     if (p->depth_copied) cudaEventDestroy(p->depth_copied);
     if (p->prep_stream) cudaStreamDestroy(p->prep_stream);
+    cudaFree(p->mc_count); cudaFree(p->mc_off); cudaFree(p->mc_tmp); cudaFree(p->mesh_xyz);
     cudaFree(p->color); cudaFree(p->rgb4_buf[0]); cudaFree(p->rgb4_buf[1]); cudaFree(p->rgb_stage);
     cudaFree(p->grid); cudaFree(p->depth_stage); cudaFree(p->pose_dev);
     cudaFreeHost(p->pose_pin); cudaFreeHost(p->ring_pin); cudaFree(p->partials); cudaFree(p->ticket);
@@ -690,6 +698,68 @@ tsdf_status tsdf_download_color(tsdf_handle h, float* cw, float* r, float* g, fl
     for (int q = 0; q < 4; q++) CK(cudaMemcpyAsync(hst[q], d[q], (size_t)p->n_stored * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     for (int q = 0; q < 4; q++) cudaFree(d[q]);
+    CK(cudaGetLastError());
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_mesh_extract(tsdf_handle h, float iso_level, int64_t* n_vertices) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    cudaFree(p->mesh_xyz); p->mesh_xyz = nullptr; p->mesh_n = 0;
+    if (n_vertices) *n_vertices = 0;
+    if (!(iso_level >= 0.0f && iso_level < 1.0f)) return TSDF_OK;         /* marching_cubes_sdf.cpp:248-254: empty cloud */
+    const int64_t n_rows = (int64_t)p->g.m * p->g.m + 1;
+    if (!p->mc_count) {
+        p->mc_tmp_bytes = mesh_scan_bytes(n_rows);
+        CK(cudaMalloc(&p->mc_count, (size_t)n_rows * sizeof(unsigned int)));
+        CK(cudaMalloc(&p->mc_off, (size_t)n_rows * sizeof(unsigned int)));
+        CK(cudaMalloc(&p->mc_tmp, p->mc_tmp_bytes ? p->mc_tmp_bytes : 16));
+    }
+    McParams P;
+    P.width = p->cfg.width; P.height = p->cfg.height; P.depth = p->cfg.depth; P.iso = iso_level;
+    launch_mesh_count(p->g, P, p->grid, p->mc_count, p->mc_off, p->mc_tmp, p->mc_tmp_bytes, p->stream);
+    p->launches += 2;
+    unsigned int total = 0;
+    CK(cudaMemcpyAsync(&total, p->mc_off + (n_rows - 1), sizeof total, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (total) {
+        cudaError_t e = cudaMalloc(&p->mesh_xyz, (size_t)total * 3 * sizeof(float));
+        if (e != cudaSuccess) { cudaGetLastError(); p->mesh_xyz = nullptr; g_err = "mesh buffer allocation failed"; return TSDF_ERR_NOMEM; }
+        launch_mesh_emit(p->g, P, p->grid, p->mc_off, p->mesh_xyz, p->stream);
+        p->launches++;
+        CK(cudaStreamSynchronize(p->stream));
+    }
+    CK(cudaGetLastError());
+    p->mesh_n = (int64_t)total;
+    if (n_vertices) *n_vertices = p->mesh_n;
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_mesh_download(tsdf_handle h, float* xyz, double* world, float* rgba) {
+    if (!h) return bad("null handle");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    const int64_t n = p->mesh_n;
+    if (n == 0) return TSDF_OK;
+    if (rgba && !p->color) return bad("vertex colours need the colour store (tsdf_enable_color)");
+    if (xyz) CK(cudaMemcpyAsync(xyz, p->mesh_xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    if (world || rgba) {
+        double* dw = nullptr; float* dc = nullptr;
+        CK(cudaMalloc(&dw, (size_t)n * 3 * sizeof(double)));
+        launch_mesh_world(p->g, p->mesh_xyz, n, dw, p->stream);
+        p->launches++;
+        if (world) CK(cudaMemcpyAsync(world, dw, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        if (rgba) {
+            CK(cudaMalloc(&dc, (size_t)n * 4 * sizeof(float)));
+            launch_sample_color(p->g, p->color, n, dw, dc, p->stream);
+            p->launches++;
+            CK(cudaMemcpyAsync(rgba, dc, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+        }
+        CK(cudaStreamSynchronize(p->stream));
+        cudaFree(dw); cudaFree(dc);
+    }
+    CK(cudaStreamSynchronize(p->stream));
     CK(cudaGetLastError());
     return TSDF_OK;
 }

@@ -104,6 +104,16 @@ void launch_exp_map(const double* twist, double* out12, cudaStream_t s);
 void launch_flush(float* buf, int64_t n, cudaStream_t s);
 void launch_stream_rmw(float2* grid, int64_t n, float neg_delta, cudaStream_t s);
 void launch_check_rcp(unsigned int lo, unsigned int hi, unsigned long long* n_bad, cudaStream_t s);
+/* mesher (tsdf_mesh.cu) */
+struct McParams {
+    float width, height, depth;       /* setBBox (marching_cubes_sdf.cpp:52-63): min_p = 0, max_p = extents */
+    float iso;                        /* setIsoLevel; must be in [0, 1) (marching_cubes_sdf.cpp:248) */
+};
+size_t mesh_scan_bytes(int64_t n_rows);
+void launch_mesh_count(const GridParams& g, const McParams& P, const float2* grid, unsigned int* row_count, unsigned int* row_off,
+                       void* scan_tmp, size_t scan_bytes, cudaStream_t s);
+void launch_mesh_emit(const GridParams& g, const McParams& P, const float2* grid, const unsigned int* row_off, float* xyz, cudaStream_t s);
+void launch_mesh_world(const GridParams& g, const float* xyz, int64_t n, double* world, cudaStream_t s);
 int  fuse_blocks_per_sm();
 int  linearize_blocks_per_sm();
 
