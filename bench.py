@@ -364,6 +364,20 @@ def main_cuda(args):
     tot = sum(share.values())
     share = {k: v / tot for k, v in share.items()}
     g.dev_free(dev)
+    mesh = None
+    if rank == 0 and n_gpus == 1 and not args.no_mesh:
+        # the visualisation thread's product (sdf.cpp:327, marching_cubes_sdf.cpp:243-287) on the volume just built
+        nv = 0
+        tm = []
+        for _ in range(3):
+            t0m = time.perf_counter()
+            nv = g.mesh_extract(0.0)
+            tm.append(time.perf_counter() - t0m)
+        t_mesh = min(tm)
+        mesh = {"kernel": "k_mc_sweep<count> + cub scan + k_mc_sweep<emit>", "ms_per_extraction": t_mesh * 1e3, "triangles": nv // 3,
+                "store_read_gbs": 2 * 8.0 * m ** 3 / t_mesh / 1e9, "peak": hbm, "frac": 2 * 8.0 * m ** 3 / t_mesh / 1e9 / hbm,
+                "note": "host wall clock around tsdf_mesh_extract (two sweeps over the 8 B/voxel store + scan + allocation + one sync each); "
+                        "algorithmic bytes = 2 x 8 B x m^3 (each sweep reads every voxel once)"}
     color = None
     if rank == 0 and n_gpus == 1 and not args.no_color:
         color = color_fuse_bench(T, m, K, 5, hbm, depth[W], Rs[W], ts[W])
@@ -432,6 +446,8 @@ def main_cuda(args):
         out["dense_fuse"] = dense_fuse_bench(T, m, K, reps=20, hbm=hbm)
     if color is not None:
         out["color_fuse"] = color
+    if mesh is not None:
+        out["mesh"] = mesh
     if rank == 0 and n_gpus == 1 and not args.no_cpu:
         nb = min(n_frames, 40)
         out["cpu_baseline"] = run_cpu_baseline(depth[:nb], Rs[:nb], ts[:nb], m, budget_s=args.cpu_budget, max_frames=nb - 1)
@@ -572,6 +588,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense fusion micro-benchmark")
     ap.add_argument("--no-color", action="store_true", help="skip the colour fusion measurement")
+    ap.add_argument("--no-mesh", action="store_true", help="skip the marching-cubes measurement")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-budget", type=float, default=90.0)
     args = ap.parse_args()

@@ -2,7 +2,7 @@
 # usage: quick_bench.sh name [lib]  -> one line: fps, stage ms, dense ms
 name=$1; lib=$2
 if [ -n "$lib" ]; then export TSDF_B200_LIB=$lib; fi
-timeout 150 python bench.py --steps 100 --warmup 10 --no-cpu --no-color > /tmp/qb_$name.json 2>/dev/null
+timeout 150 python bench.py --steps 100 --warmup 10 --no-cpu --no-color --no-mesh > /tmp/qb_$name.json 2>/dev/null
 python - <<PY
 import json
 d=json.load(open("/tmp/qb_$name.json"))

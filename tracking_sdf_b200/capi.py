@@ -308,11 +308,15 @@ class Tsdf:
         return tuple(a)
 
     # ---- mesh (marching_cubes_sdf.cpp:243-287; sdf.cpp:354-356, 380-385)
-    def mesh(self, iso_level=0.0, world=False, colors=False):
-        """-> (xyz [n,3] float32[, world [n,3] float64][, rgba [n,4] float32]); 3 vertices per triangle."""
+    def mesh_extract(self, iso_level=0.0):
+        """Run the device mesher; the mesh stays on the device.  -> number of vertices."""
         n = ctypes.c_int64()
         self._ck(self.L.tsdf_mesh_extract(self.h, ctypes.c_float(iso_level), ctypes.byref(n)))
-        n = n.value
+        return n.value
+
+    def mesh(self, iso_level=0.0, world=False, colors=False):
+        """-> (xyz [n,3] float32[, world [n,3] float64][, rgba [n,4] float32]); 3 vertices per triangle."""
+        n = self.mesh_extract(iso_level)
         xyz = np.empty((n, 3), np.float32)
         wd = np.empty((n, 3), np.float64) if world else None
         col = np.empty((n, 4), np.float32) if colors else None

@@ -58,7 +58,7 @@ struct Impl {
     void* mc_tmp = nullptr;
     size_t mc_tmp_bytes = 0;
     float* mesh_xyz = nullptr;
-    int64_t mesh_n = 0;
+    int64_t mesh_n = 0, mesh_cap = 0;
     float* depth_stage = nullptr;
     PoseState* pose_dev = nullptr;
     PoseState* pose_pin = nullptr;          /* pinned: D2H landing zone for track results */
@@ -706,10 +706,10 @@ tsdf_status tsdf_mesh_extract(tsdf_handle h, float iso_level, int64_t* n_vertice
     if (!h) return bad("null handle");
     Impl* p = I(h);
     CK(cudaSetDevice(p->device));
-    cudaFree(p->mesh_xyz); p->mesh_xyz = nullptr; p->mesh_n = 0;
+    p->mesh_n = 0;
     if (n_vertices) *n_vertices = 0;
     if (!(iso_level >= 0.0f && iso_level < 1.0f)) return TSDF_OK;         /* marching_cubes_sdf.cpp:248-254: empty cloud */
-    const int64_t n_rows = (int64_t)p->g.m * p->g.m + 1;
+    const int64_t n_rows = (int64_t)p->g.m * p->g.m * mesh_zsplit() + 1;
     if (!p->mc_count) {
         p->mc_tmp_bytes = mesh_scan_bytes(n_rows);
         CK(cudaMalloc(&p->mc_count, (size_t)n_rows * sizeof(unsigned int)));
@@ -724,8 +724,13 @@ tsdf_status tsdf_mesh_extract(tsdf_handle h, float iso_level, int64_t* n_vertice
     CK(cudaMemcpyAsync(&total, p->mc_off + (n_rows - 1), sizeof total, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     if (total) {
-        cudaError_t e = cudaMalloc(&p->mesh_xyz, (size_t)total * 3 * sizeof(float));
-        if (e != cudaSuccess) { cudaGetLastError(); p->mesh_xyz = nullptr; g_err = "mesh buffer allocation failed"; return TSDF_ERR_NOMEM; }
+        if ((int64_t)total > p->mesh_cap) {                          /* grow with head room: the next mesh is usually a bit larger */
+            cudaFree(p->mesh_xyz); p->mesh_xyz = nullptr; p->mesh_cap = 0;
+            const int64_t cap = (int64_t)total + (int64_t)total / 4 + 1024;
+            cudaError_t e = cudaMalloc(&p->mesh_xyz, (size_t)cap * 3 * sizeof(float));
+            if (e != cudaSuccess) { cudaGetLastError(); p->mesh_xyz = nullptr; g_err = "mesh buffer allocation failed"; return TSDF_ERR_NOMEM; }
+            p->mesh_cap = cap;
+        }
         launch_mesh_emit(p->g, P, p->grid, p->mc_off, p->mesh_xyz, p->stream);
         p->launches++;
         CK(cudaStreamSynchronize(p->stream));

@@ -110,6 +110,7 @@ struct McParams {
     float iso;                        /* setIsoLevel; must be in [0, 1) (marching_cubes_sdf.cpp:248) */
 };
 size_t mesh_scan_bytes(int64_t n_rows);
+int mesh_zsplit();
 void launch_mesh_count(const GridParams& g, const McParams& P, const float2* grid, unsigned int* row_count, unsigned int* row_off,
                        void* scan_tmp, size_t scan_bytes, cudaStream_t s);
 void launch_mesh_emit(const GridParams& g, const McParams& P, const float2* grid, const unsigned int* row_off, float* xyz, cudaStream_t s);

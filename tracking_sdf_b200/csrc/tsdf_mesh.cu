@@ -18,9 +18,13 @@
 namespace tsdf {
 
 constexpr int MC_WARPS = 8;      /* warps per block = consecutive j rows */
+#ifndef MC_ZSPLIT_DEF
+#define MC_ZSPLIT_DEF 4
+#endif
+constexpr int MC_ZSPLIT = MC_ZSPLIT_DEF;     /* chunks of the k sweep (more loads in flight) */
 
 template <bool EMIT>
-__global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McParams P, const float2* __restrict__ grid, int k_lo, int k_hi,
+__global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McParams P, const float2* __restrict__ grid, int k_lo_all, int k_hi_all,
                                                             unsigned int* __restrict__ row_count, const unsigned int* __restrict__ row_off,
                                                             float* __restrict__ xyz) {
     const int m = g.m;
@@ -28,6 +32,12 @@ __global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McPara
     const int i = blockIdx.x * 32 + lane;
     const int j = blockIdx.y * MC_WARPS + warp;
     if (j < 1 || j > m - 2) return;                                   /* warp-uniform */
+    /* the k range is cut into gridDim.z chunks; a row's chunks are consecutive in the output */
+    const int nz = (int)gridDim.z, zc = (int)blockIdx.z;
+    const int per = (k_hi_all - k_lo_all + nz) / nz;
+    const int k_lo = k_lo_all + zc * per;
+    const int k_hi = (k_lo + per - 1 < k_hi_all) ? (k_lo + per - 1) : k_hi_all;
+    if (k_lo > k_hi) return;
     const bool cell_ok = (i >= 1) && (i <= m - 2);
     const bool have = i < m, have1 = (i + 1) < m;
     const float fm = (float)m;
@@ -45,7 +55,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McPara
     float2 a, a1, b, b1;                                              /* layer k:   (i,j) (i+1,j) (i,j+1) (i+1,j+1) */
     load_layer(k_lo, a, a1, b, b1);
     unsigned int n_row = 0;
-    const unsigned int base = EMIT ? (cell_ok ? row_off[(size_t)i * m + j] : 0u) : 0u;
+    const unsigned int base = EMIT ? (cell_ok ? row_off[((size_t)i * m + j) * nz + zc] : 0u) : 0u;
     for (int k = k_lo; k <= k_hi; k++) {
         float2 c, c1, e, e1;                                          /* layer k+1 */
         load_layer(k + 1, c, c1, e, e1);
@@ -69,7 +79,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McPara
         }
         a = c; a1 = c1; b = e; b1 = e1;
     }
-    if (!EMIT && cell_ok) row_count[(size_t)i * m + j] = n_row;
+    if (!EMIT && cell_ok) row_count[((size_t)i * m + j) * nz + zc] = n_row;
 }
 
 /* marker points of SDF::visualize: (double)vertex + sdf_origin (sdf.cpp:354-356) */
@@ -98,16 +108,17 @@ size_t mesh_scan_bytes(int64_t n_rows) {
     return bytes;
 }
 
-/* pass 1 + scan: row_count and row_off hold m*m + 1 entries (the last row_count is 0, so the last
- * row_off is the total) */
+/* pass 1 + scan: row_count and row_off hold m*m*MC_ZSPLIT + 1 entries (the last row_count is 0, so
+ * the last row_off is the total) */
+int mesh_zsplit() { return MC_ZSPLIT; }
 void launch_mesh_count(const GridParams& g, const McParams& P, const float2* grid, unsigned int* row_count, unsigned int* row_off,
                        void* scan_tmp, size_t scan_bytes, cudaStream_t s) {
-    const int64_t n_rows = (int64_t)g.m * g.m + 1;
+    const int64_t n_rows = (int64_t)g.m * g.m * MC_ZSPLIT + 1;
     cudaMemsetAsync(row_count, 0, (size_t)n_rows * sizeof(unsigned int), s);
     int k_lo, k_hi;
     mesh_k_range(g, k_lo, k_hi);
     if (k_hi >= k_lo) {
-        dim3 grid3((g.m + 31) / 32, (g.m + MC_WARPS - 1) / MC_WARPS);
+        dim3 grid3((g.m + 31) / 32, (g.m + MC_WARPS - 1) / MC_WARPS, MC_ZSPLIT);
         k_mc_sweep<false><<<grid3, MC_WARPS * 32, 0, s>>>(g, P, grid, k_lo, k_hi, row_count, nullptr, nullptr);
     }
     cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, row_count, row_off, (int)n_rows, s);
@@ -116,7 +127,7 @@ void launch_mesh_emit(const GridParams& g, const McParams& P, const float2* grid
     int k_lo, k_hi;
     mesh_k_range(g, k_lo, k_hi);
     if (k_hi < k_lo) return;
-    dim3 grid3((g.m + 31) / 32, (g.m + MC_WARPS - 1) / MC_WARPS);
+    dim3 grid3((g.m + 31) / 32, (g.m + MC_WARPS - 1) / MC_WARPS, MC_ZSPLIT);
     k_mc_sweep<true><<<grid3, MC_WARPS * 32, 0, s>>>(g, P, grid, k_lo, k_hi, nullptr, row_off, xyz);
 }
 
