@@ -167,10 +167,14 @@ tsdf_status tsdf_mesh_download(tsdf_handle h, float* xyz, double* world, float* 
 
 /* Asynchronous variant for streaming: enqueue track+fuse of a DEVICE-resident frame; the
  * pose of frame `slot` lands in an internal pinned ring (capacity tsdf_pose_ring_capacity)
- * and is read back after tsdf_sync with tsdf_read_pose_ring.  track = 0: fuse only. */
+ * and is read back after tsdf_sync with tsdf_read_pose_ring.  track = 0: fuse only.
+ * The frame's preprocessing (back-projection, normals, certificates) runs on a second stream and
+ * overlaps the previous frame's tracking and fusion, so depth_dev must be completely written when
+ * the call is made and must not change until tsdf_sync (or until two later frames were enqueued). */
 tsdf_status tsdf_enqueue_frame(tsdf_handle h, const float* depth_dev, int32_t track, int32_t slot);
 /* The same with a HOST (preferably pinned) depth buffer: the H2D copy goes through a copy stream
- * into a small ring of device frames, so the copy of frame n+1 overlaps track+fuse of frame n.
+ * into a small ring of device frames, so the copy and the preprocessing of frame n+1 overlap
+ * track+fuse of frame n.
  * The host buffer must stay valid until tsdf_sync (or until 4 later submissions returned). */
 tsdf_status tsdf_submit_frame(tsdf_handle h, const float* depth_host, int32_t track, int32_t slot);
 tsdf_status tsdf_sync(tsdf_handle h);

@@ -44,21 +44,35 @@ __global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McPara
     const float2 zero = make_float2(0.0f, 0.0f);
     const size_t plane = (size_t)m * m;
     const float2* pj = grid + (size_t)j * m + i;                      /* (i, j, .) ; row j+1 is + m */
-    auto load_layer = [&](int k, float2& a, float2& a1, float2& b, float2& b1) {
+    /* software pipeline: the raw loads of layer k+2 are in flight while layer k+1 is shuffled and
+     * cell k is evaluated.  raw = this lane's (i,j) and (i,j+1) voxels plus, on lane 31, the i+1 pair. */
+    struct Raw { float2 a, b, xa, xb; };
+    auto load_raw = [&](int k) {
+        Raw r;
         const float2* p = pj + (size_t)(k - g.ks0) * plane;
-        a = have ? __ldg(p) : zero;
-        b = have ? __ldg(p + m) : zero;
-        a1.x = __shfl_down_sync(0xffffffffu, a.x, 1); a1.y = __shfl_down_sync(0xffffffffu, a.y, 1);
-        b1.x = __shfl_down_sync(0xffffffffu, b.x, 1); b1.y = __shfl_down_sync(0xffffffffu, b.y, 1);
-        if (lane == 31) { a1 = have1 ? __ldg(p + 1) : zero; b1 = have1 ? __ldg(p + m + 1) : zero; }
+        r.a = have ? __ldg(p) : zero;
+        r.b = have ? __ldg(p + m) : zero;
+        r.xa = zero; r.xb = zero;
+        if (lane == 31 && have1) { r.xa = __ldg(p + 1); r.xb = __ldg(p + m + 1); }
+        return r;
     };
-    float2 a, a1, b, b1;                                              /* layer k:   (i,j) (i+1,j) (i,j+1) (i+1,j+1) */
-    load_layer(k_lo, a, a1, b, b1);
+    auto neighbours = [&](const Raw& r, float2& a1, float2& b1) {     /* (i+1,j), (i+1,j+1) */
+        a1.x = __shfl_down_sync(0xffffffffu, r.a.x, 1); a1.y = __shfl_down_sync(0xffffffffu, r.a.y, 1);
+        b1.x = __shfl_down_sync(0xffffffffu, r.b.x, 1); b1.y = __shfl_down_sync(0xffffffffu, r.b.y, 1);
+        if (lane == 31) { a1 = r.xa; b1 = r.xb; }
+    };
+    Raw r0 = load_raw(k_lo), r1 = load_raw(k_lo + 1);
+    float2 a = r0.a, b = r0.b, a1, b1;                                /* layer k:   (i,j) (i+1,j) (i,j+1) (i+1,j+1) */
+    neighbours(r0, a1, b1);
     unsigned int n_row = 0;
     const unsigned int base = EMIT ? (cell_ok ? row_off[((size_t)i * m + j) * nz + zc] : 0u) : 0u;
     for (int k = k_lo; k <= k_hi; k++) {
-        float2 c, c1, e, e1;                                          /* layer k+1 */
-        load_layer(k + 1, c, c1, e, e1);
+        Raw r2;
+        r2.a = r2.b = r2.xa = r2.xb = zero;
+        if (k + 2 <= k_hi + 1) r2 = load_raw(k + 2);                  /* warp-uniform */
+        const float2 c = r1.a, e = r1.b;                              /* layer k+1 */
+        float2 c1, e1;
+        neighbours(r1, c1, e1);
         if (cell_ok) {
             const float d[8] = {a.x, a1.x, c1.x, c.x, b.x, b1.x, e1.x, e.x};
             const float w[8] = {a.y, a1.y, c1.y, c.y, b.y, b1.y, e1.y, e.y};
@@ -78,6 +92,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McPara
             }
         }
         a = c; a1 = c1; b = e; b1 = e1;
+        r1 = r2;
     }
     if (!EMIT && cell_ok) row_count[((size_t)i * m + j) * nz + zc] = n_row;
 }
