@@ -1007,17 +1007,28 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
     unsigned long long item_nxt = it + total_warps < n_items ? __ldg(&items[it + total_warps]) : 0ull;
     int k, j, x0; bool act;
     float4* ptr = decode_ptr(item_cur, k, j, x0, act);
-    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
-    if (it < n_items && act && !CHECK) { q0 = ld_f4(ptr); q1 = ld_f4(ptr + 1); }
+    /* deferred completion: the voxel loads of a unit certified as free space are issued right after
+     * its verdict and consumed one item later, after the next item's certificate arithmetic, so the
+     * HBM latency is hidden without loading anything for units that end up skipped or queued */
+    bool pend = false;
+    float4* pptr = ptr;
+    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+    auto complete = [&]() {
+        if (pend) {
+            /* free space: d < -delta => d_new = -delta, w_new = 1  (sdf.cpp:276, 285-292) */
+            fuse_apply(p0.x, p0.y, neg_delta, 1.0f);
+            fuse_apply(p0.z, p0.w, neg_delta, 1.0f);
+            fuse_apply(p1.x, p1.y, neg_delta, 1.0f);
+            fuse_apply(p1.z, p1.w, neg_delta, 1.0f);
+            pptr[0] = p0; pptr[1] = p1;
+        }
+    };
     for (; it < n_items; it += total_warps) {
-        /* stage A: descriptor two items ahead, voxel loads one item ahead */
+        /* stage A: descriptor two items ahead */
         const unsigned int it2 = it + 2 * total_warps;
         const unsigned long long item_nn = it2 < n_items ? __ldg(&items[it2]) : 0ull;
         int kn = 0, jn = 0, x0n = 0; bool actn = false;
         float4* ptrn = decode_ptr(item_nxt, kn, jn, x0n, actn);
-        float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0;
-        const bool have_n = it + total_warps < n_items;
-        if (have_n && actn && !CHECK && !queue_front) { n0 = ld_f4(ptrn); n1 = ld_f4(ptrn + 1); }
         /* stage B: certificate of the current unit (unless the whole row was already judged) */
         int verdict = UNIT_SKIP;
         const int rowv = (int)(item_cur >> 61) & 3;
@@ -1041,13 +1052,11 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
             staged += __popc(mask);
             flush(63);
         } else {
-            if (verdict == UNIT_FRONT) {
-                /* free space: d < -delta => d_new = -delta, w_new = 1  (sdf.cpp:276, 285-292) */
-                fuse_apply(q0.x, q0.y, neg_delta, 1.0f);
-                fuse_apply(q0.z, q0.w, neg_delta, 1.0f);
-                fuse_apply(q1.x, q1.y, neg_delta, 1.0f);
-                fuse_apply(q1.z, q1.w, neg_delta, 1.0f);
-                ptr[0] = q0; ptr[1] = q1;
+            complete();                                   /* the previous item's free-space units */
+            pend = (verdict == UNIT_FRONT);
+            if (pend) {
+                pptr = ptr;
+                p0 = ld_f4(ptr); p1 = ld_f4(ptr + 1);
                 if (k >= g.ko0 && k < g.ko1) my_updates += 4u;
             }
             const unsigned int mask = __ballot_sync(0xffffffffu, verdict == UNIT_UNKNOWN);
@@ -1061,8 +1070,9 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
         /* rotate the pipeline */
         item_cur = item_nxt;
         item_nxt = item_nn;
-        k = kn; j = jn; x0 = x0n; act = actn; ptr = ptrn; q0 = n0; q1 = n1;
+        k = kn; j = jn; x0 = x0n; act = actn; ptr = ptrn;
     }
+    if (!CHECK) complete();
     flush(0);
     count_updates(my_updates, lane, n_updated);
 }
