@@ -224,7 +224,8 @@ __device__ void exchange_sums(const ShardLinks& L, unsigned long long seqno, dou
  * the 6x6 elimination runs one lane per matrix element in shared memory (the serial version
  * needs ~170 registers and is a ~4 us dependent chain).  sc: >= 128 doubles of shared scratch.
  * ------------------------------------------------------------------------------------------ */
-__device__ void gn_update_warp(const GridParams& g, PoseState* pose, const double* sums, double* sc, int lane) {
+__device__ void gn_update_warp(const GridParams& g, PoseState* pose, const double* sums, double* sc, int lane,
+                               const double* Rcur, const double* tcur) {   /* current pose (already on chip in the caller) */
     double (*sA)[8] = reinterpret_cast<double (*)[8]>(sc);        /* 6 x 8: [A | b] */
     double* sRd = sc + 48;                                        /* 9  */
     double* sTd = sc + 57;                                        /* 3  */
@@ -233,8 +234,8 @@ __device__ void gn_update_warp(const GridParams& g, PoseState* pose, const doubl
     double* sNR = sc + 72;                                        /* 9  new rot */
     double* sNT = sc + 81;                                        /* 3  new trans */
     if (lane < N_SLOTS) pose->sums[lane] = sums[lane];
-    if (lane < 9) sR[lane] = pose->R[lane];
-    if (lane < 3) sT[lane] = pose->t[lane];
+    if (lane < 9) sR[lane] = Rcur[lane];
+    if (lane < 3) sT[lane] = tcur[lane];
     for (int e = lane; e < 42; e += 32) {
         const int r = e / 7, c = e - 7 * r;
         if (c < 6) {
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
         for (int r = 0; r < a.links.world; r++)
             if (tid < N_SLOTS) a.links.box[r]->sums[par][a.links.rank][tid] = sSums[tid];
     } else if (tid < 32) {
-        if (a.do_update) gn_update_warp(g, pose, sSums, &sRed[0][0], tid);
+        if (a.do_update) gn_update_warp(g, pose, sSums, &sRed[0][0], tid, sM[0], sT);
         else if (tid < N_SLOTS) pose->sums[tid] = sSums[tid];
     }
     if (tid == 0) *a.ticket = 0u;
@@ -546,7 +547,7 @@ __global__ void k_gn_combine(LinearizeArgs a, unsigned long long seqno) {
         sSums[tid] = acc;
     }
     __syncthreads();
-    if (a.do_update) gn_update_warp(a.g, pose, sSums, sScratch, tid);
+    if (a.do_update) gn_update_warp(a.g, pose, sSums, sScratch, tid, pose->R, pose->t);
     else if (tid < N_SLOTS) pose->sums[tid] = sSums[tid];
 }
 
