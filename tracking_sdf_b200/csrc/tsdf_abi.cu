@@ -113,6 +113,14 @@ struct Impl {
 
 tsdf_status bad(const char* msg) { g_err = msg; return TSDF_ERR_BAD_ARG; }
 
+/* device scratch that is released on every exit path of an accessor */
+struct DevTmp {
+    void* p = nullptr;
+    ~DevTmp() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 Impl* I(tsdf_handle h) { return reinterpret_cast<Impl*>(h); }
 
 /* the fp32/fp64 constants exactly as the reference's constructors build them */
@@ -672,15 +680,14 @@ tsdf_status tsdf_interpolate_color(tsdf_handle h, int64_t n, const double* globa
     if (!p->color) return bad("colour store not allocated (tsdf_enable_color)");
     if (n == 0) return TSDF_OK;
     CK(cudaSetDevice(p->device));
-    double* dp = nullptr; float* dout = nullptr;
-    CK(cudaMalloc(&dp, (size_t)n * 3 * sizeof(double)));
-    CK(cudaMalloc(&dout, (size_t)n * 4 * sizeof(float)));
-    CK(cudaMemcpyAsync(dp, global_pts, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    launch_sample_color(p->g, p->color, n, dp, dout, p->stream);
+    DevTmp dp, dout;
+    CK(dp.alloc((size_t)n * 3 * sizeof(double)));
+    CK(dout.alloc((size_t)n * 4 * sizeof(float)));
+    CK(cudaMemcpyAsync(dp.p, global_pts, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    launch_sample_color(p->g, p->color, n, dp.as<double>(), dout.as<float>(), p->stream);
     p->launches++;
-    CK(cudaMemcpyAsync(rgba, dout, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(rgba, dout.p, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    cudaFree(dp); cudaFree(dout);
     return TSDF_OK;
 }
 
@@ -690,14 +697,13 @@ tsdf_status tsdf_download_color(tsdf_handle h, float* cw, float* r, float* g, fl
     Impl* p = I(h);
     if (!p->color) return bad("colour store not allocated (tsdf_enable_color)");
     CK(cudaSetDevice(p->device));
-    float* d[4] = {nullptr, nullptr, nullptr, nullptr};
+    DevTmp d[4];
     float* hst[4] = {cw, r, g, b};
-    for (int q = 0; q < 4; q++) CK(cudaMalloc(&d[q], (size_t)p->n_stored * sizeof(float)));
-    launch_export_color(p->g, p->color, d[0], d[1], d[2], d[3], layout == TSDF_LAYOUT_REFERENCE ? 1 : 0, p->stream);
+    for (int q = 0; q < 4; q++) CK(d[q].alloc((size_t)p->n_stored * sizeof(float)));
+    launch_export_color(p->g, p->color, d[0].as<float>(), d[1].as<float>(), d[2].as<float>(), d[3].as<float>(), layout == TSDF_LAYOUT_REFERENCE ? 1 : 0, p->stream);
     p->launches++;
-    for (int q = 0; q < 4; q++) CK(cudaMemcpyAsync(hst[q], d[q], (size_t)p->n_stored * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    for (int q = 0; q < 4; q++) CK(cudaMemcpyAsync(hst[q], d[q].p, (size_t)p->n_stored * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    for (int q = 0; q < 4; q++) cudaFree(d[q]);
     CK(cudaGetLastError());
     return TSDF_OK;
 }
@@ -750,19 +756,18 @@ tsdf_status tsdf_mesh_download(tsdf_handle h, float* xyz, double* world, float* 
     if (rgba && !p->color) return bad("vertex colours need the colour store (tsdf_enable_color)");
     if (xyz) CK(cudaMemcpyAsync(xyz, p->mesh_xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
     if (world || rgba) {
-        double* dw = nullptr; float* dc = nullptr;
-        CK(cudaMalloc(&dw, (size_t)n * 3 * sizeof(double)));
-        launch_mesh_world(p->g, p->mesh_xyz, n, dw, p->stream);
+        DevTmp dw, dc;
+        CK(dw.alloc((size_t)n * 3 * sizeof(double)));
+        launch_mesh_world(p->g, p->mesh_xyz, n, dw.as<double>(), p->stream);
         p->launches++;
-        if (world) CK(cudaMemcpyAsync(world, dw, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        if (world) CK(cudaMemcpyAsync(world, dw.p, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
         if (rgba) {
-            CK(cudaMalloc(&dc, (size_t)n * 4 * sizeof(float)));
-            launch_sample_color(p->g, p->color, n, dw, dc, p->stream);
+            CK(dc.alloc((size_t)n * 4 * sizeof(float)));
+            launch_sample_color(p->g, p->color, n, dw.as<double>(), dc.as<float>(), p->stream);
             p->launches++;
-            CK(cudaMemcpyAsync(rgba, dc, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+            CK(cudaMemcpyAsync(rgba, dc.p, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
         }
         CK(cudaStreamSynchronize(p->stream));
-        cudaFree(dw); cudaFree(dc);
     }
     CK(cudaStreamSynchronize(p->stream));
     CK(cudaGetLastError());
@@ -877,16 +882,15 @@ tsdf_status tsdf_backproject(tsdf_handle h, const float* depth, int32_t mem, flo
     tsdf_status st = stage_depth(p, depth, mem, &dptr);
     if (st != TSDF_OK) return st;
     const size_t n = (size_t)p->g.img_w * p->g.img_h * 3;
-    float *dc = nullptr, *dn = nullptr;
-    CK(cudaMalloc(&dc, n * sizeof(float)));
-    if (normals) CK(cudaMalloc(&dn, n * sizeof(float)));
+    DevTmp dc, dn;
+    CK(dc.alloc(n * sizeof(float)));
+    if (normals) CK(dn.alloc(n * sizeof(float)));
     enqueue_prep(p, dptr, 0);
-    launch_cloud(p->g, p->pix, dc, dn, p->stream);
+    launch_cloud(p->g, p->pix, dc.as<float>(), normals ? dn.as<float>() : nullptr, p->stream);
     p->launches++;
-    CK(cudaMemcpyAsync(cloud, dc, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
-    if (normals) CK(cudaMemcpyAsync(normals, dn, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(cloud, dc.p, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    if (normals) CK(cudaMemcpyAsync(normals, dn.p, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    cudaFree(dc); cudaFree(dn);
     return TSDF_OK;
 }
 
@@ -895,17 +899,16 @@ tsdf_status tsdf_interpolate_distance(tsdf_handle h, int64_t n, const double* pt
     if (n == 0) return TSDF_OK;
     Impl* p = I(h);
     CK(cudaSetDevice(p->device));
-    double* dp = nullptr; float* dout = nullptr; uint8_t* dok = nullptr;
-    CK(cudaMalloc(&dp, (size_t)n * 3 * sizeof(double)));
-    CK(cudaMalloc(&dout, (size_t)n * sizeof(float)));
-    CK(cudaMalloc(&dok, (size_t)n));
-    CK(cudaMemcpyAsync(dp, pts, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    launch_sample(p->g, p->grid, n, dp, dout, dok, p->stream);
+    DevTmp dp, dout, dok;
+    CK(dp.alloc((size_t)n * 3 * sizeof(double)));
+    CK(dout.alloc((size_t)n * sizeof(float)));
+    CK(dok.alloc((size_t)n));
+    CK(cudaMemcpyAsync(dp.p, pts, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    launch_sample(p->g, p->grid, n, dp.as<double>(), dout.as<float>(), dok.as<uint8_t>(), p->stream);
     p->launches++;
-    CK(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
-    CK(cudaMemcpyAsync(ok, dok, (size_t)n, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(out, dout.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(ok, dok.p, (size_t)n, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    cudaFree(dp); cudaFree(dout); cudaFree(dok);
     return TSDF_OK;
 }
 
@@ -932,10 +935,11 @@ static tsdf_status xfer_grid(Impl* p, float* D, float* W, int layout, bool down)
     const int m = p->g.m, nk = p->g.ks1 - p->g.ks0;
     if (layout == TSDF_LAYOUT_XFASTEST) {
         const int kstep = 16;
-        float *dD = nullptr, *dW = nullptr;
+        DevTmp tD, tW;
         const size_t plane = (size_t)m * m;
-        CK(cudaMalloc(&dD, plane * kstep * sizeof(float)));
-        CK(cudaMalloc(&dW, plane * kstep * sizeof(float)));
+        CK(tD.alloc(plane * kstep * sizeof(float)));
+        CK(tW.alloc(plane * kstep * sizeof(float)));
+        float *dD = tD.as<float>(), *dW = tW.as<float>();
         for (int k0 = 0; k0 < nk; k0 += kstep) {
             const int kn = nk - k0 < kstep ? nk - k0 : kstep;
             GridParams gs = p->g;
@@ -953,11 +957,11 @@ static tsdf_status xfer_grid(Impl* p, float* D, float* W, int layout, bool down)
             p->launches++;
             CK(cudaStreamSynchronize(p->stream));
         }
-        cudaFree(dD); cudaFree(dW);
     } else {
-        float *dD = nullptr, *dW = nullptr;
-        CK(cudaMalloc(&dD, (size_t)p->n_stored * sizeof(float)));
-        CK(cudaMalloc(&dW, (size_t)p->n_stored * sizeof(float)));
+        DevTmp tD, tW;
+        CK(tD.alloc((size_t)p->n_stored * sizeof(float)));
+        CK(tW.alloc((size_t)p->n_stored * sizeof(float)));
+        float *dD = tD.as<float>(), *dW = tW.as<float>();
         if (down) {
             launch_export(p->g, p->grid, dD, dW, 0, p->stream);
             CK(cudaMemcpyAsync(D, dD, (size_t)p->n_stored * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
@@ -969,7 +973,6 @@ static tsdf_status xfer_grid(Impl* p, float* D, float* W, int layout, bool down)
         }
         p->launches++;
         CK(cudaStreamSynchronize(p->stream));
-        cudaFree(dD); cudaFree(dW);
     }
     CK(cudaGetLastError());
     return TSDF_OK;
