@@ -467,7 +467,7 @@ def main_sharded(args):
     rank, world, local = dist_env()
     n_gpus = max(world, 1)
     import tracking_sdf_b200 as T
-    from tracking_sdf_b200 import sharding
+    from tracking_sdf_b200 import sharding, capi
     from tools import synth
     L = T.load_library()
     if L.tsdf_device_count() < 1:
@@ -486,7 +486,15 @@ def main_sharded(args):
     depth, Rs, ts = render_frames(n_frames, start=0, pinned=True)
     frame_bytes = depth[0].nbytes
     kw = dict(m=m, gauss_newton_max_iteration=GN_ITERS, maximum_twist_diff=float("-inf"))
-    g = sharding.ShardedTsdf(dist, device, **kw) if dist is not None else T.Tsdf(T.default_config(device=device, **kw))
+    bounds = None
+    if dist is not None and not args.equal_slabs:
+        # work-balanced slabs: per-layer cost profile from 8 poses spread over the run (same frames on every rank,
+        # so every rank derives the same partition), halo layers included in each slab's cost
+        halo = capi.slab_plan(capi.default_config(n_shards=n_gpus, shard_rank=min(1, n_gpus - 1), **kw))["halo"]
+        idx = list(range(0, n_frames, max(1, n_frames // 8)))
+        wts = sharding.frustum_weights(m, K, [(Rs[i], ts[i]) for i in idx], [depth[i] for i in idx])
+        bounds = capi.balanced_slabs(wts, n_gpus, min_layers=16, halo=halo)
+    g = sharding.ShardedTsdf(dist, device, bounds=bounds, **kw) if dist is not None else T.Tsdf(T.default_config(device=device, **kw))
     g.set_intrinsics(K)
     ring = g.pose_ring_capacity()
     ks0, ks1, ko0, ko1 = g.stored_range()
@@ -539,7 +547,8 @@ def main_sharded(args):
            "scaling": "strong", "vs_baseline": None, "dtype": "f32 values / f64 geometry", "data": "synthetic",
            "config": {"workload": "%d^3 grid z-slab sharded over %d GPU(s), 640x480 synthetic depth along fr1/plant GT path, %d GN iterations/frame "
                                   "(BASELINE.json configs[2]/[3])" % (m, n_gpus, GN_ITERS),
-                      "slab_rank0": {"own": [ko0, ko1], "stored": [ks0, ks1]}, "grid_bytes_total": 8 * m ** 3,
+                      "slab_rank0": {"own": [ko0, ko1], "stored": [ks0, ks1]}, "slab_bounds": bounds if bounds is not None else "equal thickness",
+                      "grid_bytes_total": 8 * m ** 3,
                       "l2": "inputs larger than L2; no flush", "exchange": "30 doubles per GN iteration, in-kernel NVLink peer stores, rank-order sum"},
            "roofline": {"bound": "hbm", "kernel": "fusion stage (k_fuse_tables + k_fuse_plan + k_fuse_cert + k_fuse_exact)", "achieved": ach, "peak": hbm * n_gpus, "unit": "GB/s", "frac": ach / (hbm * n_gpus),
                         "traffic": None, "peak_source": peak_src + " x n_gpus", "ms_per_launch": t_fuse_max * 1e3,
@@ -589,6 +598,7 @@ def main():
     ap.add_argument("--no-dense", action="store_true", help="skip the dense fusion micro-benchmark")
     ap.add_argument("--no-color", action="store_true", help="skip the colour fusion measurement")
     ap.add_argument("--no-mesh", action="store_true", help="skip the marching-cubes measurement")
+    ap.add_argument("--equal-slabs", action="store_true", help="sharded workload: equal-thickness z slabs instead of the work-balanced partition")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-budget", type=float, default=90.0)
     args = ap.parse_args()

@@ -75,7 +75,11 @@ typedef struct tsdf_config {
     int32_t n_shards;                   /* slabs the volume is cut into along z         */
     int32_t shard_rank;                 /* which slab this handle owns                  */
     int32_t halo;                       /* extra z layers kept (and fused) on each side; <0 = auto */
-    int32_t reserved[4];
+    /* explicit owned layers [slab_k_begin, slab_k_end) of this slab; 0,0 = equal thickness.  Equal
+     * slabs are not equal work (the view frustum is not uniform in z): tsdf_balanced_slabs cuts the
+     * volume by a per-layer cost profile instead.  Every rank must use the same partition. */
+    int32_t slab_k_begin, slab_k_end;
+    int32_t reserved[2];
 } tsdf_config;
 
 typedef struct tsdf_track_stats {
@@ -159,6 +163,13 @@ tsdf_status tsdf_download_color(tsdf_handle h, float* color_w, float* r, float* 
  * vertex = extent * index / m (no half-voxel offset, :123-125).  iso_level outside [0,1) gives an empty
  * mesh like the reference (:248-254).  The mesh stays on the device until the next extract / destroy.
  * On a z-slab handle only the cells of the owned layers are meshed. */
+/* Work-balanced z partition (host only): weights[m] = relative fusion cost of each layer (e.g. the
+ * number of in-view voxels for a few representative poses); bounds[n_shards + 1] receives the cuts
+ * (bounds[0] = 0, bounds[n_shards] = m, every slab at least min_layers thick) that minimise the
+ * largest per-slab cost, where a slab's cost is the weight of every layer it fuses, i.e. its own
+ * layers plus `halo` layers on each side (use tsdf_slab_plan's halo).  Slab r = [bounds[r], bounds[r+1]). */
+tsdf_status tsdf_balanced_slabs(int32_t m, int32_t n_shards, const double* weights, int32_t min_layers, int32_t halo, int32_t* bounds);
+
 tsdf_status tsdf_mesh_extract(tsdf_handle h, float iso_level, int64_t* n_vertices);
 /* copy the last mesh to the host; any pointer may be NULL.  xyz: n*3 floats as above; world: n*3
  * doubles = (double)xyz + sdf_origin, the marker points of sdf.cpp:354-356; rgba: n*4 floats =

@@ -59,3 +59,36 @@ def test_too_small_halo_is_detected(gpu_lib, frames, K):
         grp.linearize(depth[1])
     assert e.value.status == 5
     grp.close()
+
+
+def test_unequal_slabs_equal_unsharded(gpu_lib, frames, K):
+    """Explicit (work-balanced) slab bounds: same results as the unsharded volume; bad bounds are rejected."""
+    depth, Rs, ts = frames
+    m = 128
+    kw = dict(m=m, gauss_newton_max_iteration=10, maximum_twist_diff=float("-inf"))
+    bounds = [0, 20, 52, 100, 128]
+    one = T.Tsdf(T.default_config(**kw)); one.set_intrinsics(K)
+    grp = T.ShardGroup(4, bounds=bounds, **kw); grp.set_intrinsics(K)
+    assert [s.stored_range()[2:] for s in grp.shards] == [(bounds[r], bounds[r + 1]) for r in range(4)]
+    one.set_pose(Rs[0], ts[0]); grp.set_pose(Rs[0], ts[0])
+    assert one.fuse(depth[0]) == grp.frame(depth[0], track=False, fuse=True)[3]
+    for f in range(1, 3):
+        A1, b1, s1 = one.linearize(depth[f]); A2, b2, s2 = grp.linearize(depth[f])
+        assert s1["n_valid"] == s2["n_valid"] and s2["halo_miss"] == 0
+        assert np.abs(A1 - A2).max() <= 1e-12 * np.abs(A1).max() and np.abs(b1 - b2).max() <= 1e-12 * np.abs(b1).max()
+        R1, t1, st1, nu1 = one.track_and_fuse(depth[f])
+        R2, t2, st2, nu2 = grp.frame(depth[f], track=True, fuse=True)
+        assert np.linalg.norm(t1 - t2) < 1e-9 and rot_angle(R1, R2) < 1e-9
+        one.set_pose(R2, t2)
+    one.reset(); one.set_intrinsics(K)
+    for s in grp.shards:
+        s.reset()
+    for f in range(3):
+        one.fuse(depth[f], Rs[f], ts[f])
+        grp.set_pose(Rs[f], ts[f]); grp.frame(depth[f], track=False, fuse=True)
+    D1, W1 = one.download(); D2, W2 = grp.download()
+    assert np.array_equal(D1, D2) and np.array_equal(W1, W2)
+    one.close(); grp.close()
+    for bad in (dict(slab_k_begin=4, slab_k_end=40), dict(slab_k_begin=0, slab_k_end=128), dict(slab_k_begin=0, slab_k_end=200)):
+        with pytest.raises(T.TsdfError):
+            T.Tsdf(T.default_config(m=128, n_shards=2, shard_rank=0, **bad))

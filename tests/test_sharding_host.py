@@ -35,6 +35,15 @@ owner = np.zeros(1024, int)
 for r, p in enumerate(pl):
     owner[(k >= p["own"][0]) & (k < p["own"][1])] += 1
 assert (owner == 1).all()
+# 3b. the work-balanced partition: every rank derives identical cuts from the same cost profile, the explicit
+#     slabs tile [0, m) and each rank's plan reports its own cut
+wts = np.exp(-((np.arange(1024) - 400.0) / 150.0) ** 2) + 0.05
+bounds = capi.balanced_slabs(wts, world, min_layers=16, halo=30)
+allb = sharding.gather_bytes(dist, np.array(bounds, np.int32).view(np.uint8))
+assert (allb == allb[0]).all()
+assert bounds[0] == 0 and bounds[-1] == 1024 and all(bounds[r + 1] - bounds[r] >= 16 for r in range(world))
+mine = capi.slab_plan(capi.default_config(m=1024, n_shards=world, shard_rank=rank, slab_k_begin=bounds[rank], slab_k_end=bounds[rank + 1]))
+assert mine["own"] == (bounds[rank], bounds[rank + 1])
 # 4. no GPU here: creating the shard must fail loudly, not fall back
 try:
     capi.Tsdf(capi.default_config(m=64, n_shards=world, shard_rank=rank))
@@ -75,3 +84,43 @@ def test_halo_covers_the_tracking_stencil():
                 vz = 3.5 / m
                 reach = 1 + 1 + int(np.ceil(0.01 * np.sqrt(36 + 36 + 3.5 ** 2) / vz))
                 assert p["halo"] >= reach
+
+
+def test_balanced_slabs_minimise_the_largest_cost():
+    """tsdf_balanced_slabs: cuts tile [0, m), respect min_layers, and the largest halo-inclusive slab cost is no
+    worse than equal slabs' and within a layer's weight of the brute-force optimum on a small case."""
+    import itertools
+    from tracking_sdf_b200 import capi
+    rng = np.random.default_rng(3)
+    m, n, halo, minl = 40, 4, 2, 3
+    w = rng.uniform(0.0, 1.0, m) ** 3 + 0.01
+    P = np.concatenate([[0.0], np.cumsum(w)])
+
+    def worst(b):
+        return max(P[min(b[r + 1] + halo, m)] - P[max(b[r] - halo, 0)] for r in range(n))
+
+    b = capi.balanced_slabs(w, n, min_layers=minl, halo=halo)
+    assert b[0] == 0 and b[-1] == m and all(b[r + 1] - b[r] >= minl for r in range(n))
+    best = min(worst((0,) + c + (m,)) for c in itertools.combinations(range(1, m), n - 1)
+               if all(y - x >= minl for x, y in zip((0,) + c, c + (m,))))
+    assert worst(b) <= best + 1e-9
+    eq = [m * r // n for r in range(n + 1)]
+    assert worst(b) <= worst(eq) + 1e-12
+    # uniform weights, no halo -> equal slabs
+    assert capi.balanced_slabs(np.ones(64), 4, min_layers=1, halo=0) == [0, 16, 32, 48, 64]
+    # errors are reported, not guessed around
+    import pytest
+    with pytest.raises(capi.TsdfError):
+        capi.balanced_slabs(np.ones(8), 4, min_layers=3)
+    with pytest.raises(capi.TsdfError):
+        capi.balanced_slabs(np.array([1.0, np.nan, 1.0, 1.0]), 2, min_layers=1)
+
+
+def test_frustum_weights_profile():
+    from tracking_sdf_b200 import sharding
+    from tools import synth
+    depth, Rs, ts = synth.render_sequence(2)
+    w = sharding.frustum_weights(256, synth.K_DEFAULT, [(Rs[0], ts[0])], [depth[0]])
+    assert w.shape == (256,) and (w > 0).all()
+    # the camera sits at z ~ 1.3 m looking slightly down: the layers around it carry more than the top of the volume
+    assert w[100:160].mean() > 3 * w[-20:].mean()

@@ -27,7 +27,8 @@ class Config(ctypes.Structure):
                 ("v_h", ctypes.c_float), ("w_h", ctypes.c_float), ("pixel_stride", ctypes.c_int32),
                 ("metric", ctypes.c_int32), ("image_width", ctypes.c_int32), ("image_height", ctypes.c_int32),
                 ("device", ctypes.c_int32), ("n_shards", ctypes.c_int32), ("shard_rank", ctypes.c_int32),
-                ("halo", ctypes.c_int32), ("reserved", ctypes.c_int32 * 4)]
+                ("halo", ctypes.c_int32), ("slab_k_begin", ctypes.c_int32), ("slab_k_end", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 2)]
 
 
 class TrackStats(ctypes.Structure):
@@ -75,6 +76,7 @@ PROTOTYPES = [
     ("tsdf_track_and_fuse_rgb", _I32, [_VP, _VP, _VP, _I32, c_dp, c_dp, _STP, c_i64p]),
     ("tsdf_interpolate_color", _I32, [_VP, _I64, c_dp, c_fp]),
     ("tsdf_download_color", _I32, [_VP, c_fp, c_fp, c_fp, c_fp, _I32]),
+    ("tsdf_balanced_slabs", _I32, [_I32, _I32, c_dp, _I32, _I32, ctypes.POINTER(ctypes.c_int32)]),
     ("tsdf_mesh_extract", _I32, [_VP, ctypes.c_float, c_i64p]),
     ("tsdf_mesh_download", _I32, [_VP, c_fp, c_dp, c_fp]),
     ("tsdf_enqueue_frame", _I32, [_VP, _VP, _I32, _I32]),
@@ -170,6 +172,18 @@ def slab_plan(cfg):
     if st != 0:
         raise TsdfError(st, L.tsdf_last_error().decode())
     return {"own": (out[0], out[1]), "stored": (out[2], out[3]), "halo": out[4]}
+
+
+def balanced_slabs(weights, n_shards, min_layers=8, halo=0):
+    """Cuts [b0=0, b1, ..., bn=m] of the z partition that minimises the largest per-slab cost, halo layers
+    included (host only)."""
+    L = load_library()
+    w = np.ascontiguousarray(weights, np.float64)
+    out = (ctypes.c_int32 * (n_shards + 1))()
+    st = L.tsdf_balanced_slabs(len(w), n_shards, w.ctypes.data_as(c_dp), min_layers, halo, out)
+    if st != 0:
+        raise TsdfError(st, L.tsdf_last_error().decode())
+    return [int(v) for v in out]
 
 
 def _d(a):
@@ -513,10 +527,11 @@ def pinned_empty(shape, dtype=np.float32):
 class ShardGroup:
     """z-slab shards living in this process (tsdf_shard_attach_local + tsdf_group_*)."""
 
-    def __init__(self, n_shards, devices=None, **kw):
+    def __init__(self, n_shards, devices=None, bounds=None, **kw):
         self.L = load_library()
         devices = devices if devices is not None else [0] * n_shards
-        self.shards = [Tsdf(default_config(n_shards=n_shards, shard_rank=r, device=devices[r], **kw)) for r in range(n_shards)]
+        ex = [dict(slab_k_begin=bounds[r], slab_k_end=bounds[r + 1]) if bounds is not None else {} for r in range(n_shards)]
+        self.shards = [Tsdf(default_config(n_shards=n_shards, shard_rank=r, device=devices[r], **ex[r], **kw)) for r in range(n_shards)]
         self.n = n_shards
         self.arr = (ctypes.c_void_p * n_shards)(*[s.h for s in self.shards])
         self._ck(self.L.tsdf_shard_attach_local(self.arr, n_shards))

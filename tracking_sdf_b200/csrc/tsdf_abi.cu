@@ -156,6 +156,7 @@ void slab_range(const tsdf_config& c, int& ko0, int& ko1, int& ks0, int& ks1, in
     const int G = c.n_shards < 1 ? 1 : c.n_shards;
     ko0 = (int)(((int64_t)c.m * c.shard_rank) / G);
     ko1 = (int)(((int64_t)c.m * (c.shard_rank + 1)) / G);
+    if (G > 1 && c.slab_k_end > c.slab_k_begin) { ko0 = c.slab_k_begin; ko1 = c.slab_k_end; }   /* explicit (balanced) partition */
     halo = c.halo;
     if (G == 1) halo = 0;
     else if (halo < 0) {
@@ -344,6 +345,11 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     if (cfg->metric != TSDF_POINT_TO_PLANE && cfg->metric != TSDF_POINT_TO_POINT) return bad("bad metric");
     if (cfg->n_shards < 1 || cfg->n_shards > MAX_WORLD || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->n_shards) return bad("bad shard configuration");
     if (cfg->n_shards > cfg->m / 4) return bad("too many shards for this m");
+    if (cfg->slab_k_end > cfg->slab_k_begin) {
+        if (cfg->slab_k_begin < 0 || cfg->slab_k_end > cfg->m) return bad("explicit slab outside the grid");
+        if ((cfg->shard_rank == 0) != (cfg->slab_k_begin == 0) || (cfg->shard_rank == cfg->n_shards - 1) != (cfg->slab_k_end == cfg->m))
+            return bad("explicit slabs must tile [0, m) in rank order");
+    } else if (cfg->slab_k_end != 0 || cfg->slab_k_begin != 0) return bad("empty explicit slab");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -705,6 +711,49 @@ tsdf_status tsdf_download_color(tsdf_handle h, float* cw, float* r, float* g, fl
     for (int q = 0; q < 4; q++) CK(cudaMemcpyAsync(hst[q], d[q].p, (size_t)p->n_stored * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     CK(cudaGetLastError());
+    return TSDF_OK;
+}
+
+tsdf_status tsdf_balanced_slabs(int32_t m, int32_t n_shards, const double* weights, int32_t min_layers, int32_t halo, int32_t* bounds) {
+    if (!weights || !bounds || m < 1 || n_shards < 1) return bad("bad argument");
+    if (min_layers < 1) min_layers = 1;
+    if (halo < 0) halo = 0;
+    if ((int64_t)min_layers * n_shards > m) return bad("min_layers * n_shards exceeds m");
+    std::vector<double> P((size_t)m + 1, 0.0);
+    for (int k = 0; k < m; k++) {
+        if (!(weights[k] >= 0.0) || !(weights[k] <= 1e300)) return bad("weights must be finite and non-negative");
+        P[k + 1] = P[k] + weights[k];
+    }
+    /* cost of slab [a, b) = weight of the layers it fuses, halo included */
+    auto cost = [&](int a, int b) { return P[b + halo > m ? m : b + halo] - P[a - halo < 0 ? 0 : a - halo]; };
+    /* greedy feasibility for a cost cap T: make every slab as thick as the cap allows */
+    auto plan = [&](double T, int32_t* out) {
+        int a = 0;
+        out[0] = 0;
+        for (int r = 0; r < n_shards; r++) {
+            const int hi = m - (n_shards - 1 - r) * min_layers;     /* leave room for the slabs to come */
+            int b = a + min_layers;
+            if (b > hi || cost(a, b) > T) return false;
+            int lo_b = b, hi_b = hi;                                /* largest b with cost(a, b) <= T (cost is monotone in b) */
+            while (lo_b < hi_b) {
+                const int mid = (lo_b + hi_b + 1) / 2;
+                if (cost(a, mid) <= T) lo_b = mid; else hi_b = mid - 1;
+            }
+            b = (r == n_shards - 1) ? m : lo_b;
+            if (r == n_shards - 1 && cost(a, m) > T) return false;
+            out[r + 1] = b;
+            a = b;
+        }
+        return true;
+    };
+    double lo = 0.0, hi = P[m] + 1e-300;
+    std::vector<int32_t> tmp((size_t)n_shards + 1);
+    if (!plan(hi, tmp.data())) return bad("no partition satisfies min_layers");
+    for (int it = 0; it < 100 && hi - lo > 1e-12 * P[m]; it++) {
+        const double mid = 0.5 * (lo + hi);
+        if (plan(mid, tmp.data())) hi = mid; else lo = mid;
+    }
+    plan(hi, bounds);
     return TSDF_OK;
 }
 
