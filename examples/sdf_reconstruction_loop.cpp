@@ -62,6 +62,7 @@ int main(int argc, char** argv) {
     const int n_frames = argc > 2 ? std::atoi(argv[2]) : 20;
     const int m = argc > 3 ? std::atoi(argv[3]) : 256;
     const char* out_path = argc > 4 ? argv[4] : "trajectory.txt";
+    const char* mesh_path = argc > 5 ? argv[5] : nullptr;        /* optional: the visualisation thread's mesh as a PLY file */
     const std::vector<Pose> gt = load_trajectory(traj);
     if ((int)gt.size() < n_frames) { std::fprintf(stderr, "trajectory too short\n"); return 2; }
     const double K[9] = {525.0, 0, 319.5, 0, 525.0, 239.5, 0, 0, 1};
@@ -74,6 +75,13 @@ int main(int argc, char** argv) {
         camera_tracking.camera_info_cb(K);                                       /* :90-91 */
         std::ofstream myfile(out_path, std::ios::out | std::ios::trunc);
         std::vector<float> depth((size_t)W * H);
+        /* a registered colour image (the r,g,b of the XYZRGB cloud): a fixed test pattern */
+        std::vector<uint8_t> rgb((size_t)W * H * 3);
+        for (int v = 0; v < H; v++)
+            for (int u = 0; u < W; u++) {
+                uint8_t* c = &rgb[3 * ((size_t)v * W + u)];
+                c[0] = (uint8_t)(255 * u / W); c[1] = (uint8_t)(255 * v / H); c[2] = (uint8_t)((((u / 32) + (v / 32)) & 1) ? 220 : 60);
+            }
         int frame_num = 0;
         double err = 0;
         for (int f = 0; f < n_frames; f++) {                                     /* kinect_callback, :21-80 */
@@ -85,11 +93,28 @@ int main(int argc, char** argv) {
                 camera_tracking.estimate_new_position(&sdf, depth.data());       /* :70 */
                 writePoseToFile(myfile, gt[f].stamp, camera_tracking.trans(), camera_tracking.rot());   /* :71 */
             }
-            sdf.update(&camera_tracking, depth.data());                          /* :74 */
+            if (mesh_path) sdf.update(&camera_tracking, depth.data(), rgb.data());   /* :74 with the colour part, sdf.cpp:294-304 */
+            else sdf.update(&camera_tracking, depth.data());                     /* :74 */
             const auto t = camera_tracking.trans();
             err = std::sqrt((t[0] - gt[f].t[0]) * (t[0] - gt[f].t[0]) + (t[1] - gt[f].t[1]) * (t[1] - gt[f].t[1]) + (t[2] - gt[f].t[2]) * (t[2] - gt[f].t[2]));
         }
         std::printf("frames %d  grid %d^3  final position error vs ground truth %.4f m  -> %s\n", n_frames, m, err, out_path);
+        if (mesh_path) {
+            /* SDF::visualize (sdf.cpp:317-391): marching cubes, marker points = vertices + sdf_origin, one
+             * interpolate_color per vertex - here written as an ASCII PLY triangle soup instead of a ROS marker */
+            std::vector<float> xyz, rgba;
+            std::vector<double> world;
+            const int64_t nv = sdf.mesh(xyz, &world, &rgba);
+            std::ofstream ply(mesh_path, std::ios::out | std::ios::trunc);
+            ply << "ply\nformat ascii 1.0\nelement vertex " << nv << "\nproperty float x\nproperty float y\nproperty float z\n"
+                << "property uchar red\nproperty uchar green\nproperty uchar blue\nelement face " << nv / 3
+                << "\nproperty list uchar int vertex_indices\nend_header\n";
+            auto to8 = [](float c) { const float v = c * 255.0f; return (int)(v != v ? 0 : v < 0 ? 0 : v > 255 ? 255 : v); };   /* interpolated colours are 0..1 (sdf.cpp:210-213) */
+            for (int64_t q = 0; q < nv; q++)
+                ply << world[3 * q] << " " << world[3 * q + 1] << " " << world[3 * q + 2] << " " << to8(rgba[4 * q]) << " " << to8(rgba[4 * q + 1]) << " " << to8(rgba[4 * q + 2]) << "\n";
+            for (int64_t q = 0; q < nv / 3; q++) ply << "3 " << 3 * q << " " << 3 * q + 1 << " " << 3 * q + 2 << "\n";
+            std::printf("mesh: %lld triangles -> %s\n", (long long)(nv / 3), mesh_path);
+        }
     } catch (const b200::Error& e) {
         std::fprintf(stderr, "tsdf_b200 error %d: %s\n", (int)e.status, e.what());
         return 1;

@@ -37,9 +37,14 @@ def test_cpp_example_builds_and_has_no_fallback(tmp_path):
 def test_cpp_example_runs_the_node_loop(tmp_path, gpu_lib):
     build_exe()
     out = tmp_path / "trajectory.txt"
-    r = subprocess.run([EXE, os.path.join(ROOT, "data", "fr1_plant_gt_every4.txt"), "8", "128", str(out)],
+    ply = tmp_path / "mesh.ply"
+    r = subprocess.run([EXE, os.path.join(ROOT, "data", "fr1_plant_gt_every4.txt"), "8", "128", str(out), str(ply)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    head = open(ply).read(400).split("\n")
+    nv = int([l for l in head if l.startswith("element vertex")][0].split()[-1])
+    nf = int([l for l in head if l.startswith("element face")][0].split()[-1])
+    assert nv > 3000 and nv == 3 * nf                # the visualisation thread's coloured triangle soup (sdf.cpp:352-385)
     rows = np.loadtxt(out)
     assert rows.shape == (7, 8)                       # frame 1 is not tracked (sdf_reconstruction.cpp:69)
     gt = np.loadtxt(os.path.join(ROOT, "data", "fr1_plant_gt_every4.txt"))[1:8]
