@@ -160,11 +160,14 @@ void slab_range(const tsdf_config& c, int& ko0, int& ko1, int& ks0, int& ks1, in
     halo = c.halo;
     if (G == 1) halo = 0;
     else if (halo < 0) {
-        /* centre cell (+1), +-v_h voxels, and the rotational perturbation: w_h * r_max metres
-         * along z, r_max = the volume's diagonal (no back-projected point can be further) */
-        const double diag = sqrt((double)c.width * c.width + (double)c.height * c.height + (double)c.depth * c.depth);
+        /* centre cell (+1), +-v_h voxels, and the rotational perturbation: the sample moves by
+         * w_h * e_k x v, v = world-frame vector from the camera centre to the point; its z component is
+         * w_h * v_y (k = x), -w_h * v_x (k = y), 0 (k = z), so with the camera centre and the point both
+         * over the volume's footprint |dz| <= w_h * max(width, height).  (A camera far outside the footprint
+         * can exceed this: the tracker then reports TSDF_ERR_HALO and tsdf_config.halo must be set by hand.) */
+        const double reach = (double)(c.width > c.height ? c.width : c.height);
         const double vz = (double)c.depth / c.m;
-        halo = 2 + (int)ceil(c.v_h) + (int)ceil(c.w_h * diag / vz);
+        halo = 2 + (int)ceil(c.v_h) + (int)ceil(c.w_h * reach / vz);
     }
     ks0 = ko0 - halo < 0 ? 0 : ko0 - halo;
     ks1 = ko1 + halo > c.m ? c.m : ko1 + halo;
