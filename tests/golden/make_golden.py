@@ -19,6 +19,7 @@ from oracle import pyoracle as po   # noqa: E402
 from tools import synth             # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "track_fuse_m32.npz")
+OUT_CM = os.path.join(ROOT, "tests", "golden", "color_mesh_m32.npz")
 
 
 def build():
@@ -58,6 +59,33 @@ def build():
     return out
 
 
+def build_color_mesh():
+    """Colour fusion (sdf.cpp:294-304), colour sampling (sdf.cpp:164-217) and the mesher
+    (marching_cubes_sdf.cpp:243-287 + sdf.cpp:352-385) at m = 32 on three synthetic frames."""
+    depth, Rs, ts = synth.render_sequence(3)
+    o = po.Oracle(m=32, use_coord_table=0, metric=0)
+    o.set_intrinsics(synth.K_DEFAULT)
+    sha = hashlib.sha256()
+    nupd = []
+    for f in range(3):
+        rgb = synth.synth_rgb(depth[f], Rs[f], ts[f])
+        sha.update(rgb.tobytes())
+        o.set_pose(Rs[f], ts[f])
+        nupd.append(o.fuse_rgb(depth[f], rgb))
+    CW, R, G, B = o.color()
+    out = {"rgb_sha256": np.frombuffer(sha.digest(), np.uint8), "n_updated": np.array(nupd),
+           "Color_W": CW.copy(), "R": R.copy(), "G": G.copy(), "B": B.copy()}
+    pts = np.random.default_rng(17).uniform([-3.1, -3.1, -0.6], [3.1, 3.1, 3.1], (2048, 3))
+    out["sample_pts"] = pts; out["sample_rgba"] = o.interpolate_color(pts)
+    for iso, tag in ((0.0, "iso0"), (0.1, "iso01")):
+        xyz, world, rgba = o.mesh(iso, world=True, colors=True)
+        out["mesh_%s_xyz" % tag] = xyz; out["mesh_%s_world" % tag] = world; out["mesh_%s_rgba" % tag] = rgba
+    o.close()
+    return out
+
+
 if __name__ == "__main__":
     np.savez_compressed(OUT, **build())
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
+    np.savez_compressed(OUT_CM, **build_color_mesh())
+    print("wrote", OUT_CM, os.path.getsize(OUT_CM), "bytes")

@@ -54,3 +54,28 @@ def test_exp_map_golden(gold):
     for tw, R, t in zip(gold["exp_twist"], gold["exp_R"], gold["exp_t"]):
         Ro, to = po.exp_map(tw)
         assert np.abs(Ro - R).max() < 1e-15 and np.abs(to - t).max() < 1e-15
+
+
+GOLD_CM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "color_mesh_m32.npz")
+
+
+def test_oracle_reproduces_color_and_mesh_golden(frames):
+    """Colour fusion, colour sampling and the mesher against tests/golden/color_mesh_m32.npz."""
+    gold = np.load(GOLD_CM)
+    depth, Rs, ts = frames
+    o = po.Oracle(m=32, use_coord_table=0, metric=0); o.set_intrinsics(synth.K_DEFAULT)
+    sha = hashlib.sha256()
+    for f in range(3):
+        rgb = synth.synth_rgb(depth[f], Rs[f], ts[f])
+        sha.update(rgb.tobytes())
+        o.set_pose(Rs[f], ts[f])
+        assert o.fuse_rgb(depth[f], rgb) == gold["n_updated"][f]
+    assert np.array_equal(np.frombuffer(sha.digest(), np.uint8), gold["rgb_sha256"])     # the synthetic colour images are reproducible
+    for a, k in zip(o.color(), ("Color_W", "R", "G", "B")):
+        assert np.array_equal(a, gold[k], equal_nan=True), k
+    assert np.array_equal(o.interpolate_color(gold["sample_pts"]), gold["sample_rgba"], equal_nan=True)
+    for iso, tag in ((0.0, "iso0"), (0.1, "iso01")):
+        xyz, world, rgba = o.mesh(iso, world=True, colors=True)
+        assert np.array_equal(xyz, gold["mesh_%s_xyz" % tag]) and np.array_equal(world, gold["mesh_%s_world" % tag])
+        assert np.array_equal(rgba, gold["mesh_%s_rgba" % tag], equal_nan=True)
+    o.close()

@@ -67,3 +67,21 @@ def test_mesh_after_upload_of_an_analytic_sphere(gpu_lib, K):
     r = np.linalg.norm(p - [0.0, 0.0, 1.25], axis=1)
     assert abs(r.mean() - 1.0) < 0.02 and r.std() < 0.02
     g.close(); o.close()
+
+
+def test_color_and_mesh_against_committed_golden(gpu_lib, frames, K):
+    """The CUDA path against tests/golden/color_mesh_m32.npz (made by the oracle, tests/golden/make_golden.py)."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "color_mesh_m32.npz"))
+    depth, Rs, ts = frames
+    g = T.Tsdf(T.default_config(m=32, metric=0)); g.set_intrinsics(K)
+    for f in range(3):
+        assert g.fuse_rgb(depth[f], synth.synth_rgb(depth[f], Rs[f], ts[f]), Rs[f], ts[f]) == gold["n_updated"][f]
+    for a, k in zip(g.download_color(), ("Color_W", "R", "G", "B")):
+        assert np.array_equal(a, gold[k], equal_nan=True), k
+    assert np.array_equal(g.interpolate_color(gold["sample_pts"]), gold["sample_rgba"], equal_nan=True)
+    for iso, tag in ((0.0, "iso0"), (0.1, "iso01")):
+        xyz, world, rgba = g.mesh(iso, world=True, colors=True)
+        assert np.array_equal(xyz, gold["mesh_%s_xyz" % tag]) and np.array_equal(world, gold["mesh_%s_world" % tag])
+        assert np.array_equal(rgba, gold["mesh_%s_rgba" % tag], equal_nan=True)
+    g.close()

@@ -307,6 +307,15 @@ def test_reference_class_mirror(gpu_lib, frames, K):
     assert np.abs(cam.trans - o.get_pose()[1]).max() < 1e-9 and np.abs(cam.rot - o.get_pose()[0]).max() < 1e-9
     assert np.allclose(cam.rot_inv @ cam.rot, np.eye(3), atol=1e-12)
     assert sdf.get_number_of_voxels() == 64 ** 3 and sdf.get_array_index((1, 2, 3)) == 64 * 64 + 128 + 3
+    # the colour half of update and the visualisation thread's calls (sdf.cpp:294-304, 327-385)
+    o.set_pose(cam.rot, cam.trans)
+    rgb = synth.synth_rgb(depth[1], Rs[1], ts[1])
+    assert sdf.update(cam, depth[1], rgb) == o.fuse_rgb(depth[1], rgb)
+    pts, rgba = sdf.mesh(colors=True)
+    xo, wo, co = o.mesh(0.0, world=True, colors=True)
+    assert np.array_equal(pts, wo) and np.array_equal(rgba, co, equal_nan=True)
+    assert np.array_equal(sdf.interpolate_color(wo[:50]), co[:50], equal_nan=True)
+    assert np.array_equal(sdf.Color[1], o.color()[1])
     o.close()
 
 

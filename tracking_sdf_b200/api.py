@@ -8,6 +8,9 @@
     camera_tracking->estimate_new_position(sdf, cloud)        .estimate_new_position(sdf, depth)   camera_tracking.cpp:66-245
     sdf->update(camera_tracking, cloud, normals)              .update(camera_tracking, depth)      sdf.cpp:224-315
     sdf->interpolate_distance(voxel_pt, ok)                   .interpolate_distance(pts)    sdf.cpp:127-163
+    sdf->update(...) colour part (the cloud's r,g,b)          .update(camera_tracking, depth, rgb) sdf.cpp:294-304
+    sdf->interpolate_color(global_coords, color)              .interpolate_color(pts)       sdf.cpp:164-217
+    mc->performReconstruction(cloud) + marker fill            .mesh()                       marching_cubes_sdf.cpp:243-287, sdf.cpp:327-385
     rot / trans / rot_inv / rot_inv_trans / K / isKFilled     same attribute names (properties)
 
 The two reference objects share state through raw pointers (the tracker reads the grid, the
@@ -56,11 +59,29 @@ class SDF:
         """-> (values float32 [n], is_interpolated bool [n])"""
         return self._handle().interpolate_distance(voxel_points)
 
-    def update(self, camera_tracking, depth):
-        """sdf.cpp:224-315: integrate `depth` at camera_tracking's current pose; -> #voxels updated."""
+    def update(self, camera_tracking, depth, rgb=None):
+        """sdf.cpp:224-315: integrate `depth` (and, when the registered (h, w, 3) uint8 colour image is given,
+        the colour running mean of :294-304) at camera_tracking's current pose; -> #voxels updated."""
         if not camera_tracking.isKFilled:
             raise capi.TsdfError(2, "Camera Matrix not received")   # the reference exit(0)s, sdf.cpp:227-229
+        if rgb is not None:
+            return self._handle().fuse_rgb(depth, rgb)
         return self._handle().fuse(depth)
+
+    def interpolate_color(self, global_points):
+        """sdf.cpp:164-217 for n WORLD points -> (n, 4) float32 r,g,b,a."""
+        return self._handle().interpolate_color(global_points)
+
+    def mesh(self, iso_level=0.0, colors=False):
+        """The visualisation thread's product (sdf.cpp:327-385): marching cubes on the device ->
+        (marker points [n, 3] float64 = vertices + sdf_origin[, rgba [n, 4]]); three vertices per triangle."""
+        out = self._handle().mesh(iso_level, world=True, colors=colors)
+        return out[1:] if colors else out[1]
+
+    @property
+    def Color(self):
+        """(Color_W, R, G, B) in the reference's layout (sdf.h:49-52)."""
+        return self._handle().download_color(capi.LAYOUT_REFERENCE)
 
     @property
     def D(self):
