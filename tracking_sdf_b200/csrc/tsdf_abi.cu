@@ -48,6 +48,8 @@ struct Impl {
     float4* color = nullptr;
     uchar4* rgb4_buf[2] = {nullptr, nullptr};
     uchar4* rgb4 = nullptr;
+    double* cosn_buf[2] = {nullptr, nullptr};
+    double* cosn = nullptr;
     uint8_t* rgb_stage = nullptr;
     const uint8_t* frame_rgb = nullptr;           /* device pointer consumed by the next enqueue_prep (or NULL) */
     bool frame_has_color = false;                 /* the current records carry a colour image */
@@ -235,9 +237,9 @@ void enqueue_prep(Impl* p, const float* dptr, int reset_track) {
     cudaEventRecord(p->rec_free[b ^ 1], p->stream);              /* all work on the previous frame's records is enqueued */
     if (p->prep_seq >= 2) cudaStreamWaitEvent(p->prep_stream, p->rec_free[b], 0);
     if (p->depth_ready) cudaStreamWaitEvent(p->prep_stream, p->depth_ready, 0);
-    p->pix = p->pix_buf[b]; p->pts = p->pts_buf[b]; p->cert = p->cert_buf[b]; p->rgb4 = p->rgb4_buf[b];
+    p->pix = p->pix_buf[b]; p->pts = p->pts_buf[b]; p->cert = p->cert_buf[b]; p->rgb4 = p->rgb4_buf[b]; p->cosn = p->cosn_buf[b];
     p->frame_has_color = p->frame_rgb != nullptr;
-    launch_prep(p->g, dptr, p->pix, p->cert + p->pyr.off[0], p->pts, p->frame_rgb, p->rgb4, p->prep_stream);
+    launch_prep(p->g, dptr, p->pix, p->cert + p->pyr.off[0], p->pts, p->frame_rgb, p->rgb4, p->cosn, p->prep_stream);
     p->frame_rgb = nullptr;
     launch_pyramid(p->pyr, p->cert, p->ticket + 1000, p->prep_stream);
     if (p->depth_done) cudaEventRecord(p->depth_done, p->prep_stream);
@@ -266,7 +268,7 @@ void enqueue_fuse(Impl* p) {
     f.tables = p->fuse_tables; f.items = p->fuse_items; f.item_count = p->fuse_item_count;
     f.n_updated = p->n_upd_dev; f.nblk = p->fuse_blocks; f.nblk_cert = p->fuse_cert_blocks; f.check = p->fuse_check;
     f.pyr = p->pyr; f.cert = p->cert; f.units = p->fuse_units; f.unit_count = p->fuse_item_count + 1;
-    f.color = p->frame_has_color ? p->color : nullptr; f.rgb4 = p->rgb4; f.nblk_color = p->fuse_color_blocks;
+    f.color = p->frame_has_color ? p->color : nullptr; f.rgb4 = p->rgb4; f.cosn = p->cosn; f.nblk_color = p->fuse_color_blocks;
     p->launches += launch_fuse(f, p->stream);
 }
 
@@ -474,6 +476,7 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     if (p->prep_stream) cudaStreamDestroy(p->prep_stream);
     cudaFree(p->mc_count); cudaFree(p->mc_off); cudaFree(p->mc_tmp); cudaFree(p->mesh_xyz);
     cudaFree(p->color); cudaFree(p->rgb4_buf[0]); cudaFree(p->rgb4_buf[1]); cudaFree(p->rgb_stage);
+    cudaFree(p->cosn_buf[0]); cudaFree(p->cosn_buf[1]);
     cudaFree(p->grid); cudaFree(p->depth_stage); cudaFree(p->pose_dev);
     cudaFreeHost(p->pose_pin); cudaFreeHost(p->ring_pin); cudaFree(p->partials); cudaFree(p->ticket);
     cudaFree(p->group_partials); cudaFree(p->fuse_tables); cudaFree(p->fuse_items); cudaFree(p->fuse_item_count);
@@ -619,10 +622,11 @@ tsdf_status tsdf_enable_color(tsdf_handle h) {
     const size_t npx = (size_t)p->g.img_w * p->g.img_h;
     cudaError_t e = cudaMalloc(&p->color, (size_t)p->n_stored * sizeof(float4));
     for (int q = 0; q < 2 && e == cudaSuccess; q++) e = cudaMalloc(&p->rgb4_buf[q], npx * sizeof(uchar4));
+    for (int q = 0; q < 2 && e == cudaSuccess; q++) e = cudaMalloc(&p->cosn_buf[q], npx * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&p->rgb_stage, npx * 3);
     if (e != cudaSuccess) {
         cudaFree(p->color); p->color = nullptr;
-        for (int q = 0; q < 2; q++) { cudaFree(p->rgb4_buf[q]); p->rgb4_buf[q] = nullptr; }
+        for (int q = 0; q < 2; q++) { cudaFree(p->rgb4_buf[q]); p->rgb4_buf[q] = nullptr; cudaFree(p->cosn_buf[q]); p->cosn_buf[q] = nullptr; }
         cudaFree(p->rgb_stage); p->rgb_stage = nullptr;
         cudaGetLastError();
         g_err = std::string("colour store allocation failed: ") + cudaGetErrorString(e);

@@ -442,12 +442,12 @@ TSDF_HD void fuse_apply_sel(float& D, float& W, float d_new, float w_new, bool u
  * cosine = |cam_vect . n| / ||n|| with cam_vect = (0,0,1) (sdf.cpp:235): the dot product is n_z
  * exactly (the two zero products only add a signed zero); Eigen's norm is sqrt(c0 + (c1 + c2)).
  * The colour weight is the D/W weight times the cosine: float = float * double (:299). */
-TSDF_HD float color_weight(float w_new, float nx, float ny, float nz) {
+TSDF_HD double color_cosine(float nx, float ny, float nz) {           /* per pixel: K1 tabulates it */
     const double x = (double)nx, y = (double)ny, z = (double)nz;
     const double norm = sqrt(x * x + (y * y + z * z));
-    const double cosine = fabs(z) / norm;
-    return (float)((double)w_new * cosine);
+    return fabs(z) / norm;
 }
+TSDF_HD float color_weight(float w_new, double cosine) { return (float)((double)w_new * cosine); }
 /* running mean of one voxel's colour: the uint8 channel is promoted to int, then to float (:302-304) */
 TSDF_HD void color_apply(float& CW, float& R, float& G, float& B, float w_c, int r, int g, int b) {
     const float w_old = CW;

@@ -64,7 +64,7 @@ struct LinearizeArgs {
     ShardLinks links;                      /* world = 1: no exchange */
 };
 
-void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, const uint8_t* rgb3, uchar4* rgb4, cudaStream_t s);
+void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, const uint8_t* rgb3, uchar4* rgb4, double* cosn, cudaStream_t s);
 void launch_pyramid(const CertPyramid& P, float2* cert, unsigned int* ticket, cudaStream_t s);
 /* exchange_mode: 0 none, 1 in-kernel mailbox all-reduce over peer memory (one kernel per
  * device, all running concurrently), 2 deferred (same-device shards: publish, then
@@ -88,6 +88,7 @@ struct FuseArgs {
     int check;                             /* 1: run the self-check build (no stores) */
     float4* color;                         /* {Color_W, R, G, B} per voxel, or NULL: no colour update this frame */
     const uchar4* rgb4;                    /* the frame's colour image, packed by k_prep */
+    const double* cosn;                    /* per-pixel |n_z| / ||n|| (sdf.cpp:294), tabulated by k_prep */
 };
 int launch_fuse(const FuseArgs& f, cudaStream_t s);    /* returns the number of kernels launched */
 int fuse_cert_blocks_per_sm();

@@ -39,7 +39,7 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
  * ------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restrict__ depth,
                                               PixRec* __restrict__ pix, float2* __restrict__ cert0, float4* __restrict__ pts,
-                                              const uint8_t* __restrict__ rgb3, uchar4* __restrict__ rgb4) {
+                                              const uint8_t* __restrict__ rgb3, uchar4* __restrict__ rgb4, double* __restrict__ cosn) {
     pdl_wait();
     pdl_release();
     const int u = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restr
         }
     }
     *reinterpret_cast<float4*>(&pix[o]) = make_float4(r.z, r.nx, r.ny, r.nz);
+    if (rgb3) cosn[o] = color_cosine(r.nx, r.ny, r.nz);        /* sdf.cpp:294: a per-pixel quantity, hoisted out of the voxel loop */
     float zf, zb;
     cert_pixel(g, kp, u, v, r, zf, zb);               /* level 0 of the fusion certificates */
     cert0[o] = make_float2(zf, zb);
@@ -72,9 +73,9 @@ __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restr
     }
 }
 
-void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, const uint8_t* rgb3, uchar4* rgb4, cudaStream_t s) {
+void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, const uint8_t* rgb3, uchar4* rgb4, double* cosn, cudaStream_t s) {
     dim3 grid((g.img_w + 31) / 32, (g.img_h + 7) / 8);
-    launch_pdl(k_prep, grid, dim3(256), s, g, depth, pix, cert0, pts, rgb3, rgb4);
+    launch_pdl(k_prep, grid, dim3(256), s, g, depth, pix, cert0, pts, rgb3, rgb4, cosn);
 }
 
 /* organised cloud + normals for the accessor / tests */
@@ -692,7 +693,8 @@ template <bool COLOR = false>
 __device__ __forceinline__ void exact_four(const GridParams& g, const K1Params& kp, const PixRec* __restrict__ pix,
                                            const double* cx, const double* cy, const double* cz,
                                            bool* upd, float* dnew, float* wnew,
-                                           unsigned int* pidx = nullptr, float* wcol = nullptr) {
+                                           unsigned int* pidx = nullptr, float* wcol = nullptr, const double* __restrict__ cosn = nullptr,
+                                           bool certified_front = false) {
     int iu[4], iv[4];
     bool ok[4], need_exact[4];
 #pragma unroll
@@ -707,6 +709,17 @@ __device__ __forceinline__ void exact_four(const GridParams& g, const K1Params& 
                 ok[v] = project_exact(g, ij0, ij1, ij2, eu_, ev_);
                 if (ok[v]) { iu[v] = eu_; iv[v] = ev_; }
             }
+    }
+    if (COLOR && certified_front) {
+        /* the unit carries a free-space certificate: every voxel is updated with d = -delta, w = 1
+         * (sdf.cpp:276, 285-287); only the pixel (for its cosine and colour) is still needed */
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            upd[v] = true; dnew[v] = -g.delta; wnew[v] = 1.0f;
+            pidx[v] = (unsigned int)(iv[v] * g.img_w + iu[v]);
+            wcol[v] = color_weight(1.0f, __ldg(&cosn[pidx[v]]));
+        }
+        return;
     }
     float4 rr[4];
 #pragma unroll
@@ -730,7 +743,7 @@ __device__ __forceinline__ void exact_four(const GridParams& g, const K1Params& 
 #pragma unroll
         for (int v = 0; v < 4; v++) {
             pidx[v] = (unsigned int)(iv[v] * g.img_w + iu[v]);
-            wcol[v] = color_weight(wnew[v], rr[v].y, rr[v].z, rr[v].w);      /* sdf.cpp:294,299 */
+            wcol[v] = color_weight(wnew[v], __ldg(&cosn[pidx[v]]));          /* sdf.cpp:294,299 */
         }
     }
 }
@@ -797,7 +810,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, COLOR ? 4 : FUSE_MIN_BLOCKS) k_f
                                                                 const unsigned long long* __restrict__ items,
                                                                 const unsigned int* __restrict__ item_count,
                                                                 unsigned long long* n_updated,
-                                                                float4* __restrict__ color, const uchar4* __restrict__ rgb4) {
+                                                                float4* __restrict__ color, const uchar4* __restrict__ rgb4, const double* __restrict__ cosn) {
     pdl_wait();
     pdl_release();
     GridParams g = g_in;
@@ -825,7 +838,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, COLOR ? 4 : FUSE_MIN_BLOCKS) k_f
         if (COLOR) {
             unsigned int pidx[4];
             float wcol[4];
-            exact_four<true>(g, kp, pix, cx, cy, cz, upd, dnew, wnew, pidx, wcol);
+            exact_four<true>(g, kp, pix, cx, cy, cz, upd, dnew, wnew, pidx, wcol, cosn);
             color_four(reinterpret_cast<float4*>(color) + (((size_t)(k - g.ks0) * m + j) * m + x0), rgb4, upd, pidx, wcol);
         } else {
             exact_four(g, kp, pix, cx, cy, cz, upd, dnew, wnew);
@@ -1044,7 +1057,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
         }
         /* colour fusion needs every updated voxel's pixel (normal, rgb): certified free space is
          * queued for the exact pass too; only the skip certificate is used */
-        if (queue_front && verdict == UNIT_FRONT) verdict = UNIT_UNKNOWN;
+        const bool front_queued = queue_front && verdict == UNIT_FRONT;     /* queued WITH its certificate */
         if (CHECK) {
             /* self-check build: queue EVERY unit with its verdict; pass 2 compares, nothing is written */
             const unsigned int mask = __ballot_sync(0xffffffffu, act);
@@ -1054,15 +1067,16 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
             flush(63);
         } else {
             complete();                                   /* the previous item's free-space units */
-            pend = (verdict == UNIT_FRONT);
+            pend = (verdict == UNIT_FRONT) && !front_queued;
             if (pend) {
                 pptr = ptr;
                 p0 = ld_f4(ptr); p1 = ld_f4(ptr + 1);
                 if (k >= g.ko0 && k < g.ko1) my_updates += 4u;
             }
-            const unsigned int mask = __ballot_sync(0xffffffffu, verdict == UNIT_UNKNOWN);
+            const bool to_queue = (verdict == UNIT_UNKNOWN) | front_queued;
+            const unsigned int mask = __ballot_sync(0xffffffffu, to_queue);
             if (mask) {
-                if (verdict == UNIT_UNKNOWN) stage[staged + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, UNIT_UNKNOWN);
+                if (to_queue) stage[staged + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, verdict);
                 __syncwarp();
                 staged += __popc(mask);
                 flush(63);
@@ -1085,7 +1099,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, COLOR ? 4 : FUSE_MIN_BLOCKS) k_f
                                                                               const unsigned long long* __restrict__ units,
                                                                               const unsigned int* __restrict__ unit_count,
                                                                               unsigned long long* n_updated,
-                                                                              float4* __restrict__ color, const uchar4* __restrict__ rgb4) {
+                                                                              float4* __restrict__ color, const uchar4* __restrict__ rgb4, const double* __restrict__ cosn) {
     pdl_wait();
     pdl_release();
     GridParams g = g_in;
@@ -1109,7 +1123,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, COLOR ? 4 : FUSE_MIN_BLOCKS) k_f
         if (COLOR) {
             unsigned int pidx[4];
             float wcol[4];
-            exact_four<true>(g, kp, pix, cx, cy, cz, upd, dnew, wnew, pidx, wcol);
+            exact_four<true>(g, kp, pix, cx, cy, cz, upd, dnew, wnew, pidx, wcol, cosn, verdict == UNIT_FRONT);
             color_four(reinterpret_cast<float4*>(color) + (((size_t)(k - g.ks0) * m + j) * m + x0), rgb4, upd, pidx, wcol);
         } else {
             exact_four(g, kp, pix, cx, cy, cz, upd, dnew, wnew);
@@ -1146,21 +1160,21 @@ int launch_fuse(const FuseArgs& f, cudaStream_t s) {
     launch_pdl(k_fuse_plan, dim3((nrows + 255) / 256), dim3(256), s, g, f.pyr, f.cert, f.check, f.pose, f.tables, f.items, f.item_count);
     const bool color = f.color != nullptr;      /* plane metric only (checked by the caller) */
     if (!g.k_simple) {          /* skewed intrinsics: the exact path for every in-view voxel */
-        if (color) launch_pdl(k_fuse_items<0, 0, true>, dim3(f.nblk_color), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated, f.color, f.rgb4);
-        else if (g.metric == 0) launch_pdl(k_fuse_items<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated, f.color, f.rgb4);
-        else launch_pdl(k_fuse_items<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated, f.color, f.rgb4);
+        if (color) launch_pdl(k_fuse_items<0, 0, true>, dim3(f.nblk_color), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated, f.color, f.rgb4, f.cosn);
+        else if (g.metric == 0) launch_pdl(k_fuse_items<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated, f.color, f.rgb4, f.cosn);
+        else launch_pdl(k_fuse_items<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated, f.color, f.rgb4, f.cosn);
         return 3;
     }
     if (f.check) {
         launch_pdl(k_fuse_cert<1>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_count, f.units, f.unit_count, f.n_updated, 0);
-        if (g.metric == 0) launch_pdl(k_fuse_exact<0, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4);
-        else launch_pdl(k_fuse_exact<1, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4);
+        if (g.metric == 0) launch_pdl(k_fuse_exact<0, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
+        else launch_pdl(k_fuse_exact<1, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
         return 4;
     }
     launch_pdl(k_fuse_cert<0>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_count, f.units, f.unit_count, f.n_updated, color ? 1 : 0);
-    if (color) launch_pdl(k_fuse_exact<0, 0, true>, dim3(f.nblk_color), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4);
-    else if (g.metric == 0) launch_pdl(k_fuse_exact<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4);
-    else launch_pdl(k_fuse_exact<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4);
+    if (color) launch_pdl(k_fuse_exact<0, 0, true>, dim3(f.nblk_color), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
+    else if (g.metric == 0) launch_pdl(k_fuse_exact<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
+    else launch_pdl(k_fuse_exact<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
     return 4;
 }
 int fuse_color_blocks_per_sm() {
