@@ -75,6 +75,37 @@ class Emul:
         self.last_fast = self.L.emul_last_fast_count()
         return n
 
+    # colour (k_fuse_cert in queue_front mode + k_fuse_exact<colour>, k_sample_color) and the mesher (k_mc_sweep)
+    def fuse_rgb(self, rgb, use_clip=1, use_fast=1):
+        if not hasattr(self, "color"):
+            self.color = np.empty((self.m, self.m, self.m, 4), np.float32)       # [k, j, i, {Color_W,R,G,B}]
+            self.color[..., 0] = 0.0; self.color[..., 1:] = np.float32(0.4)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        self.L.emul_fuse_rgb.restype = ctypes.c_int64
+        n = self.L.emul_fuse_rgb(self.g, _f(self.grid), _f(self.pix), self.pose, use_clip, use_fast, _f(self.color),
+                                 rgb.ctypes.data_as(c_u8p))
+        self.last_fast = self.L.emul_last_fast_count()
+        return n
+
+    def color_ref(self):
+        """(Color_W, R, G, B) in the reference's [i, j, k] indexing."""
+        return tuple(self.color[..., q].transpose(2, 1, 0) for q in range(4))
+
+    def interpolate_color(self, gpts):
+        gpts = np.ascontiguousarray(gpts, np.float64).reshape(-1, 3)
+        out = np.empty((len(gpts), 4), np.float32)
+        self.L.emul_interpolate_color(self.g, _f(self.color), ctypes.c_int64(len(gpts)), _d(gpts), _f(out))
+        return out
+
+    def mesh(self, iso=0.0, extents=(6.0, 6.0, 3.5)):
+        self.L.emul_mesh.restype = ctypes.c_int64
+        args = (self.g, ctypes.c_float(extents[0]), ctypes.c_float(extents[1]), ctypes.c_float(extents[2]), ctypes.c_float(iso), _f(self.grid))
+        n = self.L.emul_mesh(*args, None)
+        xyz = np.empty((n, 3), np.float32)
+        if n:
+            self.L.emul_mesh(*args, _f(xyz))
+        return xyz
+
     def interpolate(self, pts):
         pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
         out = np.empty(len(pts), np.float32); ok = np.empty(len(pts), np.uint8)

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <vector>
 #include "tsdf_core.cuh"
+#include "mc_core.cuh"
 
 using namespace tsdf;
 
@@ -108,7 +109,16 @@ void emul_interpolate(const GridParams* g, const float* grid, int64_t n, const d
 static int64_t g_last_fast = 0, g_rows_front = 0, g_rows_skip = 0, g_rows_unknown = 0;
 void emul_row_stats(int64_t out[3]) { out[0] = g_rows_front; out[1] = g_rows_skip; out[2] = g_rows_unknown; }
 int64_t emul_last_fast_count() { return g_last_fast; }
+int64_t emul_fuse_rgb(const GridParams* gp, float* grid, const float* pix, const PoseState* pose, int use_clip, int use_cert,
+                      float* color /* [k][j][i]{Color_W,R,G,B} or NULL */, const uint8_t* rgb3 /* [h*w*3] or NULL */);
 int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const PoseState* pose, int use_clip, int use_cert) {
+    return emul_fuse_rgb(gp, grid, pix, pose, use_clip, use_cert, nullptr, nullptr);
+}
+/* with colour (k_fuse_cert in queue_front mode + k_fuse_exact<colour>): the free-space certificate no longer
+ * updates in place, the exact pass takes the unit WITH its certificate (d = -delta, w = 1 without the distance
+ * arithmetic) and every updated voxel gets the colour running mean from its pixel's tabulated cosine and rgb */
+int64_t emul_fuse_rgb(const GridParams* gp, float* grid, const float* pix, const PoseState* pose, int use_clip, int use_cert,
+                      float* color, const uint8_t* rgb3) {
     const GridParams& g = *gp;
     const int m = g.m;
     const double* Ri = pose->Rinv; const double* ti = pose->tinv;
@@ -172,7 +182,7 @@ int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const Pos
                 if (verdict == UNIT_SKIP) { n_fast += 4; continue; }
                 for (int v = 0; v < 4; v++) {
                     const size_t o = (((size_t)(k - g.ks0) * m + j) * m + x0 + v) * 2;
-                    if (verdict == UNIT_FRONT) {
+                    if (verdict == UNIT_FRONT && !color) {
                         fuse_apply(grid[o], grid[o + 1], -g.delta, 1.0f);
                         n_updated++; n_fast++;
                         continue;
@@ -189,14 +199,25 @@ int64_t emul_fuse(const GridParams* gp, float* grid, const float* pix, const Pos
                     }
                     const float* rr = pix + 4 * ((size_t)iv * g.img_w + iu);      /* unconditional, clamped */
                     PixRec rec; rec.z = rr[0]; rec.nx = rr[1]; rec.ny = rr[2]; rec.nz = rr[3];
-                    float fx_, fy_, dn, eb;
-                    bool band;
-                    backproject_px(kp, iu, iv, rec.z, fx_, fy_);
-                    const bool upd = fuse_distance_flags(g, cx[v], cy[v], cz[v], fx_, fy_, rec, dn, eb, band) & ok;
-                    if (!upd) continue;
-                    const float wn = fuse_weight(band, eb);
+                    float dn, wn;
+                    if (verdict == UNIT_FRONT) {                                  /* colour mode: certified unit in the exact pass */
+                        dn = -g.delta; wn = 1.0f; n_fast++;
+                    } else {
+                        float fx_, fy_, eb;
+                        bool band;
+                        backproject_px(kp, iu, iv, rec.z, fx_, fy_);
+                        const bool upd = fuse_distance_flags(g, cx[v], cy[v], cz[v], fx_, fy_, rec, dn, eb, band) & ok;
+                        if (!upd) continue;
+                        wn = fuse_weight(band, eb);
+                    }
                     fuse_apply(grid[o], grid[o + 1], dn, wn);
                     n_updated++;
+                    if (color) {
+                        float* c = color + 2 * o;                                 /* 4 floats per voxel */
+                        const uint8_t* px = rgb3 + 3 * ((size_t)iv * g.img_w + iu);
+                        const float wc = color_weight(wn, color_cosine(rec.nx, rec.ny, rec.nz));   /* K1 tabulates the cosine per pixel */
+                        color_apply(c[0], c[1], c[2], c[3], wc, (int)px[0], (int)px[1], (int)px[2]);
+                    }
                 }
             }
         }
@@ -344,6 +365,52 @@ void emul_fuse_stats(const GridParams* gp, const float* pix, const PoseState* po
         for (int q = 0; q < 16; q++) c[q] += lc[q];
     }
     for (int q = 0; q < 16; q++) out[q] = c[q];
+}
+
+/* SDF::interpolate_color through the kernels' core (k_sample_color) */
+void emul_interpolate_color(const GridParams* gp, const float* color, int64_t n, const double* gpts, float* rgba) {
+    const GridParams& g = *gp;
+    const int m = g.m;
+    auto fetch = [&](int ci, int cj, int ck, float& cw, float& r, float& gg, float& b) {
+        if ((unsigned)ci >= (unsigned)m || (unsigned)cj >= (unsigned)m || (unsigned)ck >= (unsigned)m) return false;
+        const float* c = color + 4 * (((size_t)ck * m + cj) * m + ci);
+        cw = c[0]; r = c[1]; gg = c[2]; b = c[3];
+        return true;
+    };
+    for (int64_t q = 0; q < n; q++) {
+        const double vx = ((gpts[3 * q] - g.origin[0]) * (double)g.m_div_width - 0.5);
+        const double vy = ((gpts[3 * q + 1] - g.origin[1]) * (double)g.m_div_height - 0.5);
+        const double vz = ((gpts[3 * q + 2] - g.origin[2]) * (double)g.m_div_depth - 0.5);
+        interpolate_color(vx, vy, vz, fetch, rgba + 4 * q);
+    }
+}
+
+/* the mesher through the kernels' core (k_mc_sweep): cells in (i,j,k) order, vertices via mc_edge_vertex.
+ * First call with xyz = NULL to get the vertex count. */
+int64_t emul_mesh(const GridParams* gp, float width, float height, float depth, float iso, const float* grid, float* xyz) {
+    const GridParams& g = *gp;
+    const int m = g.m;
+    if (!(iso >= 0.0f && iso < 1.0f)) return 0;
+    McParams P; P.width = width; P.height = height; P.depth = depth; P.iso = iso;
+    const float fm = (float)m;
+    int64_t n = 0;
+    auto at = [&](int i, int j, int k) { return grid + 2 * (((size_t)k * m + j) * m + i); };
+    for (int i = 1; i <= m - 2; i++)
+        for (int j = 1; j <= m - 2; j++)
+            for (int k = 1; k <= m - 2; k++) {
+                const float* c[8] = {at(i, j, k), at(i + 1, j, k), at(i + 1, j, k + 1), at(i, j, k + 1),
+                                     at(i, j + 1, k), at(i + 1, j + 1, k), at(i + 1, j + 1, k + 1), at(i, j + 1, k + 1)};
+                float d[8], w[8];
+                for (int q = 0; q < 8; q++) { d[q] = c[q][0]; w[q] = c[q][1]; }
+                const int ci = mc_cube_index(d, w, P.iso);
+                if (ci == 0 || ci == 255) continue;
+                const unsigned long long row = c_mc_tri[ci];
+                const int nv = mc_vertex_count(row);
+                if (xyz)
+                    for (int q = 0; q < nv; q++) mc_edge_vertex(P, fm, i, j, k, (int)((row >> (4 * q)) & 0xFull), d, xyz + 3 * (n + q));
+                n += nv;
+            }
+    return n;
 }
 
 void emul_gn_update(const GridParams* g, PoseState* pose, const double* sums) { gn_update(*g, *pose, sums); }

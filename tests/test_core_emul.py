@@ -171,3 +171,31 @@ def test_int_cast_semantics():
     L = emul.lib()
     assert L.emul_trunc_f2i(-0.7) == 0 and L.emul_trunc_f2i(3.99) == 3 and L.emul_trunc_f2i(-1.5) == -1
     assert L.emul_trunc_f2i(float("nan")) == -2 ** 31 and L.emul_trunc_f2i(3e9) == -2 ** 31 and L.emul_trunc_f2i(-3e9) == -2 ** 31
+
+
+@pytest.mark.parametrize("m", [32, 48])
+def test_color_fusion_sampling_and_mesh_core_bit_exact(frames, K, m):
+    """The kernels' colour path (skip certificates only, certified free-space units in the exact pass, per-pixel
+    cosine) and the mesher core (mc_core.cuh), compiled for the host, against the oracle: bit for bit."""
+    depth, Rs, ts = frames
+    o, e = _pair(m, 0, K)
+    for f in range(3):
+        d = depth[f].copy()
+        if f == 1:
+            d[60:120, 300:500] = np.nan; d[::19, ::11] = np.nan                # ragged validity
+        rgb = synth.synth_rgb(depth[f], Rs[f], ts[f])
+        o.set_pose(Rs[f], ts[f]); e.set_pose(Rs[f], ts[f]); e.prep(d)
+        assert o.fuse_rgb(d, rgb) == e.fuse_rgb(rgb)
+        assert e.last_fast > 0                                                 # certificates were actually used
+    assert np.array_equal(o.D, e.D) and np.array_equal(o.W, e.W)
+    for a, b, name in zip(o.color(), e.color_ref(), ("Color_W", "R", "G", "B")):
+        assert np.array_equal(a, b, equal_nan=True), name
+    pts = np.random.default_rng(3).uniform([-3.1, -3.1, -0.6], [3.1, 3.1, 3.1], (4000, 3))
+    cw = o.color()[0]
+    centres = np.array([o.get_global_coordinates(q) for q in np.argwhere(cw > 0)[:200]])
+    pts = np.concatenate([pts, centres])
+    assert np.array_equal(o.interpolate_color(pts), e.interpolate_color(pts), equal_nan=True)
+    for iso in (0.0, 0.15):
+        assert np.array_equal(o.mesh(iso)[0], e.mesh(iso))
+    assert len(e.mesh(0.0)) > 500 and len(e.mesh(1.0)) == 0
+    o.close()

@@ -12,7 +12,7 @@
  */
 #pragma once
 #include "tsdf_core.cuh"
-#include "tsdf_internal.h"
+#include "mc_params.h"
 
 namespace tsdf {
 
@@ -25,7 +25,6 @@ MC_TABLE_SPACE unsigned long long c_mc_tri[256] = {
 #include "mc_tables.inc"
 };
 
-struct McParams;   /* tsdf_internal.h */
 
 /* configuration index of a cell: bit n set when corner n is below the iso level
  * (marching_cubes_sdf.cpp:107-115).  When any corner was never observed (W <= 0) the reference

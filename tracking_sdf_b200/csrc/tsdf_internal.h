@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "tsdf_core.cuh"
+#include "mc_params.h"
 
 namespace tsdf {
 
@@ -106,10 +107,6 @@ void launch_flush(float* buf, int64_t n, cudaStream_t s);
 void launch_stream_rmw(float2* grid, int64_t n, float neg_delta, cudaStream_t s);
 void launch_check_rcp(unsigned int lo, unsigned int hi, unsigned long long* n_bad, cudaStream_t s);
 /* mesher (tsdf_mesh.cu) */
-struct McParams {
-    float width, height, depth;       /* setBBox (marching_cubes_sdf.cpp:52-63): min_p = 0, max_p = extents */
-    float iso;                        /* setIsoLevel; must be in [0, 1) (marching_cubes_sdf.cpp:248) */
-};
 size_t mesh_scan_bytes(int64_t n_rows);
 int mesh_zsplit();
 void launch_mesh_count(const GridParams& g, const McParams& P, const float2* grid, unsigned int* row_count, unsigned int* row_off,
