@@ -403,20 +403,18 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
             kc = kc < 0 ? 0 : (kc > g.m - 1 ? g.m - 1 : kc);
             mine = (kc >= g.ko0 && kc < g.ko1);
         }
-        if (s < 13) {
-            ok = false;
-            if (valid_pt && mine) {
-                double vx, vy, vz;
-                sample_coords_off(g, M, sT, off_x, off_y, off_z, (double)x, (double)y, (double)z, vx, vy, vz);
-                /* camera_tracking.cpp:261-268: only the centre sample's (s = 0) verdict is used */
-                oob = (fmin(fmin(vx, vy), vz) < 0.0) | (fmax(fmax(vx, vy), vz) >= dm);
-                bool is_interp;
-                val = interpolate_distance(vx, vy, vz, fetch, is_interp);
-                ok = is_interp;
-            }
+        ok = (s >= 13);                                                      /* idle lanes never veto the pixel */
+        if ((s < 13) & valid_pt & mine) {                                    /* one divergent region per sweep */
+            double vx, vy, vz;
+            sample_coords_off(g, M, sT, off_x, off_y, off_z, (double)x, (double)y, (double)z, vx, vy, vz);
+            /* camera_tracking.cpp:261-268: only the centre sample's (s = 0) verdict is used */
+            oob = (fmin(fmin(vx, vy), vz) < 0.0) | (fmax(fmax(vx, vy), vz) >= dm);
+            bool is_interp;
+            val = interpolate_distance(vx, vy, vz, fetch, is_interp);
+            ok = is_interp;
         }
         const unsigned okb = __ballot_sync(0xffffffffu, ok);
-        const unsigned oobb = __ballot_sync(0xffffffffu, oob && s == 0);
+        const unsigned oobb = __ballot_sync(0xffffffffu, oob & (s == 0));
         const bool allok = ((okb >> base) & 0xffffu) == 0xffffu;
         const bool is_oob = ((oobb >> base) & 1u) != 0u;
         const int flag = !valid_pt ? 0 : (!mine ? 4 : (is_oob ? 2 : (allok ? 1 : 3)));
@@ -432,11 +430,13 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
         const double xb0 = (double)__shfl_sync(0xffffffffu, xv, base + b0);
         const double xa1 = (double)__shfl_sync(0xffffffffu, xv, base + a1);
         const double xb1 = (double)__shfl_sync(0xffffffffu, xv, base + b1);
-        if (flag == 1) {                                                     /* camera_tracking.cpp:178-182 */
-            acc0 = acc0 + xa0 * xb0;
-            if (k1 == 0) acc1 = acc1 + xa1 * xb1; else if (k1 == 1) acc1 = acc1 + 1.0;
-        } else if (flag == 2) {
-            if (k1 == 2) acc1 = acc1 + 1.0;
+        {
+            /* camera_tracking.cpp:178-182, branch-free: the addend is selected (an invalid pixel's products may be
+             * NaN), and adding +0.0 leaves a sum unchanged */
+            const bool f1 = (flag == 1), f2 = (flag == 2);
+            const double one = ((f1 & (k1 == 1)) | (f2 & (k1 == 2))) ? 1.0 : 0.0;
+            acc0 = acc0 + (f1 ? xa0 * xb0 : 0.0);
+            acc1 = acc1 + ((f1 & (k1 == 0)) ? xa1 * xb1 : one);
         }
         if (a.dbgFlag && have) {
             if (s < 6) a.dbgJ[(size_t)p * 6 + s] = (flag == 1) ? Ja : 0.0f;
