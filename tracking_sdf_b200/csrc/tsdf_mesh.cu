@@ -23,13 +23,15 @@ constexpr int MC_WARPS = 8;      /* warps per block = consecutive j rows */
 #endif
 constexpr int MC_ZSPLIT = MC_ZSPLIT_DEF;     /* chunks of the k sweep (more loads in flight) */
 
+constexpr int MC_TILE = 31;      /* cells per warp along i: 32 lanes load 32 voxels, lanes 0..30 own a cell (i+1 comes from lane+1) */
+
 template <bool EMIT>
 __global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McParams P, const float2* __restrict__ grid, int k_lo_all, int k_hi_all,
                                                             unsigned int* __restrict__ row_count, const unsigned int* __restrict__ row_off,
                                                             float* __restrict__ xyz) {
     const int m = g.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + lane;
+    const int i = 1 + blockIdx.x * MC_TILE + lane;                    /* this lane's voxel column; its cell if lane < 31 */
     const int j = blockIdx.y * MC_WARPS + warp;
     if (j < 1 || j > m - 2) return;                                   /* warp-uniform */
     /* the k range is cut into gridDim.z chunks; a row's chunks are consecutive in the output */
@@ -38,49 +40,47 @@ __global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McPara
     const int k_lo = k_lo_all + zc * per;
     const int k_hi = (k_lo + per - 1 < k_hi_all) ? (k_lo + per - 1) : k_hi_all;
     if (k_lo > k_hi) return;
-    const bool cell_ok = (i >= 1) && (i <= m - 2);
-    const bool have = i < m, have1 = (i + 1) < m;
+    const bool cell_ok = (lane < MC_TILE) && (i <= m - 2);
     const float fm = (float)m;
-    const float2 zero = make_float2(0.0f, 0.0f);
     const size_t plane = (size_t)m * m;
-    const float2* pj = grid + (size_t)j * m + i;                      /* (i, j, .) ; row j+1 is + m */
-    /* software pipeline: the raw loads of layer k+2 are in flight while layer k+1 is shuffled and
-     * cell k is evaluated.  raw = this lane's (i,j) and (i,j+1) voxels plus, on lane 31, the i+1 pair. */
-    struct Raw { float2 a, b, xa, xb; };
-    auto load_raw = [&](int k) {
-        Raw r;
-        const float2* p = pj + (size_t)(k - g.ks0) * plane;
-        r.a = have ? __ldg(p) : zero;
-        r.b = have ? __ldg(p + m) : zero;
-        r.xa = zero; r.xb = zero;
-        if (lane == 31 && have1) { r.xa = __ldg(p + 1); r.xb = __ldg(p + m + 1); }
-        return r;
+    const float iso = P.iso;
+    /* lanes past the row end load the last voxel again (never used: their cells are not cell_ok) */
+    const float2* p = grid + (size_t)(k_lo - g.ks0) * plane + (size_t)j * m + (i < m ? i : m - 1);   /* (i, j, k_lo); row j+1 is + m */
+    /* Per layer each lane keeps two voxels, a = (i,j) and b = (i,j+1), and a 4-bit summary of them
+     * (below-iso and W>0 flags); one shuffle brings the neighbour column's summary, so a cell is
+     * classified from four small words.  The eight distances are only gathered (four more shuffles)
+     * when some cell of the warp actually holds surface.  Loads run two layers ahead. */
+    auto summary = [&](const float2& a, const float2& b) {
+        return (unsigned)(a.x < iso) | ((unsigned)(b.x < iso) << 1) | ((unsigned)(a.y > 0.0f) << 2) | ((unsigned)(b.y > 0.0f) << 3);
     };
-    auto neighbours = [&](const Raw& r, float2& a1, float2& b1) {     /* (i+1,j), (i+1,j+1) */
-        a1.x = __shfl_down_sync(0xffffffffu, r.a.x, 1); a1.y = __shfl_down_sync(0xffffffffu, r.a.y, 1);
-        b1.x = __shfl_down_sync(0xffffffffu, r.b.x, 1); b1.y = __shfl_down_sync(0xffffffffu, r.b.y, 1);
-        if (lane == 31) { a1 = r.xa; b1 = r.xb; }
-    };
-    Raw r0 = load_raw(k_lo), r1 = load_raw(k_lo + 1);
-    float2 a = r0.a, b = r0.b, a1, b1;                                /* layer k:   (i,j) (i+1,j) (i,j+1) (i+1,j+1) */
-    neighbours(r0, a1, b1);
+    float2 a0 = __ldg(p), b0 = __ldg(p + m);                          /* layer k   */
+    p += plane;
+    float2 a1 = __ldg(p), b1 = __ldg(p + m);                          /* layer k+1 */
+    p += plane;
+    unsigned s0 = summary(a0, b0);
+    unsigned t0 = __shfl_down_sync(0xffffffffu, s0, 1);               /* column i+1 */
     unsigned int n_row = 0;
     const unsigned int base = EMIT ? (cell_ok ? row_off[((size_t)i * m + j) * nz + zc] : 0u) : 0u;
     for (int k = k_lo; k <= k_hi; k++) {
-        Raw r2;
-        r2.a = r2.b = r2.xa = r2.xb = zero;
-        if (k + 2 <= k_hi + 1) r2 = load_raw(k + 2);                  /* warp-uniform */
-        const float2 c = r1.a, e = r1.b;                              /* layer k+1 */
-        float2 c1, e1;
-        neighbours(r1, c1, e1);
-        if (cell_ok) {
-            const float d[8] = {a.x, a1.x, c1.x, c.x, b.x, b1.x, e1.x, e.x};
-            const float w[8] = {a.y, a1.y, c1.y, c.y, b.y, b1.y, e1.y, e.y};
-            const int ci = mc_cube_index(d, w, P.iso);
-            if (ci != 0 && ci != 255) {
+        float2 a2 = a1, b2 = b1;
+        if (k + 2 <= k_hi + 1) { a2 = __ldg(p); b2 = __ldg(p + m); p += plane; }     /* warp-uniform */
+        const unsigned s1 = summary(a1, b1);
+        const unsigned t1 = __shfl_down_sync(0xffffffffu, s1, 1);
+        /* corners: 0 (i,j,k) 1 (i+1,j,k) 2 (i+1,j,k+1) 3 (i,j,k+1) 4 (i,j+1,k) 5 (i+1,j+1,k) 6 (i+1,j+1,k+1) 7 (i,j+1,k+1) */
+        const unsigned all_w = (s0 & t0 & s1 & t1) >> 2;              /* == 3: all eight corners observed (marching_cubes_sdf.cpp:221) */
+        const unsigned lo = (s0 & 3u) | ((t0 & 3u) << 2), hi = (s1 & 3u) | ((t1 & 3u) << 2);   /* below-iso flags of the two layers */
+        const bool surf = cell_ok && (all_w == 3u) && ((lo | hi) != 0u) && ((lo & hi) != 15u);
+        const unsigned any = __ballot_sync(0xffffffffu, surf);
+        if (any) {                                                    /* warp-uniform, rare */
+            const float a0n = __shfl_down_sync(0xffffffffu, a0.x, 1), b0n = __shfl_down_sync(0xffffffffu, b0.x, 1);
+            const float a1n = __shfl_down_sync(0xffffffffu, a1.x, 1), b1n = __shfl_down_sync(0xffffffffu, b1.x, 1);
+            if (surf) {
+                const int ci = (int)((lo & 1u) | ((lo >> 1) & 2u) | ((hi >> 0) & 4u) | ((hi & 1u) << 3) |
+                                     ((lo & 2u) << 3) | ((lo & 8u) << 2) | ((hi & 8u) << 3) | ((hi & 2u) << 6));
                 const unsigned long long row = c_mc_tri[ci];
                 const int nv = mc_vertex_count(row);
                 if (EMIT) {
+                    const float d[8] = {a0.x, a0n, a1n, a1.x, b0.x, b0n, b1n, b1.x};
                     float* o = xyz + 3 * (size_t)(base + n_row);
                     for (int q = 0; q < nv; q++) {
                         float v[3];
@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McPara
                 n_row += (unsigned int)nv;
             }
         }
-        a = c; a1 = c1; b = e; b1 = e1;
-        r1 = r2;
+        a0 = a1; b0 = b1; s0 = s1; t0 = t1;
+        a1 = a2; b1 = b2;
     }
     if (!EMIT && cell_ok) row_count[((size_t)i * m + j) * nz + zc] = n_row;
 }
@@ -133,7 +133,7 @@ void launch_mesh_count(const GridParams& g, const McParams& P, const float2* gri
     int k_lo, k_hi;
     mesh_k_range(g, k_lo, k_hi);
     if (k_hi >= k_lo) {
-        dim3 grid3((g.m + 31) / 32, (g.m + MC_WARPS - 1) / MC_WARPS, MC_ZSPLIT);
+        dim3 grid3((g.m - 2 + MC_TILE - 1) / MC_TILE, (g.m + MC_WARPS - 1) / MC_WARPS, MC_ZSPLIT);
         k_mc_sweep<false><<<grid3, MC_WARPS * 32, 0, s>>>(g, P, grid, k_lo, k_hi, row_count, nullptr, nullptr);
     }
     cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, row_count, row_off, (int)n_rows, s);
@@ -142,7 +142,7 @@ void launch_mesh_emit(const GridParams& g, const McParams& P, const float2* grid
     int k_lo, k_hi;
     mesh_k_range(g, k_lo, k_hi);
     if (k_hi < k_lo) return;
-    dim3 grid3((g.m + 31) / 32, (g.m + MC_WARPS - 1) / MC_WARPS, MC_ZSPLIT);
+    dim3 grid3((g.m - 2 + MC_TILE - 1) / MC_TILE, (g.m + MC_WARPS - 1) / MC_WARPS, MC_ZSPLIT);
     k_mc_sweep<true><<<grid3, MC_WARPS * 32, 0, s>>>(g, P, grid, k_lo, k_hi, nullptr, row_off, xyz);
 }
 
