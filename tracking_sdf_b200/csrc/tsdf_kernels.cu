@@ -485,22 +485,25 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
             double t = 0.0;
 #pragma unroll
             for (int w = 0; w < LIN_THREADS / 32; w++) t = t + sRed[w][tid];
-            a.group_partials[(size_t)grp_id * LIN_PARTIAL_STRIDE + tid] = t;
+            if (ngroups == 1) sSums[tid] = t;             /* single group: this IS the grid total, no second level */
+            else a.group_partials[(size_t)grp_id * LIN_PARTIAL_STRIDE + tid] = t;
         }
         if (tid == 0) a.group_ticket[grp_id] = 0u;
     }
     /* ---- level 2: the last group sums the groups */
-    if (tid < 32) {
-        __threadfence();
-        __syncwarp();
-        if (tid == 0) sLast = (ngroups == 1) || (atomicAdd(a.ticket, 1u) == (unsigned)(ngroups - 1));
+    if (ngroups > 1) {
+        if (tid < 32) {
+            __threadfence();
+            __syncwarp();
+            if (tid == 0) sLast = (atomicAdd(a.ticket, 1u) == (unsigned)(ngroups - 1));
+        }
+        __syncthreads();
+        if (!sLast) return;
     }
-    __syncthreads();
-    if (!sLast) return;
     if (a.dbg_times && tid == 0) a.dbg_times[2] = gtime();
     if (a.first && tid == 0) { pose->iterations = 0; pose->stopped = 0; pose->singular = 0; pose->halo_miss = 0; }
-    __threadfence();
-    {
+    if (ngroups > 1) {
+        __threadfence();
         const int slot = tid & 31, sub = tid >> 5;
         double v = 0.0;
         for (int q = sub; q < ngroups; q += LIN_THREADS / 32) v = v + __ldcg(&a.group_partials[(size_t)q * LIN_PARTIAL_STRIDE + slot]);
