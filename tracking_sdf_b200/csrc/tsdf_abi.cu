@@ -42,7 +42,7 @@ struct Impl {
     cudaEvent_t depth_copied = nullptr;               /* synchronous-API H2D of the depth image    */
     cudaEvent_t depth_ready = nullptr, depth_done = nullptr;   /* optional events for the next enqueue_prep */
     unsigned long long prep_seq = 0;
-    int lin_first = 0;
+    int lin_first = 0, lin_iter = 0;
     /* colour (tsdf_enable_color): {Color_W, R, G, B} per voxel, the frame's packed colour image
      * (double-buffered like the other records) and a staging buffer for host images */
     float4* color = nullptr;
@@ -223,6 +223,7 @@ LinearizeArgs lin_args(Impl* p, int do_update, bool debug) {
     a.dbg_times = p->dbg_times;
     a.do_update = do_update;
     a.first = 0;
+    a.iter = 0;
     a.px_per_block = p->px_per_block;
     a.links = p->links;
     return a;
@@ -248,18 +249,23 @@ void enqueue_prep(Impl* p, const float* dptr, int reset_track) {
     p->depth_ready = nullptr; p->depth_done = nullptr;
     p->prep_seq++;
     p->lin_first = reset_track;
+    if (reset_track) p->lin_iter = 0;
     p->launches += 2;
 }
 void enqueue_linearize(Impl* p, int do_update, bool debug) {
     p->seqno++;
     LinearizeArgs a = lin_args(p, do_update, debug);
     a.first = p->lin_first;
+    a.iter = p->lin_iter;
     p->lin_first = 0;
+    if (do_update) p->lin_iter++;
     launch_linearize(a, p->lin_blocks, p->exchange_mode, p->seqno, p->stream);
     p->launches++;
 }
 void enqueue_combine(Impl* p, int do_update) {
-    launch_gn_combine(lin_args(p, do_update, false), p->seqno, p->stream);
+    LinearizeArgs a = lin_args(p, do_update, false);
+    a.iter = p->lin_iter > 0 ? p->lin_iter - 1 : 0;        /* the iteration enqueue_linearize just counted */
+    launch_gn_combine(a, p->seqno, p->stream);
     p->launches++;
 }
 void enqueue_fuse(Impl* p) {

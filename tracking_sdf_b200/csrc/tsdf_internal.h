@@ -61,6 +61,7 @@ struct LinearizeArgs {
     unsigned long long* dbg_times;         /* optional: globaltimer stamps of the kernel's phases */
     int32_t do_update;                     /* 1: solve + pose update in the last block */
     int32_t first;                         /* 1: first launch of a frame (resets the per-frame tracking state) */
+    int32_t iter;                          /* 0-based index of this launch within the frame's GN loop */
     int32_t px_per_block;
     ShardLinks links;                      /* world = 1: no exchange */
 };

@@ -226,7 +226,9 @@ __device__ void exchange_sums(const ShardLinks& L, unsigned long long seqno, dou
  * needs ~170 registers and is a ~4 us dependent chain).  sc: >= 128 doubles of shared scratch.
  * ------------------------------------------------------------------------------------------ */
 __device__ void gn_update_warp(const GridParams& g, PoseState* pose, const double* sums, double* sc, int lane,
-                               const double* Rcur, const double* tcur) {   /* current pose (already on chip in the caller) */
+                               const double* Rcur, const double* tcur,      /* current pose (already on chip in the caller) */
+                               int iter) {                                  /* launches after the stop test return at once, so
+                                                                             * iterations executed = index of this launch + 1 */
     double (*sA)[8] = reinterpret_cast<double (*)[8]>(sc);        /* 6 x 8: [A | b] */
     double* sRd = sc + 48;                                        /* 9  */
     double* sTd = sc + 57;                                        /* 3  */
@@ -286,7 +288,7 @@ __device__ void gn_update_warp(const GridParams& g, PoseState* pose, const doubl
     }
 #pragma unroll
     for (int q = 0; q < 6; q++) if (!(fabs(x[q]) <= 1.7976931348623157e308)) singular = 1;
-    if (lane == 0) pose->iterations = pose->iterations + 1;
+    if (lane == 0) pose->iterations = iter + 1;        /* no load of the old count on the critical path */
     if (singular) {                                  /* keep the previous pose, report (TRAP 12) */
         if (lane == 0) { pose->singular = 1; pose->stopped = 1; }
         return;
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
         for (int r = 0; r < a.links.world; r++)
             if (tid < N_SLOTS) a.links.box[r]->sums[par][a.links.rank][tid] = sSums[tid];
     } else if (tid < 32) {
-        if (a.do_update) gn_update_warp(g, pose, sSums, &sRed[0][0], tid, sM[0], sT);
+        if (a.do_update) gn_update_warp(g, pose, sSums, &sRed[0][0], tid, sM[0], sT, a.iter);
         else if (tid < N_SLOTS) pose->sums[tid] = sSums[tid];
     }
     if (tid == 0) *a.ticket = 0u;
@@ -551,7 +553,7 @@ __global__ void k_gn_combine(LinearizeArgs a, unsigned long long seqno) {
         sSums[tid] = acc;
     }
     __syncthreads();
-    if (a.do_update) gn_update_warp(a.g, pose, sSums, sScratch, tid, pose->R, pose->t);
+    if (a.do_update) gn_update_warp(a.g, pose, sSums, sScratch, tid, pose->R, pose->t, a.iter);
     else if (tid < N_SLOTS) pose->sums[tid] = sSums[tid];
 }
 
