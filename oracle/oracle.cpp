@@ -422,6 +422,7 @@ static int solve6(const double Ain[36], const double bin[6], double x[6]) {
     memcpy(A, Ain, sizeof A);
     memcpy(b, bin, sizeof b);
     int singular = 0;
+    double inv[6] = {0, 0, 0, 0, 0, 0};
     for (int c = 0; c < 6; c++) {
         int piv = c;
         double best = std::fabs(A[6 * c + c]);
@@ -434,8 +435,9 @@ static int solve6(const double Ain[36], const double bin[6], double x[6]) {
             for (int q = 0; q < 6; q++) { double t = A[6 * c + q]; A[6 * c + q] = A[6 * piv + q]; A[6 * piv + q] = t; }
             double t = b[c]; b[c] = b[piv]; b[piv] = t;
         }
+        inv[c] = 1.0 / A[6 * c + c];                      /* one reciprocal per pivot, reused by the back substitution */
         for (int r = c + 1; r < 6; r++) {
-            double f = A[6 * r + c] / A[6 * c + c];
+            double f = A[6 * r + c] * inv[c];
             A[6 * r + c] = f;
             for (int q = c + 1; q < 6; q++) A[6 * r + q] = A[6 * r + q] - f * A[6 * c + q];
             b[r] = b[r] - f * b[c];
@@ -444,7 +446,7 @@ static int solve6(const double Ain[36], const double bin[6], double x[6]) {
     for (int r = 5; r >= 0; r--) {
         double s = b[r];
         for (int q = r + 1; q < 6; q++) s = s - A[6 * r + q] * x[q];
-        x[r] = s / A[6 * r + r];
+        x[r] = s * inv[r];
     }
     for (int q = 0; q < 6; q++) if (!std::isfinite(x[q])) singular = 1;
     return singular;

@@ -680,7 +680,7 @@ enum { SLOT_A = 0, SLOT_B = 21, SLOT_RES = 27, SLOT_NVALID = 28, SLOT_NOOB = 29,
  * conditional swaps instead of a dynamic index) */
 template <int C>
 struct Solve6Col {
-    static TSDF_HD void run(double (&A)[6][6], double (&b)[6], int& singular) {
+    static TSDF_HD void run(double (&A)[6][6], double (&b)[6], double (&inv)[6], int& singular) {
         int piv = C;
         double best = fabs(A[C][C]);
 #pragma unroll
@@ -701,33 +701,34 @@ struct Solve6Col {
             const double u = b[C], v = b[r];
             b[C] = sw ? v : u; b[r] = sw ? u : v;
         }
+        inv[C] = 1.0 / A[C][C];                          /* one reciprocal per pivot, reused by the back substitution */
 #pragma unroll
         for (int r = C + 1; r < 6; r++) {
-            const double f = A[r][C] / A[C][C];
+            const double f = A[r][C] * inv[C];
 #pragma unroll
             for (int q = C + 1; q < 6; q++) A[r][q] = good ? (A[r][q] - f * A[C][q]) : A[r][q];
             b[r] = good ? (b[r] - f * b[C]) : b[r];
         }
-        Solve6Col<C + 1>::run(A, b, singular);
+        Solve6Col<C + 1>::run(A, b, inv, singular);
     }
 };
 template <>
 struct Solve6Col<6> {
-    static TSDF_HD void run(double (&)[6][6], double (&)[6], int&) {}
+    static TSDF_HD void run(double (&)[6][6], double (&)[6], double (&)[6], int&) {}
 };
 template <int R>
 struct Solve6Back {
-    static TSDF_HD void run(const double (&A)[6][6], const double (&b)[6], double* x) {
+    static TSDF_HD void run(const double (&A)[6][6], const double (&b)[6], const double (&inv)[6], double* x) {
         double sacc = b[R];
 #pragma unroll
         for (int q = R + 1; q < 6; q++) sacc = sacc - A[R][q] * x[q];
-        x[R] = sacc / A[R][R];
-        Solve6Back<R - 1>::run(A, b, x);
+        x[R] = sacc * inv[R];
+        Solve6Back<R - 1>::run(A, b, inv, x);
     }
 };
 template <>
 struct Solve6Back<-1> {
-    static TSDF_HD void run(const double (&)[6][6], const double (&)[6], double*) {}
+    static TSDF_HD void run(const double (&)[6][6], const double (&)[6], const double (&)[6], double*) {}
 };
 TSDF_HD int solve6(const double* Ain, const double* bin, double* x) {
     double A[6][6], b[6];
@@ -738,8 +739,9 @@ TSDF_HD int solve6(const double* Ain, const double* bin, double* x) {
         b[r] = bin[r];
     }
     int singular = 0;
-    Solve6Col<0>::run(A, b, singular);
-    Solve6Back<5>::run(A, b, x);
+    double inv[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    Solve6Col<0>::run(A, b, inv, singular);
+    Solve6Back<5>::run(A, b, inv, x);
 #pragma unroll
     for (int q = 0; q < 6; q++) if (!(fabs(x[q]) <= 1.7976931348623157e308)) singular = 1;
     return singular;

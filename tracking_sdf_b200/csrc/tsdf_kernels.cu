@@ -248,6 +248,7 @@ __device__ void gn_update_warp(const GridParams& g, PoseState* pose, const doubl
     }
     __syncwarp();
     int singular = 0;
+    double inv[6];                                   /* one reciprocal per pivot (every lane keeps all six) */
 #pragma unroll
     for (int c = 0; c < 6; c++) {
         int piv = c;
@@ -267,11 +268,12 @@ __device__ void gn_update_warp(const GridParams& g, PoseState* pose, const doubl
         __syncwarp();
         const int nq = 6 - c, nr = 5 - c;
         const bool act = good && lane < nr * nq;
+        inv[c] = 1.0 / sA[c][c];
         double val = 0.0;
         int r = 0, q = 0;
         if (act) {
             r = c + 1 + lane / nq; q = c + 1 + lane % nq;
-            const double f = sA[r][c] / sA[c][c];
+            const double f = sA[r][c] * inv[c];
             val = sA[r][q] - f * sA[c][q];
         }
         __syncwarp();
@@ -284,7 +286,7 @@ __device__ void gn_update_warp(const GridParams& g, PoseState* pose, const doubl
         double sacc = sA[r][6];
 #pragma unroll
         for (int q = r + 1; q < 6; q++) sacc = sacc - sA[r][q] * x[q];
-        x[r] = sacc / sA[r][r];
+        x[r] = sacc * inv[r];
     }
 #pragma unroll
     for (int q = 0; q < 6; q++) if (!(fabs(x[q]) <= 1.7976931348623157e308)) singular = 1;
