@@ -82,7 +82,7 @@ struct FuseArgs {
     unsigned long long* items;             /* capacity rows * (m/128 + 1) */
     unsigned int* item_count;
     unsigned long long* n_updated;         /* [0] this launch, [1] running total, [2..3] self-check counters */
-    CertPyramid pyr;                       /* certificate pyramid (levels 0..6) */
+    CertPyramid pyr;                       /* certificate pyramid (CERT_LEVELS levels, up to the whole image) */
     const float2* cert;
     unsigned long long* units;             /* queue of uncertified lane units (capacity: stored voxels / 4) */
     unsigned int* unit_count;

@@ -573,7 +573,7 @@ int linearize_blocks_per_sm() {
 }
 
 /* ------------------------------------------------------------------------------------------
- * K3: TSDF fusion (sdf.cpp:232-292), three launches per frame:
+ * K3: TSDF fusion (sdf.cpp:232-292), four launches per frame (tables, plan, cert, exact):
  *
  *  k_fuse_tables  T[0..2][i] = Rinv(r,0)*gx(i), T[3..5][j] = Rinv(r,1)*gy(j), T[6..8][k] =
  *                 Rinv(r,2)*gz(k), T[9][0..2] = tinv: the three products of the reference's
@@ -583,10 +583,13 @@ int linearize_blocks_per_sm() {
  *                 the view frustum (row_clip), rows cut into items of 128 voxels, appended to a
  *                 compact work list (one atomic per warp).  Rows outside the frustum cost nothing
  *                 afterwards, and the item list is what balances the load across SMs.
- *  k_fuse_items   persistent warps take items round-robin; a lane owns 4 consecutive voxels = one
- *                 32-byte sector of the {D,W} store = two 16-byte loads + stores.  The D/W loads and
- *                 the table loads are issued first, the exact double-precision geometry runs under
- *                 their latency, stores are predicated on "any of my 4 voxels updated".
+ *  k_fuse_cert    persistent warps take items round-robin; a lane owns 4 consecutive voxels = one
+ *                 32-byte sector of the {D,W} store.  Each lane unit is judged against the certificate
+ *                 pyramid (unit_certificate): certainly free space -> pure read-modify-write here,
+ *                 certainly behind the surface / outside the image -> nothing, else -> queued.
+ *  k_fuse_exact   the exact double-precision path of the reference on the queued units (and, with
+ *                 colour, on the certified free-space units too: they need their pixel).
+ *  k_fuse_items   the exact path on every voxel of every item; used when K has skew (no certificates).
  * ------------------------------------------------------------------------------------------ */
 __global__ void k_fuse_tables(GridParams g, const PoseState* __restrict__ pose, double* __restrict__ T,
                               unsigned long long* n_updated, unsigned int* item_count, unsigned int* unit_count) {
@@ -855,7 +858,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, COLOR ? 4 : FUSE_MIN_BLOCKS) k_f
     count_updates(my_updates, lane, n_updated);
 }
 
-/* ---- certificate pyramid: level 0 is written by k_prep; this builds levels 1..6 (min zfree, max zbehind) */
+/* ---- certificate pyramid: level 0 is written by k_prep; this builds levels 1..CERT_LEVELS-1 (min zfree, max zbehind) */
 __global__ void __launch_bounds__(256) k_pyramid(CertPyramid P, float2* __restrict__ cert, unsigned int* ticket) {
     pdl_wait();
     pdl_release();
@@ -965,10 +968,9 @@ __device__ __forceinline__ unsigned long long pack_unit(int k, int j, int x0, in
 
 /* ---- pass 1: certify lane units against the pyramid.  Free-space units are updated right here
  * (32 bytes in, 32 bytes out, four fp32 divisions); skipped units cost nothing; the rest is queued.
- * Software pipeline over the warp's items: item descriptors are fetched two items ahead and the
- * (speculative) voxel loads one item ahead, so HBM latency overlaps the certificate arithmetic of
- * the previous item (loads for units that end up skipped or queued are wasted bandwidth, which
- * only the HBM-bound dense case would notice, and there every unit is free space). */
+ * Software pipeline over the warp's items: item descriptors are fetched two items ahead; the voxel
+ * loads of a certified unit are issued right after its verdict and completed after the NEXT item's
+ * certificate arithmetic, so HBM latency is hidden and nothing is loaded for skipped or queued units. */
 template <int CHECK>
 __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(GridParams g, CertPyramid P, float2* __restrict__ grid,
                                                                const float2* __restrict__ cert, const double* __restrict__ T,
