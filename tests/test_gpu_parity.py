@@ -349,3 +349,21 @@ def test_certificates_are_certified(gpu_lib, frames, K):
         D, W = g.download()
         assert (W == 0).all()                      # the self-check never writes
         g.close()
+
+
+def test_64bit_index_path_of_the_tracker(gpu_lib, frames, K, monkeypatch):
+    """Stores of 2^32 voxels and more (>= 32 GiB) take the tracker's 64-bit index path; force it on a small
+    store and compare with the 32-bit path: identical normal equations and pose."""
+    depth, Rs, ts = frames
+    kw = dict(m=64, gauss_newton_max_iteration=10, maximum_twist_diff=float("-inf"))
+    out = []
+    for force in ("0", "1"):
+        monkeypatch.setenv("TSDF_B200_IDX64", force)
+        g = T.Tsdf(T.default_config(**kw)); g.set_intrinsics(K)
+        g.fuse(depth[0], Rs[0], ts[0])
+        A, b, st = g.linearize(depth[1])
+        R, t, st2 = g.track(depth[1])
+        out.append((A, b, R, t))
+        g.close()
+    for x, y in zip(out[0], out[1]):
+        assert np.array_equal(x, y)

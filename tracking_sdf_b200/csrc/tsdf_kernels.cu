@@ -10,6 +10,8 @@
  * north_star); K3 is HBM/fp64-issue bound, K2 is L1/L2-gather-latency bound.
  * Compiled with -fmad=false: see tsdf_core.cuh.
  */
+#include <stdlib.h>
+
 #include "tsdf_internal.h"
 
 namespace tsdf {
@@ -98,7 +100,8 @@ void launch_cloud(const GridParams& g, const PixRec* pix, float* cloud, float* n
 /* ------------------------------------------------------------------------------------------
  * voxel fetch used by the tracker and the sampler: {D,W} interleaved, x-fastest, read-only path
  * ------------------------------------------------------------------------------------------ */
-struct GridFetch {
+template <bool IDX32 = false>
+struct GridFetchT {
     const float2* __restrict__ grid;
     int m, ks0, ks1;
     int* miss;
@@ -112,16 +115,28 @@ struct GridFetch {
     __device__ __forceinline__ bool interior(int bi, int bj, int bk) const {
         return bi >= 0 && bj >= 0 && bi < m - 1 && bj < m - 1 && bk >= ks0 && bk < ks1 - 1;
     }
-    /* eight independent 8-byte loads, issued back to back (n = io*4 + jo*2 + ko) */
+    /* eight independent 8-byte loads, issued back to back (n = io*4 + jo*2 + ko).  IDX32: the store
+     * holds fewer than 2^32 voxels, so the voxel index is 32-bit arithmetic and each of the four row
+     * pointers is one IMAD.WIDE (index * 8 + base) instead of a chain of 64-bit multiplies and adds. */
     __device__ __forceinline__ void load8(int bi, int bj, int bk, float* d, float* w) const {
-        const float2* p = grid + (((size_t)(bk - ks0) * m + bj) * m + bi);
-        const size_t sj = (size_t)m, sk = (size_t)m * m;
-        const float2 v0 = __ldg(p), v1 = __ldg(p + sk), v2 = __ldg(p + sj), v3 = __ldg(p + sj + sk);
-        const float2 v4 = __ldg(p + 1), v5 = __ldg(p + 1 + sk), v6 = __ldg(p + 1 + sj), v7 = __ldg(p + 1 + sj + sk);
+        const float2 *p00, *p01, *p10, *p11;                           /* rows (jo, ko) */
+        if (IDX32) {
+            const unsigned um = (unsigned)m;
+            const unsigned i00 = ((unsigned)(bk - ks0) * um + (unsigned)bj) * um + (unsigned)bi;
+            const unsigned smm = um * um;
+            p00 = grid + i00; p01 = grid + (i00 + smm); p10 = grid + (i00 + um); p11 = grid + (i00 + um + smm);
+        } else {
+            const size_t sj = (size_t)m, sk = (size_t)m * m;
+            p00 = grid + (((size_t)(bk - ks0) * m + bj) * m + bi);
+            p01 = p00 + sk; p10 = p00 + sj; p11 = p00 + sj + sk;
+        }
+        const float2 v0 = __ldg(p00), v1 = __ldg(p01), v2 = __ldg(p10), v3 = __ldg(p11);
+        const float2 v4 = __ldg(p00 + 1), v5 = __ldg(p01 + 1), v6 = __ldg(p10 + 1), v7 = __ldg(p11 + 1);
         d[0] = v0.x; w[0] = v0.y; d[1] = v1.x; w[1] = v1.y; d[2] = v2.x; w[2] = v2.y; d[3] = v3.x; w[3] = v3.y;
         d[4] = v4.x; w[4] = v4.y; d[5] = v5.x; w[5] = v5.y; d[6] = v6.x; w[6] = v6.y; d[7] = v7.x; w[7] = v7.y;
     }
 };
+using GridFetch = GridFetchT<false>;
 
 __global__ void k_sample(GridParams g, const float2* __restrict__ grid, int64_t n, const double* __restrict__ pts,
                          float* out, uint8_t* ok) {
@@ -331,6 +346,7 @@ __device__ void gn_update_warp(const GridParams& g, PoseState* pose, const doubl
     }
 }
 
+template <bool IDX32>
 __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(LinearizeArgs a, int exchange_mode, unsigned long long seqno) {
     __shared__ double sM[7][9];
     __shared__ double sT[3];
@@ -374,7 +390,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     const float step = (s == 0) ? g.v_h2_width : (s == 1) ? g.v_h2_height : (s == 2) ? g.v_h2_depth : g.two_w_h;
     const double* M = sM[(s < 7) ? 0 : (s - 6)];
     int miss = 0;
-    GridFetch fetch{a.grid, g.m, g.ks0, g.ks1, &miss};
+    GridFetchT<IDX32> fetch{a.grid, g.m, g.ks0, g.ks1, &miss};
 
     const bool sharded = (g.ko0 > 0 || g.ko1 < g.m);
     const double dm = (double)g.m;
@@ -560,7 +576,11 @@ __global__ void k_gn_combine(LinearizeArgs a, unsigned long long seqno) {
 }
 
 void launch_linearize(const LinearizeArgs& a, int nblk, int exchange_mode, unsigned long long seqno, cudaStream_t s) {
-    launch_pdl(k_linearize, dim3(nblk), dim3(LIN_THREADS), s, a, exchange_mode, seqno);
+    /* 32-bit voxel indices whenever the stored slab has fewer than 2^32 voxels (everything up to 32 GiB) */
+    const unsigned long long n_stored = (unsigned long long)(a.g.ks1 - a.g.ks0) * a.g.m * a.g.m;
+    const char* force64 = getenv("TSDF_B200_IDX64");             /* tests: exercise the 64-bit index path on small stores */
+    if (n_stored < (1ull << 32) && !(force64 && force64[0] == '1')) launch_pdl(k_linearize<true>, dim3(nblk), dim3(LIN_THREADS), s, a, exchange_mode, seqno);
+    else launch_pdl(k_linearize<false>, dim3(nblk), dim3(LIN_THREADS), s, a, exchange_mode, seqno);
 }
 void launch_gn_combine(const LinearizeArgs& a, unsigned long long seqno, cudaStream_t s) {
     launch_pdl(k_gn_combine, dim3(1), dim3(32), s, a, seqno);
@@ -568,7 +588,7 @@ void launch_gn_combine(const LinearizeArgs& a, unsigned long long seqno, cudaStr
 
 int linearize_blocks_per_sm() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_linearize, LIN_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_linearize<true>, LIN_THREADS, 0);
     return n;
 }
 
