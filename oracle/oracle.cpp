@@ -3,8 +3,9 @@
  *
  * A restatement, in plain C++ with no third-party dependency, of the arithmetic of
  * the reference's per-frame hot path.  Paths cited below are relative to
- * /root/reference/src/.  PARITY UNPINNED (see oracle.h): the reference has no tests
- * or golden vectors and cannot be built in this image.
+ * /root/reference/src/.  Pinned against the reference itself (see oracle.h): its hot-path
+ * translation units, compiled unmodified over oracle/shim/, are compared with this file
+ * function by function in tests/test_oracle_vs_ref.py.
  *
  * Build discipline: g++ -O2 -fopenmp -ffp-contract=off, no fast-math,
  * no -march (so no FMA contraction).  Every fp32/fp64 boundary of the reference is
@@ -16,8 +17,11 @@
  *   - fixed-size matrix*vector / matrix*matrix coefficients accumulate left to right:
  *       ((a0*b0 + a1*b1) + a2*b2)                 [Eigen CoeffBasedProduct]
  *   - Vector3d::dot reduces as  c0 + (c1 + c2)    [Eigen redux_novec_unroller]
- *   - Matrix3d::inverse() = cofactor matrix * (1/det)
- *   - Matrix<double,6,6>::inverse() = partial-pivot LU; here: LU solve of A x = b
+ *   - Matrix3d::inverse() = cofactor matrix * (1/det), det expanded along column 0
+ *   - Matrix<double,6,6>::inverse() = partial-pivot LU whose column scaling and triangular
+ *     solves multiply by ONE reciprocal per pivot (Eigen 3.2: `col /= pivot` is `*= 1/pivot`,
+ *     triangular_solve_matrix uses `a = 1/tri(i,i)`); here: LU solve of A x = b with the same
+ *     reciprocals (differs from inverse-then-multiply by a few ulp, see test_solve_and_pose_update)
  *   - Affine3d::rotation() (SVD polar of an already orthonormal matrix) = linear part
  */
 #include "oracle.h"
@@ -52,11 +56,15 @@ static inline void inverse3(const double M[9], double inv[9]) {
     double c00 = M[4] * M[8] - M[5] * M[7];
     double c01 = M[5] * M[6] - M[3] * M[8];
     double c02 = M[3] * M[7] - M[4] * M[6];
-    double det = (M[0] * c00 + M[1] * c01) + M[2] * c02;
+    /* Eigen compute_inverse<.,.,3>: det = (cofactors_col0 .* col(0)).sum(), a 3-term redux c0 + (c1 + c2);
+     * pinned against the reference compiled over oracle/shim (tests/test_oracle_vs_ref.py) */
+    double c10 = M[7] * M[2] - M[8] * M[1];
+    double c20 = M[1] * M[5] - M[2] * M[4];
+    double det = c00 * M[0] + (c10 * M[3] + c20 * M[6]);
     double id = 1.0 / det;
     inv[0] = c00 * id;
-    inv[1] = (M[2] * M[7] - M[1] * M[8]) * id;
-    inv[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+    inv[1] = c10 * id;
+    inv[2] = c20 * id;
     inv[3] = c01 * id;
     inv[4] = (M[0] * M[8] - M[2] * M[6]) * id;
     inv[5] = (M[2] * M[3] - M[0] * M[5]) * id;

@@ -6,12 +6,20 @@
  * cpu_baseline / --impl reference legs use it, and there only as the checker / the
  * timed CPU baseline, never as a fallback.
  *
- * PARITY UNPINNED: the reference has no tests, golden vectors or fixtures
- *  and cannot be compiled here (needs ROS, PCL, Eigen, Boost).
- * This is a line-by-line restatement of the reference's arithmetic; each function
- * in oracle.cpp cites the reference file:line it follows.  What pins it instead:
- * the known-answer tests in tests/test_oracle_kat.py and the committed fixtures in
- * tests/golden/ (generated by tests/golden/make_golden.py from this oracle).
+ * PINNED AGAINST THE REFERENCE ITSELF: the reference has no tests, golden vectors or fixtures
+ *  and its build needs ROS, PCL, Eigen and Boost, none of which exist in this
+ * image — but its four hot-path translation units (sdf.cpp, camera_tracking.cpp, eigen_utils.cpp,
+ * marching_cubes_sdf.cpp) compile UNMODIFIED against the small shim headers in oracle/shim/
+ * (oracle/Makefile target `ref` -> oracle/_ref/libtsdf_ref.so, C ABI in ref_bridge.cpp).
+ * tests/test_oracle_vs_ref.py compares this restatement with that library function by function:
+ * bit-equal for the index maps, interpolate_distance, update (D, W, colour), get_partial_derivative
+ * (J, psi per pixel), the normal equations (one thread), the exp map, set_camera_transformation,
+ * marching cubes, interpolate_color; a few ulp for A.inverse()*b (Eigen's 6x6 LU inverse, stated
+ * in oracle/shim/eigen_shim.h, not verifiable without Eigen).  tests/golden/ is generated from
+ * that library.  STILL UNPINNED (third-party code that is not under /root/reference): Eigen's
+ * own rounding inside Matrix<6,6>::inverse() and Affine3d::rotation(); the ROS depth_image_proc
+ * back-projection and the PCL normals upstream of the boundary (orc_backproject is one definition
+ * shared by oracle and GPU).  Each function in oracle.cpp cites the reference file:line it follows.
  */
 #ifndef TSDF_ORACLE_H_
 #define TSDF_ORACLE_H_

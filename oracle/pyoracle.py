@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs as the checker or the timed CPU baseline.  The product package
-(tracking_sdf_b200) never imports this module.  PARITY UNPINNED (no reference tests exist).
+(tracking_sdf_b200) never imports this module.  Pinned against the reference itself: oracle/pyref.py binds the
+reference's own translation units (compiled over oracle/shim/) and tests/test_oracle_vs_ref.py compares the two.
 """
 import ctypes
 import os

@@ -1,0 +1,1 @@
+#include "../../pcl_shim.h"

@@ -6,7 +6,10 @@
   build_emul()   -> tests/_build/libcore_emul.so             (g++; host compile of the kernels'
                                                               __host__ __device__ core, CPU tests only)
 
-The reference itself (oracle/_ref) cannot be built in this image (needs ROS/PCL/Eigen/Boost).
+  build_ref()    -> oracle/_ref/libtsdf_ref.so               (g++; THE REFERENCE ITSELF: its four hot-path
+                                                              translation units compiled unmodified from
+                                                              /root/reference against oracle/shim/; only where
+                                                              the reference sources are present; pins the oracle)
 """
 import os
 import subprocess
@@ -49,6 +52,17 @@ def build_oracle(force=False, verbose=False):
     if force or _newer(out, srcs):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         _run([GXX] + HOST_FLAGS + ["-shared", "-o", out, srcs[0]], verbose)
+    return out
+
+
+def build_ref(force=False, verbose=False):
+    """oracle/Makefile target `ref`.  Returns the library path, or None when neither the reference sources
+    (/root/reference, build container only) nor a prebuilt library are present."""
+    d = os.path.join(ROOT, "oracle")
+    out = os.path.join(d, "_ref", "libtsdf_ref.so")
+    if not os.path.exists("/root/reference/src/src/sdf.cpp"):
+        return out if os.path.exists(out) else None
+    _run(["make", "-C", d, "ref"] + (["-B"] if force else []), verbose)
     return out
 
 
@@ -96,4 +110,4 @@ if __name__ == "__main__":
     v = True
     what = sys.argv[1:] or ["oracle", "synth", "cuda"]
     for w in what:
-        print(w, "->", {"oracle": build_oracle, "synth": build_synth, "cuda": build_cuda, "emul": build_emul}[w](force=True, verbose=v))
+        print(w, "->", {"oracle": build_oracle, "synth": build_synth, "cuda": build_cuda, "emul": build_emul, "ref": build_ref}[w](force=True, verbose=v))

@@ -143,11 +143,15 @@ TSDF_HD void inverse3(const double* M, double* inv) {
     double c00 = M[4] * M[8] - M[5] * M[7];
     double c01 = M[5] * M[6] - M[3] * M[8];
     double c02 = M[3] * M[7] - M[4] * M[6];
-    double det = (M[0] * c00 + M[1] * c01) + M[2] * c02;
+    /* Eigen compute_inverse<.,.,3>: det = (cofactors_col0 .* col(0)).sum(), a 3-term redux c0 + (c1 + c2);
+     * pinned against the reference compiled over oracle/shim (tests/test_oracle_vs_ref.py) */
+    double c10 = M[7] * M[2] - M[8] * M[1];
+    double c20 = M[1] * M[5] - M[2] * M[4];
+    double det = c00 * M[0] + (c10 * M[3] + c20 * M[6]);
     double id = 1.0 / det;
     inv[0] = c00 * id;
-    inv[1] = (M[2] * M[7] - M[1] * M[8]) * id;
-    inv[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+    inv[1] = c10 * id;
+    inv[2] = c20 * id;
     inv[3] = c01 * id;
     inv[4] = (M[0] * M[8] - M[2] * M[6]) * id;
     inv[5] = (M[2] * M[3] - M[0] * M[5]) * id;
