@@ -149,6 +149,8 @@ public:
         c.maximum_twist_diff = maximum_twist_diff;
         c.v_h = v_h; c.w_h = w_h;
         c.image_width = image_width; c.image_height = image_height; c.device = device;
+        /* one device volume per SDF: a second tracker on the same SDF would orphan the first handle */
+        if (sdf->h_) throw Error(TSDF_ERR_BAD_ARG, "this SDF is already attached to a CameraTracking");
         check(tsdf_create(&c, &sdf->h_));
         h_ = sdf->h_;
     }

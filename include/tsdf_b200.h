@@ -40,7 +40,8 @@ typedef enum tsdf_status {
     TSDF_ERR_CUDA = 3,
     TSDF_ERR_TRACKING_LOST = 4,   /* singular normal equations / non-finite twist (unguarded at camera_tracking.cpp:191) */
     TSDF_ERR_HALO = 5,            /* sharded: a tracking sample needed a voxel outside slab+halo */
-    TSDF_ERR_NOMEM = 6
+    TSDF_ERR_NOMEM = 6,
+    TSDF_ERR_PEER = 7             /* sharded: a peer rank did not deliver its normal equations in time; pose kept */
 } tsdf_status;
 
 typedef enum tsdf_metric {
@@ -181,15 +182,19 @@ tsdf_status tsdf_mesh_download(tsdf_handle h, float* xyz, double* world, float* 
  * and is read back after tsdf_sync with tsdf_read_pose_ring.  track = 0: fuse only.
  * The frame's preprocessing (back-projection, normals, certificates) runs on a second stream and
  * overlaps the previous frame's tracking and fusion, so depth_dev must be completely written when
- * the call is made and must not change until tsdf_sync (or until two later frames were enqueued). */
+ * the call is made and must not change until tsdf_sync (or until two later frames were enqueued:
+ * the call waits on the host for the preprocessing of the frame enqueued two calls earlier). */
 tsdf_status tsdf_enqueue_frame(tsdf_handle h, const float* depth_dev, int32_t track, int32_t slot);
 /* The same with a HOST (preferably pinned) depth buffer: the H2D copy goes through a copy stream
  * into a small ring of device frames, so the copy and the preprocessing of frame n+1 overlap
  * track+fuse of frame n.
- * The host buffer must stay valid until tsdf_sync (or until 4 later submissions returned). */
+ * The host buffer must stay valid until tsdf_sync (or until 4 later submissions returned: the call
+ * waits on the host for the H2D copy issued four submissions earlier). */
 tsdf_status tsdf_submit_frame(tsdf_handle h, const float* depth_host, int32_t track, int32_t slot);
 tsdf_status tsdf_sync(tsdf_handle h);
 int32_t     tsdf_pose_ring_capacity(void);
+/* Returns the frame's tracking status exactly like tsdf_track: TSDF_ERR_TRACKING_LOST, TSDF_ERR_HALO or
+ * TSDF_ERR_PEER when that frame's record says so (R, t, stats are filled in either way). */
 tsdf_status tsdf_read_pose_ring(tsdf_handle h, int32_t slot, double R[9], double t[3], tsdf_track_stats* stats);
 
 /* One linearisation at the current pose with NO pose update (the body of the loop at

@@ -17,7 +17,7 @@ c_u8p = ctypes.POINTER(ctypes.c_uint8)
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 c_i64p = ctypes.POINTER(ctypes.c_int64)
 
-STATUS_NAMES = {0: "OK", 1: "BAD_ARG", 2: "NO_INTRINSICS", 3: "CUDA", 4: "TRACKING_LOST", 5: "HALO", 6: "NOMEM"}
+STATUS_NAMES = {0: "OK", 1: "BAD_ARG", 2: "NO_INTRINSICS", 3: "CUDA", 4: "TRACKING_LOST", 5: "HALO", 6: "NOMEM", 7: "PEER"}
 
 
 class Config(ctypes.Structure):

@@ -19,6 +19,11 @@ namespace {
 thread_local std::string g_err;
 
 constexpr int POSE_RING = 4096;
+/* ticket words: [0] final tracker ticket, [1 .. MAX_LIN_GROUPS] group tickets, [PYRAMID_TICKET] k_pyramid (it runs
+ * concurrently on the preprocessing stream, so it must never alias a group ticket) */
+constexpr int MAX_LIN_GROUPS = 999;
+constexpr int PYRAMID_TICKET = 1000;
+constexpr int N_TICKETS = 1024;
 constexpr int64_t FLUSH_BYTES = 256ll << 20;   /* > 126 MB L2 */
 
 struct Impl {
@@ -26,7 +31,7 @@ struct Impl {
     GridParams g;
     int device = 0;
     cudaStream_t stream = nullptr;
-    bool own_stream = true;
+    int* stream_refs = nullptr;             /* handles sharing `stream` (same-device shard groups); the last one destroys it */
     float2* grid = nullptr;
     int64_t n_stored = 0;
     /* per-frame records, double-buffered: frame n+1 is preprocessed on prep_stream while frame n
@@ -86,6 +91,8 @@ struct Impl {
     unsigned long long seqno = 0;
     std::vector<void*> ipc_opened;
     bool have_K = false;
+    int force_idx64 = 0;                    /* TSDF_B200_IDX64=1 in the environment at create (tests) */
+    bool ev_recorded = false;               /* p->ev[] hold a frame (not the stage-timing ring) */
     cudaEvent_t ev[4];
     cudaEvent_t tmr[2];
     bool stage_valid = false;
@@ -114,6 +121,15 @@ struct Impl {
     } while (0)
 
 tsdf_status bad(const char* msg) { g_err = msg; return TSDF_ERR_BAD_ARG; }
+
+/* every kernel launch and event / stream-wait call of the enqueue helpers reports into note_cuda();
+ * this turns the first failure since the last check into a status */
+tsdf_status launch_status() {
+    cudaError_t e = take_launch_error();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { g_err = std::string("enqueue failed: ") + cudaGetErrorString(e); return TSDF_ERR_CUDA; }
+    return TSDF_OK;
+}
 
 /* device scratch that is released on every exit path of an accessor */
 struct DevTmp {
@@ -225,6 +241,7 @@ LinearizeArgs lin_args(Impl* p, int do_update, bool debug) {
     a.first = 0;
     a.iter = 0;
     a.px_per_block = p->px_per_block;
+    a.force_idx64 = p->force_idx64;
     a.links = p->links;
     return a;
 }
@@ -235,17 +252,24 @@ LinearizeArgs lin_args(Impl* p, int do_update, bool debug) {
  * covers every consumer of it. */
 void enqueue_prep(Impl* p, const float* dptr, int reset_track) {
     const int b = (int)(p->prep_seq & 1ull);
-    cudaEventRecord(p->rec_free[b ^ 1], p->stream);              /* all work on the previous frame's records is enqueued */
-    if (p->prep_seq >= 2) cudaStreamWaitEvent(p->prep_stream, p->rec_free[b], 0);
-    if (p->depth_ready) cudaStreamWaitEvent(p->prep_stream, p->depth_ready, 0);
+    note_cuda(cudaEventRecord(p->rec_free[b ^ 1], p->stream));   /* all work on the previous frame's records is enqueued */
+    if (p->prep_seq >= 2) {
+        /* HOST wait: the preprocessing of the frame enqueued two calls ago has read its depth image.  This is
+         * what makes the documented lifetime true ("depth_dev must not change until two later frames were
+         * enqueued"): the host can no longer run further ahead of K1 than that.  K1 runs early on its own
+         * stream, so in steady state the event is long complete and the wait costs nothing. */
+        note_cuda(cudaEventSynchronize(p->prepped[b]));
+        note_cuda(cudaStreamWaitEvent(p->prep_stream, p->rec_free[b], 0));
+    }
+    if (p->depth_ready) note_cuda(cudaStreamWaitEvent(p->prep_stream, p->depth_ready, 0));
     p->pix = p->pix_buf[b]; p->pts = p->pts_buf[b]; p->cert = p->cert_buf[b]; p->rgb4 = p->rgb4_buf[b]; p->cosn = p->cosn_buf[b];
     p->frame_has_color = p->frame_rgb != nullptr;
     launch_prep(p->g, dptr, p->pix, p->cert + p->pyr.off[0], p->pts, p->frame_rgb, p->rgb4, p->cosn, p->prep_stream);
     p->frame_rgb = nullptr;
-    launch_pyramid(p->pyr, p->cert, p->ticket + 1000, p->prep_stream);
-    if (p->depth_done) cudaEventRecord(p->depth_done, p->prep_stream);
-    cudaEventRecord(p->prepped[b], p->prep_stream);
-    cudaStreamWaitEvent(p->stream, p->prepped[b], 0);
+    launch_pyramid(p->pyr, p->cert, p->ticket + PYRAMID_TICKET, p->prep_stream);
+    if (p->depth_done) note_cuda(cudaEventRecord(p->depth_done, p->prep_stream));
+    note_cuda(cudaEventRecord(p->prepped[b], p->prep_stream));
+    note_cuda(cudaStreamWaitEvent(p->stream, p->prepped[b], 0));
     p->depth_ready = nullptr; p->depth_done = nullptr;
     p->prep_seq++;
     p->lin_first = reset_track;
@@ -284,17 +308,17 @@ tsdf_status enqueue_frame(Impl* p, const float* dptr, bool do_track, bool do_fus
     if (p->exchange_mode == 2) return bad("same-device shard group: use tsdf_group_* entry points");
     cudaEvent_t* ev = p->ev;
     if (p->ring_pos < p->ring_frames) { ev = &p->ring_ev[(size_t)4 * p->ring_pos]; p->ring_pos++; }
-    cudaEventRecord(ev[0], p->stream);
+    else p->ev_recorded = true;
+    note_cuda(cudaEventRecord(ev[0], p->stream));
     enqueue_prep(p, dptr, do_track ? 1 : 0);
-    cudaEventRecord(ev[1], p->stream);
+    note_cuda(cudaEventRecord(ev[1], p->stream));
     if (do_track)
         for (int it = 0; it < p->g.max_iter; it++) enqueue_linearize(p, 1, false);
-    cudaEventRecord(ev[2], p->stream);
+    note_cuda(cudaEventRecord(ev[2], p->stream));
     if (do_fuse) enqueue_fuse(p);
-    cudaEventRecord(ev[3], p->stream);
+    note_cuda(cudaEventRecord(ev[3], p->stream));
     p->stage_valid = true;
-    CK(cudaGetLastError());
-    return TSDF_OK;
+    return launch_status();
 }
 
 void fill_stats(const PoseState& ps, tsdf_track_stats* st) {
@@ -309,15 +333,19 @@ void fill_stats(const PoseState& ps, tsdf_track_stats* st) {
     for (int r = 0; r < 6; r++) { st->b[r] = ps.sums[SLOT_B + r]; st->twist[r] = ps.twist[r]; }
 }
 
+/* status of one frame's tracking record — the same mapping for the synchronous calls and the pose ring */
+tsdf_status pose_status(const PoseState& ps) {
+    if (ps.halo_miss & 0x40000000) { g_err = "sharded tracking: a peer rank did not deliver its normal equations within 2 s; the pose was not updated"; return TSDF_ERR_PEER; }
+    if (ps.halo_miss) { g_err = "a tracking sample needed a voxel outside this shard's slab+halo (increase tsdf_config.halo)"; return TSDF_ERR_HALO; }
+    if (ps.singular) { g_err = "tracking lost: singular normal equations or non-finite twist"; return TSDF_ERR_TRACKING_LOST; }
+    return TSDF_OK;
+}
 tsdf_status track_result(Impl* p, double R_out[9], double t_out[3], tsdf_track_stats* stats) {
     const PoseState& ps = *p->pose_pin;
     if (R_out) memcpy(R_out, ps.R, sizeof ps.R);
     if (t_out) memcpy(t_out, ps.t, sizeof ps.t);
     fill_stats(ps, stats);
-    if (ps.halo_miss & 0x40000000) { g_err = "sharded tracking: a peer rank did not deliver its normal equations within 2 s"; return TSDF_ERR_CUDA; }
-    if (ps.halo_miss) { g_err = "a tracking sample needed a voxel outside this shard's slab+halo (increase tsdf_config.halo)"; return TSDF_ERR_HALO; }
-    if (ps.singular) { g_err = "tracking lost: singular normal equations or non-finite twist"; return TSDF_ERR_TRACKING_LOST; }
-    return TSDF_OK;
+    return pose_status(ps);
 }
 
 }  // namespace
@@ -386,6 +414,7 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     A(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    p->stream_refs = new int(1);
     A(cudaMalloc(&p->grid, (size_t)p->n_stored * sizeof(float2)));
     A(cudaStreamCreateWithFlags(&p->prep_stream, cudaStreamNonBlocking));
     for (int q = 0; q < 2; q++) {
@@ -400,7 +429,7 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     A(cudaMalloc(&p->pose_dev, sizeof(PoseState)));
     A(cudaMallocHost(&p->pose_pin, sizeof(PoseState)));
     A(cudaMallocHost(&p->ring_pin, sizeof(PoseState) * POSE_RING));
-    A(cudaMalloc(&p->ticket, 1024 * sizeof(unsigned int)));
+    A(cudaMalloc(&p->ticket, N_TICKETS * sizeof(unsigned int)));
     A(cudaMalloc(&p->fuse_tables, ((size_t)9 * cfg->m + 8) * sizeof(double)));
     A(cudaMalloc(&p->fuse_items, (size_t)(p->g.ks1 - p->g.ks0) * cfg->m * ((cfg->m + 127) / 128 + 1) * sizeof(unsigned long long)));
     A(cudaMalloc(&p->fuse_item_count, 2 * sizeof(unsigned int)));
@@ -436,7 +465,11 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
         tsdf_destroy(reinterpret_cast<tsdf_handle>(p));
         return e == cudaErrorMemoryAllocation ? TSDF_ERR_NOMEM : TSDF_ERR_CUDA;
     }
-    cudaMemset(p->ticket, 0, 1024 * sizeof(unsigned int));
+    cudaMemset(p->ticket, 0, N_TICKETS * sizeof(unsigned int));
+    {
+        const char* force64 = getenv("TSDF_B200_IDX64");       /* tests: exercise the 64-bit voxel index path on small stores */
+        p->force_idx64 = (force64 && force64[0] == '1') ? 1 : 0;
+    }
     cudaMemset(p->n_upd_dev, 0, 4 * sizeof(unsigned long long));
     cudaMemset(p->mailbox, 0, sizeof(Mailbox));
     p->links.box[0] = p->mailbox;
@@ -447,7 +480,7 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     /* K2: one block per LIN_TW x LIN_TH tile of the strided pixel grid */
     const int ppb = LIN_TW * LIN_TH;
     const int nb = ((p->g.ni + LIN_TW - 1) / LIN_TW) * ((p->g.nj + LIN_TH - 1) / LIN_TH);
-    if ((nb + LIN_GROUP - 1) / LIN_GROUP > 1000) { g_err = "image too large for the reduction tree"; tsdf_destroy(reinterpret_cast<tsdf_handle>(p)); return TSDF_ERR_BAD_ARG; }
+    if ((nb + LIN_GROUP - 1) / LIN_GROUP > MAX_LIN_GROUPS) { g_err = "image too large for the reduction tree"; tsdf_destroy(reinterpret_cast<tsdf_handle>(p)); return TSDF_ERR_BAD_ARG; }
     p->px_per_block = ppb; p->lin_blocks = nb;
     A(cudaMalloc(&p->partials, (size_t)nb * LIN_PARTIAL_STRIDE * sizeof(double)));
     A(cudaMalloc(&p->group_partials, (size_t)((nb + LIN_GROUP - 1) / LIN_GROUP) * LIN_PARTIAL_STRIDE * sizeof(double)));
@@ -499,7 +532,10 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     }
     for (int q = 0; q < 4; q++) if (p->ev[q]) cudaEventDestroy(p->ev[q]);
     for (int q = 0; q < 2; q++) if (p->tmr[q]) cudaEventDestroy(p->tmr[q]);
-    if (p->stream && p->own_stream) cudaStreamDestroy(p->stream);
+    if (p->stream_refs && --*p->stream_refs == 0) {           /* last handle on this stream */
+        if (p->stream) cudaStreamDestroy(p->stream);
+        delete p->stream_refs;
+    }
     cudaGetLastError();
     delete p;
     return TSDF_OK;
@@ -858,7 +894,12 @@ tsdf_status tsdf_submit_frame(tsdf_handle h, const float* depth_host, int32_t tr
     if (!p->have_K) { g_err = "camera matrix not set (tsdf_set_intrinsics)"; return TSDF_ERR_NO_INTRINSICS; }
     const int b = (int)(p->submit_seq % Impl::NSTAGE);
     const size_t bytes = (size_t)p->g.img_w * p->g.img_h * sizeof(float);
-    if (p->submit_seq >= (unsigned long long)Impl::NSTAGE) CK(cudaStreamWaitEvent(p->copy_stream, p->consumed[b], 0));
+    if (p->submit_seq >= (unsigned long long)Impl::NSTAGE) {
+        /* HOST wait for the H2D copy issued NSTAGE submissions ago (same stage buffer): when this call returns,
+         * that call's host buffer has been read — the documented lifetime ("until 4 later submissions returned") */
+        CK(cudaEventSynchronize(p->copied[b]));
+        CK(cudaStreamWaitEvent(p->copy_stream, p->consumed[b], 0));
+    }
     CK(cudaMemcpyAsync(p->stage[b], depth_host, bytes, cudaMemcpyHostToDevice, p->copy_stream));
     CK(cudaEventRecord(p->copied[b], p->copy_stream));
     p->depth_ready = p->copied[b];               /* K1 waits for the copy and releases the stage buffer itself */
@@ -884,7 +925,7 @@ tsdf_status tsdf_read_pose_ring(tsdf_handle h, int32_t slot, double R[9], double
     if (R) memcpy(R, ps.R, sizeof ps.R);
     if (t) memcpy(t, ps.t, sizeof ps.t);
     fill_stats(ps, stats);
-    return TSDF_OK;
+    return pose_status(ps);                 /* same mapping as tsdf_track: lost / halo / peer timeout are reported here too */
 }
 
 tsdf_status tsdf_linearize(tsdf_handle h, const float* depth, int32_t mem, double A[36], double b[6], tsdf_track_stats* stats) {
@@ -898,7 +939,8 @@ tsdf_status tsdf_linearize(tsdf_handle h, const float* depth, int32_t mem, doubl
     if (st != TSDF_OK) return st;
     enqueue_prep(p, dptr, 1);
     enqueue_linearize(p, 0, false);
-    CK(cudaGetLastError());
+    st = launch_status();
+    if (st != TSDF_OK) return st;
     st = fetch_pose(p);
     if (st != TSDF_OK) return st;
     tsdf_track_stats s;
@@ -927,7 +969,8 @@ tsdf_status tsdf_linearize_pixels(tsdf_handle h, const float* depth, int32_t mem
     CK(cudaMemsetAsync(p->dbgPsi, 0, (size_t)P * sizeof(float), p->stream));
     enqueue_prep(p, dptr, 1);
     enqueue_linearize(p, 0, true);
-    CK(cudaGetLastError());
+    st = launch_status();
+    if (st != TSDF_OK) return st;
     if (J) CK(cudaMemcpyAsync(J, p->dbgJ, (size_t)P * 6 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
     if (psi) CK(cudaMemcpyAsync(psi, p->dbgPsi, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
     if (flag) CK(cudaMemcpyAsync(flag, p->dbgFlag, (size_t)P, cudaMemcpyDeviceToHost, p->stream));
@@ -1126,7 +1169,7 @@ tsdf_status tsdf_host_free_pinned(void* host_ptr) {
 tsdf_status tsdf_last_stage_ms(tsdf_handle h, float out[3]) {
     if (!h || !out) return bad("null argument");
     Impl* p = I(h);
-    if (!p->stage_valid) return bad("no frame enqueued yet");
+    if (!p->stage_valid || !p->ev_recorded) return bad("no frame enqueued outside a tsdf_stage_timing_begin/end window yet");
     CK(cudaSetDevice(p->device));
     CK(cudaEventSynchronize(p->ev[3]));
     for (int q = 0; q < 3; q++) CK(cudaEventElapsedTime(&out[q], p->ev[q], p->ev[q + 1]));
@@ -1351,12 +1394,14 @@ tsdf_status tsdf_shard_attach_local(tsdf_handle* handles, int32_t world) {
         }
         p->exchange_mode = world > 1 ? (same_dev ? 2 : 1) : 0;
         p->seqno = 0;
-        if (same_dev && r > 0) {
-            /* one stream for the whole group: program order is the cross-shard dependency */
+        if (same_dev && r > 0 && p->stream != I(handles[0])->stream) {
+            /* one stream for the whole group: program order is the cross-shard dependency.  The stream is
+             * reference-counted, so the handles may be destroyed in any order (and attaching twice is a no-op) */
             CK(cudaStreamSynchronize(p->stream));
-            if (p->own_stream) cudaStreamDestroy(p->stream);
+            if (--*p->stream_refs == 0) { cudaStreamDestroy(p->stream); delete p->stream_refs; }
             p->stream = I(handles[0])->stream;
-            p->own_stream = false;
+            p->stream_refs = I(handles[0])->stream_refs;
+            ++*p->stream_refs;
         }
     }
     return TSDF_OK;
@@ -1407,7 +1452,8 @@ tsdf_status tsdf_group_linearize(tsdf_handle* handles, int32_t world, const floa
     if (st != TSDF_OK) return st;
     for (int r = 0; r < world; r++) { cudaSetDevice(I(handles[r])->device); enqueue_prep(I(handles[r]), dptr[r], 1); }
     group_gn_iteration(handles, world, 0);
-    CK(cudaGetLastError());
+    st = launch_status();
+    if (st != TSDF_OK) return st;
     int miss = 0;
     for (int r = world - 1; r >= 0; r--) {
         Impl* p = I(handles[r]);
@@ -1441,9 +1487,10 @@ tsdf_status tsdf_group_frame(tsdf_handle* handles, int32_t world, const float* d
             Impl* p = I(handles[r]);
             cudaSetDevice(p->device);
             enqueue_fuse(p);
-            cudaMemcpyAsync(p->n_upd_pin, p->n_upd_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream);
+            note_cuda(cudaMemcpyAsync(p->n_upd_pin, p->n_upd_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
         }
-    CK(cudaGetLastError());
+    st = launch_status();
+    if (st != TSDF_OK) return st;
     int64_t nupd = 0;
     int miss = 0;
     for (int r = world - 1; r >= 0; r--) {

@@ -63,8 +63,13 @@ struct LinearizeArgs {
     int32_t first;                         /* 1: first launch of a frame (resets the per-frame tracking state) */
     int32_t iter;                          /* 0-based index of this launch within the frame's GN loop */
     int32_t px_per_block;
+    int32_t force_idx64;                   /* tests: take the 64-bit voxel index path on a small store (TSDF_B200_IDX64=1 at create) */
     ShardLinks links;                      /* world = 1: no exchange */
 };
+
+/* result of every launch / event call since the last take: checked by the ABI after enqueueing a frame */
+void note_cuda(cudaError_t e);
+cudaError_t take_launch_error();
 
 void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, const uint8_t* rgb3, uchar4* rgb4, double* cosn, cudaStream_t s);
 void launch_pyramid(const CertPyramid& P, float2* cert, unsigned int* ticket, cudaStream_t s);

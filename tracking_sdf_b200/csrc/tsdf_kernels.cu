@@ -23,6 +23,20 @@ namespace tsdf {
  * dependent launches per frame). */
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;"); }
+/* Loads of data written by the PROGRAMMATIC-DEPENDENT-LAUNCH predecessor chain (the voxel store, the fusion
+ * tables, the item / unit lists, the pose block): the consumer grid is already resident while the producer
+ * still writes, so the read-only (ld.global.nc) path, which requires the data to be constant for the kernel's
+ * lifetime, is formally off limits; griddepcontrol.wait orders the ordinary (coherent, L1-cached) path.
+ * __ldg stays on data produced on the preprocessing stream and joined through an event (pixel records,
+ * certificates, strided points, colour image). */
+template <typename T> __device__ __forceinline__ T ld_dep(const T* p) { return __ldca(p); }
+
+/* first launch / stream-ordering error since the last take_launch_error(): the per-frame sequence is
+ * sixteen launches enqueued back to back, so the result of every one is kept and the ABI entry point
+ * that enqueued them reports it (tsdf_abi.cu: enqueue_frame) */
+static thread_local cudaError_t t_launch_err = cudaSuccess;
+void note_cuda(cudaError_t e) { if (e != cudaSuccess && t_launch_err == cudaSuccess) t_launch_err = e; }
+cudaError_t take_launch_error() { const cudaError_t e = t_launch_err; t_launch_err = cudaSuccess; return e; }
 
 template <typename... KArgs, typename... Args>
 static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args) {
@@ -32,7 +46,7 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    note_cuda(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -102,13 +116,13 @@ void launch_cloud(const GridParams& g, const PixRec* pix, float* cloud, float* n
  * ------------------------------------------------------------------------------------------ */
 template <bool IDX32 = false>
 struct GridFetchT {
-    const float2* __restrict__ grid;
+    const float2* grid;                                   /* written by the previous frame's fusion: ordinary loads (ld_dep) */
     int m, ks0, ks1;
     int* miss;
     __device__ __forceinline__ bool operator()(int ci, int cj, int ck, float& d, float& w) const {
         if ((unsigned)ci >= (unsigned)m || (unsigned)cj >= (unsigned)m || (unsigned)ck >= (unsigned)m) return false;   /* sdf.h:114-119 */
         if (ck < ks0 || ck >= ks1) { *miss = 1; d = 0.0f; w = 0.0f; return true; }   /* not held by this shard */
-        const float2 dw = __ldg(&grid[((size_t)(ck - ks0) * m + cj) * m + ci]);
+        const float2 dw = ld_dep(&grid[((size_t)(ck - ks0) * m + cj) * m + ci]);
         d = dw.x; w = dw.y;
         return true;
     }
@@ -130,8 +144,8 @@ struct GridFetchT {
             p00 = grid + (((size_t)(bk - ks0) * m + bj) * m + bi);
             p01 = p00 + sk; p10 = p00 + sj; p11 = p00 + sj + sk;
         }
-        const float2 v0 = __ldg(p00), v1 = __ldg(p01), v2 = __ldg(p10), v3 = __ldg(p11);
-        const float2 v4 = __ldg(p00 + 1), v5 = __ldg(p01 + 1), v6 = __ldg(p10 + 1), v7 = __ldg(p11 + 1);
+        const float2 v0 = ld_dep(p00), v1 = ld_dep(p01), v2 = ld_dep(p10), v3 = ld_dep(p11);
+        const float2 v4 = ld_dep(p00 + 1), v5 = ld_dep(p01 + 1), v6 = ld_dep(p10 + 1), v7 = ld_dep(p11 + 1);
         d[0] = v0.x; w[0] = v0.y; d[1] = v1.x; w[1] = v1.y; d[2] = v2.x; w[2] = v2.y; d[3] = v3.x; w[3] = v3.y;
         d[4] = v4.x; w[4] = v4.y; d[5] = v5.x; w[5] = v5.y; d[6] = v6.x; w[6] = v6.y; d[7] = v7.x; w[7] = v7.y;
     }
@@ -205,11 +219,12 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) { return *rei
 
 /* sum of the 30 slots over all ranks, rank order; runs in the last block after its local sums
  * are in s_sums.  mode 1: in-kernel exchange over peer-mapped mailboxes. */
-__device__ void exchange_sums(const ShardLinks& L, unsigned long long seqno, double* s_sums, int tid, PoseState* pose) {
+__device__ bool exchange_sums(const ShardLinks& L, unsigned long long seqno, double* s_sums, int tid, PoseState* pose) {
     /* executed by warp 0 of the final block only (tid = lane).  Data stores by lanes < 30, then one
      * system-scope fence per publishing lane (cumulative over the warp's stores via __syncwarp),
      * then the sequence flag; the reader side mirrors it. */
     const int par = (int)(seqno & 1ull);
+    bool timed_out = false;
     for (int r = 0; r < L.world; r++) {
         if (tid < N_SLOTS) L.box[r]->sums[par][L.rank][tid] = s_sums[tid];      /* peer stores over NVLink */
     }
@@ -221,17 +236,21 @@ __device__ void exchange_sums(const ShardLinks& L, unsigned long long seqno, dou
         const volatile unsigned long long* flag = &L.box[L.rank]->seq[par][tid];
         const unsigned long long t0 = gtime();
         while (*flag != seqno) {
-            if (gtime() - t0 > 2000000000ull) { atomicOr(&pose->halo_miss, 0x40000000); break; }
+            if (gtime() - t0 > 2000000000ull) { atomicOr(&pose->halo_miss, 0x40000000); timed_out = true; break; }
         }
         __threadfence_system();
     }
     __syncwarp();
+    /* a peer that did not deliver: the mailbox holds stale or partial sums.  Never solve with them — the
+     * caller keeps the pose, ends the frame's GN loop and the status reaches the host (TSDF_ERR_PEER) */
+    if (__any_sync(0xffffffffu, timed_out)) return false;
     if (tid < N_SLOTS) {
         double acc = 0.0;
         for (int r = 0; r < L.world; r++) acc = acc + ld_volatile_f64(&L.box[L.rank]->sums[par][r][tid]);   /* rank order */
         s_sums[tid] = acc;
     }
     __syncwarp();
+    return true;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -540,7 +559,8 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     __syncthreads();
     if (a.dbg_times && tid == 0) a.dbg_times[3] = gtime();
     if (tid == 0 && sSums[SLOT_MISS] > 0.0) atomicAdd(&pose->halo_miss, (int)sSums[SLOT_MISS]);
-    if (exchange_mode == 1 && a.links.world > 1 && tid < 32) exchange_sums(a.links, seqno, sSums, tid, pose);
+    bool peers_ok = true;                                  /* meaningful in warp 0 only (the warp that goes on) */
+    if (exchange_mode == 1 && a.links.world > 1 && tid < 32) peers_ok = exchange_sums(a.links, seqno, sSums, tid, pose);
     if (exchange_mode == 2 && a.links.world > 1) {
         /* deferred (single-process emulation): publish our sums into every mailbox; a separate
          * k_gn_combine launch sums them in rank order and updates the pose */
@@ -548,7 +568,8 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
         for (int r = 0; r < a.links.world; r++)
             if (tid < N_SLOTS) a.links.box[r]->sums[par][a.links.rank][tid] = sSums[tid];
     } else if (tid < 32) {
-        if (a.do_update) gn_update_warp(g, pose, sSums, &sRed[0][0], tid, sM[0], sT, a.iter);
+        if (!peers_ok) { if (tid == 0) { pose->stopped = 1; pose->iterations = a.iter + 1; } }
+        else if (a.do_update) gn_update_warp(g, pose, sSums, &sRed[0][0], tid, sM[0], sT, a.iter);
         else if (tid < N_SLOTS) pose->sums[tid] = sSums[tid];
     }
     if (tid == 0) *a.ticket = 0u;
@@ -578,8 +599,7 @@ __global__ void k_gn_combine(LinearizeArgs a, unsigned long long seqno) {
 void launch_linearize(const LinearizeArgs& a, int nblk, int exchange_mode, unsigned long long seqno, cudaStream_t s) {
     /* 32-bit voxel indices whenever the stored slab has fewer than 2^32 voxels (everything up to 32 GiB) */
     const unsigned long long n_stored = (unsigned long long)(a.g.ks1 - a.g.ks0) * a.g.m * a.g.m;
-    const char* force64 = getenv("TSDF_B200_IDX64");             /* tests: exercise the 64-bit index path on small stores */
-    if (n_stored < (1ull << 32) && !(force64 && force64[0] == '1')) launch_pdl(k_linearize<true>, dim3(nblk), dim3(LIN_THREADS), s, a, exchange_mode, seqno);
+    if (n_stored < (1ull << 32) && !a.force_idx64) launch_pdl(k_linearize<true>, dim3(nblk), dim3(LIN_THREADS), s, a, exchange_mode, seqno);
     else launch_pdl(k_linearize<false>, dim3(nblk), dim3(LIN_THREADS), s, a, exchange_mode, seqno);
 }
 void launch_gn_combine(const LinearizeArgs& a, unsigned long long seqno, cudaStream_t s) {
@@ -611,7 +631,7 @@ int linearize_blocks_per_sm() {
  *                 colour, on the certified free-space units too: they need their pixel).
  *  k_fuse_items   the exact path on every voxel of every item; used when K has skew (no certificates).
  * ------------------------------------------------------------------------------------------ */
-__global__ void k_fuse_tables(GridParams g, const PoseState* __restrict__ pose, double* __restrict__ T,
+__global__ void k_fuse_tables(GridParams g, const PoseState* pose, double* __restrict__ T,
                               unsigned long long* n_updated, unsigned int* item_count, unsigned int* unit_count) {
     pdl_wait();
     pdl_release();
@@ -638,8 +658,8 @@ __device__ __forceinline__ unsigned long long pack_item(int k, int j, int xs, in
 }
 
 __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, CertPyramid P, const float2* __restrict__ cert, int check,
-                                                   const PoseState* __restrict__ pose,
-                                                   const double* __restrict__ T, unsigned long long* __restrict__ items,
+                                                   const PoseState* pose,      /* written by the PDL predecessor: no __restrict__/nc */
+                                                   const double* T, unsigned long long* __restrict__ items,
                                                    unsigned int* item_count) {
     pdl_wait();
     pdl_release();
@@ -796,13 +816,13 @@ __device__ __forceinline__ void color_four(float4* cptr, const uchar4* __restric
 
 /* camera-space centres of the four voxels x0..x0+3 of row (j,k): camera_tracking.cpp:51-54 with
  * the three products hoisted into the tables, the three additions in the reference's order */
-__device__ __forceinline__ void cam_four(const double* __restrict__ T, unsigned int um, int x0, int j, int k,
+__device__ __forceinline__ void cam_four(const double* T, unsigned int um, int x0, int j, int k,
                                          double ti0, double ti1, double ti2, double* cx, double* cy, double* cz) {
-    const double2 a0 = __ldg(reinterpret_cast<const double2*>(T + (unsigned int)x0)), a1 = __ldg(reinterpret_cast<const double2*>(T + (unsigned int)x0 + 2));
-    const double2 b0 = __ldg(reinterpret_cast<const double2*>(T + (um + x0))), b1 = __ldg(reinterpret_cast<const double2*>(T + (um + x0 + 2)));
-    const double2 c0 = __ldg(reinterpret_cast<const double2*>(T + (2u * um + x0))), c1 = __ldg(reinterpret_cast<const double2*>(T + (2u * um + x0 + 2)));
-    const double qy0 = __ldg(T + (3u * um + j)), qy1 = __ldg(T + (4u * um + j)), qy2 = __ldg(T + (5u * um + j));
-    const double pz0 = __ldg(T + (6u * um + k)), pz1 = __ldg(T + (7u * um + k)), pz2 = __ldg(T + (8u * um + k));
+    const double2 a0 = ld_dep(reinterpret_cast<const double2*>(T + (unsigned int)x0)), a1 = ld_dep(reinterpret_cast<const double2*>(T + (unsigned int)x0 + 2));
+    const double2 b0 = ld_dep(reinterpret_cast<const double2*>(T + (um + x0))), b1 = ld_dep(reinterpret_cast<const double2*>(T + (um + x0 + 2)));
+    const double2 c0 = ld_dep(reinterpret_cast<const double2*>(T + (2u * um + x0))), c1 = ld_dep(reinterpret_cast<const double2*>(T + (2u * um + x0 + 2)));
+    const double qy0 = ld_dep(T + (3u * um + j)), qy1 = ld_dep(T + (4u * um + j)), qy2 = ld_dep(T + (5u * um + j));
+    const double pz0 = ld_dep(T + (6u * um + k)), pz1 = ld_dep(T + (7u * um + k)), pz2 = ld_dep(T + (8u * um + k));
     const double px0[4] = {a0.x, a0.y, a1.x, a1.y}, px1[4] = {b0.x, b0.y, b1.x, b1.y}, px2[4] = {c0.x, c0.y, c1.x, c1.y};
 #pragma unroll
     for (int v = 0; v < 4; v++) {
@@ -836,9 +856,9 @@ __device__ __forceinline__ void count_updates(unsigned int my_updates, int lane,
 template <int METRIC, int KSIMPLE, bool COLOR = false>
 __global__ void __launch_bounds__(FUSE_THREADS, COLOR ? 4 : FUSE_MIN_BLOCKS) k_fuse_items(GridParams g_in, float2* __restrict__ grid,
                                                                 const PixRec* __restrict__ pix,
-                                                                const double* __restrict__ T,
-                                                                const unsigned long long* __restrict__ items,
-                                                                const unsigned int* __restrict__ item_count,
+                                                                const double* T,
+                                                                const unsigned long long* items,
+                                                                const unsigned int* item_count,
                                                                 unsigned long long* n_updated,
                                                                 float4* __restrict__ color, const uchar4* __restrict__ rgb4, const double* __restrict__ cosn) {
     pdl_wait();
@@ -854,7 +874,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, COLOR ? 4 : FUSE_MIN_BLOCKS) k_f
     const double ti0 = T[9 * (size_t)m + 0], ti1 = T[9 * (size_t)m + 1], ti2 = T[9 * (size_t)m + 2];
     unsigned int my_updates = 0;
     for (unsigned int it = gw; it < n_items; it += total_warps) {
-        const unsigned long long item = __ldg(&items[it]);
+        const unsigned long long item = ld_dep(&items[it]);
         const int k = (int)(item & 0xfff), j = (int)((item >> 12) & 0xfff), xs = (int)((item >> 24) & 0xfff);
         const int ihi = (int)((item >> 48) & 0x1fff);
         const int x0 = xs + 4 * lane;                     /* four consecutive voxels = one 32-byte sector */
@@ -993,9 +1013,9 @@ __device__ __forceinline__ unsigned long long pack_unit(int k, int j, int x0, in
  * certificate arithmetic, so HBM latency is hidden and nothing is loaded for skipped or queued units. */
 template <int CHECK>
 __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(GridParams g, CertPyramid P, float2* __restrict__ grid,
-                                                               const float2* __restrict__ cert, const double* __restrict__ T,
-                                                               const unsigned long long* __restrict__ items,
-                                                               const unsigned int* __restrict__ item_count,
+                                                               const float2* __restrict__ cert, const double* T,
+                                                               const unsigned long long* items,
+                                                               const unsigned int* item_count,
                                                                unsigned long long* __restrict__ units, unsigned int* unit_count,
                                                                unsigned long long* n_updated, int queue_front) {
     pdl_wait();
@@ -1046,8 +1066,8 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
     };
     /* pipeline prologue */
     unsigned int it = gw;
-    unsigned long long item_cur = it < n_items ? __ldg(&items[it]) : 0ull;
-    unsigned long long item_nxt = it + total_warps < n_items ? __ldg(&items[it + total_warps]) : 0ull;
+    unsigned long long item_cur = it < n_items ? ld_dep(&items[it]) : 0ull;
+    unsigned long long item_nxt = it + total_warps < n_items ? ld_dep(&items[it + total_warps]) : 0ull;
     int k, j, x0; bool act;
     float4* ptr = decode_ptr(item_cur, k, j, x0, act);
     /* deferred completion: the voxel loads of a unit certified as free space are issued right after
@@ -1069,7 +1089,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
     for (; it < n_items; it += total_warps) {
         /* stage A: descriptor two items ahead */
         const unsigned int it2 = it + 2 * total_warps;
-        const unsigned long long item_nn = it2 < n_items ? __ldg(&items[it2]) : 0ull;
+        const unsigned long long item_nn = it2 < n_items ? ld_dep(&items[it2]) : 0ull;
         int kn = 0, jn = 0, x0n = 0; bool actn = false;
         float4* ptrn = decode_ptr(item_nxt, kn, jn, x0n, actn);
         /* stage B: certificate of the current unit (unless the whole row was already judged) */
@@ -1077,11 +1097,11 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
         const int rowv = (int)(item_cur >> 61) & 3;
         if (act && rowv != UNIT_UNKNOWN) verdict = rowv;
         else if (act) {
-            const double qy0 = __ldg(T + (3u * um + j)), qy1 = __ldg(T + (4u * um + j)), qy2 = __ldg(T + (5u * um + j));
-            const double pz0 = __ldg(T + (6u * um + k)), pz1 = __ldg(T + (7u * um + k)), pz2 = __ldg(T + (8u * um + k));
-            const double ax = ((__ldg(T + (unsigned int)x0) + qy0) + pz0) + ti0, bx = ((__ldg(T + (unsigned int)x0 + 3) + qy0) + pz0) + ti0;
-            const double ay = ((__ldg(T + (um + x0)) + qy1) + pz1) + ti1, by = ((__ldg(T + (um + x0 + 3)) + qy1) + pz1) + ti1;
-            const double az = ((__ldg(T + (2u * um + x0)) + qy2) + pz2) + ti2, bz = ((__ldg(T + (2u * um + x0 + 3)) + qy2) + pz2) + ti2;
+            const double qy0 = ld_dep(T + (3u * um + j)), qy1 = ld_dep(T + (4u * um + j)), qy2 = ld_dep(T + (5u * um + j));
+            const double pz0 = ld_dep(T + (6u * um + k)), pz1 = ld_dep(T + (7u * um + k)), pz2 = ld_dep(T + (8u * um + k));
+            const double ax = ((ld_dep(T + (unsigned int)x0) + qy0) + pz0) + ti0, bx = ((ld_dep(T + (unsigned int)x0 + 3) + qy0) + pz0) + ti0;
+            const double ay = ((ld_dep(T + (um + x0)) + qy1) + pz1) + ti1, by = ((ld_dep(T + (um + x0 + 3)) + qy1) + pz1) + ti1;
+            const double az = ((ld_dep(T + (2u * um + x0)) + qy2) + pz2) + ti2, bz = ((ld_dep(T + (2u * um + x0 + 3)) + qy2) + pz2) + ti2;
             verdict = unit_certificate(g, P, ax, ay, az, bx, by, bz, fetch);
         }
         /* colour fusion needs every updated voxel's pixel (normal, rgb): certified free space is
@@ -1124,9 +1144,9 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
 /* ---- pass 2: the exact path on the queued units, one unit (four voxels) per thread */
 template <int METRIC, int CHECK, bool COLOR = false>
 __global__ void __launch_bounds__(FUSE_THREADS, COLOR ? 4 : FUSE_MIN_BLOCKS) k_fuse_exact(GridParams g_in, float2* __restrict__ grid,
-                                                                              const PixRec* __restrict__ pix, const double* __restrict__ T,
-                                                                              const unsigned long long* __restrict__ units,
-                                                                              const unsigned int* __restrict__ unit_count,
+                                                                              const PixRec* __restrict__ pix, const double* T,
+                                                                              const unsigned long long* units,
+                                                                              const unsigned int* unit_count,
                                                                               unsigned long long* n_updated,
                                                                               float4* __restrict__ color, const uchar4* __restrict__ rgb4, const double* __restrict__ cosn) {
     pdl_wait();
@@ -1140,7 +1160,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, COLOR ? 4 : FUSE_MIN_BLOCKS) k_f
     const double ti0 = T[9 * (size_t)m + 0], ti1 = T[9 * (size_t)m + 1], ti2 = T[9 * (size_t)m + 2];
     unsigned int my_updates = 0, chk_n = 0, chk_bad = 0;
     for (unsigned int q = blockIdx.x * FUSE_THREADS + threadIdx.x; q < n_units; q += gridDim.x * FUSE_THREADS) {
-        const unsigned long long unit = __ldg(&units[q]);
+        const unsigned long long unit = ld_dep(&units[q]);
         const int k = (int)(unit & 0xfff), j = (int)((unit >> 12) & 0xfff), x0 = (int)((unit >> 24) & 0x3ff) << 2;
         const int verdict = (int)((unit >> 34) & 3);
         float4* ptr = reinterpret_cast<float4*>(&grid[((size_t)(k - g.ks0) * m + j) * m + x0]);
