@@ -155,44 +155,92 @@ def render_frames(n, start, pinned):
     return depth, Rs, ts
 
 
+def host_threads():
+    """Host cores this process may use.  Launchers such as torchrun export OMP_NUM_THREADS=1, so the CPU arms
+    set their OpenMP thread count to this explicitly instead of inheriting the environment."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def workload_config(m, n_gpus):
+    """`config` of the JSON line — built in ONE place so the CUDA arm and the reference arm describe the
+    workload with identical strings (the driver compares them)."""
+    return {"workload": "%d^3 grid, 640x480 synthetic depth along fr1/plant GT path, %d GN iterations/frame, point-to-plane fusion "
+                        "(BASELINE.json configs[1]%s)" % (m, GN_ITERS, "; one independent sequence per GPU, configs[4]" if n_gpus > 1 else ""),
+            "grid_bytes": 8 * m ** 3, "l2": "inputs larger than L2 (1 GiB grid vs 126 MB); no flush",
+            "gn_iterations": GN_ITERS, "pixel_stride": 3, "frames_source": "tools/synth.py + data/fr1_plant_gt_every4.txt"}
+
+
 def run_cpu_baseline(depth, Rs, ts, m, budget_s, max_frames):
-    """The oracle port of the reference on the first frames of the workload, all host threads,
-    timed where the reference prints its own timings (camera_tracking.cpp:68,243; sdf.cpp:225,306)."""
+    """The reference's CPU implementation on the first frames of the workload, all host threads, timed where the
+    reference prints its own timings (camera_tracking.cpp:68,243; sdf.cpp:225,306).
+    kind "reference": oracle/_ref — the reference's own sdf.cpp / camera_tracking.cpp / eigen_utils.cpp compiled
+    unmodified over oracle/shim (its SDF::update includes the colour running mean and the global_coords table);
+    kind "port": the oracle restatement, only when that library is absent."""
     from oracle import pyoracle as po
+    from oracle import pyref as pr
     from tools import synth
+    nthr = host_threads()
+    po.set_num_threads(nthr)
+    use_ref = os.path.exists(pr.PATH) or pr.sources_present()
+    kw = dict(m=m, gauss_newton_max_iteration=GN_ITERS, maximum_twist_diff=float("-inf"))
     t_setup = time.time()
-    o = po.Oracle(m=m, use_coord_table=1, gauss_newton_max_iteration=GN_ITERS, maximum_twist_diff=float("-inf"))
+    if use_ref:
+        pr.set_num_threads(nthr)
+        o = pr.Reference(**kw)
+    else:
+        o = po.Oracle(use_coord_table=1, **kw)
     o.set_intrinsics(synth.K_DEFAULT)
     o.set_pose(Rs[0], ts[0])
-    o.fuse(depth[0])
+    if use_ref:
+        o.fuse(depth[0], count=False); o.timers(reset=True)
+    else:
+        o.fuse(depth[0])
     setup = time.time() - t_setup
     t_track = t_fuse = 0.0
     n = 0
-    n_upd = 0
+    n_upd = None
     t_begin = time.time()
     for f in range(1, len(depth)):
-        t0 = time.time(); st = o.track(depth[f]); t1 = time.time(); n_upd += o.fuse(depth[f]); t2 = time.time()
-        t_track += t1 - t0; t_fuse += t2 - t1; n += 1
+        if use_ref:
+            cloud, normals = o.backproject(depth[f])           # upstream of the reference (ROS/PCL): not timed
+            o.track_cloud(cloud)
+            nu = o.fuse_cloud(cloud, normals, None, count=(f == 1))
+            if f == 1:
+                n_upd = nu
+            t_track, t_fuse = o.timers()
+        else:
+            t0 = time.time(); o.track(depth[f]); t1 = time.time(); nu = o.fuse(depth[f]); t2 = time.time()
+            t_track += t1 - t0; t_fuse += t2 - t1
+            if f == 1:
+                n_upd = nu
+        n += 1
         if n >= max_frames or (time.time() - t_begin) > budget_s:
             break
     R, t = o.get_pose()
     err = float(np.linalg.norm(t - ts[n]))
     o.close()
     tot = t_track + t_fuse
-    return {"value": n / tot, "unit": "frames/s", "cores": po.num_threads(), "kind": "port",
-            "sample": "frames 1..%d of the same 512^3 workload (frame 0 fused untimed), %d GN iterations each; "
-                      "oracle port of the reference (it cannot be built here: ROS/PCL/Eigen absent), OpenMP, "
-                      "precomputed global_coords table like sdf.cpp:11" % (n, GN_ITERS),
+    kind = "reference" if use_ref else "port"
+    what = ("the reference's own translation units (sdf.cpp, camera_tracking.cpp, eigen_utils.cpp) compiled unmodified over oracle/shim "
+            "(oracle/_ref); SDF::update incl. its colour running mean and global_coords table; clouds + normals from the shared K1 definition, not timed"
+            if use_ref else "oracle port of the reference (oracle/_ref absent), OpenMP, precomputed global_coords table like sdf.cpp:11")
+    return {"value": n / tot, "unit": "frames/s", "cores": nthr, "kind": kind,
+            "sample": "frames 1..%d of the same %d^3 workload (frame 0 fused untimed), %d GN iterations each; %s; "
+                      "time = the spans the reference prints itself (estimate_new_position + update)" % (n, m, GN_ITERS, what),
             "ms_per_frame_track": 1e3 * t_track / n, "ms_per_frame_fuse": 1e3 * t_fuse / n,
-            "voxels_visited_per_s": (m ** 3) * n / t_fuse, "voxel_updates_per_s": n_upd / t_fuse,
+            "voxels_visited_per_s": (m ** 3) * n / t_fuse, "voxels_updated_frame1": n_upd,
             "frames": n, "setup_s": setup, "final_pos_err_m": err}
 
 
 def main_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
     rank, world, local = dist_env()
     if rank != 0:
         return 0
+    n_gpus = max(world, 1, args.gpus)
     n_need = min(args.steps + args.warmup, 64) + 1
     depth, Rs, ts = render_frames(n_need, 0, pinned=False)
     t0 = time.time()
@@ -201,8 +249,9 @@ def main_reference(args):
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 values / f64 geometry",
            "data": "synthetic", "impl": "reference",
-           "config": {"workload": "%d^3 grid, 640x480 synthetic depth along fr1/plant GT path, %d GN iterations/frame (BASELINE.json configs[1])" % (args.m, GN_ITERS),
-                      "note": "rate measured on a bounded sample of the requested steps (%d frames, %.0f s budget); host CPU only" % (cb["frames"], args.ref_budget)},
+           "config": workload_config(args.m, n_gpus),
+           "note": "rate measured on a bounded sample of the requested steps (%d frames, %.0f s budget); host CPU only, %d threads; "
+                   "one sequence (the CPU arm does not replicate per GPU)" % (cb["frames"], args.ref_budget, cb["cores"]),
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": time.time() - t0}
@@ -430,10 +479,7 @@ def main_cuda(args):
     out = {"metric": METRIC if m == 512 else METRIC.replace("512", str(m)), "value": value, "unit": "frames/s", "n_gpus": n_gpus,
            "steps": Ksteps, "warmup": W, "ms_per_step": ms_total / Ksteps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32 values / f64 geometry", "data": "synthetic",
-           "config": {"workload": "%d^3 grid, 640x480 synthetic depth along fr1/plant GT path, %d GN iterations/frame, point-to-plane fusion "
-                                  "(BASELINE.json configs[1]%s)" % (m, GN_ITERS, "; one independent sequence per GPU, configs[4]" if n_gpus > 1 else ""),
-                      "grid_bytes": 8 * m ** 3, "l2": "inputs larger than L2 (1 GiB grid vs 126 MB); no flush",
-                      "gn_iterations": GN_ITERS, "pixel_stride": 3, "frames_source": "tools/synth.py + data/fr1_plant_gt_every4.txt"},
+           "config": workload_config(m, n_gpus),
            "roofline": roof_fuse, "roofline_track": roof_track, "stage_share": share,
            "stage_ms": {"prep": t_prep * 1e3, "track": t_track * 1e3, "fuse": t_fuse * 1e3},
            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -451,6 +497,12 @@ def main_cuda(args):
     if rank == 0 and n_gpus == 1 and not args.no_cpu:
         nb = min(n_frames, 40)
         out["cpu_baseline"] = run_cpu_baseline(depth[:nb], Rs[:nb], ts[:nb], m, budget_s=args.cpu_budget, max_frames=nb - 1)
+    if not args.no_sharded:
+        # BASELINE.json configs[2]: the SAME run also measures one 1024^3 volume z-slab sharded over the N ranks
+        # (N = 1: the whole volume on one GPU — the 1-GPU point of the strong-scaling curve)
+        sh = run_sharded(dist, tdev, device, n_gpus, args.sharded_grid, W, min(Ksteps, args.sharded_steps), False, hbm, peak_src)
+        out["sharded"] = {k: sh[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "config", "roofline",
+                                             "stage_ms", "e2e", "shard_check", "tracking")}
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -459,38 +511,26 @@ def main_cuda(args):
     return 0
 
 
-def main_sharded(args):
-    """BASELINE.json configs[2,3]: ONE large volume cut into z-slabs, one slab per GPU (strong scaling:
-    the frame sequence and the total voxel count are fixed as N grows).  Fusion needs no exchange
-    (halos are fused redundantly); tracking exchanges 30 doubles per Gauss-Newton iteration
-    in-kernel over NVLink peer stores."""
-    rank, world, local = dist_env()
-    n_gpus = max(world, 1)
+def run_sharded(dist, tdev, device, n_gpus, m, W, Ksteps, equal_slabs, hbm, peak_src):
+    """BASELINE.json configs[2,3]: ONE m^3 volume cut into z-slabs, one slab per GPU (strong scaling: the frame
+    sequence and the total voxel count are fixed as N grows).  Fusion needs no exchange (halos are fused
+    redundantly); tracking exchanges 30 doubles per Gauss-Newton iteration in-kernel over NVLink peer stores.
+    Returns the record (same on every rank)."""
     import tracking_sdf_b200 as T
     from tracking_sdf_b200 import sharding, capi
     from tools import synth
-    L = T.load_library()
-    if L.tsdf_device_count() < 1:
-        raise SystemExit("bench.py: no CUDA device visible (the product has no CPU path)")
-    device = local % L.tsdf_device_count()
-    dist = init_dist(world, local, "nccl")
-    tdev = None
-    if dist is not None:
-        import torch
-        tdev = torch.device("cuda", device)
-    hbm, peak_src = peaks()
     K = synth.K_DEFAULT
-    m = args.m
-    W, Ksteps = args.warmup, args.steps
     n_frames = W + Ksteps
     depth, Rs, ts = render_frames(n_frames, start=0, pinned=True)
     frame_bytes = depth[0].nbytes
     kw = dict(m=m, gauss_newton_max_iteration=GN_ITERS, maximum_twist_diff=float("-inf"))
     bounds = None
-    if dist is not None and not args.equal_slabs:
+    halo = 0
+    if dist is not None:
+        halo = capi.slab_plan(capi.default_config(n_shards=n_gpus, shard_rank=min(1, n_gpus - 1), **kw))["halo"]
+    if dist is not None and not equal_slabs:
         # work-balanced slabs: per-layer cost profile from 8 poses spread over the run (same frames on every rank,
         # so every rank derives the same partition), halo layers included in each slab's cost
-        halo = capi.slab_plan(capi.default_config(n_shards=n_gpus, shard_rank=min(1, n_gpus - 1), **kw))["halo"]
         idx = list(range(0, n_frames, max(1, n_frames // 8)))
         wts = sharding.frustum_weights(m, K, [(Rs[i], ts[i]) for i in idx], [depth[i] for i in idx])
         bounds = capi.balanced_slabs(wts, n_gpus, min_layers=16, halo=halo)
@@ -520,25 +560,36 @@ def main_sharded(args):
     launches = g.kernel_launch_count() - launches0
     stage = g.stage_timing_end()
     n_upd_local = g.total_updates()
-    R_l, t_l, st_l = g.read_pose_ring((n_frames - 1) % ring)
+    R_l, t_l, st_l = g.read_pose_ring((n_frames - 1) % ring)      # raises on lost / halo / peer-timeout records
     t_prep, t_track, t_fuse = [float(x) * 1e-3 for x in stage.mean(axis=0)]
     t_fuse_max = barrier_max(dist, t_fuse, tdev)
     t_track_max = barrier_max(dist, t_track, tdev)
     n_upd = n_upd_local
+    pose_spread = 0.0
     if dist is not None:
         import torch
         tt = torch.tensor([float(n_upd_local)], dtype=torch.float64, device=tdev)
         dist.all_reduce(tt); n_upd = float(tt.item())
-    # e2e: host buffers, synchronous per frame, every rank feeds the same frame
-    g.reset(); g.set_intrinsics(K); g.fuse(depth[0], Rs[0], ts[0])
+        # every rank solved the same summed system: the final poses must be the same bits on all ranks
+        pv = torch.tensor(np.concatenate([R_l.ravel(), t_l]), dtype=torch.float64, device=tdev)
+        lo = pv.clone(); hi = pv.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        pose_spread = float((hi - lo).abs().max().item())
+    # e2e: host buffers streamed through tsdf_submit_frame on every rank (H2D of frame n+1 overlaps frame n)
+    g.reset(); g.set_intrinsics(K)
+    g.set_pose(Rs[0], ts[0])
+    g.submit_frame(depth[0], track=0, slot=0)
     for f in range(1, W):
-        g.track_and_fuse(depth[f])
+        g.submit_frame(depth[f], track=1, slot=f % ring)
+    g.sync()
     if dist is not None:
         import torch
         dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for f in range(W, n_frames):
-        R_e, t_e, st_e, nu_e = g.track_and_fuse(depth[f])
+        g.submit_frame(depth[f], track=1, slot=f % ring)
+    g.sync()
+    R_e, t_e, st_e = g.read_pose_ring((n_frames - 1) % ring)
     e2e_s = barrier_max(dist, time.perf_counter() - t0, tdev)
     upd_per_frame = n_upd / Ksteps
     ach = 16.0 * upd_per_frame / t_fuse_max / 1e9
@@ -548,18 +599,41 @@ def main_sharded(args):
            "config": {"workload": "%d^3 grid z-slab sharded over %d GPU(s), 640x480 synthetic depth along fr1/plant GT path, %d GN iterations/frame "
                                   "(BASELINE.json configs[2]/[3])" % (m, n_gpus, GN_ITERS),
                       "slab_rank0": {"own": [ko0, ko1], "stored": [ks0, ks1]}, "slab_bounds": bounds if bounds is not None else "equal thickness",
-                      "grid_bytes_total": 8 * m ** 3,
+                      "halo_layers": halo, "grid_bytes_total": 8 * m ** 3,
                       "l2": "inputs larger than L2; no flush", "exchange": "30 doubles per GN iteration, in-kernel NVLink peer stores, rank-order sum"},
            "roofline": {"bound": "hbm", "kernel": "fusion stage (k_fuse_tables + k_fuse_plan + k_fuse_cert + k_fuse_exact)", "achieved": ach, "peak": hbm * n_gpus, "unit": "GB/s", "frac": ach / (hbm * n_gpus),
                         "traffic": None, "peak_source": peak_src + " x n_gpus", "ms_per_launch": t_fuse_max * 1e3,
                         "voxels_updated_per_launch": upd_per_frame},
            "stage_ms": {"prep": t_prep * 1e3, "track_max_over_ranks": t_track_max * 1e3, "fuse_max_over_ranks": t_fuse_max * 1e3},
-           "e2e": {"value": Ksteps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(frame_bytes) * n_gpus, "d2h_bytes_per_step": 504 * n_gpus,
-                   "ms_per_step": 1e3 * e2e_s / Ksteps, "timing": "host wall clock, synchronous tsdf_track_and_fuse(HOST depth) on every rank"},
+           "e2e": {"value": Ksteps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(frame_bytes) * n_gpus, "d2h_bytes_per_step": 496 * n_gpus,
+                   "ms_per_step": 1e3 * e2e_s / Ksteps, "timing": "host wall clock, K tsdf_submit_frame(HOST pinned depth) calls + final tsdf_sync on every rank "
+                                                                  "(every rank copies the whole frame: the depth image is replicated)"},
            "gpu_launches": int(launches), "clocks": clocks,
+           "shard_check": {"pose_spread_across_ranks": pose_spread, "ok": bool(pose_spread == 0.0 and st_l["halo_miss"] == 0 and st_l["iterations"] == GN_ITERS),
+                           "e2e_vs_resident_pose_diff_m": float(np.linalg.norm(t_e - t_l)),
+                           "note": "every rank solves the same rank-order sum, so the final pose must be the same bits everywhere; slab contents vs the "
+                                   "unsharded volume are compared by tools/shard_check.py (logs under profiles/)"},
            "tracking": {"final_pos_err_vs_gt_m": float(np.linalg.norm(t_l - ts[n_frames - 1])), "n_valid_last": int(st_l["n_valid"])}}
     g.dev_free(dev)
     g.close()
+    return out
+
+
+def main_sharded(args):
+    rank, world, local = dist_env()
+    n_gpus = max(world, 1)
+    import tracking_sdf_b200 as T
+    L = T.load_library()
+    if L.tsdf_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device visible (the product has no CPU path)")
+    device = local % L.tsdf_device_count()
+    dist = init_dist(world, local, "nccl")
+    tdev = None
+    if dist is not None:
+        import torch
+        tdev = torch.device("cuda", device)
+    hbm, peak_src = peaks()
+    out = run_sharded(dist, tdev, device, n_gpus, args.m, args.warmup, args.steps, args.equal_slabs, hbm, peak_src)
     if dist is not None:
         dist.destroy_process_group()
     if rank == 0:
@@ -598,6 +672,9 @@ def main():
     ap.add_argument("--no-dense", action="store_true", help="skip the dense fusion micro-benchmark")
     ap.add_argument("--no-color", action="store_true", help="skip the colour fusion measurement")
     ap.add_argument("--no-mesh", action="store_true", help="skip the marching-cubes measurement")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the z-slab sharded sub-record (1024^3 over the N ranks)")
+    ap.add_argument("--sharded-grid", type=int, default=1024)
+    ap.add_argument("--sharded-steps", type=int, default=200)
     ap.add_argument("--equal-slabs", action="store_true", help="sharded workload: equal-thickness z slabs instead of the work-balanced partition")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-budget", type=float, default=90.0)

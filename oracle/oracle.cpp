@@ -859,5 +859,6 @@ void orc_get_constants(void* h, float out[6]) {
 }
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
+void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 }  // extern "C"

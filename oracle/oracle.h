@@ -123,6 +123,7 @@ void orc_create_circle(void* h, float radius, float cx, float cy, float cz);
 void orc_get_constants(void* h, float out[6]); /* m_div_width,height,depth, v_h2_width,height,depth */
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);   /* launchers such as torchrun export OMP_NUM_THREADS=1: benches set the count explicitly */
 
 #ifdef __cplusplus
 }

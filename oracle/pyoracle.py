@@ -82,6 +82,7 @@ def lib():
     L.orc_create_circle.argtypes = [vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float]
     L.orc_get_constants.argtypes = [vp, c_fp]
     L.orc_num_threads.restype = ctypes.c_int
+    L.orc_set_num_threads.argtypes = [ctypes.c_int]
     _lib = L
     return L
 
@@ -282,3 +283,7 @@ def exp_map(twist):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))

@@ -87,6 +87,7 @@ def lib():
     L.ref_visualize.argtypes = [vp]; L.ref_visualize.restype = ctypes.c_int64
     L.ref_marker_copy.argtypes = [vp, c_dp, c_fp]
     L.ref_get_constants.argtypes = [vp, c_fp]
+    L.ref_timers.argtypes = [vp, c_dp, ctypes.c_int]
     L.ref_num_threads.restype = ctypes.c_int
     L.ref_set_num_threads.argtypes = [ctypes.c_int]
     _lib = L
@@ -264,6 +265,12 @@ class Reference:
         c = np.empty(6, np.float32)
         self.L.ref_get_constants(self.h, _f(c))
         return c
+
+    def timers(self, reset=False):
+        """Seconds spent inside (estimate_new_position, update) — the spans the reference prints itself."""
+        t = np.empty(2)
+        self.L.ref_timers(self.h, _d(t), 1 if reset else 0)
+        return float(t[0]), float(t[1])
 
 
 def exp_map(twist):

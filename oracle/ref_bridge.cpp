@@ -14,6 +14,7 @@
  * own translation units are compiled without any define.
  */
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cmath>
 #include <condition_variable>
@@ -48,7 +49,10 @@ struct Ref {
     pcl::PointCloud<pcl::Normal>::Ptr normals;
     pcl::PointCloud<pcl::PointXYZ> mesh;
     std::vector<float> w_before;
+    double t_track = 0, t_update = 0;          /* seconds inside the reference's own calls (conversions excluded) */
 };
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 /* the reference reports through std::cout; capture it so tests stay quiet and the GN stop step can be read */
 struct CoutCapture {
@@ -150,7 +154,9 @@ int64_t ref_fuse_cloud(void* h, const float* cloud, const float* normals, const 
     if (count) r->w_before.assign(r->sdf->W, r->sdf->W + nv);
     {
         CoutCapture cap;
+        const double t0 = now_s();
         r->sdf->update(r->tracker, r->cloud, r->normals);
+        r->t_update += now_s() - t0;
     }
     int64_t n = 0;
     if (count)
@@ -165,7 +171,9 @@ void ref_track_cloud(void* h, const float* cloud, orc_track_stats* st) {
     std::string log;
     {
         CoutCapture cap;
+        const double t0 = now_s();
         r->tracker->estimate_new_position(r->sdf, r->cloud);
+        r->t_track += now_s() - t0;
         log = cap.ss.str();
     }
     if (st) {
@@ -365,6 +373,14 @@ void ref_get_constants(void* h, float out[6]) {
     Ref* r = (Ref*)h;
     out[0] = r->sdf->m_div_width; out[1] = r->sdf->m_div_height; out[2] = r->sdf->m_div_depth;
     out[3] = r->tracker->v_h2_width; out[4] = r->tracker->v_h2_height; out[5] = r->tracker->v_h2_depth;
+}
+
+/* accumulated wall time inside estimate_new_position / update — exactly the spans the reference itself
+ * prints ("camera estimation method", camera_tracking.cpp:68,243; "update method", sdf.cpp:225,306) */
+void ref_timers(void* h, double out[2], int reset) {
+    Ref* r = (Ref*)h;
+    out[0] = r->t_track; out[1] = r->t_update;
+    if (reset) { r->t_track = 0; r->t_update = 0; }
 }
 
 int ref_num_threads(void) { return omp_get_max_threads(); }
