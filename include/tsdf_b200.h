@@ -258,6 +258,11 @@ tsdf_status tsdf_debug_phase_times(tsdf_handle h, const float* depth, int32_t me
 /* debugging aid: exhaustive device check of the tracker's short fp32 reciprocal against IEEE
  * 1.0f/x for every float in [x_lo, x_hi]; *n_bad = mismatches (must be 0 on [2^-17, 4]) */
 tsdf_status tsdf_debug_check_rcp(tsdf_handle h, float x_lo, float x_hi, int64_t* n_bad);
+/* Debugging aid: the fusion weight of sdf.cpp:278, w = (float)exp(-0.5 e^2), evaluated on the device for EVERY
+ * float e = d_new - epsilon in [e_lo, e_hi] (0 <= e_lo).  *n_ambiguous counts the operands whose device weight is
+ * not provably the correctly rounded float of the true exponential; the first `cap` of them are returned as
+ * (e_list[i], w_list[i]) so a test can compare them with the host libm the reference calls. */
+tsdf_status tsdf_debug_check_weight_exp(tsdf_handle h, float e_lo, float e_hi, int64_t* n_ambiguous, float* e_list, float* w_list, int32_t cap);
 /* debugging aid: fusion self-check at the current pose, no voxel written: out[0] = voxels decided
  * by the certified fp32 fast path, out[1] = of those, verdicts that disagree with the exact fp64
  * path (must be 0), out[2] = work items */

@@ -367,6 +367,71 @@ void emul_fuse_stats(const GridParams* gp, const float* pix, const PoseState* po
     for (int q = 0; q < 16; q++) out[q] = c[q];
 }
 
+/* brick-level certificate statistics: bricks of bx*by*bz voxels.  out: [0] bricks, [1] FRONT, [2] SKIP, [3] UNKNOWN,
+ * [4..6] units UNKNOWN/FRONT/SKIP inside UNKNOWN bricks, [7] units in FRONT bricks, [8] units in SKIP bricks that are in view
+ * (unit verdict not SKIP-by-geometry), [9] certified-brick units whose own verdict CONTRADICTS the brick (must be 0) */
+void emul_brick_stats(const GridParams* gp, const float* pix, const PoseState* pose, int bx, int by, int bz, int64_t out[16]) {
+    const GridParams& g = *gp;
+    const int m = g.m;
+    const double* Ri = pose->Rinv; const double* ti = pose->tinv;
+    const K1Params kp = k1_params(g.K);
+    CertPyramid P;
+    std::vector<std::vector<float>> zf(CERT_LEVELS), zb(CERT_LEVELS);
+    for (int l = 0; l < CERT_LEVELS; l++) {
+        P.w[l] = (g.img_w + (1 << l) - 1) >> l; P.h[l] = (g.img_h + (1 << l) - 1) >> l; P.off[l] = 0;
+        zf[l].assign((size_t)P.w[l] * P.h[l], 3.402823466e+38f); zb[l].assign((size_t)P.w[l] * P.h[l], -3.402823466e+38f);
+    }
+    for (int v = 0; v < g.img_h; v++)
+        for (int u = 0; u < g.img_w; u++) {
+            const float* q = pix + 4 * ((size_t)v * g.img_w + u);
+            PixRec r; r.z = q[0]; r.nx = q[1]; r.ny = q[2]; r.nz = q[3];
+            cert_pixel(g, kp, u, v, r, zf[0][(size_t)v * P.w[0] + u], zb[0][(size_t)v * P.w[0] + u]);
+        }
+    for (int l = 1; l < CERT_LEVELS; l++)
+        for (int y = 0; y < P.h[l - 1]; y++)
+            for (int x = 0; x < P.w[l - 1]; x++) {
+                const size_t o = (size_t)(y >> 1) * P.w[l] + (x >> 1), i = (size_t)y * P.w[l - 1] + x;
+                zf[l][o] = fminf(zf[l][o], zf[l - 1][i]); zb[l][o] = fmaxf(zb[l][o], zb[l - 1][i]);
+            }
+    auto fetch = [&](int level, int x, int y, float& f, float& b) { f = zf[level][(size_t)y * P.w[level] + x]; b = zb[level][(size_t)y * P.w[level] + x]; };
+    auto cam = [&](int x, int j, int k, double& X, double& Y, double& Z) {
+        const double gx = voxel_centre(g.vs_x, x, g.origin[0]), gy = voxel_centre(g.vs_y, j, g.origin[1]), gz = voxel_centre(g.vs_z, k, g.origin[2]);
+        X = ((Ri[0] * gx + Ri[1] * gy) + Ri[2] * gz) + ti[0]; Y = ((Ri[3] * gx + Ri[4] * gy) + Ri[5] * gz) + ti[1]; Z = ((Ri[6] * gx + Ri[7] * gy) + Ri[8] * gz) + ti[2];
+    };
+    int64_t c[16] = {0};
+#pragma omp parallel
+    {
+        int64_t lc[16] = {0};
+#pragma omp for schedule(dynamic, 1)
+        for (int k0 = g.ks0; k0 < g.ks1; k0 += bz)
+            for (int j0 = 0; j0 < m; j0 += by)
+                for (int i0 = 0; i0 < m; i0 += bx) {
+                    const int i1 = std::min(i0 + bx, m) - 1, j1 = std::min(j0 + by, m) - 1, k1 = std::min(k0 + bz, g.ks1) - 1;
+                    float X[8], Y[8], Z[8];
+                    for (int q = 0; q < 8; q++) {
+                        double x, y, z;
+                        cam((q & 1) ? i1 : i0, (q & 2) ? j1 : j0, (q & 4) ? k1 : k0, x, y, z);
+                        X[q] = (float)x; Y[q] = (float)y; Z[q] = (float)z;
+                    }
+                    const int bv = box_certificate(g, P, X, Y, Z, fetch);
+                    lc[0]++; lc[1 + (bv == UNIT_FRONT ? 0 : bv == UNIT_SKIP ? 1 : 2)]++;
+                    for (int k = k0; k <= k1; k++)
+                        for (int j = j0; j <= j1; j++)
+                            for (int x0 = i0; x0 <= i1; x0 += 4) {
+                                double ax, ay, az, bx_, by_, bz_;
+                                cam(x0, j, k, ax, ay, az); cam(x0 + 3, j, k, bx_, by_, bz_);
+                                const int v = unit_certificate(g, P, ax, ay, az, bx_, by_, bz_, fetch);
+                                if (bv == UNIT_UNKNOWN) lc[4 + (v == UNIT_UNKNOWN ? 0 : v == UNIT_FRONT ? 1 : 2)]++;
+                                else if (bv == UNIT_FRONT) { lc[7]++; if (v == UNIT_SKIP) lc[9]++; }
+                                else { lc[8]++; if (v == UNIT_FRONT) lc[9]++; }
+                            }
+                }
+#pragma omp critical
+        for (int q = 0; q < 16; q++) c[q] += lc[q];
+    }
+    for (int q = 0; q < 16; q++) out[q] = c[q];
+}
+
 /* SDF::interpolate_color through the kernels' core (k_sample_color) */
 void emul_interpolate_color(const GridParams* gp, const float* color, int64_t n, const double* gpts, float* rgba) {
     const GridParams& g = *gp;

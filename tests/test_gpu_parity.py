@@ -327,6 +327,25 @@ def test_fast_reciprocal_is_exact_on_its_range(gpu_lib):
     g.close()
 
 
+def test_fusion_weight_exp_exhaustive(gpu_lib):
+    """sdf.cpp:278: w = (float)exp(-0.5 (d - eps)^2) for eps <= d <= delta, i.e. e = d - eps in [0, 0.275].  The device
+    evaluates the exponential with a degree-9 polynomial in double (x >= -0.04) or CUDA's exp.  EVERY float e in
+    [0, 0.3] (1.05e9 operands) is checked on the device: the weight is provably the correctly rounded float of the
+    true exponential except for the listed operands (true value within 6e-16 relative of a float rounding
+    boundary); those are compared here with the host libm the reference calls.  What remains is the exact number
+    of operands, out of 1.05e9, where device and reference can differ — by one float ulp (6e-8) of a weight near 1."""
+    import math
+    g = T.Tsdf(T.default_config(m=32))
+    n, e, w = g.debug_check_weight_exp(0.0, 0.3)
+    g.close()
+    assert n == len(e) and n < 200                               # ~1e9 * 2 * 6e-16 / 2^-24 expected: a few dozen
+    w_host = np.array([np.float32(math.exp(-0.5 * float(x) * float(x))) for x in e], np.float32)
+    differ = int((w_host != w).sum())
+    ulp = np.abs(w_host.view(np.int32) - w.view(np.int32)).max() if n else 0
+    print("weight_exp: %d ambiguous of ~1.05e9 operands, %d differ from the host libm, max %d float ulp" % (n, differ, ulp))
+    assert differ <= 8 and ulp <= 1                              # <= 6e-8 relative in w: far inside the 1e-6 on D/W
+
+
 def test_certificates_are_certified(gpu_lib, frames, K):
     """Fusion decides whole four-voxel units from the certificate pyramid (free space: updated with
     d = -delta, w = 1; or skipped).  The self-check build runs the exact fp64 path on EVERY voxel of

@@ -50,6 +50,47 @@ def test_sharded_equals_unsharded(gpu_lib, frames, K, n_shards, m):
     one.close(); grp.close()
 
 
+@pytest.mark.parametrize("n_dev", [2, 4])
+def test_cross_device_exchange(gpu_lib, frames, K, n_dev):
+    """The REAL inter-GPU path (exchange_mode 1): one slab per device in this process, every k_linearize launch
+    stores its 30 partial sums into every peer's mailbox over NVLink (system-scope fence + sequence flag) and
+    sums all of them in rank order.  Needs >= n_dev visible devices (gpurun --gpus N); skipped otherwise.
+    Compared with the unsharded volume on device 0: normal equations to reduction order, poses to 1e-9, every
+    rank the same pose bits, slabs (halo included) bit-equal after fusion from identical poses."""
+    if gpu_lib.tsdf_device_count() < n_dev:
+        pytest.skip("needs %d devices" % n_dev)
+    depth, Rs, ts = frames
+    m = 128
+    kw = dict(m=m, gauss_newton_max_iteration=10, maximum_twist_diff=float("-inf"))
+    one = T.Tsdf(T.default_config(**kw)); one.set_intrinsics(K)
+    grp = T.ShardGroup(n_dev, devices=list(range(n_dev)), **kw); grp.set_intrinsics(K)
+    one.set_pose(Rs[0], ts[0]); grp.set_pose(Rs[0], ts[0])
+    assert one.fuse(depth[0]) == grp.frame(depth[0], track=False, fuse=True)[3]
+    for f in range(1, 6):
+        A1, b1, s1 = one.linearize(depth[f]); A2, b2, s2 = grp.linearize(depth[f])
+        assert s1["n_valid"] == s2["n_valid"] and s2["halo_miss"] == 0
+        assert np.abs(A1 - A2).max() <= 1e-12 * np.abs(A1).max() and np.abs(b1 - b2).max() <= 1e-12 * np.abs(b1).max()
+        R1, t1, st1, nu1 = one.track_and_fuse(depth[f])
+        R2, t2, st2, nu2 = grp.frame(depth[f], track=True, fuse=True)
+        assert st2["iterations"] == 10 and st2["halo_miss"] == 0
+        assert np.linalg.norm(t1 - t2) < 1e-9 and rot_angle(R1, R2) < 1e-9
+        poses = [s.get_pose() for s in grp.shards]               # each rank solved the same rank-order sum
+        assert all(np.array_equal(p[0], poses[0][0]) and np.array_equal(p[1], poses[0][1]) for p in poses)
+        one.set_pose(R2, t2)
+    one.reset(); one.set_intrinsics(K)
+    for s in grp.shards:
+        s.reset()
+    for f in range(3):
+        one.fuse(depth[f], Rs[f], ts[f])
+        grp.set_pose(Rs[f], ts[f]); grp.frame(depth[f], track=False, fuse=True)
+    D1, W1 = one.download()
+    for s in grp.shards:
+        ks0, ks1, ko0, ko1 = s.stored_range()
+        d, w = s.download()
+        assert np.array_equal(d, D1[:, :, ks0:ks1]) and np.array_equal(w, W1[:, :, ks0:ks1])
+    one.close(); grp.close()
+
+
 def test_too_small_halo_is_detected(gpu_lib, frames, K):
     depth, Rs, ts = frames
     grp = T.ShardGroup(4, m=128, halo=0)

@@ -116,6 +116,7 @@ PROTOTYPES = [
     ("tsdf_debug_stream_rmw", _I32, [_VP, _I32, c_fp]),
     ("tsdf_debug_fuse_check", _I32, [_VP, _VP, _I32, c_i64p]),
     ("tsdf_debug_check_rcp", _I32, [_VP, ctypes.c_float, ctypes.c_float, c_i64p]),
+    ("tsdf_debug_check_weight_exp", _I32, [_VP, ctypes.c_float, ctypes.c_float, c_i64p, c_fp, c_fp, _I32]),
     ("tsdf_slab_plan", _I32, [_CFGP, c_i32p]),
     ("tsdf_shard_ipc_export", _I32, [_VP, c_u8p]),
     ("tsdf_shard_ipc_attach", _I32, [_VP, _I32, c_u8p]),
@@ -491,6 +492,14 @@ class Tsdf:
         n = ctypes.c_int64()
         self._ck(self.L.tsdf_debug_check_rcp(self.h, x_lo, x_hi, ctypes.byref(n)))
         return n.value
+
+    def debug_check_weight_exp(self, e_lo, e_hi, cap=65536):
+        """-> (n_ambiguous, e[n], w_device[n]) — see tsdf_debug_check_weight_exp."""
+        n = ctypes.c_int64()
+        e = np.empty(cap, np.float32); w = np.empty(cap, np.float32)
+        self._ck(self.L.tsdf_debug_check_weight_exp(self.h, e_lo, e_hi, ctypes.byref(n), _f(e), _f(w), cap))
+        k = min(n.value, cap)
+        return n.value, e[:k].copy(), w[:k].copy()
 
     def debug_phase_times(self, depth):
         p, mem, keep = _depth_arg(depth)

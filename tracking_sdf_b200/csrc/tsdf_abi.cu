@@ -1264,6 +1264,34 @@ tsdf_status tsdf_debug_check_rcp(tsdf_handle h, float x_lo, float x_hi, int64_t*
     return TSDF_OK;
 }
 
+/* debugging aid: the fusion weight w = (float)exp(-0.5 e^2) (sdf.cpp:278) for EVERY float e in [e_lo, e_hi]:
+ * *n_ambiguous = operands whose weight is not provably the correctly rounded float (see k_check_wexp); the first
+ * `cap` of them come back as (e, w_device) pairs for a comparison with the host libm */
+tsdf_status tsdf_debug_check_weight_exp(tsdf_handle h, float e_lo, float e_hi, int64_t* n_ambiguous, float* e_list, float* w_list, int32_t cap) {
+    if (!h || !n_ambiguous || !e_list || !w_list || cap < 1 || !(e_lo >= 0.0f) || !(e_hi >= e_lo)) return bad("bad argument");
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    unsigned int lo, hi;
+    memcpy(&lo, &e_lo, 4); memcpy(&hi, &e_hi, 4);
+    DevTmp de, dw;
+    CK(de.alloc((size_t)cap * sizeof(float)));
+    CK(dw.alloc((size_t)cap * sizeof(float)));
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(p->scratch_d);
+    CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), p->stream));
+    launch_check_wexp(lo, hi + 1u, d, de.as<float>(), dw.as<float>(), cap, p->stream);
+    p->launches++;
+    unsigned long long r = 0;
+    CK(cudaMemcpyAsync(&r, d, sizeof r, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    const size_t n = r < (unsigned long long)cap ? (size_t)r : (size_t)cap;
+    if (n) {
+        CK(cudaMemcpy(e_list, de.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(w_list, dw.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    *n_ambiguous = (int64_t)r;
+    return TSDF_OK;
+}
+
 /* debugging aid: run fusion's self-check build for `depth` at the current pose (no voxel is
  * written): every voxel of every unit certified by the pyramid is compared with the exact fp64 path.
  * out[0] = voxels in certified units, out[1] = of those, wrong (must be 0), out[2] = work items */

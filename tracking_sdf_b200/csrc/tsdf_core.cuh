@@ -589,6 +589,48 @@ TSDF_HD int unit_certificate(const GridParams& g, const CertPyramid& P, double a
     return UNIT_UNKNOWN;
 }
 
+/* Verdict for a BRICK of voxels (an axis-aligned box of the grid): the camera-space centres of all its voxels lie
+ * in the convex hull of its eight corner centres c[0..7], and projection maps a convex set in front of the camera
+ * into the convex hull of the projected corners, so the pixel bounding box of the corners (dilated by one pixel, as
+ * in unit_certificate) contains every voxel's pixel and [zmin, zmax] of the corners contains every voxel's depth.
+ * Same pyramid query and the same two tests as unit_certificate. */
+template <class TexFetch>
+TSDF_HD int box_certificate(const GridParams& g, const CertPyramid& P, const float* cx, const float* cy, const float* cz, TexFetch&& fetch) {
+    if (!g.k_simple) return UNIT_UNKNOWN;
+    float zmin = cz[0], zmax = cz[0];
+#pragma unroll
+    for (int q = 1; q < 8; q++) { zmin = fminf(zmin, cz[q]); zmax = fmaxf(zmax, cz[q]); }
+    if (zmax < -FAST_ZMIN) return UNIT_SKIP;                          /* all behind the camera, sdf.cpp:247 */
+    if (!(zmin >= FAST_ZMIN)) return UNIT_UNKNOWN;
+    const float fxf = (float)g.K[0], fyf = (float)g.K[4], cxf = (float)g.K[2], cyf = (float)g.K[5];
+    float umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const float r = rcp_approx32(cz[q]);
+        const float u = fmaf(fxf, cx[q] * r, cxf), v = fmaf(fyf, cy[q] * r, cyf);
+        umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+    }
+    if (!(fabsf(umin) < 1e6f && fabsf(umax) < 1e6f && fabsf(vmin) < 1e6f && fabsf(vmax) < 1e6f)) return UNIT_UNKNOWN;
+    int u0 = (int)floorf(umin) - 1, u1 = (int)floorf(umax) + 1;
+    int v0 = (int)floorf(vmin) - 1, v1 = (int)floorf(vmax) + 1;
+    if (u1 < -1 || v1 < -1 || u0 > g.img_w || v0 > g.img_h) return UNIT_SKIP;   /* certainly outside the image, sdf.cpp:254 */
+    const bool inside = (u0 >= 1) & (v0 >= 1) & (u1 <= g.img_w - 2) & (v1 <= g.img_h - 2);
+    u0 = imin(imax(u0, 0), g.img_w - 1); v0 = imin(imax(v0, 0), g.img_h - 1);
+    u1 = imax(imin(u1, g.img_w - 1), 0); v1 = imax(imin(v1, g.img_h - 1), 0);
+    const int ext = imax(u1 - u0, v1 - v0);
+    const int level = bit_length(ext);
+    if (level >= CERT_LEVELS) return UNIT_UNKNOWN;
+    const int x0 = u0 >> level, x1 = u1 >> level, y0 = v0 >> level, y1 = v1 >> level;
+    float f00, b00, f10, b10, f01, b01, f11, b11;
+    fetch(level, x0, y0, f00, b00); fetch(level, x1, y0, f10, b10);
+    fetch(level, x0, y1, f01, b01); fetch(level, x1, y1, f11, b11);
+    const float zfree = fminf(fminf(f00, f10), fminf(f01, f11));
+    const float zbehind = fmaxf(fmaxf(b00, b10), fmaxf(b01, b11));
+    if (inside && zmax * (1.0f + 1e-6f) < zfree) return UNIT_FRONT;
+    if (zmin * (1.0f - 1e-6f) > zbehind) return UNIT_SKIP;
+    return UNIT_UNKNOWN;
+}
+
 /* ---- scan-line clipping for the fusion kernel ------------------------------------------------
  * Along a grid row (fixed j,k; i = 0..m-1) the camera-space centre is affine in i, so each of
  * the five acceptance tests of sdf.cpp:247-254 (z >= 0, -1 < u < width, -1 < v < height, the

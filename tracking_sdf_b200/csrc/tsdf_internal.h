@@ -112,6 +112,7 @@ void launch_exp_map(const double* twist, double* out12, cudaStream_t s);
 void launch_flush(float* buf, int64_t n, cudaStream_t s);
 void launch_stream_rmw(float2* grid, int64_t n, float neg_delta, cudaStream_t s);
 void launch_check_rcp(unsigned int lo, unsigned int hi, unsigned long long* n_bad, cudaStream_t s);
+void launch_check_wexp(unsigned int lo, unsigned int hi, unsigned long long* n_amb, float* e_list, float* w_list, int cap, cudaStream_t s);
 /* mesher (tsdf_mesh.cu) */
 size_t mesh_scan_bytes(int64_t n_rows);
 int mesh_zsplit();

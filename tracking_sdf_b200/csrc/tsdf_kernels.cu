@@ -1369,6 +1369,29 @@ void launch_check_rcp(unsigned int lo, unsigned int hi, unsigned long long* n_ba
     k_check_rcp<<<148 * 16, 256, 0, s>>>(lo, hi, n_bad);
 }
 
+/* exhaustive check of the fusion weight (sdf.cpp:278) over every float e = d_new - epsilon with bit pattern in
+ * [lo, hi): w = (float)weight_exp(-0.5 * e * e).  The double result p carries a relative error <= 3e-16
+ * (polynomial branch) or <= 1 ulp (exp branch); if p(1 - 6e-16) and p(1 + 6e-16) round to the same float, w IS
+ * the correctly rounded float of the true exponential and any other <= 1-ulp double exp (glibc's, which the
+ * reference calls) rounds to it too.  The remaining operands — the true value sits within 6e-16 relative of a
+ * float rounding boundary — are listed so the host can compare them with the reference's libm one by one. */
+__global__ void k_check_wexp(unsigned int lo, unsigned int hi, unsigned long long* n_amb, float* e_list, float* w_list, int cap) {
+    for (unsigned long long b = (unsigned long long)lo + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; b < hi;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const float e = __uint_as_float((unsigned int)b);
+        const double p = weight_exp(-0.5 * (double)e * (double)e);
+        const float w = (float)p;
+        const float wl = (float)(p * (1.0 - 6e-16)), wh = (float)(p * (1.0 + 6e-16));
+        if (wl != wh) {
+            const unsigned long long q = atomicAdd(n_amb, 1ull);
+            if (q < (unsigned long long)cap) { e_list[q] = e; w_list[q] = w; }
+        }
+    }
+}
+void launch_check_wexp(unsigned int lo, unsigned int hi, unsigned long long* n_amb, float* e_list, float* w_list, int cap, cudaStream_t s) {
+    k_check_wexp<<<148 * 16, 256, 0, s>>>(lo, hi, n_amb, e_list, w_list, cap);
+}
+
 /* ceiling probe: the free-space update applied to EVERY stored voxel by a plain grid-stride stream
  * (no geometry, no certificate): what a pure read-modify-write of the store costs on this GPU */
 __global__ void __launch_bounds__(256) k_stream_rmw(float4* __restrict__ grid, int64_t n4, float neg_delta) {
