@@ -80,7 +80,14 @@ typedef struct tsdf_config {
      * slabs are not equal work (the view frustum is not uniform in z): tsdf_balanced_slabs cuts the
      * volume by a per-layer cost profile instead.  Every rank must use the same partition. */
     int32_t slab_k_begin, slab_k_end;
-    int32_t reserved[2];
+    /* 1: run K0 on every frame before anything else — the pre-processing the reference's node applies at
+     * sdf_reconstruction.cpp:37-49 (pcl::FastBilateralFilter with PCL's defaults, then
+     * pcl::IntegralImageNormalEstimation AVERAGE_3D_GRADIENT, 0.02, 10): the FILTERED depth feeds tracking and
+     * fusion (cloud_filtered at :70, :74) and its normals replace K1's own.  PCL is un-vendored: the definition
+     * is this library's (shared with the oracle), parity unpinned at that boundary.  0 (default): no filter,
+     * K1's 4-neighbour normals — the noise-free benchmark configuration. */
+    int32_t preprocess;
+    int32_t reserved[1];
 } tsdf_config;
 
 typedef struct tsdf_track_stats {
@@ -211,6 +218,11 @@ tsdf_status tsdf_linearize_pixels(tsdf_handle h, const float* depth, int32_t mem
 /* K1 (not in the reference; upstream ROS depth_image_proc + PCL normals): organised cloud
  * and normals, each [height*width*3] floats on the host, NaN = invalid. normals may be NULL. */
 tsdf_status tsdf_backproject(tsdf_handle h, const float* depth, int32_t mem, float* cloud, float* normals);
+
+/* K0 alone (needs tsdf_config.preprocess = 1): the filtered depth image [height*width] and the normals
+ * [height*width*3, NaN = none] the frame paths would use; host buffers.  normals may be NULL.
+ * Replaces the node's calls at sdf_reconstruction.cpp:37-49. */
+tsdf_status tsdf_preprocess(tsdf_handle h, const float* depth, int32_t mem, float* depth_filtered, float* normals);
 
 /* SDF::interpolate_distance (sdf.cpp:127-163) evaluated on the device: pts n x 3 doubles in
  * continuous voxel coordinates (host), out n floats, ok n bytes (host). */

@@ -242,6 +242,176 @@ static void backproject(const Oracle* o, const float* depth, float* cloud, float
     }
 }
 
+/* ---- K0: the node's pre-processing (sdf_reconstruction.cpp:37-49).  NOT in the reference (PCL); see oracle.h.
+ * Parameters = the node's call sites / PCL defaults. */
+static const float K0_SIGMA_S = 15.0f, K0_SIGMA_R = 0.05f;        /* pcl::FastBilateralFilter defaults (:38-41 sets none) */
+static const int K0_PAD = 2, K0_SD_MAX = 256;
+static const float K0_MAX_DEPTH_CHANGE = 0.02f;                    /* ne.setMaxDepthChangeFactor(0.02f), :46 */
+static const float K0_SMOOTHING = 10.0f;                           /* ne.setNormalSmoothingSize(10.0f),   :47 */
+
+struct K0Grid { int sw, sh, sd; float zmin; std::vector<float> a, b; };   /* cells hold (sum z, count) interleaved */
+
+/* fast bilateral filter of the depth channel (bilateral grid, Paris & Durand; PCL fast_bilateral.hpp) */
+static void k0_bilateral(const Oracle* o, const float* depth, float* out) {
+    const int Wd = o->cfg.image_width, Hd = o->cfg.image_height;
+    float zmin = 3.402823466e+38f, zmax = -3.402823466e+38f;
+    for (size_t p = 0; p < (size_t)Wd * Hd; p++) {
+        const float z = depth[p];
+        if (std::isfinite(z) && z > 0.0f) { zmin = std::fmin(zmin, z); zmax = std::fmax(zmax, z); }
+    }
+    for (size_t p = 0; p < (size_t)Wd * Hd; p++) out[p] = std::nanf("");
+    if (!(zmax >= zmin)) return;                                     /* no valid pixel */
+    K0Grid G;
+    G.zmin = zmin;
+    G.sw = (int)((float)(Wd - 1) / K0_SIGMA_S) + 1 + 2 * K0_PAD;
+    G.sh = (int)((float)(Hd - 1) / K0_SIGMA_S) + 1 + 2 * K0_PAD;
+    G.sd = (int)((zmax - zmin) / K0_SIGMA_R) + 1 + 2 * K0_PAD;
+    if (G.sd > K0_SD_MAX) G.sd = K0_SD_MAX;                          /* depth ranges beyond 12.5 m share the last bins */
+    const size_t nc = (size_t)G.sw * G.sh * G.sd;
+    G.a.assign(2 * nc, 0.0f); G.b.assign(2 * nc, 0.0f);
+    auto cell = [&](int x, int y, int z) { return 2 * (((size_t)x * G.sh + y) * G.sd + z); };
+    /* splat, pixels in row-major order */
+    for (int v = 0; v < Hd; v++)
+        for (int u = 0; u < Wd; u++) {
+            const float z = depth[(size_t)v * Wd + u];
+            if (!(std::isfinite(z) && z > 0.0f)) continue;
+            const int sx = (int)((float)u / K0_SIGMA_S + 0.5f) + K0_PAD;
+            const int sy = (int)((float)v / K0_SIGMA_S + 0.5f) + K0_PAD;
+            int sz = (int)((z - zmin) / K0_SIGMA_R + 0.5f) + K0_PAD;
+            if (sz > G.sd - 1 - K0_PAD) sz = G.sd - 1 - K0_PAD;
+            const size_t c = cell(sx, sy, sz);
+            G.a[c] = G.a[c] + z; G.a[c + 1] = G.a[c + 1] + 1.0f;
+        }
+    /* blur: along x, y, z in turn, two passes each, interior cells only: (l + r + 2 c) / 4 */
+    const long off[3] = {(long)G.sh * G.sd, (long)G.sd, 1};
+    for (int dim = 0; dim < 3; dim++)
+        for (int it = 0; it < 2; it++) {
+            std::swap(G.a, G.b);
+            for (int x = 1; x < G.sw - 1; x++)
+                for (int y = 1; y < G.sh - 1; y++)
+                    for (int z = 1; z < G.sd - 1; z++) {
+                        const size_t c = cell(x, y, z);
+                        for (int q = 0; q < 2; q++)
+                            G.a[c + q] = ((G.b[c - 2 * off[dim] + q] + G.b[c + 2 * off[dim] + q]) + 2.0f * G.b[c + q]) / 4.0f;
+                    }
+            /* cells on the faces are never written; they hold zeros (the padding is never splatted into) */
+        }
+    /* slice: trilinear interpolation of (sum, count) at the pixel's grid position */
+    for (int v = 0; v < Hd; v++)
+        for (int u = 0; u < Wd; u++) {
+            const float z = depth[(size_t)v * Wd + u];
+            if (!(std::isfinite(z) && z > 0.0f)) continue;
+            const float gx = (float)u / K0_SIGMA_S + (float)K0_PAD, gy = (float)v / K0_SIGMA_S + (float)K0_PAD;
+            float gz = (z - zmin) / K0_SIGMA_R + (float)K0_PAD;
+            if (gz > (float)(G.sd - 1 - K0_PAD)) gz = (float)(G.sd - 1 - K0_PAD);
+            const int x0 = (int)gx, y0 = (int)gy, z0 = (int)gz;
+            const int x1 = x0 + 1 > G.sw - 1 ? G.sw - 1 : x0 + 1, y1 = y0 + 1 > G.sh - 1 ? G.sh - 1 : y0 + 1, z1 = z0 + 1 > G.sd - 1 ? G.sd - 1 : z0 + 1;
+            const float ax = gx - (float)x0, ay = gy - (float)y0, az = gz - (float)z0;
+            float acc[2];
+            for (int q = 0; q < 2; q++) {
+                float s = ((1.0f - ax) * (1.0f - ay)) * (1.0f - az) * G.a[cell(x0, y0, z0) + q];
+                s = s + (ax * (1.0f - ay)) * (1.0f - az) * G.a[cell(x1, y0, z0) + q];
+                s = s + ((1.0f - ax) * ay) * (1.0f - az) * G.a[cell(x0, y1, z0) + q];
+                s = s + (ax * ay) * (1.0f - az) * G.a[cell(x1, y1, z0) + q];
+                s = s + ((1.0f - ax) * (1.0f - ay)) * az * G.a[cell(x0, y0, z1) + q];
+                s = s + (ax * (1.0f - ay)) * az * G.a[cell(x1, y0, z1) + q];
+                s = s + ((1.0f - ax) * ay) * az * G.a[cell(x0, y1, z1) + q];
+                s = s + (ax * ay) * az * G.a[cell(x1, y1, z1) + q];
+                acc[q] = s;
+            }
+            out[(size_t)v * Wd + u] = acc[0] / acc[1];
+        }
+}
+
+/* average-3D-gradient normals over an adaptive window (PCL integral_image_normal.hpp, AVERAGE_3D_GRADIENT) */
+static void k0_normals(const Oracle* o, const float* zf, float* normals) {
+    const int Wd = o->cfg.image_width, Hd = o->cfg.image_height;
+    const float cxf = (float)o->K[2], cyf = (float)o->K[5];
+    const float inv_fx = 1.0f / (float)o->K[0], inv_fy = 1.0f / (float)o->K[4];
+    const float nanf_ = std::nanf("");
+    const size_t N = (size_t)Wd * Hd;
+    std::vector<float> P(3 * N), DX(3 * N), DY(3 * N);
+    std::vector<uint8_t> edge(N, 0);
+    for (int v = 0; v < Hd; v++)
+        for (int u = 0; u < Wd; u++) {
+            const size_t p = (size_t)v * Wd + u;
+            const float z = zf[p];
+            if (z == z) { P[3 * p] = ((float)u - cxf) * z * inv_fx; P[3 * p + 1] = ((float)v - cyf) * z * inv_fy; P[3 * p + 2] = z; }
+            else P[3 * p] = P[3 * p + 1] = P[3 * p + 2] = nanf_;
+        }
+    /* depth discontinuities (PCL's depthChangeMap): every pixel but the last row / column compares itself with its
+     * right and lower neighbour; a missing depth on either side or a step above the threshold (computed from the
+     * pixel's own depth) marks BOTH pixels of the pair */
+    auto pair_bad = [&](float za, float zb) {
+        const float thr = K0_MAX_DEPTH_CHANGE * (std::fabs(za) + 1.0f) * 2.0f;
+        return !(za == za) || !(zb == zb) || std::fabs(za - zb) > thr;
+    };
+    for (int v = 0; v < Hd - 1; v++)
+        for (int u = 0; u < Wd - 1; u++) {
+            const size_t p = (size_t)v * Wd + u;
+            if (pair_bad(zf[p], zf[p + 1])) { edge[p] = 1; edge[p + 1] = 1; }
+            if (pair_bad(zf[p], zf[p + Wd])) { edge[p] = 1; edge[p + Wd] = 1; }
+        }
+    /* central-difference 3-D gradients */
+    for (int v = 0; v < Hd; v++)
+        for (int u = 0; u < Wd; u++) {
+            const size_t p = (size_t)v * Wd + u;
+            for (int c = 0; c < 3; c++) {
+                DX[3 * p + c] = (u > 0 && u < Wd - 1) ? P[3 * (p + 1) + c] - P[3 * (p - 1) + c] : nanf_;
+                DY[3 * p + c] = (v > 0 && v < Hd - 1) ? P[3 * (p + Wd) + c] - P[3 * (p - Wd) + c] : nanf_;
+            }
+        }
+    const int R = (int)K0_SMOOTHING;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int v = 0; v < Hd; v++)
+        for (int u = 0; u < Wd; u++) {
+            const size_t p = (size_t)v * Wd + u;
+            float* n = normals + 3 * p;
+            n[0] = n[1] = n[2] = nanf_;
+            if (!(zf[p] == zf[p])) continue;
+            /* chamfer (1 / 1.4) distance to the nearest discontinuity within the smoothing radius, capped */
+            float dist = K0_SMOOTHING;
+            for (int dv = -R; dv <= R; dv++)
+                for (int du = -R; du <= R; du++) {
+                    const int uu = u + du, vv = v + dv;
+                    if (uu < 0 || vv < 0 || uu >= Wd || vv >= Hd) continue;
+                    if (!edge[(size_t)vv * Wd + uu]) continue;
+                    const int a = du < 0 ? -du : du, b = dv < 0 ? -dv : dv;
+                    const int mn = a < b ? a : b, mx = a < b ? b : a;
+                    const float d = 1.4f * (float)mn + 1.0f * (float)(mx - mn);
+                    dist = std::fmin(dist, d);
+                }
+            if (!(dist > 2.0f)) continue;                           /* PCL: smoothing > 2.0f */
+            const int rw = (int)dist, r2 = rw / 2;                   /* setRectSize(w, h): width w, starts w/2 left of the pixel */
+            double gx[3] = {0, 0, 0}, gy[3] = {0, 0, 0};
+            int cx_ = 0, cy_ = 0;
+            for (int vv = v - r2; vv < v - r2 + rw; vv++)
+                for (int uu = u - r2; uu < u - r2 + rw; uu++) {
+                    if (uu < 0 || vv < 0 || uu >= Wd || vv >= Hd) continue;
+                    const size_t q = (size_t)vv * Wd + uu;
+                    if (DX[3 * q] == DX[3 * q] && DX[3 * q + 1] == DX[3 * q + 1] && DX[3 * q + 2] == DX[3 * q + 2]) {
+                        gx[0] = gx[0] + (double)DX[3 * q]; gx[1] = gx[1] + (double)DX[3 * q + 1]; gx[2] = gx[2] + (double)DX[3 * q + 2]; cx_++;
+                    }
+                    if (DY[3 * q] == DY[3 * q] && DY[3 * q + 1] == DY[3 * q + 1] && DY[3 * q + 2] == DY[3 * q + 2]) {
+                        gy[0] = gy[0] + (double)DY[3 * q]; gy[1] = gy[1] + (double)DY[3 * q + 1]; gy[2] = gy[2] + (double)DY[3 * q + 2]; cy_++;
+                    }
+                }
+            if (cx_ == 0 || cy_ == 0) continue;
+            /* normal = gradient_y x gradient_x, normalised */
+            const double nx = gy[1] * gx[2] - gy[2] * gx[1];
+            const double ny = gy[2] * gx[0] - gy[0] * gx[2];
+            const double nz = gy[0] * gx[1] - gy[1] * gx[0];
+            const double len2 = (nx * nx + ny * ny) + nz * nz;
+            if (!(len2 > 0.0)) continue;
+            const double len = std::sqrt(len2);
+            float fx = (float)(nx / len), fy = (float)(ny / len), fz = (float)(nz / len);
+            /* flipNormalTowardsViewpoint, viewpoint = origin */
+            const float dotp = (fx * P[3 * p] + fy * P[3 * p + 1]) + fz * P[3 * p + 2];
+            if (dotp > 0.0f) { fx = -fx; fy = -fy; fz = -fz; }
+            n[0] = fx; n[1] = fy; n[2] = fz;
+        }
+}
+
 /* sdf.cpp:224-305; the colour part (:294-304) runs when an RGB image is given (rgb: h*w*3 bytes, the
  * r,g,b of pcl::PointXYZRGB at (col,row)) */
 static int64_t fuse_cloud(Oracle* o, const float* cloud, const float* normals, const uint8_t* rgb = nullptr) {
@@ -514,7 +684,7 @@ void orc_default_config(orc_config* c) {
     c->distance_delta = 0.3f; c->distance_epsilon = 0.025f;
     c->gauss_newton_max_iteration = 20; c->maximum_twist_diff = 0.001f;
     c->v_h = 1.0f; c->w_h = 0.01f; c->pixel_stride = 3; c->metric = 0;
-    c->image_width = 640; c->image_height = 480; c->use_coord_table = 1;
+    c->image_width = 640; c->image_height = 480; c->use_coord_table = 1; c->preprocess = 0;
 }
 
 void* orc_create(const orc_config* cfg) {
@@ -632,11 +802,25 @@ void orc_get_pose_inv(void* h, double Rinv[9], double tinv[3]) {
 void orc_backproject(void* h, const float* depth, float* cloud, float* normals) {
     backproject((Oracle*)h, depth, cloud, normals);
 }
+void orc_k0_normals(void* h, const float* depth_filtered, float* normals) { k0_normals((Oracle*)h, depth_filtered, normals); }
+void orc_preprocess(void* h, const float* depth, float* depth_out, float* normals) {
+    Oracle* o = (Oracle*)h;
+    k0_bilateral(o, depth, depth_out);
+    if (normals) k0_normals(o, depth_out, normals);
+}
 
 static void ensure_cloud(Oracle* o, const float* depth, bool want_normals) {
     size_t n = (size_t)o->cfg.image_width * o->cfg.image_height * 3;
     o->cloud.resize(n);
     if (want_normals) o->normals.resize(n);
+    if (o->cfg.preprocess) {
+        /* sdf_reconstruction.cpp:37-49: filter first, the filtered cloud feeds tracking AND fusion; normals from K0 */
+        std::vector<float> zf(n / 3);
+        k0_bilateral(o, depth, zf.data());
+        backproject(o, zf.data(), o->cloud.data(), nullptr);
+        if (want_normals) k0_normals(o, zf.data(), o->normals.data());
+        return;
+    }
     backproject(o, depth, o->cloud.data(), want_normals ? o->normals.data() : nullptr);
 }
 

@@ -44,6 +44,8 @@ typedef struct orc_config {
     int32_t metric;            /* 0 = point-to-plane (sdf.cpp:272), 1 = point-to-point (sdf.h:169) */
     int32_t image_width, image_height;
     int32_t use_coord_table;   /* 1 = precompute global_coords[] like sdf.cpp:11,40-41 */
+    int32_t preprocess;        /* 1 = K0 before K1 (the node's pre-processing, sdf_reconstruction.cpp:37-49): fast bilateral
+                                * depth filter + average-3D-gradient normals over an adaptive window; 0 = K1's own normals */
 } orc_config;
 
 typedef struct orc_track_stats {
@@ -65,6 +67,18 @@ void orc_set_intrinsics(void* h, const double K[9]);                 /* camera_t
 void orc_set_pose(void* h, const double R[9], const double t[3]);    /* camera_tracking.cpp:59-65 */
 void orc_get_pose(void* h, double R[9], double t[3]);
 void orc_get_pose_inv(void* h, double Rinv[9], double tinv[3]);
+
+/* K0 (call sites sdf_reconstruction.cpp:37-49).  The node filters the organised cloud with
+ * pcl::FastBilateralFilter (defaults sigma_s = 15 px, sigma_r = 0.05 m) and estimates normals with
+ * pcl::IntegralImageNormalEstimation (AVERAGE_3D_GRADIENT, MaxDepthChangeFactor 0.02, NormalSmoothingSize 10).
+ * PCL is not under /root/reference and not in this image: PARITY UNPINNED at this boundary.  What is restated
+ * here is PCL's published algorithm (bilateral grid: splat, [1 2 1]/4 blur twice per axis, trilinear slice;
+ * normals: cross product of the summed central-difference 3-D gradients over a window whose size is the chamfer
+ * distance to the nearest depth discontinuity, capped at the smoothing size), as ONE definition shared with the
+ * device kernels (tsdf_k0.cu), which must reproduce it bit for bit.  depth_out: filtered depth [h*w];
+ * normals: [h*w*3], NaN = none. */
+void orc_preprocess(void* h, const float* depth, float* depth_out, float* normals);
+void orc_k0_normals(void* h, const float* depth_filtered, float* normals);   /* the normal stage alone */
 
 /* K1: depth -> organised cloud (x,y,z) + normals; both [h*w*3] floats, NaN = invalid */
 void orc_backproject(void* h, const float* depth, float* cloud, float* normals);

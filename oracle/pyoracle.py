@@ -24,7 +24,7 @@ class Config(ctypes.Structure):
                 ("gauss_newton_max_iteration", ctypes.c_int32), ("maximum_twist_diff", ctypes.c_float),
                 ("v_h", ctypes.c_float), ("w_h", ctypes.c_float), ("pixel_stride", ctypes.c_int32),
                 ("metric", ctypes.c_int32), ("image_width", ctypes.c_int32), ("image_height", ctypes.c_int32),
-                ("use_coord_table", ctypes.c_int32)]
+                ("use_coord_table", ctypes.c_int32), ("preprocess", ctypes.c_int32)]
 
 
 class TrackStats(ctypes.Structure):
@@ -57,6 +57,8 @@ def lib():
     L.orc_get_pose.argtypes = [vp, c_dp, c_dp]
     L.orc_get_pose_inv.argtypes = [vp, c_dp, c_dp]
     L.orc_backproject.argtypes = [vp, c_fp, c_fp, c_fp]
+    L.orc_preprocess.argtypes = [vp, c_fp, c_fp, c_fp]
+    L.orc_k0_normals.argtypes = [vp, c_fp, c_fp]
     L.orc_fuse.argtypes = [vp, c_fp]; L.orc_fuse.restype = ctypes.c_int64
     L.orc_fuse_cloud.argtypes = [vp, c_fp, c_fp]; L.orc_fuse_cloud.restype = ctypes.c_int64
     L.orc_fuse_rgb.argtypes = [vp, c_fp, c_u8p]; L.orc_fuse_rgb.restype = ctypes.c_int64
@@ -156,6 +158,20 @@ class Oracle:
         normals = np.empty((self.hgt, self.w, 3), np.float32)
         self.L.orc_backproject(self.h, _f(depth), _f(cloud), _f(normals))
         return cloud, normals
+
+    # K0: the node's pre-processing (sdf_reconstruction.cpp:37-49), own definition after PCL's algorithm
+    def preprocess(self, depth):
+        depth = np.ascontiguousarray(depth, np.float32)
+        out = np.empty((self.hgt, self.w), np.float32)
+        normals = np.empty((self.hgt, self.w, 3), np.float32)
+        self.L.orc_preprocess(self.h, _f(depth), _f(out), _f(normals))
+        return out, normals
+
+    def k0_normals(self, depth_filtered):
+        d = np.ascontiguousarray(depth_filtered, np.float32)
+        normals = np.empty((self.hgt, self.w, 3), np.float32)
+        self.L.orc_k0_normals(self.h, _f(d), _f(normals))
+        return normals
 
     # sdf.cpp:224-305
     def fuse(self, depth):

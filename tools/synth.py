@@ -81,6 +81,19 @@ def render_sequence(n_frames, start=0, K=K_DEFAULT, w=WIDTH, h=HEIGHT, out=None)
     return out, Rs[idx].copy(), ts[idx].copy()
 
 
+def add_sensor_noise(depth, seed=1234, dropout=0.002):
+    """Noisy mode for robustness runs (fixed seed): axial Kinect-style noise, sigma_z(z) =
+    0.0012 + 0.0019 (z - 0.4)^2 m (Nguyen et al. 2012), plus a small fraction of dropped (NaN) pixels.
+    Deterministic for a given (frame contents, seed); accepts [h,w] or [n,h,w]; returns float32."""
+    d = np.asarray(depth, np.float32)
+    rng = np.random.default_rng(seed)
+    sigma = (0.0012 + 0.0019 * (d.astype(np.float64) - 0.4) ** 2)
+    out = (d + rng.standard_normal(d.shape) * sigma).astype(np.float32)
+    if dropout > 0:
+        out[rng.random(d.shape) < dropout] = np.nan
+    return out
+
+
 def synth_rgb(depth, R, t, K=None):
     """Procedural colour image registered to a depth frame: a 3-D checker/gradient texture evaluated at
     the world position of every pixel (so the same surface point keeps its colour across frames).

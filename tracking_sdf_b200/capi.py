@@ -28,7 +28,7 @@ class Config(ctypes.Structure):
                 ("metric", ctypes.c_int32), ("image_width", ctypes.c_int32), ("image_height", ctypes.c_int32),
                 ("device", ctypes.c_int32), ("n_shards", ctypes.c_int32), ("shard_rank", ctypes.c_int32),
                 ("halo", ctypes.c_int32), ("slab_k_begin", ctypes.c_int32), ("slab_k_end", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 2)]
+                ("preprocess", ctypes.c_int32), ("reserved", ctypes.c_int32 * 1)]
 
 
 class TrackStats(ctypes.Structure):
@@ -115,6 +115,7 @@ PROTOTYPES = [
     ("tsdf_debug_phase_times", _I32, [_VP, _VP, _I32, c_i64p]),
     ("tsdf_debug_stream_rmw", _I32, [_VP, _I32, c_fp]),
     ("tsdf_debug_fuse_check", _I32, [_VP, _VP, _I32, c_i64p]),
+    ("tsdf_preprocess", _I32, [_VP, ctypes.c_void_p, _I32, c_fp, c_fp]),
     ("tsdf_debug_check_rcp", _I32, [_VP, ctypes.c_float, ctypes.c_float, c_i64p]),
     ("tsdf_debug_check_weight_exp", _I32, [_VP, ctypes.c_float, ctypes.c_float, c_i64p, c_fp, c_fp, _I32]),
     ("tsdf_slab_plan", _I32, [_CFGP, c_i32p]),
@@ -492,6 +493,13 @@ class Tsdf:
         n = ctypes.c_int64()
         self._ck(self.L.tsdf_debug_check_rcp(self.h, x_lo, x_hi, ctypes.byref(n)))
         return n.value
+
+    def preprocess(self, depth):
+        """K0 alone: (filtered depth [h,w], normals [h,w,3]) — see tsdf_preprocess."""
+        p, mem, keep = _depth_arg(depth)
+        zf = np.empty((self.hgt, self.w), np.float32); n = np.empty((self.hgt, self.w, 3), np.float32)
+        self._ck(self.L.tsdf_preprocess(self.h, p, mem, _f(zf), _f(n)))
+        return zf, n
 
     def debug_check_weight_exp(self, e_lo, e_hi, cap=65536):
         """-> (n_ambiguous, e[n], w_device[n]) — see tsdf_debug_check_weight_exp."""

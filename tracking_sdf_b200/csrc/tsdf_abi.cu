@@ -67,6 +67,9 @@ struct Impl {
     float* mesh_xyz = nullptr;
     int64_t mesh_n = 0, mesh_cap = 0;
     float* depth_stage = nullptr;
+    /* K0 (tsdf_config.preprocess): bilateral grid, filtered depth, discontinuity map, gradients, normals */
+    bool k0 = false;
+    K0Buffers k0b = {};
     PoseState* pose_dev = nullptr;
     PoseState* pose_pin = nullptr;          /* pinned: D2H landing zone for track results */
     PoseState* ring_pin = nullptr;          /* pinned pose ring for the async path */
@@ -229,6 +232,16 @@ tsdf_status stage_rgb(Impl* p, const uint8_t* rgb, int mem) {
     return TSDF_OK;
 }
 
+K0Params k0_params(const Impl* p) {
+    K0Params P;
+    P.img_w = p->g.img_w; P.img_h = p->g.img_h;
+    P.sigma_s = 15.0f; P.sigma_r = 0.05f;              /* pcl::FastBilateralFilter defaults; the node sets none (:38-41) */
+    P.max_depth_change = 0.02f; P.smoothing = 10.0f;   /* sdf_reconstruction.cpp:46-47 */
+    const K1Params kp = k1_params(p->g.K);
+    P.cx = kp.cx; P.cy = kp.cy; P.inv_fx = kp.inv_fx; P.inv_fy = kp.inv_fy;
+    return P;
+}
+
 LinearizeArgs lin_args(Impl* p, int do_update, bool debug) {
     LinearizeArgs a;
     a.g = p->g;
@@ -264,7 +277,15 @@ void enqueue_prep(Impl* p, const float* dptr, int reset_track) {
     if (p->depth_ready) note_cuda(cudaStreamWaitEvent(p->prep_stream, p->depth_ready, 0));
     p->pix = p->pix_buf[b]; p->pts = p->pts_buf[b]; p->cert = p->cert_buf[b]; p->rgb4 = p->rgb4_buf[b]; p->cosn = p->cosn_buf[b];
     p->frame_has_color = p->frame_rgb != nullptr;
-    launch_prep(p->g, dptr, p->pix, p->cert + p->pyr.off[0], p->pts, p->frame_rgb, p->rgb4, p->cosn, p->prep_stream);
+    const float4* nrm_in = nullptr;
+    if (p->k0) {
+        /* sdf_reconstruction.cpp:37-49: filter the frame, estimate normals on the filtered cloud; the filtered
+         * image is what tracking and fusion see (cloud_filtered at :70 and :74) */
+        p->launches += launch_k0(k0_params(p), p->k0b, dptr, p->prep_stream);
+        dptr = p->k0b.zf;
+        nrm_in = p->k0b.normals;
+    }
+    launch_prep(p->g, dptr, nrm_in, p->pix, p->cert + p->pyr.off[0], p->pts, p->frame_rgb, p->rgb4, p->cosn, p->prep_stream);
     p->frame_rgb = nullptr;
     launch_pyramid(p->pyr, p->cert, p->ticket + PYRAMID_TICKET, p->prep_stream);
     if (p->depth_done) note_cuda(cudaEventRecord(p->depth_done, p->prep_stream));
@@ -382,6 +403,7 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     if (cfg->pixel_stride < 1) return bad("pixel_stride must be >= 1");
     if (cfg->gauss_newton_max_iteration < 0 || cfg->gauss_newton_max_iteration > 1000) return bad("bad iteration count");
     if (cfg->metric != TSDF_POINT_TO_PLANE && cfg->metric != TSDF_POINT_TO_POINT) return bad("bad metric");
+    if (cfg->preprocess != 0 && cfg->preprocess != 1) return bad("preprocess must be 0 or 1");
     if (cfg->n_shards < 1 || cfg->n_shards > MAX_WORLD || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->n_shards) return bad("bad shard configuration");
     if (cfg->n_shards > cfg->m / 4) return bad("too many shards for this m");
     if (cfg->slab_k_end > cfg->slab_k_begin) {
@@ -426,6 +448,19 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     A(cudaEventCreateWithFlags(&p->depth_copied, cudaEventDisableTiming));
     p->pix = p->pix_buf[0]; p->pts = p->pts_buf[0];
     A(cudaMalloc(&p->depth_stage, npx * sizeof(float)));
+    p->k0 = cfg->preprocess != 0;
+    if (p->k0) {
+        const size_t sw = (size_t)((float)(cfg->image_width - 1) / 15.0f) + 1 + 2 * K0_PAD, sh = (size_t)((float)(cfg->image_height - 1) / 15.0f) + 1 + 2 * K0_PAD;
+        const size_t ncell = sw * sh * K0_SD_MAX;
+        A(cudaMalloc(&p->k0b.minmax, 2 * sizeof(unsigned int)));
+        A(cudaMalloc(&p->k0b.grid_a, ncell * sizeof(float2)));
+        A(cudaMalloc(&p->k0b.grid_b, ncell * sizeof(float2)));
+        A(cudaMalloc(&p->k0b.zf, npx * sizeof(float)));
+        A(cudaMalloc(&p->k0b.edge, npx));
+        A(cudaMalloc(&p->k0b.DX, npx * sizeof(float4)));
+        A(cudaMalloc(&p->k0b.DY, npx * sizeof(float4)));
+        A(cudaMalloc(&p->k0b.normals, npx * sizeof(float4)));
+    }
     A(cudaMalloc(&p->pose_dev, sizeof(PoseState)));
     A(cudaMallocHost(&p->pose_pin, sizeof(PoseState)));
     A(cudaMallocHost(&p->ring_pin, sizeof(PoseState) * POSE_RING));
@@ -516,6 +551,8 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     cudaFree(p->mc_count); cudaFree(p->mc_off); cudaFree(p->mc_tmp); cudaFree(p->mesh_xyz);
     cudaFree(p->color); cudaFree(p->rgb4_buf[0]); cudaFree(p->rgb4_buf[1]); cudaFree(p->rgb_stage);
     cudaFree(p->cosn_buf[0]); cudaFree(p->cosn_buf[1]);
+    cudaFree(p->k0b.minmax); cudaFree(p->k0b.grid_a); cudaFree(p->k0b.grid_b); cudaFree(p->k0b.zf); cudaFree(p->k0b.edge);
+    cudaFree(p->k0b.DX); cudaFree(p->k0b.DY); cudaFree(p->k0b.normals);
     cudaFree(p->grid); cudaFree(p->depth_stage); cudaFree(p->pose_dev);
     cudaFreeHost(p->pose_pin); cudaFreeHost(p->ring_pin); cudaFree(p->partials); cudaFree(p->ticket);
     cudaFree(p->group_partials); cudaFree(p->fuse_tables); cudaFree(p->fuse_items); cudaFree(p->fuse_item_count);
@@ -995,6 +1032,34 @@ tsdf_status tsdf_backproject(tsdf_handle h, const float* depth, int32_t mem, flo
     p->launches++;
     CK(cudaMemcpyAsync(cloud, dc.p, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
     if (normals) CK(cudaMemcpyAsync(normals, dn.p, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return TSDF_OK;
+}
+
+/* K0 alone, for tests: filtered depth [h*w] and normals [h*w*3] (NaN = none) on the host */
+tsdf_status tsdf_preprocess(tsdf_handle h, const float* depth, int32_t mem, float* depth_filtered, float* normals) {
+    if (!h || !depth_filtered) return bad("null argument");
+    Impl* p = I(h);
+    if (!p->k0) return bad("handle created without tsdf_config.preprocess");
+    CK(cudaSetDevice(p->device));
+    if (!p->have_K) { g_err = "camera matrix not set"; return TSDF_ERR_NO_INTRINSICS; }
+    const float* dptr;
+    tsdf_status st = stage_depth(p, depth, mem, &dptr);
+    if (st != TSDF_OK) return st;
+    enqueue_prep(p, dptr, 0);                     /* K0 + K1 on the preprocessing stream; the main stream joins */
+    st = launch_status();
+    if (st != TSDF_OK) return st;
+    const size_t npx = (size_t)p->g.img_w * p->g.img_h;
+    CK(cudaMemcpyAsync(depth_filtered, p->k0b.zf, npx * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    if (normals) {
+        DevTmp dc, dn;
+        CK(dc.alloc(npx * 3 * sizeof(float)));
+        CK(dn.alloc(npx * 3 * sizeof(float)));
+        launch_cloud(p->g, p->pix, dc.as<float>(), dn.as<float>(), p->stream);     /* the records K1 built from K0's output */
+        p->launches++;
+        CK(cudaMemcpyAsync(normals, dn.p, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+    }
     CK(cudaStreamSynchronize(p->stream));
     return TSDF_OK;
 }

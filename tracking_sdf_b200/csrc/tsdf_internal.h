@@ -71,7 +71,28 @@ struct LinearizeArgs {
 void note_cuda(cudaError_t e);
 cudaError_t take_launch_error();
 
-void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, const uint8_t* rgb3, uchar4* rgb4, double* cosn, cudaStream_t s);
+/* K0 (tsdf_k0.cu): the node's pre-processing, sdf_reconstruction.cpp:37-49 */
+constexpr int K0_PAD = 2;                  /* bilateral grid padding (PCL padding_xy = padding_z = 2) */
+constexpr int K0_SD_MAX = 256;             /* depth bins: ranges beyond (256 - 5) * sigma_r share the last bins */
+constexpr int K0_RADIUS = 10;              /* largest normal smoothing size supported (the node uses 10) */
+struct K0Params {
+    int32_t img_w, img_h;
+    float sigma_s, sigma_r;                /* pcl::FastBilateralFilter defaults 15, 0.05 (the node sets none, :38-41) */
+    float max_depth_change, smoothing;     /* 0.02, 10 (:46-47) */
+    float cx, cy, inv_fx, inv_fy;          /* K1's back-projection constants */
+};
+struct K0Buffers {
+    unsigned int* minmax;                  /* [0] ~bits(zmin), [1] bits(zmax) */
+    float2 *grid_a, *grid_b;               /* bilateral grid, (sum z, count) per cell */
+    float* zf;                             /* filtered depth */
+    uint8_t* edge;                         /* depth-discontinuity map */
+    float4 *DX, *DY;                       /* central-difference 3-D gradients (+ validity) */
+    float4* normals;                       /* nx, ny, nz, valid */
+};
+int launch_k0(const K0Params& P, const K0Buffers& B, const float* depth, cudaStream_t s);   /* returns #launches */
+
+/* nrm_in: per-pixel normals from K0 (NULL: K1 computes its own 4-neighbour normals) */
+void launch_prep(const GridParams& g, const float* depth, const float4* nrm_in, PixRec* pix, float2* cert0, float4* pts, const uint8_t* rgb3, uchar4* rgb4, double* cosn, cudaStream_t s);
 void launch_pyramid(const CertPyramid& P, float2* cert, unsigned int* ticket, cudaStream_t s);
 /* exchange_mode: 0 none, 1 in-kernel mailbox all-reduce over peer memory (one kernel per
  * device, all running concurrently), 2 deferred (same-device shards: publish, then

@@ -53,7 +53,7 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
  * K1: back-projection + normals.  One thread per pixel; 5 depth reads (L1/L2 resident),
  * one 16-byte record out.  Thread 0 also re-arms the tracker state for the coming frame.
  * ------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restrict__ depth,
+__global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restrict__ depth, const float4* __restrict__ nrm_in,
                                               PixRec* __restrict__ pix, float2* __restrict__ cert0, float4* __restrict__ pts,
                                               const uint8_t* __restrict__ rgb3, uchar4* __restrict__ rgb4, double* __restrict__ cosn) {
     pdl_wait();
@@ -69,7 +69,10 @@ __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restr
     PixRec r;
     r.z = depth_valid(zc) ? zc : qnan;
     r.nx = r.ny = r.nz = qnan;
-    if (u > 0 && v > 0 && u < g.img_w - 1 && v < g.img_h - 1) {
+    if (nrm_in) {                                       /* K0 ran: depth is the filtered image, normals come with it */
+        const float4 n = nrm_in[o];
+        if (n.w != 0.0f && depth_valid(zc)) { r.nx = n.x; r.ny = n.y; r.nz = n.z; }
+    } else if (u > 0 && v > 0 && u < g.img_w - 1 && v < g.img_h - 1) {
         float nx, ny, nz;
         if (normal_px(kp, u, v, zc, depth[o - 1], depth[o + 1], depth[o - g.img_w], depth[o + g.img_w], nx, ny, nz)) {
             r.nx = nx; r.ny = ny; r.nz = nz;
@@ -89,9 +92,9 @@ __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restr
     }
 }
 
-void launch_prep(const GridParams& g, const float* depth, PixRec* pix, float2* cert0, float4* pts, const uint8_t* rgb3, uchar4* rgb4, double* cosn, cudaStream_t s) {
+void launch_prep(const GridParams& g, const float* depth, const float4* nrm_in, PixRec* pix, float2* cert0, float4* pts, const uint8_t* rgb3, uchar4* rgb4, double* cosn, cudaStream_t s) {
     dim3 grid((g.img_w + 31) / 32, (g.img_h + 7) / 8);
-    launch_pdl(k_prep, grid, dim3(256), s, g, depth, pix, cert0, pts, rgb3, rgb4, cosn);
+    launch_pdl(k_prep, grid, dim3(256), s, g, depth, nrm_in, pix, cert0, pts, rgb3, rgb4, cosn);
 }
 
 /* organised cloud + normals for the accessor / tests */
