@@ -62,7 +62,8 @@ int main(int argc, char** argv) {
     const int n_frames = argc > 2 ? std::atoi(argv[2]) : 20;
     const int m = argc > 3 ? std::atoi(argv[3]) : 256;
     const char* out_path = argc > 4 ? argv[4] : "trajectory.txt";
-    const char* mesh_path = argc > 5 ? argv[5] : nullptr;        /* optional: the visualisation thread's mesh as a PLY file */
+    const char* mesh_path = argc > 5 && argv[5][0] != '-' ? argv[5] : nullptr;   /* optional: the visualisation thread's mesh as a PLY file ("-" = none) */
+    const bool k0 = argc > 6 && std::atoi(argv[6]) != 0;         /* optional: 1 = the node's bilateral filter + normal estimation (:37-49) on the device */
     const std::vector<Pose> gt = load_trajectory(traj);
     if ((int)gt.size() < n_frames) { std::fprintf(stderr, "trajectory too short\n"); return 2; }
     const double K[9] = {525.0, 0, 319.5, 0, 525.0, 239.5, 0, 0, 1};
@@ -71,7 +72,7 @@ int main(int argc, char** argv) {
         /* sdf_reconstruction.cpp:83-88 */
         const double sdf_origin[3] = {-3.0, -3.0, -0.5};
         b200::SDF sdf(m, 6.0f, 6.0f, 3.5f, sdf_origin, 0.3f, 0.025f);
-        b200::CameraTracking camera_tracking(20, 0.001f, 1.0f, 0.01f, &sdf, W, H);
+        b200::CameraTracking camera_tracking(20, 0.001f, 1.0f, 0.01f, &sdf, W, H, 0, k0);
         camera_tracking.camera_info_cb(K);                                       /* :90-91 */
         std::ofstream myfile(out_path, std::ios::out | std::ios::trunc);
         std::vector<float> depth((size_t)W * H);

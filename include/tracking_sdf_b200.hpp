@@ -142,13 +142,15 @@ public:
 
     /* camera_tracking.cpp:3-4 — NB the definition's parameter order (max_iter, max_twist_diff, v_h, w_h) */
     CameraTracking(int gauss_newton_max_iteration, float maximum_twist_diff, float v_h, float w_h, SDF* sdf,
-                   int image_width = 640, int image_height = 480, int device = 0)
+                   int image_width = 640, int image_height = 480, int device = 0,
+                   bool preprocess = false /* the node's bilateral filter + normal estimation, sdf_reconstruction.cpp:37-49, on the device (K0) */)
         : sdf_(sdf) {
         tsdf_config c = sdf->cfg_;
         c.gauss_newton_max_iteration = gauss_newton_max_iteration;
         c.maximum_twist_diff = maximum_twist_diff;
         c.v_h = v_h; c.w_h = w_h;
         c.image_width = image_width; c.image_height = image_height; c.device = device;
+        c.preprocess = preprocess ? 1 : 0;
         /* one device volume per SDF: a second tracker on the same SDF would orphan the first handle */
         if (sdf->h_) throw Error(TSDF_ERR_BAD_ARG, "this SDF is already attached to a CameraTracking");
         check(tsdf_create(&c, &sdf->h_));

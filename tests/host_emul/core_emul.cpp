@@ -145,6 +145,10 @@ int64_t emul_fuse_rgb(const GridParams* gp, float* grid, const float* pix, const
     auto fetch = [&](int level, int x, int y, float& f, float& b) { f = zf[level][(size_t)y * P.w[level] + x]; b = zb[level][(size_t)y * P.w[level] + x]; };
     int64_t n_updated = 0, n_fast = 0;
     g_rows_front = g_rows_skip = g_rows_unknown = 0;
+    /* per-unit certificates by the fp32 affine form of the row, exactly as k_fuse_cert evaluates them */
+    const bool affine = affine_ok(g, pose->t);
+    float stx, sty, stz;
+    affine_step(g, Ri, stx, sty, stz);
 #pragma omp parallel for reduction(+ : n_updated, n_fast) schedule(dynamic, 1)
     for (int k = g.ks0; k < g.ks1; k++) {
         const double gz = voxel_centre(g.vs_z, k, g.origin[2]);
@@ -155,6 +159,9 @@ int64_t emul_fuse_rgb(const GridParams* gp, float* grid, const float* pix, const
             int ilo = 0, ihi = m;
             if (use_clip) row_clip(g, Ri, ti, py0, py1, py2, pz0, pz1, pz2, ilo, ihi);
             int rowv = UNIT_UNKNOWN, itemv = UNIT_UNKNOWN;
+            const double gx0 = voxel_centre(g.vs_x, 0, g.origin[0]);
+            const float c0x = (float)(((Ri[0] * gx0 + py0) + pz0) + ti[0]), c0y = (float)(((Ri[3] * gx0 + py1) + pz1) + ti[1]),
+                        c0z = (float)(((Ri[6] * gx0 + py2) + pz2) + ti[2]);
             if (use_cert && ihi > ilo) {
                 const double gxa = voxel_centre(g.vs_x, ilo, g.origin[0]), gxb = voxel_centre(g.vs_x, ihi - 1, g.origin[0]);
                 rowv = unit_certificate(g, P, ((Ri[0] * gxa + py0) + pz0) + ti[0], ((Ri[3] * gxa + py1) + pz1) + ti[1], ((Ri[6] * gxa + py2) + pz2) + ti[2],
@@ -178,7 +185,9 @@ int64_t emul_fuse_rgb(const GridParams* gp, float* grid, const float* pix, const
                     cy[v] = ((Ri[3] * gx + py1) + pz1) + ti[1];
                     cz[v] = ((Ri[6] * gx + py2) + pz2) + ti[2];
                 }
-                const int verdict = !use_cert ? UNIT_UNKNOWN : (rowv != UNIT_UNKNOWN ? rowv : itemv != UNIT_UNKNOWN ? itemv : unit_certificate(g, P, cx[0], cy[0], cz[0], cx[3], cy[3], cz[3], fetch));
+                const int verdict = !use_cert ? UNIT_UNKNOWN : (rowv != UNIT_UNKNOWN ? rowv : itemv != UNIT_UNKNOWN ? itemv :
+                                    affine ? unit_certificate_affine(g, P, c0x, c0y, c0z, stx, sty, stz, x0, fetch)
+                                           : unit_certificate(g, P, cx[0], cy[0], cz[0], cx[3], cy[3], cz[3], fetch));
                 if (verdict == UNIT_SKIP) { n_fast += 4; continue; }
                 for (int v = 0; v < 4; v++) {
                     const size_t o = (((size_t)(k - g.ks0) * m + j) * m + x0 + v) * 2;

@@ -13,6 +13,6 @@ for spec in sys.argv[1:]:
     if r.returncode: print(r.stderr); raise SystemExit(1)
     lines = r.stderr.splitlines()
     for i, l in enumerate(lines):
-        if "Compiling entry" in l and ("k_fuse_items" in l or "k_linearize" in l):
-            kn = "k_fuse_items" if "k_fuse_items" in l else "k_linearize"
+        if "Compiling entry" in l and ("k_fuse_exact" in l or "k_linearize" in l or "k_fuse_cert" in l):
+            kn = "k_fuse_exact" if "k_fuse_exact" in l else "k_linearize" if "k_linearize" in l else "k_fuse_cert"
             print(name, kn, "|", lines[i + 1].split(":")[-1].strip() if i + 1 < len(lines) else "", "|", lines[i + 2].split(":")[-1].strip() if i + 2 < len(lines) else "")

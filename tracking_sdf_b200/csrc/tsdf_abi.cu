@@ -78,6 +78,7 @@ struct Impl {
     unsigned int* ticket = nullptr;         /* [0] final ticket, [1..] group tickets */
     double* fuse_tables = nullptr;
     unsigned long long* fuse_items = nullptr;
+    float4* fuse_item_c = nullptr;
     unsigned int* fuse_item_count = nullptr;      /* [0] items, [1] units */
     unsigned long long* fuse_units = nullptr;
     float2* cert = nullptr;
@@ -316,7 +317,7 @@ void enqueue_combine(Impl* p, int do_update) {
 void enqueue_fuse(Impl* p) {
     FuseArgs f;
     f.g = p->g; f.grid = p->grid; f.pix = p->pix; f.pose = p->pose_dev;
-    f.tables = p->fuse_tables; f.items = p->fuse_items; f.item_count = p->fuse_item_count;
+    f.tables = p->fuse_tables; f.items = p->fuse_items; f.item_c = p->fuse_item_c; f.item_count = p->fuse_item_count;
     f.n_updated = p->n_upd_dev; f.nblk = p->fuse_blocks; f.nblk_cert = p->fuse_cert_blocks; f.check = p->fuse_check;
     f.pyr = p->pyr; f.cert = p->cert; f.units = p->fuse_units; f.unit_count = p->fuse_item_count + 1;
     f.color = p->frame_has_color ? p->color : nullptr; f.rgb4 = p->rgb4; f.cosn = p->cosn; f.nblk_color = p->fuse_color_blocks;
@@ -467,6 +468,7 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     A(cudaMalloc(&p->ticket, N_TICKETS * sizeof(unsigned int)));
     A(cudaMalloc(&p->fuse_tables, ((size_t)9 * cfg->m + 8) * sizeof(double)));
     A(cudaMalloc(&p->fuse_items, (size_t)(p->g.ks1 - p->g.ks0) * cfg->m * ((cfg->m + 127) / 128 + 1) * sizeof(unsigned long long)));
+    A(cudaMalloc(&p->fuse_item_c, (size_t)(p->g.ks1 - p->g.ks0) * cfg->m * ((cfg->m + 127) / 128 + 1) * sizeof(float4)));
     A(cudaMalloc(&p->fuse_item_count, 2 * sizeof(unsigned int)));
     A(cudaMalloc(&p->fuse_units, (size_t)(p->n_stored / 4 + 64) * sizeof(unsigned long long)));
     {
@@ -555,7 +557,7 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     cudaFree(p->k0b.DX); cudaFree(p->k0b.DY); cudaFree(p->k0b.normals);
     cudaFree(p->grid); cudaFree(p->depth_stage); cudaFree(p->pose_dev);
     cudaFreeHost(p->pose_pin); cudaFreeHost(p->ring_pin); cudaFree(p->partials); cudaFree(p->ticket);
-    cudaFree(p->group_partials); cudaFree(p->fuse_tables); cudaFree(p->fuse_items); cudaFree(p->fuse_item_count);
+    cudaFree(p->group_partials); cudaFree(p->fuse_tables); cudaFree(p->fuse_items); cudaFree(p->fuse_item_c); cudaFree(p->fuse_item_count);
     cudaFree(p->fuse_units);
     cudaFree(p->n_upd_dev); cudaFreeHost(p->n_upd_pin);
     cudaFree(p->dbgJ); cudaFree(p->dbgPsi); cudaFree(p->dbgFlag); cudaFree(p->mailbox);

@@ -554,11 +554,12 @@ TSDF_HD int bit_length(int x) {             /* number of bits needed for x >= 0 
  * (the lane's four consecutive x voxels): project both ends in fp32 (error < 3e-4 px), take the
  * pixel bounding box dilated by one pixel, query the pyramid at the level where the box spans at
  * most 2x2 texels.  fetch(level, x, y) -> (min zfree, max zbehind) of that texel. */
+/* core: float end points, plus an absolute pad on the two depth comparisons (0 for end points that are the
+ * rounded double centres; > 0 when the end points come from the fp32 affine evaluation below) */
 template <class TexFetch>
-TSDF_HD int unit_certificate(const GridParams& g, const CertPyramid& P, double ax, double ay, double az,
-                             double bx, double by, double bz, TexFetch&& fetch) {
+TSDF_HD int unit_certificate_f(const GridParams& g, const CertPyramid& P, float XA, float YA, float ZA,
+                               float XB, float YB, float ZB, float zpad, TexFetch&& fetch) {
     if (!g.k_simple) return UNIT_UNKNOWN;
-    const float XA = (float)ax, YA = (float)ay, ZA = (float)az, XB = (float)bx, YB = (float)by, ZB = (float)bz;
     const float zmin = fminf(ZA, ZB), zmax = fmaxf(ZA, ZB);
     if (zmax < -FAST_ZMIN) return UNIT_SKIP;                          /* all behind the camera, sdf.cpp:247 */
     if (!(zmin >= FAST_ZMIN)) return UNIT_UNKNOWN;
@@ -584,9 +585,50 @@ TSDF_HD int unit_certificate(const GridParams& g, const CertPyramid& P, double a
     fetch(level, x0, y1, f01, b01); fetch(level, x1, y1, f11, b11);
     const float zfree = fminf(fminf(f00, f10), fminf(f01, f11));
     const float zbehind = fmaxf(fmaxf(b00, b10), fmaxf(b01, b11));
-    if (inside && zmax * (1.0f + 1e-6f) < zfree) return UNIT_FRONT;
-    if (zmin * (1.0f - 1e-6f) > zbehind) return UNIT_SKIP;           /* pixels outside the image skip anyway */
+    if (inside && zmax * (1.0f + 1e-6f) + zpad < zfree) return UNIT_FRONT;
+    if (zmin * (1.0f - 1e-6f) - zpad > zbehind) return UNIT_SKIP;    /* pixels outside the image skip anyway */
     return UNIT_UNKNOWN;
+}
+template <class TexFetch>
+TSDF_HD int unit_certificate(const GridParams& g, const CertPyramid& P, double ax, double ay, double az,
+                             double bx, double by, double bz, TexFetch&& fetch) {
+    return unit_certificate_f(g, P, (float)ax, (float)ay, (float)az, (float)bx, (float)by, (float)bz, 0.0f, fetch);
+}
+
+/* fp32 affine evaluation of a row's camera-space centres for the per-unit certificates.  Along a grid row the
+ * exact centre is affine in i:  c(i) = c(0) + i * step,  step = Rinv(:,0) * vs_x  (the tables hold Rinv(r,0) * gx(i)
+ * with gx(i) = vs_x (i + 0.5) + origin_x).  c0 = fl32(c(0)) per row, step = fl32(step) per frame, and
+ * c~(i) = fmaf(i, step, c0).  Error: |c0| rounding <= ulp/2, step rounding <= 6e-8 * |i step|, fmaf rounding
+ * <= ulp/2: for centres within +-32 m and rows of <= 4092 voxels that is < 8e-6 m per coordinate.  It enters the
+ * certificate in two places: the pixel positions (f * 8e-6 / FAST_ZMIN < 0.1 px for f < 600: absorbed by the
+ * one-pixel dilation of the box) and the two depth comparisons (padded by AFFINE_ZPAD = 2.5e-5 m).  The device
+ * self-check (tsdf_debug_fuse_check) and the CPU emulation compare every certified voxel with the exact path. */
+#define AFFINE_ZPAD 2.5e-5f
+#define AFFINE_MAX_COORD 32.0         /* metres */
+#define AFFINE_MAX_FOCAL 1200.0       /* pixels: 8e-6 m * (1 + |x/z|) * f / FAST_ZMIN stays below half a pixel */
+/* per frame: every voxel centre lies within AFFINE_MAX_COORD of the camera (a rigid transform keeps distances, so
+ * the farthest corner of the volume bounds every camera-space coordinate) and the focal lengths are moderate;
+ * otherwise the certificates take the double-precision end points */
+TSDF_HD bool affine_ok(const GridParams& g, const double* t) {
+    if (!g.k_simple || g.K[0] > AFFINE_MAX_FOCAL || g.K[4] > AFFINE_MAX_FOCAL) return false;
+    double far2 = 0.0;
+    for (int q = 0; q < 8; q++) {
+        const double x = g.origin[0] + ((q & 1) ? (double)g.vs_x * g.m : 0.0) - t[0];
+        const double y = g.origin[1] + ((q & 2) ? (double)g.vs_y * g.m : 0.0) - t[1];
+        const double z = g.origin[2] + ((q & 4) ? (double)g.vs_z * g.m : 0.0) - t[2];
+        far2 = fmax(far2, x * x + y * y + z * z);
+    }
+    return far2 <= AFFINE_MAX_COORD * AFFINE_MAX_COORD;
+}
+TSDF_HD void affine_step(const GridParams& g, const double* Rinv, float& sx, float& sy, float& sz) {
+    sx = (float)(Rinv[0] * (double)g.vs_x); sy = (float)(Rinv[3] * (double)g.vs_x); sz = (float)(Rinv[6] * (double)g.vs_x);
+}
+template <class TexFetch>
+TSDF_HD int unit_certificate_affine(const GridParams& g, const CertPyramid& P, float c0x, float c0y, float c0z,
+                                    float sx, float sy, float sz, int x0, TexFetch&& fetch) {
+    const float ia = (float)x0, ib = (float)(x0 + 3);
+    return unit_certificate_f(g, P, fmaf(ia, sx, c0x), fmaf(ia, sy, c0y), fmaf(ia, sz, c0z),
+                              fmaf(ib, sx, c0x), fmaf(ib, sy, c0y), fmaf(ib, sz, c0z), AFFINE_ZPAD, fetch);
 }
 
 /* Verdict for a BRICK of voxels (an axis-aligned box of the grid): the camera-space centres of all its voxels lie

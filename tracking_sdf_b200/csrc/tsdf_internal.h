@@ -28,6 +28,9 @@ constexpr int FUSE_THREADS = 128;
 #ifndef FUSE_MIN_BLOCKS
 #define FUSE_MIN_BLOCKS 5               /* resident blocks per SM the fusion kernel is compiled for */
 #endif
+#ifndef FUSE_COLOR_MIN_BLOCKS
+#define FUSE_COLOR_MIN_BLOCKS 4         /* colour variants of the exact pass (more live state per voxel) */
+#endif
 #ifndef CERT_MIN_BLOCKS
 #define CERT_MIN_BLOCKS 8
 #endif
@@ -104,8 +107,9 @@ struct FuseArgs {
     float2* grid;
     const PixRec* pix;
     const PoseState* pose;
-    double* tables;                        /* 9*m + 3 doubles */
+    double* tables;                        /* 9*m + 8 doubles: nine tables, tinv[3], affine flag, affine step[3] */
     unsigned long long* items;             /* capacity rows * (m/128 + 1) */
+    float4* item_c;                        /* per item: the row's camera-space centre at i = 0 in fp32 (affine certificates) */
     unsigned int* item_count;
     unsigned long long* n_updated;         /* [0] this launch, [1] running total, [2..3] self-check counters */
     CertPyramid pyr;                       /* certificate pyramid (CERT_LEVELS levels, up to the whole image) */

@@ -640,7 +640,18 @@ __global__ void k_fuse_tables(GridParams g, const PoseState* pose, double* __res
     pdl_release();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = g.m;
-    if (i == 0) { n_updated[0] = 0ull; *item_count = 0u; *unit_count = 0u; }
+    if (i == 0) {
+        n_updated[0] = 0ull; *item_count = 0u; *unit_count = 0u;
+        /* fp32 affine evaluation of the certificates' end points (tsdf_core.cuh): usable flag + per-frame steps */
+        float sx, sy, sz;
+        affine_step(g, pose->Rinv, sx, sy, sz);
+#ifdef TSDF_NO_AFFINE                                     /* tuning variant: certificates from the double-precision end points */
+        T[9 * (size_t)m + 3] = 0.0;
+#else
+        T[9 * (size_t)m + 3] = affine_ok(g, pose->t) ? 1.0 : 0.0;
+#endif
+        T[9 * (size_t)m + 4] = (double)sx; T[9 * (size_t)m + 5] = (double)sy; T[9 * (size_t)m + 6] = (double)sz;
+    }
     if (i < 3) T[9 * (size_t)m + i] = pose->tinv[i];
     if (i >= m) return;
     const double gx = voxel_centre(g.vs_x, i, g.origin[0]);
@@ -663,7 +674,7 @@ __device__ __forceinline__ unsigned long long pack_item(int k, int j, int xs, in
 __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, CertPyramid P, const float2* __restrict__ cert, int check,
                                                    const PoseState* pose,      /* written by the PDL predecessor: no __restrict__/nc */
                                                    const double* T, unsigned long long* __restrict__ items,
-                                                   unsigned int* item_count) {
+                                                   float4* __restrict__ item_c, unsigned int* item_count) {
     pdl_wait();
     pdl_release();
     const int m = g.m;
@@ -726,13 +737,21 @@ __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, CertPyramid P, 
     if (lane == 31 && total > 0) basei = atomicAdd(item_count, (unsigned int)total);
     basei = __shfl_sync(0xffffffffu, basei, 31);
     unsigned int o = basei + (unsigned int)(scan - cnt);
+    /* the row's camera-space centre at i = 0, rounded to float: the constant of the fp32 affine evaluation */
+    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cnt > 0) {
+        const unsigned int um = (unsigned int)m;
+        c0.x = (float)(((T[0] + T[3u * um + j]) + T[6u * um + k]) + pose->tinv[0]);
+        c0.y = (float)(((T[um] + T[4u * um + j]) + T[7u * um + k]) + pose->tinv[1]);
+        c0.z = (float)(((T[2u * um] + T[5u * um + j]) + T[8u * um + k]) + pose->tinv[2]);
+    }
     if (!per_item) {
-        for (int c = 0; c < cnt; c++) items[o + c] = pack_item(k, j, xs + 128 * c, ilo, ihi) | ((unsigned long long)rowv << 61);
+        for (int c = 0; c < cnt; c++) { items[o + c] = pack_item(k, j, xs + 128 * c, ilo, ihi) | ((unsigned long long)rowv << 61); item_c[o + c] = c0; }
     } else {
         const int n_items_row = (ihi - xs + 127) >> 7;
         for (int c = 0; c < n_items_row; c++) {
             const int iv = (int)(itemv >> (2 * c)) & 3;
-            if (iv != UNIT_SKIP || check) items[o++] = pack_item(k, j, xs + 128 * c, ilo, ihi) | ((unsigned long long)iv << 61);
+            if (iv != UNIT_SKIP || check) { items[o] = pack_item(k, j, xs + 128 * c, ilo, ihi) | ((unsigned long long)iv << 61); item_c[o] = c0; o++; }
         }
     }
 }
@@ -857,7 +876,7 @@ __device__ __forceinline__ void count_updates(unsigned int my_updates, int lane,
 
 /* ---- item kernel: exact path for every voxel of every item (used when K has skew: no certificates) */
 template <int METRIC, int KSIMPLE, bool COLOR = false>
-__global__ void __launch_bounds__(FUSE_THREADS, COLOR ? 4 : FUSE_MIN_BLOCKS) k_fuse_items(GridParams g_in, float2* __restrict__ grid,
+__global__ void __launch_bounds__(FUSE_THREADS, COLOR ? FUSE_COLOR_MIN_BLOCKS : FUSE_MIN_BLOCKS) k_fuse_items(GridParams g_in, float2* __restrict__ grid,
                                                                 const PixRec* __restrict__ pix,
                                                                 const double* T,
                                                                 const unsigned long long* items,
@@ -1017,7 +1036,7 @@ __device__ __forceinline__ unsigned long long pack_unit(int k, int j, int x0, in
 template <int CHECK>
 __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(GridParams g, CertPyramid P, float2* __restrict__ grid,
                                                                const float2* __restrict__ cert, const double* T,
-                                                               const unsigned long long* items,
+                                                               const unsigned long long* items, const float4* item_c,
                                                                const unsigned int* item_count,
                                                                unsigned long long* __restrict__ units, unsigned int* unit_count,
                                                                unsigned long long* n_updated, int queue_front) {
@@ -1030,6 +1049,8 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
     const unsigned int um = (unsigned int)m;
     const unsigned int n_items = *item_count;
     const double ti0 = T[9 * (size_t)m + 0], ti1 = T[9 * (size_t)m + 1], ti2 = T[9 * (size_t)m + 2];
+    const bool affine = T[9 * (size_t)m + 3] != 0.0;                 /* per frame, warp uniform */
+    const float stx = (float)T[9 * (size_t)m + 4], sty = (float)T[9 * (size_t)m + 5], stz = (float)T[9 * (size_t)m + 6];
     const float neg_delta = -g.delta;
     unsigned int my_updates = 0;
     /* queue appends are staged per warp in shared memory and flushed 32+ at a time, so the
@@ -1071,6 +1092,8 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
     unsigned int it = gw;
     unsigned long long item_cur = it < n_items ? ld_dep(&items[it]) : 0ull;
     unsigned long long item_nxt = it + total_warps < n_items ? ld_dep(&items[it + total_warps]) : 0ull;
+    /* the row constant of the affine certificates is fetched only for items that need per-unit certificates
+     * (row- or item-certified work, e.g. the dense case, never touches it) */
     int k, j, x0; bool act;
     float4* ptr = decode_ptr(item_cur, k, j, x0, act);
     /* deferred completion: the voxel loads of a unit certified as free space are issued right after
@@ -1099,6 +1122,15 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
         int verdict = UNIT_SKIP;
         const int rowv = (int)(item_cur >> 61) & 3;
         if (act && rowv != UNIT_UNKNOWN) verdict = rowv;
+#ifndef TSDF_AFFINE_OUT
+        else if (act && affine) {
+            /* end points of the lane's four voxels by the fp32 affine form of the row: six FFMA instead of twelve
+             * table loads and eighteen double additions */
+            const float4 c0_cur = ld_dep(&item_c[it]);       /* only items with per-unit certificates touch it (never the dense case) */
+            verdict = unit_certificate_affine(g, P, c0_cur.x, c0_cur.y, c0_cur.z, stx, sty, stz, x0, fetch);
+        }
+#endif
+#ifndef TSDF_DOUBLE_OUT
         else if (act) {
             const double qy0 = ld_dep(T + (3u * um + j)), qy1 = ld_dep(T + (4u * um + j)), qy2 = ld_dep(T + (5u * um + j));
             const double pz0 = ld_dep(T + (6u * um + k)), pz1 = ld_dep(T + (7u * um + k)), pz2 = ld_dep(T + (8u * um + k));
@@ -1107,6 +1139,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
             const double az = ((ld_dep(T + (2u * um + x0)) + qy2) + pz2) + ti2, bz = ((ld_dep(T + (2u * um + x0 + 3)) + qy2) + pz2) + ti2;
             verdict = unit_certificate(g, P, ax, ay, az, bx, by, bz, fetch);
         }
+#endif
         /* colour fusion needs every updated voxel's pixel (normal, rgb): certified free space is
          * queued for the exact pass too; only the skip certificate is used */
         const bool front_queued = queue_front && verdict == UNIT_FRONT;     /* queued WITH its certificate */
@@ -1146,7 +1179,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
 
 /* ---- pass 2: the exact path on the queued units, one unit (four voxels) per thread */
 template <int METRIC, int CHECK, bool COLOR = false>
-__global__ void __launch_bounds__(FUSE_THREADS, COLOR ? 4 : FUSE_MIN_BLOCKS) k_fuse_exact(GridParams g_in, float2* __restrict__ grid,
+__global__ void __launch_bounds__(FUSE_THREADS, COLOR ? FUSE_COLOR_MIN_BLOCKS : FUSE_MIN_BLOCKS) k_fuse_exact(GridParams g_in, float2* __restrict__ grid,
                                                                               const PixRec* __restrict__ pix, const double* T,
                                                                               const unsigned long long* units,
                                                                               const unsigned int* unit_count,
@@ -1209,7 +1242,7 @@ int launch_fuse(const FuseArgs& f, cudaStream_t s) {
     const GridParams& g = f.g;
     launch_pdl(k_fuse_tables, dim3((g.m + 127) / 128), dim3(128), s, g, f.pose, f.tables, f.n_updated, f.item_count, f.unit_count);
     const int nrows = (g.ks1 - g.ks0) * g.m;
-    launch_pdl(k_fuse_plan, dim3((nrows + 255) / 256), dim3(256), s, g, f.pyr, f.cert, f.check, f.pose, f.tables, f.items, f.item_count);
+    launch_pdl(k_fuse_plan, dim3((nrows + 255) / 256), dim3(256), s, g, f.pyr, f.cert, f.check, f.pose, f.tables, f.items, f.item_c, f.item_count);
     const bool color = f.color != nullptr;      /* plane metric only (checked by the caller) */
     if (!g.k_simple) {          /* skewed intrinsics: the exact path for every in-view voxel */
         if (color) launch_pdl(k_fuse_items<0, 0, true>, dim3(f.nblk_color), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated, f.color, f.rgb4, f.cosn);
@@ -1218,12 +1251,12 @@ int launch_fuse(const FuseArgs& f, cudaStream_t s) {
         return 3;
     }
     if (f.check) {
-        launch_pdl(k_fuse_cert<1>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_count, f.units, f.unit_count, f.n_updated, 0);
+        launch_pdl(k_fuse_cert<1>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_c, f.item_count, f.units, f.unit_count, f.n_updated, 0);
         if (g.metric == 0) launch_pdl(k_fuse_exact<0, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
         else launch_pdl(k_fuse_exact<1, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
         return 4;
     }
-    launch_pdl(k_fuse_cert<0>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_count, f.units, f.unit_count, f.n_updated, color ? 1 : 0);
+    launch_pdl(k_fuse_cert<0>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_c, f.item_count, f.units, f.unit_count, f.n_updated, color ? 1 : 0);
     if (color) launch_pdl(k_fuse_exact<0, 0, true>, dim3(f.nblk_color), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
     else if (g.metric == 0) launch_pdl(k_fuse_exact<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
     else launch_pdl(k_fuse_exact<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
