@@ -325,21 +325,26 @@ void enqueue_fuse(Impl* p) {
 }
 
 /* the per-frame sequence of sdf_reconstruction.cpp:69-74 on the stream, no host round trip */
-tsdf_status enqueue_frame(Impl* p, const float* dptr, bool do_track, bool do_fuse) {
+/* stage_events: record the four stage-boundary events (tsdf_last_stage_ms / tsdf_stage_timing_*).  An event record
+ * between two kernels ends the programmatic-dependent-launch chain there (the successor can no longer start
+ * early), so the streaming entry points record them only inside a tsdf_stage_timing_begin/end window. */
+tsdf_status enqueue_frame(Impl* p, const float* dptr, bool do_track, bool do_fuse, bool stage_events = true) {
     if (!p->have_K) { g_err = "camera matrix not set (tsdf_set_intrinsics)"; return TSDF_ERR_NO_INTRINSICS; }
     if (p->exchange_mode == 2) return bad("same-device shard group: use tsdf_group_* entry points");
     cudaEvent_t* ev = p->ev;
-    if (p->ring_pos < p->ring_frames) { ev = &p->ring_ev[(size_t)4 * p->ring_pos]; p->ring_pos++; }
-    else p->ev_recorded = true;
-    note_cuda(cudaEventRecord(ev[0], p->stream));
+    const bool in_window = p->ring_pos < p->ring_frames;
+    if (in_window) { ev = &p->ring_ev[(size_t)4 * p->ring_pos]; p->ring_pos++; }
+    const bool rec = stage_events || in_window;
+    if (rec && !in_window) p->ev_recorded = true;
+    if (rec) note_cuda(cudaEventRecord(ev[0], p->stream));
     enqueue_prep(p, dptr, do_track ? 1 : 0);
-    note_cuda(cudaEventRecord(ev[1], p->stream));
+    if (rec) note_cuda(cudaEventRecord(ev[1], p->stream));
     if (do_track)
         for (int it = 0; it < p->g.max_iter; it++) enqueue_linearize(p, 1, false);
-    note_cuda(cudaEventRecord(ev[2], p->stream));
+    if (rec) note_cuda(cudaEventRecord(ev[2], p->stream));
     if (do_fuse) enqueue_fuse(p);
-    note_cuda(cudaEventRecord(ev[3], p->stream));
-    p->stage_valid = true;
+    if (rec) note_cuda(cudaEventRecord(ev[3], p->stream));
+    if (rec) p->stage_valid = true;
     return launch_status();
 }
 
@@ -918,7 +923,7 @@ tsdf_status tsdf_enqueue_frame(tsdf_handle h, const float* depth_dev, int32_t tr
     if (slot < 0 || slot >= POSE_RING) return bad("slot out of range");
     Impl* p = I(h);
     CK(cudaSetDevice(p->device));
-    tsdf_status st = enqueue_frame(p, depth_dev, track != 0, true);
+    tsdf_status st = enqueue_frame(p, depth_dev, track != 0, true, false);
     if (st != TSDF_OK) return st;
     CK(cudaMemcpyAsync(&p->ring_pin[slot], p->pose_dev, sizeof(PoseState), cudaMemcpyDeviceToHost, p->stream));
     return TSDF_OK;
@@ -943,7 +948,7 @@ tsdf_status tsdf_submit_frame(tsdf_handle h, const float* depth_host, int32_t tr
     CK(cudaEventRecord(p->copied[b], p->copy_stream));
     p->depth_ready = p->copied[b];               /* K1 waits for the copy and releases the stage buffer itself */
     p->depth_done = p->consumed[b];
-    tsdf_status st = enqueue_frame(p, p->stage[b], track != 0, true);
+    tsdf_status st = enqueue_frame(p, p->stage[b], track != 0, true, false);
     if (st != TSDF_OK) return st;
     CK(cudaMemcpyAsync(&p->ring_pin[slot], p->pose_dev, sizeof(PoseState), cudaMemcpyDeviceToHost, p->stream));
     p->submit_seq++;
