@@ -596,8 +596,11 @@ def run_sharded(dist, tdev, device, n_gpus, m, W, Ksteps, equal_slabs, hbm, peak
         # work-balanced slabs: per-layer cost profile from 8 poses spread over the run (same frames on every rank,
         # so every rank derives the same partition), halo layers included in each slab's cost
         idx = list(range(0, n_frames, max(1, n_frames // 8)))
-        wts = sharding.frustum_weights(m, K, [(Rs[i], ts[i]) for i in idx], [depth[i] for i in idx])
-        bounds = capi.balanced_slabs(wts, n_gpus, min_layers=16, halo=halo)
+        # cost of a slab = what it fuses (halo included) + the tracked pixels it owns, in milliseconds of a frame
+        # (single-GPU fusion time of this volume ~ 0.85 ms x (m/1024)^3; pixel loop of a frame's tracking 0.16 ms)
+        wts, wown = sharding.frame_cost_weights(m, K, [(Rs[i], ts[i]) for i in idx], [depth[i] for i in idx],
+                                                fuse_ms=0.85 * (m / 1024.0) ** 3, track_px_ms=0.16)
+        bounds = capi.balanced_slabs(wts, n_gpus, min_layers=16, halo=halo, weights_own=wown)
     g = sharding.ShardedTsdf(dist, device, bounds=bounds, **kw) if dist is not None else T.Tsdf(T.default_config(device=device, **kw))
     g.set_intrinsics(K)
     ring = g.pose_ring_capacity()

@@ -177,6 +177,11 @@ tsdf_status tsdf_download_color(tsdf_handle h, float* color_w, float* r, float* 
  * largest per-slab cost, where a slab's cost is the weight of every layer it fuses, i.e. its own
  * layers plus `halo` layers on each side (use tsdf_slab_plan's halo).  Slab r = [bounds[r], bounds[r+1]). */
 tsdf_status tsdf_balanced_slabs(int32_t m, int32_t n_shards, const double* weights, int32_t min_layers, int32_t halo, int32_t* bounds);
+/* The same with a second per-layer profile that counts for the OWNER of a layer only (no halo): the tracked pixels
+ * whose centre cell lies in the layer, in the same cost unit as `weights` — a rank linearises only the pixels it
+ * owns, so a slab's frame time is (what it fuses, halo included) + (what it tracks).  weights_own may be NULL. */
+tsdf_status tsdf_balanced_slabs2(int32_t m, int32_t n_shards, const double* weights, const double* weights_own,
+                                 int32_t min_layers, int32_t halo, int32_t* bounds);
 
 tsdf_status tsdf_mesh_extract(tsdf_handle h, float iso_level, int64_t* n_vertices);
 /* copy the last mesh to the host; any pointer may be NULL.  xyz: n*3 floats as above; world: n*3

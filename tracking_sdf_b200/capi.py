@@ -77,6 +77,7 @@ PROTOTYPES = [
     ("tsdf_interpolate_color", _I32, [_VP, _I64, c_dp, c_fp]),
     ("tsdf_download_color", _I32, [_VP, c_fp, c_fp, c_fp, c_fp, _I32]),
     ("tsdf_balanced_slabs", _I32, [_I32, _I32, c_dp, _I32, _I32, ctypes.POINTER(ctypes.c_int32)]),
+    ("tsdf_balanced_slabs2", _I32, [_I32, _I32, c_dp, c_dp, _I32, _I32, ctypes.POINTER(ctypes.c_int32)]),
     ("tsdf_mesh_extract", _I32, [_VP, ctypes.c_float, c_i64p]),
     ("tsdf_mesh_download", _I32, [_VP, c_fp, c_dp, c_fp]),
     ("tsdf_enqueue_frame", _I32, [_VP, _VP, _I32, _I32]),
@@ -176,13 +177,18 @@ def slab_plan(cfg):
     return {"own": (out[0], out[1]), "stored": (out[2], out[3]), "halo": out[4]}
 
 
-def balanced_slabs(weights, n_shards, min_layers=8, halo=0):
+def balanced_slabs(weights, n_shards, min_layers=8, halo=0, weights_own=None):
     """Cuts [b0=0, b1, ..., bn=m] of the z partition that minimises the largest per-slab cost, halo layers
-    included (host only)."""
+    included (host only).  weights_own: a second profile that counts for a layer's owner only (tracked pixels)."""
     L = load_library()
     w = np.ascontiguousarray(weights, np.float64)
     out = (ctypes.c_int32 * (n_shards + 1))()
-    st = L.tsdf_balanced_slabs(len(w), n_shards, w.ctypes.data_as(c_dp), min_layers, halo, out)
+    if weights_own is not None:
+        wo = np.ascontiguousarray(weights_own, np.float64)
+        assert len(wo) == len(w)
+        st = L.tsdf_balanced_slabs2(len(w), n_shards, w.ctypes.data_as(c_dp), wo.ctypes.data_as(c_dp), min_layers, halo, out)
+    else:
+        st = L.tsdf_balanced_slabs(len(w), n_shards, w.ctypes.data_as(c_dp), min_layers, halo, out)
     if st != 0:
         raise TsdfError(st, L.tsdf_last_error().decode())
     return [int(v) for v in out]

@@ -807,18 +807,22 @@ tsdf_status tsdf_download_color(tsdf_handle h, float* cw, float* r, float* g, fl
     return TSDF_OK;
 }
 
-tsdf_status tsdf_balanced_slabs(int32_t m, int32_t n_shards, const double* weights, int32_t min_layers, int32_t halo, int32_t* bounds) {
+/* cost of slab [a, b) = weight of every layer it FUSES (its own layers plus `halo` on each side: weights) plus the
+ * weight of what it alone does for its OWN layers (weights_own, may be NULL: e.g. the tracked pixels it owns) */
+tsdf_status tsdf_balanced_slabs2(int32_t m, int32_t n_shards, const double* weights, const double* weights_own,
+                                 int32_t min_layers, int32_t halo, int32_t* bounds) {
     if (!weights || !bounds || m < 1 || n_shards < 1) return bad("bad argument");
     if (min_layers < 1) min_layers = 1;
     if (halo < 0) halo = 0;
     if ((int64_t)min_layers * n_shards > m) return bad("min_layers * n_shards exceeds m");
-    std::vector<double> P((size_t)m + 1, 0.0);
+    std::vector<double> P((size_t)m + 1, 0.0), Q((size_t)m + 1, 0.0);
     for (int k = 0; k < m; k++) {
         if (!(weights[k] >= 0.0) || !(weights[k] <= 1e300)) return bad("weights must be finite and non-negative");
+        if (weights_own && (!(weights_own[k] >= 0.0) || !(weights_own[k] <= 1e300))) return bad("weights must be finite and non-negative");
         P[k + 1] = P[k] + weights[k];
+        Q[k + 1] = Q[k] + (weights_own ? weights_own[k] : 0.0);
     }
-    /* cost of slab [a, b) = weight of the layers it fuses, halo included */
-    auto cost = [&](int a, int b) { return P[b + halo > m ? m : b + halo] - P[a - halo < 0 ? 0 : a - halo]; };
+    auto cost = [&](int a, int b) { return (P[b + halo > m ? m : b + halo] - P[a - halo < 0 ? 0 : a - halo]) + (Q[b] - Q[a]); };
     /* greedy feasibility for a cost cap T: make every slab as thick as the cap allows */
     auto plan = [&](double T, int32_t* out) {
         int a = 0;
@@ -839,15 +843,19 @@ tsdf_status tsdf_balanced_slabs(int32_t m, int32_t n_shards, const double* weigh
         }
         return true;
     };
-    double lo = 0.0, hi = P[m] + 1e-300;
+    const double total = P[m] + Q[m];
+    double lo = 0.0, hi = total * 3.0 + 1e-300;                    /* halos count twice at most */
     std::vector<int32_t> tmp((size_t)n_shards + 1);
     if (!plan(hi, tmp.data())) return bad("no partition satisfies min_layers");
-    for (int it = 0; it < 100 && hi - lo > 1e-12 * P[m]; it++) {
+    for (int it = 0; it < 100 && hi - lo > 1e-12 * total; it++) {
         const double mid = 0.5 * (lo + hi);
         if (plan(mid, tmp.data())) hi = mid; else lo = mid;
     }
     plan(hi, bounds);
     return TSDF_OK;
+}
+tsdf_status tsdf_balanced_slabs(int32_t m, int32_t n_shards, const double* weights, int32_t min_layers, int32_t halo, int32_t* bounds) {
+    return tsdf_balanced_slabs2(m, n_shards, weights, nullptr, min_layers, halo, bounds);
 }
 
 tsdf_status tsdf_mesh_extract(tsdf_handle h, float iso_level, int64_t* n_vertices) {

@@ -41,8 +41,13 @@ constexpr int FUSE_THREADS = 128;
 /* cross-shard exchange of the reduced normal equations (one slot per rank, double-buffered
  * by sequence parity so a fast rank cannot overwrite a slot a slow rank still reads) */
 struct Mailbox {
-    double sums[2][MAX_WORLD][32];
-    unsigned long long seq[2][MAX_WORLD];   /* sequence number of the data in sums[parity][rank] */
+    double sums[2][MAX_WORLD][32];          /* deferred same-device exchange (mode 2): plain values, ordered by the shared stream */
+    unsigned long long seq[2][MAX_WORLD];   /* (unused by mode 1 since the self-validating words below) */
+    /* cross-device exchange (mode 1): every 64-bit word carries 32 bits of payload and the 32-bit sequence tag of
+     * the iteration it belongs to, so a word is either entirely old or entirely new (naturally aligned 8-byte
+     * peer stores are single transactions): no system-scope fence and no separate flag round trip.
+     * [parity][source rank][slot][low / high half of the double] */
+    unsigned long long w[2][MAX_WORLD][32][2];
 };
 
 struct ShardLinks {

@@ -223,34 +223,43 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) { return *rei
 /* sum of the 30 slots over all ranks, rank order; runs in the last block after its local sums
  * are in s_sums.  mode 1: in-kernel exchange over peer-mapped mailboxes. */
 __device__ bool exchange_sums(const ShardLinks& L, unsigned long long seqno, double* s_sums, int tid, PoseState* pose) {
-    /* executed by warp 0 of the final block only (tid = lane).  Data stores by lanes < 30, then one
-     * system-scope fence per publishing lane (cumulative over the warp's stores via __syncwarp),
-     * then the sequence flag; the reader side mirrors it. */
+    /* executed by warp 0 of the final block only (tid = lane).  Low-latency protocol: lane s splits its double into
+     * two 32-bit halves, tags each with the iteration's 32-bit sequence number and stores the two 64-bit words into
+     * EVERY rank's mailbox (its own included) over NVLink; then it polls its own mailbox until both words of every
+     * source rank carry this iteration's tag and adds the values in rank order.  A word is valid as soon as it is
+     * visible (tag and payload travel in one 8-byte store), so there is no fence.sys and no flag round trip: the
+     * exchange costs one peer-store latency.  Parity double-buffers the slots: a rank can be at most one iteration
+     * ahead of a peer that still reads (it needs that peer's next contribution to go further). */
     const int par = (int)(seqno & 1ull);
+    const unsigned long long tag = (seqno & 0xffffffffull) << 32;
     bool timed_out = false;
-    for (int r = 0; r < L.world; r++) {
-        if (tid < N_SLOTS) L.box[r]->sums[par][L.rank][tid] = s_sums[tid];      /* peer stores over NVLink */
-    }
-    __syncwarp();
-    if (tid < L.world) {
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long*>(&L.box[tid]->seq[par][L.rank]) = seqno;
-        /* wait for rank `tid`'s contribution; bounded (2 s) so a dead peer cannot hang the GPU */
-        const volatile unsigned long long* flag = &L.box[L.rank]->seq[par][tid];
-        const unsigned long long t0 = gtime();
-        while (*flag != seqno) {
-            if (gtime() - t0 > 2000000000ull) { atomicOr(&pose->halo_miss, 0x40000000); timed_out = true; break; }
-        }
-        __threadfence_system();
-    }
-    __syncwarp();
-    /* a peer that did not deliver: the mailbox holds stale or partial sums.  Never solve with them — the
-     * caller keeps the pose, ends the frame's GN loop and the status reaches the host (TSDF_ERR_PEER) */
-    if (__any_sync(0xffffffffu, timed_out)) return false;
     if (tid < N_SLOTS) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(s_sums[tid]);
+        const unsigned long long lo = tag | (bits & 0xffffffffull), hi = tag | (bits >> 32);
+        for (int r = 0; r < L.world; r++) {
+            volatile unsigned long long* dst = &L.box[r]->w[par][L.rank][tid][0];
+            dst[0] = lo; dst[1] = hi;                          /* peer stores over NVLink */
+        }
         double acc = 0.0;
-        for (int r = 0; r < L.world; r++) acc = acc + ld_volatile_f64(&L.box[L.rank]->sums[par][r][tid]);   /* rank order */
+        const unsigned long long t0 = gtime();
+        for (int r = 0; r < L.world && !timed_out; r++) {
+            const volatile unsigned long long* src = &L.box[L.rank]->w[par][r][tid][0];
+            unsigned long long a = src[0], b = src[1];
+            unsigned int spins = 0;
+            while ((a & 0xffffffff00000000ull) != tag || (b & 0xffffffff00000000ull) != tag) {
+                /* bounded (2 s) so a dead peer cannot hang the GPU; the clock is read every 1024 polls */
+                if ((++spins & 1023u) == 0u && gtime() - t0 > 2000000000ull) { timed_out = true; break; }
+                a = src[0]; b = src[1];
+            }
+            acc = acc + __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));   /* rank order */
+        }
         s_sums[tid] = acc;
+    }
+    /* a peer that did not deliver: never solve with partial sums — the caller keeps the pose, ends the frame's GN
+     * loop and the status reaches the host (TSDF_ERR_PEER) */
+    if (__any_sync(0xffffffffu, timed_out)) {
+        if (tid == 0) atomicOr(&pose->halo_miss, 0x40000000);
+        return false;
     }
     __syncwarp();
     return true;
@@ -424,10 +433,29 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     const int tile_x = blockIdx.x / tiles_y, tile_y = blockIdx.x - tile_x * tiles_y;
     double acc0 = 0.0, acc1 = 0.0;
 
-    for (int t0 = 0; t0 < LIN_TW * LIN_TH; t0 += (LIN_THREADS / 32) * 2) {  /* warp-uniform trip count */
+    /* Sharded volumes: a rank linearises only the pixels whose centre cell it owns — a compact region of the image —
+     * and with one tile per block the launch would still last as long as its slowest (fully owned) tile.  So the
+     * sweeps of a block are spread over the image instead: sweep q of block b takes the 4 x 4 micro-tile
+     * b + q * gridDim.x, owned micro-tiles end up evenly over all blocks and a rank that owns 1/G of the pixels
+     * finishes its pixel loop in about 1/G of the time.  (Same pixels, same per-block order every launch: the
+     * reduction stays deterministic.) */
+    constexpr int PX_SWEEP = (LIN_THREADS / 32) * 2;                         /* 16 pixels per sweep */
+    const int mty = (g.nj + 3) >> 2, n_micro = ((g.ni + 3) >> 2) * mty;
+    const int n_sweeps = sharded ? (n_micro + (int)gridDim.x - 1) / (int)gridDim.x : (LIN_TW * LIN_TH + PX_SWEEP - 1) / PX_SWEEP;
+    for (int q = 0; q < n_sweeps; q++) {                                     /* warp-uniform trip count */
+        const int t0 = q * PX_SWEEP;
         const int t = t0 + warp * 2 + grp;
-        const int ii = tile_x * LIN_TW + t / LIN_TH, jj = tile_y * LIN_TH + t % LIN_TH;
-        const bool have = (t < LIN_TW * LIN_TH) & (ii < g.ni) & (jj < g.nj);
+        int ii, jj;
+        bool have;
+        if (sharded) {
+            const int mt = (int)blockIdx.x + q * (int)gridDim.x, tl = warp * 2 + grp;
+            const int mx = mt / mty, my = mt - mx * mty;
+            ii = (mx << 2) + (tl >> 2); jj = (my << 2) + (tl & 3);
+            have = (PX_SWEEP == 16) & (mt < n_micro) & (ii < g.ni) & (jj < g.nj);
+        } else {
+            ii = tile_x * LIN_TW + t / LIN_TH; jj = tile_y * LIN_TH + t % LIN_TH;
+            have = (t < LIN_TW * LIN_TH) & (ii < g.ni) & (jj < g.nj);
+        }
         const int p = ii * g.nj + jj;                                        /* reference loop order, camera_tracking.cpp:162-163 */
         float x = 0.0f, y = 0.0f, z = __int_as_float(0x7fc00000);
         if (have) {

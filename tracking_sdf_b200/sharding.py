@@ -47,6 +47,36 @@ def frustum_weights(m, K, poses, depths, extents=(6.0, 6.0, 3.5), origin=(-3.0, 
     return np.repeat(w_layer, (m + coarse - 1) // coarse)[:m] if m >= coarse else w_layer[:: coarse // m][:m]
 
 
+def pixel_weights(m, K, poses, depths, extent_z=3.5, origin_z=-0.5, stride=3):
+    """Per-layer count of TRACKED pixels (every `stride`-th pixel, camera_tracking.cpp:162-163) whose back-projected
+    point falls into the layer, summed over representative (R, t, depth): the tracker's ownership profile (a rank
+    linearises the pixels whose centre cell it owns).  Returns m counts."""
+    K = np.asarray(K, float).reshape(3, 3)
+    w = np.zeros(m)
+    for (R, t), depth in zip(poses, depths):
+        R = np.asarray(R, float); t = np.asarray(t, float)
+        d = np.asarray(depth, np.float64)[::stride, ::stride]
+        v, u = np.meshgrid(np.arange(0, depth.shape[0], stride), np.arange(0, depth.shape[1], stride), indexing="ij")
+        ok = np.isfinite(d) & (d > 0)
+        x = (u - K[0, 2]) * d / K[0, 0]; y = (v - K[1, 2]) * d / K[1, 1]
+        wz = R[2, 0] * x + R[2, 1] * y + R[2, 2] * d + t[2]
+        k = np.floor((wz - origin_z) * m / extent_z - 0.5).astype(np.int64)
+        ok &= (k >= 0) & (k < m)
+        w += np.bincount(k[ok], minlength=m)[:m]
+    return w
+
+
+def frame_cost_weights(m, K, poses, depths, fuse_ms=1.0, track_px_ms=0.16, **kw):
+    """(weights, weights_own) for capi.balanced_slabs in one unit (milliseconds of a frame): the fusion profile scaled
+    to the single-GPU fusion time of the whole volume, the pixel profile scaled to the pixel-loop time of a whole
+    frame's tracking (10 iterations x 16 us on one B200: the part of tracking that shrinks with ownership)."""
+    wf = frustum_weights(m, K, poses, depths, **kw)
+    wp = pixel_weights(m, K, poses, depths)
+    wf = wf * (fuse_ms / max(wf.sum(), 1e-300))
+    wp = wp * (track_px_ms / max(wp.sum(), 1e-300))
+    return wf, wp
+
+
 def gather_bytes(dist, payload: np.ndarray) -> np.ndarray:
     """All-gather a fixed-size uint8 payload; returns [world, len] in rank order."""
     import torch
