@@ -437,6 +437,21 @@ def main_cuda(args):
     est_xyz = np.array([pp[1] for pp in poses_dev]); gt_xyz = ts[first_kept:n_frames]
     ate_aligned, _ = evaluate_ate.ate_rmse(est_xyz, gt_xyz, do_align=True)
     ate_raw, _ = evaluate_ate.ate_rmse(est_xyz, gt_xyz, do_align=False)
+    mesh = None
+    if rank == 0 and n_gpus == 1 and not args.no_mesh:
+        # the visualisation thread's product (sdf.cpp:327, marching_cubes_sdf.cpp:243-287) on the volume just built
+        # (all K timed frames fused)
+        nv = 0
+        tm = []
+        for _ in range(3):
+            t0m = time.perf_counter()
+            nv = g.mesh_extract(0.0)
+            tm.append(time.perf_counter() - t0m)
+        t_mesh = min(tm)
+        mesh = {"kernel": "k_mc_sweep (count + surface-cell list) + cub scan + k_mc_emit_list", "ms_per_extraction": t_mesh * 1e3, "triangles": nv // 3,
+                "store_read_gbs": 8.0 * m ** 3 / t_mesh / 1e9, "peak": hbm, "frac": 8.0 * m ** 3 / t_mesh / 1e9 / hbm,
+                "note": "host wall clock around tsdf_mesh_extract (ONE sweep over the 8 B/voxel store + scan + list emit + allocation + two syncs); "
+                        "algorithmic bytes = 8 B x m^3 (every voxel read once); cub::DeviceScan is library code, off the frame path"}
     value = n_gpus * Ksteps / (ms_total * 1e-3)
     # stage breakdown: a SECOND pass over the same frames with the per-stage CUDA events on (an event record between
     # two kernels ends the programmatic-dependent-launch chain there, so the timed region above runs without them)
@@ -474,20 +489,6 @@ def main_cuda(args):
     tot = sum(share.values())
     share = {k: v / tot for k, v in share.items()}
     g.dev_free(dev)
-    mesh = None
-    if rank == 0 and n_gpus == 1 and not args.no_mesh:
-        # the visualisation thread's product (sdf.cpp:327, marching_cubes_sdf.cpp:243-287) on the volume just built
-        nv = 0
-        tm = []
-        for _ in range(3):
-            t0m = time.perf_counter()
-            nv = g.mesh_extract(0.0)
-            tm.append(time.perf_counter() - t0m)
-        t_mesh = min(tm)
-        mesh = {"kernel": "k_mc_sweep<count> + cub scan + k_mc_sweep<emit>", "ms_per_extraction": t_mesh * 1e3, "triangles": nv // 3,
-                "store_read_gbs": 2 * 8.0 * m ** 3 / t_mesh / 1e9, "peak": hbm, "frac": 2 * 8.0 * m ** 3 / t_mesh / 1e9 / hbm,
-                "note": "host wall clock around tsdf_mesh_extract (two sweeps over the 8 B/voxel store + scan + allocation + one sync each); "
-                        "algorithmic bytes = 2 x 8 B x m^3 (each sweep reads every voxel once)"}
     color = None
     if rank == 0 and n_gpus == 1 and not args.no_color:
         color = color_fuse_bench(T, m, K, 5, hbm, depth[W], Rs[W], ts[W])

@@ -66,6 +66,9 @@ struct Impl {
     size_t mc_tmp_bytes = 0;
     float* mesh_xyz = nullptr;
     int64_t mesh_n = 0, mesh_cap = 0;
+    unsigned long long* mc_cells = nullptr;   /* surface-cell list of the one-sweep path */
+    unsigned int* mc_cell_counter = nullptr;
+    unsigned int mc_cell_cap = 0;
     float* depth_stage = nullptr;
     /* K0 (tsdf_config.preprocess): bilateral grid, filtered depth, discontinuity map, gradients, normals */
     bool k0 = false;
@@ -555,7 +558,7 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     }
     if (p->depth_copied) cudaEventDestroy(p->depth_copied);
     if (p->prep_stream) cudaStreamDestroy(p->prep_stream);
-    cudaFree(p->mc_count); cudaFree(p->mc_off); cudaFree(p->mc_tmp); cudaFree(p->mesh_xyz);
+    cudaFree(p->mc_count); cudaFree(p->mc_off); cudaFree(p->mc_tmp); cudaFree(p->mesh_xyz); cudaFree(p->mc_cells); cudaFree(p->mc_cell_counter);
     cudaFree(p->color); cudaFree(p->rgb4_buf[0]); cudaFree(p->rgb4_buf[1]); cudaFree(p->rgb_stage);
     cudaFree(p->cosn_buf[0]); cudaFree(p->cosn_buf[1]);
     cudaFree(p->k0b.minmax); cudaFree(p->k0b.grid_a); cudaFree(p->k0b.grid_b); cudaFree(p->k0b.zf); cudaFree(p->k0b.edge);
@@ -871,13 +874,19 @@ tsdf_status tsdf_mesh_extract(tsdf_handle h, float iso_level, int64_t* n_vertice
         CK(cudaMalloc(&p->mc_count, (size_t)n_rows * sizeof(unsigned int)));
         CK(cudaMalloc(&p->mc_off, (size_t)n_rows * sizeof(unsigned int)));
         CK(cudaMalloc(&p->mc_tmp, p->mc_tmp_bytes ? p->mc_tmp_bytes : 16));
+        CK(cudaMalloc(&p->mc_cell_counter, sizeof(unsigned int)));
+    }
+    if (!p->mc_cells) {
+        p->mc_cell_cap = 1u << 20;                                    /* grows to fit the surface, see below */
+        CK(cudaMalloc(&p->mc_cells, (size_t)p->mc_cell_cap * sizeof(unsigned long long)));
     }
     McParams P;
     P.width = p->cfg.width; P.height = p->cfg.height; P.depth = p->cfg.depth; P.iso = iso_level;
-    launch_mesh_count(p->g, P, p->grid, p->mc_count, p->mc_off, p->mc_tmp, p->mc_tmp_bytes, p->stream);
+    launch_mesh_count(p->g, P, p->grid, p->mc_count, p->mc_off, p->mc_tmp, p->mc_tmp_bytes, p->mc_cells, p->mc_cell_counter, p->mc_cell_cap, p->stream);
     p->launches += 2;
-    unsigned int total = 0;
+    unsigned int total = 0, n_cells = 0;
     CK(cudaMemcpyAsync(&total, p->mc_off + (n_rows - 1), sizeof total, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(&n_cells, p->mc_cell_counter, sizeof n_cells, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     if (total) {
         if ((int64_t)total > p->mesh_cap) {                          /* grow with head room: the next mesh is usually a bit larger */
@@ -887,7 +896,17 @@ tsdf_status tsdf_mesh_extract(tsdf_handle h, float iso_level, int64_t* n_vertice
             if (e != cudaSuccess) { cudaGetLastError(); p->mesh_xyz = nullptr; g_err = "mesh buffer allocation failed"; return TSDF_ERR_NOMEM; }
             p->mesh_cap = cap;
         }
-        launch_mesh_emit(p->g, P, p->grid, p->mc_off, p->mesh_xyz, p->stream);
+        if (n_cells <= p->mc_cell_cap) {
+            /* one sweep: the triangles come from the listed surface cells */
+            launch_mesh_emit_list(p->g, P, p->grid, p->mc_cells, p->mc_cell_counter, n_cells, p->mc_off, p->mesh_xyz, p->stream);
+        } else {
+            /* the list overflowed: second sweep over the store this time, a larger list for the next extraction */
+            launch_mesh_emit(p->g, P, p->grid, p->mc_off, p->mesh_xyz, p->stream);
+            cudaFree(p->mc_cells); p->mc_cells = nullptr;
+            const unsigned int cap = n_cells + n_cells / 2 + 1024u;
+            if (cudaMalloc(&p->mc_cells, (size_t)cap * sizeof(unsigned long long)) == cudaSuccess) p->mc_cell_cap = cap;
+            else { cudaGetLastError(); p->mc_cells = nullptr; p->mc_cell_cap = 0; }
+        }
         p->launches++;
         CK(cudaStreamSynchronize(p->stream));
     }

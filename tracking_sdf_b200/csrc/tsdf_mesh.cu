@@ -7,8 +7,15 @@
  *
  * The store is x fastest, the output order is k fastest, so a warp takes 32 consecutive i at a fixed
  * j and sweeps k: every load is a coalesced 256-byte row segment, each lane walks one (i,j) row of
- * cells in output order.  Two sweeps: count vertices per row -> exclusive scan over the m*m rows ->
- * emit.  HBM-bound: the store is read about once per sweep (the j+1 row is an L1/L2 hit).
+ * cells in output order.
+ *
+ * ONE sweep over the store: it counts the vertices of every (row, k-chunk) segment AND appends one 8-byte record
+ * per surface cell (i, j, k, configuration, vertex offset inside its segment — the lane's running count) to a
+ * compact list (warp-staged appends, one atomic per >= 33 records).  After the exclusive scan of the segment
+ * counts, a second kernel walks the LIST (about 1 % of the cells), re-gathers each cell's eight corners and
+ * writes its triangles at row_off[segment] + offset: the soup comes out in the reference's order although the
+ * list is unordered.  The store is read once (plus the listed cells' corners); the previous two-sweep emit
+ * (k_mc_sweep<true>) remains as the fallback when the list overflows its capacity.
  */
 #include <cub/device/device_scan.cuh>
 
@@ -25,15 +32,35 @@ constexpr int MC_ZSPLIT = MC_ZSPLIT_DEF;     /* chunks of the k sweep (more load
 
 constexpr int MC_TILE = 31;      /* cells per warp along i: 32 lanes load 32 voxels, lanes 0..30 own a cell (i+1 comes from lane+1) */
 
+/* surface-cell record: i (12 bits) | j (12) | k (12) | configuration (8) | vertex offset inside the segment (16) */
+__device__ __forceinline__ unsigned long long mc_pack_cell(int i, int j, int k, int ci, unsigned int off) {
+    return (unsigned long long)i | ((unsigned long long)j << 12) | ((unsigned long long)k << 24) | ((unsigned long long)ci << 36) |
+           ((unsigned long long)off << 44);
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McParams P, const float2* __restrict__ grid, int k_lo_all, int k_hi_all,
                                                             unsigned int* __restrict__ row_count, const unsigned int* __restrict__ row_off,
-                                                            float* __restrict__ xyz) {
+                                                            float* __restrict__ xyz,
+                                                            unsigned long long* __restrict__ cells, unsigned int* cell_counter, unsigned int cell_cap) {
+    __shared__ unsigned long long s_stage[EMIT ? 1 : MC_WARPS][EMIT ? 1 : 96];
+    int staged = 0;                                                   /* warp-uniform */
     const int m = g.m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = 1 + blockIdx.x * MC_TILE + lane;                    /* this lane's voxel column; its cell if lane < 31 */
     const int j = blockIdx.y * MC_WARPS + warp;
     if (j < 1 || j > m - 2) return;                                   /* warp-uniform */
+    unsigned long long* stage = s_stage[EMIT ? 0 : warp];
+    auto flush = [&]() {                                              /* append the warp's staged records: one atomic */
+        if (staged == 0) return;
+        unsigned int basec = 0;
+        if (lane == 0) basec = atomicAdd(cell_counter, (unsigned int)staged);
+        basec = __shfl_sync(0xffffffffu, basec, 0);
+        for (int q = lane; q < staged; q += 32)
+            if (basec + (unsigned int)q < cell_cap) cells[basec + q] = stage[q];     /* past the capacity: counted, not stored */
+        __syncwarp();
+        staged = 0;
+    };
     /* the k range is cut into gridDim.z chunks; a row's chunks are consecutive in the output */
     const int nz = (int)gridDim.z, zc = (int)blockIdx.z;
     const int per = (k_hi_all - k_lo_all + nz) / nz;
@@ -79,6 +106,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McPara
                                      ((lo & 2u) << 3) | ((lo & 8u) << 2) | ((hi & 8u) << 3) | ((hi & 2u) << 6));
                 const unsigned long long row = c_mc_tri[ci];
                 const int nv = mc_vertex_count(row);
+                if (!EMIT) stage[staged + __popc(any & ((1u << lane) - 1u))] = mc_pack_cell(i, j, k, ci, n_row);
                 if (EMIT) {
                     const float d[8] = {a0.x, a0n, a1n, a1.x, b0.x, b0n, b1n, b1.x};
                     float* o = xyz + 3 * (size_t)(base + n_row);
@@ -90,11 +118,46 @@ __global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McPara
                 }
                 n_row += (unsigned int)nv;
             }
+            if (!EMIT) {
+                __syncwarp();
+                staged += __popc(any);
+                if (staged > 64) flush();
+            }
         }
         a0 = a1; b0 = b1; s0 = s1; t0 = t1;
         a1 = a2; b1 = b2;
     }
+    if (!EMIT) flush();
     if (!EMIT && cell_ok) row_count[((size_t)i * m + j) * nz + zc] = n_row;
+}
+
+/* pass 2 of the one-sweep path: one thread per listed surface cell */
+__global__ void __launch_bounds__(128) k_mc_emit_list(GridParams g, McParams P, const float2* __restrict__ grid, int k_lo_all, int k_hi_all, int nz,
+                                                      const unsigned long long* __restrict__ cells, const unsigned int* __restrict__ cell_counter,
+                                                      const unsigned int* __restrict__ row_off, float* __restrict__ xyz) {
+    const unsigned int n = *cell_counter;
+    const unsigned int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const unsigned long long c = cells[q];
+    const int i = (int)(c & 0xfff), j = (int)((c >> 12) & 0xfff), k = (int)((c >> 24) & 0xfff), ci = (int)((c >> 36) & 0xff);
+    const unsigned int off = (unsigned int)(c >> 44);
+    const int m = g.m;
+    const int per = (k_hi_all - k_lo_all + nz) / nz;
+    const int zc = (k - k_lo_all) / per;
+    const size_t plane = (size_t)m * m;
+    const float2* p = grid + (size_t)(k - g.ks0) * plane + (size_t)j * m + i;
+    /* corners: 0 (i,j,k) 1 (i+1,j,k) 2 (i+1,j,k+1) 3 (i,j,k+1) 4 (i,j+1,k) 5 (i+1,j+1,k) 6 (i+1,j+1,k+1) 7 (i,j+1,k+1) */
+    const float d[8] = {__ldg(p).x, __ldg(p + 1).x, __ldg(p + plane + 1).x, __ldg(p + plane).x,
+                        __ldg(p + m).x, __ldg(p + m + 1).x, __ldg(p + plane + m + 1).x, __ldg(p + plane + m).x};
+    const unsigned long long row = c_mc_tri[ci];
+    const int nv = mc_vertex_count(row);
+    const float fm = (float)m;
+    float* o = xyz + 3 * (size_t)(row_off[((size_t)i * m + j) * nz + zc] + off);
+    for (int t = 0; t < nv; t++) {
+        float v[3];
+        mc_edge_vertex(P, fm, i, j, k, (int)((row >> (4 * t)) & 0xFull), d, v);
+        o[3 * t] = v[0]; o[3 * t + 1] = v[1]; o[3 * t + 2] = v[2];
+    }
 }
 
 /* marker points of SDF::visualize: (double)vertex + sdf_origin (sdf.cpp:354-356) */
@@ -127,14 +190,15 @@ size_t mesh_scan_bytes(int64_t n_rows) {
  * the last row_off is the total) */
 int mesh_zsplit() { return MC_ZSPLIT; }
 void launch_mesh_count(const GridParams& g, const McParams& P, const float2* grid, unsigned int* row_count, unsigned int* row_off,
-                       void* scan_tmp, size_t scan_bytes, cudaStream_t s) {
+                       void* scan_tmp, size_t scan_bytes, unsigned long long* cells, unsigned int* cell_counter, unsigned int cell_cap, cudaStream_t s) {
     const int64_t n_rows = (int64_t)g.m * g.m * MC_ZSPLIT + 1;
     cudaMemsetAsync(row_count, 0, (size_t)n_rows * sizeof(unsigned int), s);
+    cudaMemsetAsync(cell_counter, 0, sizeof(unsigned int), s);
     int k_lo, k_hi;
     mesh_k_range(g, k_lo, k_hi);
     if (k_hi >= k_lo) {
         dim3 grid3((g.m - 2 + MC_TILE - 1) / MC_TILE, (g.m + MC_WARPS - 1) / MC_WARPS, MC_ZSPLIT);
-        k_mc_sweep<false><<<grid3, MC_WARPS * 32, 0, s>>>(g, P, grid, k_lo, k_hi, row_count, nullptr, nullptr);
+        k_mc_sweep<false><<<grid3, MC_WARPS * 32, 0, s>>>(g, P, grid, k_lo, k_hi, row_count, nullptr, nullptr, cells, cell_counter, cell_cap);
     }
     cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, row_count, row_off, (int)n_rows, s);
 }
@@ -143,7 +207,15 @@ void launch_mesh_emit(const GridParams& g, const McParams& P, const float2* grid
     mesh_k_range(g, k_lo, k_hi);
     if (k_hi < k_lo) return;
     dim3 grid3((g.m - 2 + MC_TILE - 1) / MC_TILE, (g.m + MC_WARPS - 1) / MC_WARPS, MC_ZSPLIT);
-    k_mc_sweep<true><<<grid3, MC_WARPS * 32, 0, s>>>(g, P, grid, k_lo, k_hi, nullptr, row_off, xyz);
+    k_mc_sweep<true><<<grid3, MC_WARPS * 32, 0, s>>>(g, P, grid, k_lo, k_hi, nullptr, row_off, xyz, nullptr, nullptr, 0u);
+}
+/* pass 2 of the one-sweep path (n_cells <= the list's capacity) */
+void launch_mesh_emit_list(const GridParams& g, const McParams& P, const float2* grid, const unsigned long long* cells, const unsigned int* cell_counter,
+                           unsigned int n_cells, const unsigned int* row_off, float* xyz, cudaStream_t s) {
+    int k_lo, k_hi;
+    mesh_k_range(g, k_lo, k_hi);
+    if (k_hi < k_lo || n_cells == 0) return;
+    k_mc_emit_list<<<(n_cells + 127) / 128, 128, 0, s>>>(g, P, grid, k_lo, k_hi, MC_ZSPLIT, cells, cell_counter, row_off, xyz);
 }
 
 }  // namespace tsdf
