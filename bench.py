@@ -319,7 +319,8 @@ def color_fuse_bench(T, m, K, reps, hbm, depth_frame, R, t):
         tt.append(float(g.last_stage_ms()[2]))
     g.close()
     ach = 48.0 * n / t_dense / 1e9
-    return {"bound": "hbm", "kernel": "k_fuse_cert (skip certificates) + k_fuse_exact<colour> (every updated voxel needs its pixel: normal + rgb)",
+    return {"bound": "hbm", "kernel": "k_fuse_cert (skip certificates; rows certified as free space bypass the unit queue) + k_fuse_exact<colour> "
+                                 "(every updated voxel needs its pixel: normal + rgb)",
             "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "bytes_per_updated_voxel": 48,
             "dense_ms_per_launch": t_dense * 1e3, "dense_voxels_updated": int(n),
             "trajectory_ms_per_launch": float(np.mean(tt)), "trajectory_voxels_updated": int(nt)}

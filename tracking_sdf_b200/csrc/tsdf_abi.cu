@@ -477,7 +477,7 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     A(cudaMalloc(&p->fuse_tables, ((size_t)9 * cfg->m + 8) * sizeof(double)));
     A(cudaMalloc(&p->fuse_items, (size_t)(p->g.ks1 - p->g.ks0) * cfg->m * ((cfg->m + 127) / 128 + 1) * sizeof(unsigned long long)));
     A(cudaMalloc(&p->fuse_item_c, (size_t)(p->g.ks1 - p->g.ks0) * cfg->m * ((cfg->m + 127) / 128 + 1) * sizeof(float4)));
-    A(cudaMalloc(&p->fuse_item_count, 2 * sizeof(unsigned int)));
+    A(cudaMalloc(&p->fuse_item_count, 4 * sizeof(unsigned int)));      /* [0] items, [1] units, [2] items of row-certified free space */
     A(cudaMalloc(&p->fuse_units, (size_t)(p->n_stored / 4 + 64) * sizeof(unsigned long long)));
     {
         int64_t off = 0;

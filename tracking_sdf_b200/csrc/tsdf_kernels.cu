@@ -669,7 +669,7 @@ __global__ void k_fuse_tables(GridParams g, const PoseState* pose, double* __res
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = g.m;
     if (i == 0) {
-        n_updated[0] = 0ull; *item_count = 0u; *unit_count = 0u;
+        n_updated[0] = 0ull; *item_count = 0u; *unit_count = 0u; item_count[2] = 0u;
         /* fp32 affine evaluation of the certificates' end points (tsdf_core.cuh): usable flag + per-frame steps */
         float sx, sy, sz;
         affine_step(g, pose->Rinv, sx, sy, sz);
@@ -761,6 +761,13 @@ __global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, CertPyramid P, 
         if (lane >= o) scan += t;
     }
     const int total = __shfl_sync(0xffffffffu, scan, 31);
+    {
+        /* items of rows certified as free space as a whole: with colour they bypass the unit queue (item_count[2]) */
+        int nf = (!per_item && rowv == UNIT_FRONT) ? cnt : 0;
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o2);
+        if (lane == 0 && nf > 0) atomicAdd(item_count + 2, (unsigned int)nf);
+    }
     unsigned int basei = 0;
     if (lane == 31 && total > 0) basei = atomicAdd(item_count, (unsigned int)total);
     basei = __shfl_sync(0xffffffffu, basei, 31);
@@ -1170,6 +1177,9 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
 #endif
         /* colour fusion needs every updated voxel's pixel (normal, rgb): certified free space is
          * queued for the exact pass too; only the skip certificate is used */
+        /* ... except whole rows certified as free space: the colour pass takes those straight from the item list
+         * (no 8-byte queue entry per unit, no staging) */
+        if (queue_front && rowv == UNIT_FRONT && !CHECK) verdict = UNIT_SKIP;
         const bool front_queued = queue_front && verdict == UNIT_FRONT;     /* queued WITH its certificate */
         if (CHECK) {
             /* self-check build: queue EVERY unit with its verdict; pass 2 compares, nothing is written */
@@ -1212,7 +1222,8 @@ __global__ void __launch_bounds__(FUSE_THREADS, COLOR ? FUSE_COLOR_MIN_BLOCKS : 
                                                                               const unsigned long long* units,
                                                                               const unsigned int* unit_count,
                                                                               unsigned long long* n_updated,
-                                                                              float4* __restrict__ color, const uchar4* __restrict__ rgb4, const double* __restrict__ cosn) {
+                                                                              float4* __restrict__ color, const uchar4* __restrict__ rgb4, const double* __restrict__ cosn,
+                                                                              const unsigned long long* items, const unsigned int* item_count) {
     pdl_wait();
     pdl_release();
     GridParams g = g_in;
@@ -1223,10 +1234,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, COLOR ? FUSE_COLOR_MIN_BLOCKS : 
     const K1Params kp = k1_params(g.K);
     const double ti0 = T[9 * (size_t)m + 0], ti1 = T[9 * (size_t)m + 1], ti2 = T[9 * (size_t)m + 2];
     unsigned int my_updates = 0, chk_n = 0, chk_bad = 0;
-    for (unsigned int q = blockIdx.x * FUSE_THREADS + threadIdx.x; q < n_units; q += gridDim.x * FUSE_THREADS) {
-        const unsigned long long unit = ld_dep(&units[q]);
-        const int k = (int)(unit & 0xfff), j = (int)((unit >> 12) & 0xfff), x0 = (int)((unit >> 24) & 0x3ff) << 2;
-        const int verdict = (int)((unit >> 34) & 3);
+    auto process = [&](int k, int j, int x0, int verdict) {
         float4* ptr = reinterpret_cast<float4*>(&grid[((size_t)(k - g.ks0) * m + j) * m + x0]);
         const float4 q0 = ld_f4(ptr), q1 = ld_f4(ptr + 1);
         double cx[4], cy[4], cz[4];
@@ -1250,9 +1258,24 @@ __global__ void __launch_bounds__(FUSE_THREADS, COLOR ? FUSE_COLOR_MIN_BLOCKS : 
                     if (!good) chk_bad++;
                 }
             }
-            continue;
+            return;
         }
         my_updates += apply_four(g, ptr, q0, q1, k, upd, dnew, wnew);
+    };
+    for (unsigned int q = blockIdx.x * FUSE_THREADS + threadIdx.x; q < n_units; q += gridDim.x * FUSE_THREADS) {
+        const unsigned long long unit = ld_dep(&units[q]);
+        process((int)(unit & 0xfff), (int)((unit >> 12) & 0xfff), (int)((unit >> 24) & 0x3ff) << 2, (int)((unit >> 34) & 3));
+    }
+    if (COLOR && !CHECK && item_count[2] != 0u) {
+        /* rows certified as free space as a whole (the dense case): straight from the item list, a warp per item */
+        const unsigned int n_items = item_count[0];
+        const unsigned int gw = blockIdx.x * (FUSE_THREADS / 32) + (threadIdx.x >> 5), total_warps = gridDim.x * (FUSE_THREADS / 32);
+        for (unsigned int it = gw; it < n_items; it += total_warps) {
+            const unsigned long long item = ld_dep(&items[it]);
+            if (((int)(item >> 61) & 3) != UNIT_FRONT) continue;
+            const int x0 = (int)((item >> 24) & 0xfff) + 4 * lane;
+            if (x0 < (int)((item >> 48) & 0x1fff)) process((int)(item & 0xfff), (int)((item >> 12) & 0xfff), x0, UNIT_FRONT);
+        }
     }
     if (CHECK) {
         if (chk_n) atomicAdd(&n_updated[2], (unsigned long long)chk_n);
@@ -1280,14 +1303,14 @@ int launch_fuse(const FuseArgs& f, cudaStream_t s) {
     }
     if (f.check) {
         launch_pdl(k_fuse_cert<1>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_c, f.item_count, f.units, f.unit_count, f.n_updated, 0);
-        if (g.metric == 0) launch_pdl(k_fuse_exact<0, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
-        else launch_pdl(k_fuse_exact<1, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
+        if (g.metric == 0) launch_pdl(k_fuse_exact<0, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn, f.items, f.item_count);
+        else launch_pdl(k_fuse_exact<1, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn, f.items, f.item_count);
         return 4;
     }
     launch_pdl(k_fuse_cert<0>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_c, f.item_count, f.units, f.unit_count, f.n_updated, color ? 1 : 0);
-    if (color) launch_pdl(k_fuse_exact<0, 0, true>, dim3(f.nblk_color), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
-    else if (g.metric == 0) launch_pdl(k_fuse_exact<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
-    else launch_pdl(k_fuse_exact<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn);
+    if (color) launch_pdl(k_fuse_exact<0, 0, true>, dim3(f.nblk_color), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn, f.items, f.item_count);
+    else if (g.metric == 0) launch_pdl(k_fuse_exact<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn, f.items, f.item_count);
+    else launch_pdl(k_fuse_exact<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn, f.items, f.item_count);
     return 4;
 }
 int fuse_color_blocks_per_sm() {
