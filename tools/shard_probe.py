@@ -18,4 +18,10 @@ for rep in range(3):
     t = g.debug_phase_times(depth[6])
     print("rank %d: main loop %.2f us | to final block %.2f | reduce %.2f | exchange+update %.2f | total %.2f" % ((dist.get_rank(),) + tuple(
         (b - a) / 1e3 for a, b in [(t[0], t[1]), (t[1], t[2]), (t[2], t[3]), (t[3], t[4]), (t[0], t[4])])), flush=True)
+# ten chained iterations (one tsdf_track call) after a barrier: the track stage as the device saw it
+for rep in range(3):
+    g.set_pose(Rs[5], ts[5])
+    dist.barrier(); torch.cuda.synchronize()
+    g.track(depth[6])
+    print("rank %d: track() of 10 chained iterations: %.1f us" % (dist.get_rank(), 1e3 * g.last_stage_ms()[1]), flush=True)
 g.close(); dist.destroy_process_group()
