@@ -482,10 +482,17 @@ def main_cuda(args):
                  "note": "algorithmic bytes = 16 B x voxels updated (read+write D,W); skipped voxels move no bytes. On this workload only ~5 % of the "
                          "134 M voxels are in view, so the stage is bound by certificate/fp64 latency on in-view voxels, not by HBM: see dense_fuse for the "
                          "HBM-bound case (every voxel updated), which is where north_star's >= 70 % target is defined"}
-    roof_track = {"bound": "l2-gather-latency", "kernel": "k_linearize", "achieved": gather, "peak": hbm, "unit": "GB/s",
+    # floor of one GN iteration: the pixel loop cannot beat the L1 data pipe (ncu: 17.5 k LSU data-pipe wavefronts
+    # per SM per launch = 8.9 us at one wavefront per clock, 1965 MHz), and the serial tail is five dependent global round trips
+    # (partial -> ticket -> group sum -> ticket -> final sum, ~0.7 us each), a ~2 us chain of dependent fp64 divisions (6x6 LU,
+    # exp map, 3x3 inverse) and the dependent launch (~1 us)
+    floor_us = 8.9 + 3.5 + 2.0 + 1.0
+    roof_track = {"bound": "l1-data-pipe + dependent-latency chain", "kernel": "k_linearize", "achieved": gather, "peak": hbm, "unit": "GB/s",
                   "frac": gather / hbm, "ms_per_launch": t_track * 1e3 / GN_ITERS, "launches_per_frame": GN_ITERS,
-                  "note": "832 B gathered per valid pixel-iteration (13 samples x 8 neighbours x {D,W}); working set is L2-resident, "
-                          "so HBM peak is only a yardstick here"}
+                  "floor_us_per_launch": floor_us, "frac_of_floor": floor_us / (t_track * 1e6 / GN_ITERS),
+                  "note": "832 B gathered per valid pixel-iteration (13 samples x 8 neighbours x {D,W}); the working set is L2-resident, so the HBM "
+                          "peak (achieved/peak/frac) is only a yardstick; the bound that applies is floor_us_per_launch: L1 data-pipe wavefronts of "
+                          "the gathers (8.9 us) + the serial reduction/solve/launch tail (6.5 us); frac_of_floor = floor / measured"}
     share = {"prep": t_prep, "track": t_track, "fuse": t_fuse}
     tot = sum(share.values())
     share = {k: v / tot for k, v in share.items()}
@@ -635,6 +642,20 @@ def run_sharded(dist, tdev, device, n_gpus, m, W, Ksteps, equal_slabs, hbm, peak
     t_track_max = barrier_max(dist, t_track, tdev)
     n_upd = n_upd_local
     pose_spread = 0.0
+    per_rank = None
+    if dist is not None:
+        # per-rank, per-frame stage times: the ranks run in lock step (every GN iteration waits for all of them), so a
+        # frame lasts as long as its slowest fuser plus the tracking chain; which rank is slowest changes along the path
+        import torch
+        mine = torch.tensor(stage[:, 1:3].astype(np.float64), device=tdev)            # [frames, (track, fuse)]
+        allr = [torch.empty_like(mine) for _ in range(n_gpus)]
+        dist.all_gather(allr, mine)
+        A = torch.stack(allr).cpu().numpy()                                           # [ranks, frames, 2]
+        per_rank = {"track_ms_mean": [float(x) for x in A[:, :, 0].mean(axis=1)], "fuse_ms_mean": [float(x) for x in A[:, :, 1].mean(axis=1)],
+                    "fuse_ms_max_over_ranks_mean_over_frames": float(A[:, :, 1].max(axis=0).mean()),
+                    "track_ms_min_over_ranks_mean_over_frames": float(A[:, :, 0].min(axis=0).mean()),
+                    "note": "track includes the wait for the slowest rank's fusion of the previous frame (the first GN iteration "
+                            "cannot complete before every rank has joined); min over ranks = the tracking chain itself"}
     if dist is not None:
         import torch
         tt = torch.tensor([float(n_upd_local)], dtype=torch.float64, device=tdev)
@@ -673,7 +694,8 @@ def run_sharded(dist, tdev, device, n_gpus, m, W, Ksteps, equal_slabs, hbm, peak
            "roofline": {"bound": "hbm", "kernel": "fusion stage (k_fuse_tables + k_fuse_plan + k_fuse_cert + k_fuse_exact)", "achieved": ach, "peak": hbm * n_gpus, "unit": "GB/s", "frac": ach / (hbm * n_gpus),
                         "traffic": None, "peak_source": peak_src + " x n_gpus", "ms_per_launch": t_fuse_max * 1e3,
                         "voxels_updated_per_launch": upd_per_frame},
-           "stage_ms": {"prep": t_prep * 1e3, "track_max_over_ranks": t_track_max * 1e3, "fuse_max_over_ranks": t_fuse_max * 1e3},
+           "stage_ms": {"prep": t_prep * 1e3, "track_max_over_ranks": t_track_max * 1e3, "fuse_max_over_ranks": t_fuse_max * 1e3,
+                        "per_rank": per_rank},
            "e2e": {"value": Ksteps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(frame_bytes) * n_gpus, "d2h_bytes_per_step": 496 * n_gpus,
                    "ms_per_step": 1e3 * e2e_s / Ksteps, "timing": "host wall clock, K tsdf_submit_frame(HOST pinned depth) calls + final tsdf_sync on every rank "
                                                                   "(every rank copies the whole frame: the depth image is replicated)"},

@@ -136,3 +136,32 @@ def test_frustum_weights_profile():
     assert w.shape == (256,) and (w > 0).all()
     # the camera sits at z ~ 1.3 m looking slightly down: the layers around it carry more than the top of the volume
     assert w[100:160].mean() > 3 * w[-20:].mean()
+
+
+def test_pixel_aware_balancing():
+    """tsdf_balanced_slabs2: a second profile that counts for a layer's OWNER only (the tracked pixels).  With no
+    second profile it equals tsdf_balanced_slabs; with one, the largest (halo-inclusive fusion + owned pixels) cost is
+    no larger than for the fusion-only cuts, and matches brute force on a small case."""
+    import itertools
+    import numpy as np
+    from tracking_sdf_b200 import capi, sharding
+    rng = np.random.default_rng(3)
+    m, n, halo, minl = 48, 4, 3, 4
+    wf = rng.random(m) + 0.05
+    wo = np.zeros(m); wo[20:28] = 3.0                                 # the surface band sits in a few layers
+    assert capi.balanced_slabs(wf, n, min_layers=minl, halo=halo) == capi.balanced_slabs(wf, n, min_layers=minl, halo=halo, weights_own=np.zeros(m))
+    P = np.concatenate([[0], np.cumsum(wf)]); Q = np.concatenate([[0], np.cumsum(wo)])
+
+    def worst(b):
+        return max((P[min(b[r + 1] + halo, m)] - P[max(b[r] - halo, 0)]) + (Q[b[r + 1]] - Q[b[r]]) for r in range(n))
+    b_f = capi.balanced_slabs(wf, n, min_layers=minl, halo=halo)
+    b_p = capi.balanced_slabs(wf, n, min_layers=minl, halo=halo, weights_own=wo)
+    assert b_p[0] == 0 and b_p[-1] == m and all(b_p[r + 1] - b_p[r] >= minl for r in range(n))
+    best = min(worst((0,) + c + (m,)) for c in itertools.combinations(range(minl, m - minl + 1), n - 1)
+               if all(y - x >= minl for x, y in zip((0,) + c, c + (m,))))
+    assert worst(b_p) <= worst(b_f) + 1e-12 and abs(worst(b_p) - best) <= 1e-9 * best
+    # the pixel profile itself: every tracked, valid pixel of a frame lands in exactly one layer
+    from tools import synth
+    depth, Rs, ts = synth.render_sequence(2)
+    w = sharding.pixel_weights(64, synth.K_DEFAULT, [(Rs[0], ts[0])], [depth[0]])
+    assert w.sum() == 214 * 160 and (w >= 0).all()

@@ -826,35 +826,31 @@ tsdf_status tsdf_balanced_slabs2(int32_t m, int32_t n_shards, const double* weig
         Q[k + 1] = Q[k] + (weights_own ? weights_own[k] : 0.0);
     }
     auto cost = [&](int a, int b) { return (P[b + halo > m ? m : b + halo] - P[a - halo < 0 ? 0 : a - halo]) + (Q[b] - Q[a]); };
-    /* greedy feasibility for a cost cap T: make every slab as thick as the cap allows */
-    auto plan = [&](double T, int32_t* out) {
-        int a = 0;
-        out[0] = 0;
-        for (int r = 0; r < n_shards; r++) {
-            const int hi = m - (n_shards - 1 - r) * min_layers;     /* leave room for the slabs to come */
-            int b = a + min_layers;
-            if (b > hi || cost(a, b) > T) return false;
-            int lo_b = b, hi_b = hi;                                /* largest b with cost(a, b) <= T (cost is monotone in b) */
-            while (lo_b < hi_b) {
-                const int mid = (lo_b + hi_b + 1) / 2;
-                if (cost(a, mid) <= T) lo_b = mid; else hi_b = mid - 1;
+    /* exact: dynamic programme over the cut positions, f[r][b] = min over a <= b - min_layers of max(f[r-1][a], cost(a, b)).
+     * (With a minimum thickness the classic greedy "as thick as the cap allows" is not optimal: the cost of the thinnest
+     * admissible slab is a sliding window, not monotone in its start.)  O(n_shards * m^2) on the host, once per run. */
+    const double INF = 1e308;
+    std::vector<double> prev((size_t)m + 1, INF), cur((size_t)m + 1, INF);
+    std::vector<std::vector<int32_t>> arg((size_t)n_shards, std::vector<int32_t>((size_t)m + 1, -1));
+    for (int bq = min_layers; bq <= m; bq++) { prev[bq] = cost(0, bq); arg[0][bq] = 0; }
+    for (int r = 1; r < n_shards; r++) {
+        std::fill(cur.begin(), cur.end(), INF);
+        for (int bq = (r + 1) * min_layers; bq <= m; bq++) {
+            double best = INF; int besta = -1;
+            for (int a = r * min_layers; a <= bq - min_layers; a++) {
+                if (prev[a] >= best) continue;
+                const double c = cost(a, bq);
+                const double v = prev[a] > c ? prev[a] : c;
+                if (v < best) { best = v; besta = a; }
             }
-            b = (r == n_shards - 1) ? m : lo_b;
-            if (r == n_shards - 1 && cost(a, m) > T) return false;
-            out[r + 1] = b;
-            a = b;
+            cur[bq] = best; arg[r][bq] = besta;
         }
-        return true;
-    };
-    const double total = P[m] + Q[m];
-    double lo = 0.0, hi = total * 3.0 + 1e-300;                    /* halos count twice at most */
-    std::vector<int32_t> tmp((size_t)n_shards + 1);
-    if (!plan(hi, tmp.data())) return bad("no partition satisfies min_layers");
-    for (int it = 0; it < 100 && hi - lo > 1e-12 * total; it++) {
-        const double mid = 0.5 * (lo + hi);
-        if (plan(mid, tmp.data())) hi = mid; else lo = mid;
+        prev.swap(cur);
     }
-    plan(hi, bounds);
+    if (!(prev[m] < INF)) return bad("no partition satisfies min_layers");
+    int bq = m;
+    bounds[n_shards] = m;
+    for (int r = n_shards - 1; r >= 0; r--) { bq = arg[r][bq]; bounds[r] = bq; }
     return TSDF_OK;
 }
 tsdf_status tsdf_balanced_slabs(int32_t m, int32_t n_shards, const double* weights, int32_t min_layers, int32_t halo, int32_t* bounds) {
