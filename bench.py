@@ -367,7 +367,7 @@ def k0_bench(T, m, K, n_frames, hbm):
                     "final_pos_err_vs_gt_m": float(np.linalg.norm(est[okf][-1] - ts[1:n_frames][okf][-1])),
                     "stage_ms": {"prep": float(stage[:, 0].mean()), "track": float(stage[:, 1].mean()), "fuse": float(stage[:, 2].mean())}}
         g.dev_free(dev); g.close()
-    out["note"] = ("K0 = 11 launches on the preprocessing stream (bilateral grid: min/max, splat, 6 blur passes, slice; gradients + "
+    out["note"] = ("K0 = 12 launches on the preprocessing stream (bilateral grid: min/max, bins, splat, 6 blur passes, slice; gradients + "
                    "discontinuity map; window normals), overlapped with the previous frame; parity with PCL unpinned (own definition, "
                    "bit-equal to the oracle's: tests/test_gpu_k0.py)")
     return out

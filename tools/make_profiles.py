@@ -13,13 +13,17 @@ for r in rows[hi + 1:]:
 tot = sum(a[1] for a in agg.values())
 with open(R + "profiles/%s_launch_list_summary.csv" % TAG, "w") as f:
     f.write("# ncu launch list summary (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)\n")
-    f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 300 python bench.py --steps 40 --warmup 10 --no-cpu --no-dense --no-color --no-mesh   (tools/profile_all.sh)\n")
+    f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 300 python bench.py --steps 40 --warmup 10 --no-cpu --no-dense --no-color --no-mesh [--no-sharded --no-k0]   (tools/profile_all.sh / tools/profile_r02.sh)\n")
     f.write("kernel,launches,mean_us,total_us,share\n")
     for k, (n, t) in agg.items():
         f.write("%s,%d,%.2f,%.1f,%.3f\n" % (k, n, t / n, t, t / tot))
 open(R + "profiles/%s_launches_raw.csv" % TAG, "w").write(open(R + "gpurun_out/%s_launches.csv" % TAG).read())
-desc = {"k_linearize": "512^3 trajectory workload, one GN iteration", "k_fuse_traj": "512^3 trajectory frame: k_fuse_cert then k_fuse_exact",
-        "k_fuse_dense": "512^3 dense micro-benchmark: every voxel updated", "k_mesh": "512^3, volume fused from 10 trajectory frames: count sweep then emit sweep"}
+desc = {"k_linearize": "512^3 trajectory workload, one GN iteration" + (", --cache-control none (steady state of iterations 2..10)" if TAG != "r01" else ""),
+        "k_fuse_traj": "512^3 trajectory frame: k_fuse_plan, k_fuse_cert, k_fuse_exact" if TAG != "r01" else "512^3 trajectory frame: k_fuse_cert then k_fuse_exact",
+        "k_fuse_dense": "512^3 dense micro-benchmark: every voxel updated",
+        "k_mesh": "512^3, volume fused from 10 trajectory frames: " + ("one sweep (count + surface-cell list) then the list emit" if TAG != "r01" else "count sweep then emit sweep")}
+if TAG != "r01":
+    desc["k_color"] = "512^3 dense colour pass (48 B per voxel): k_fuse_cert (rows certified free bypass the queue) then k_fuse_exact<colour>"
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 traffic = {}
 for f in desc:
@@ -36,6 +40,7 @@ for f in desc:
     traffic[f] = sum(float(a) * UNIT[b] for a, b in re.findall(r"dram__bytes_(?:read|write).sum\s+([0-9.]+) (\w+)", summ))
     print(f, n, "kernels, dram traffic %.1f MB" % (traffic[f] / 1e6), re.findall(r"gpu__time_duration.sum\s+([0-9.]+)", summ))
 json.dump({"fuse_dense": traffic["k_fuse_dense"], "fuse_trajectory": traffic["k_fuse_traj"], "k_linearize": traffic["k_linearize"], "mesh": traffic["k_mesh"],
+           "color_dense": traffic.get("k_color"),
            "source": "profiles/%s_k_fuse_dense_summary.txt, %s_k_fuse_traj_summary.txt, %s_k_linearize_summary.txt, %s_k_mesh_summary.txt (ncu --set full, "
                      "dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over the kernels of the stage; cold cache)" % (TAG, TAG, TAG, TAG)},
           open(R + "profiles/ncu_traffic.json", "w"), indent=1)

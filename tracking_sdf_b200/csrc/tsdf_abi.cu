@@ -464,6 +464,7 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
         A(cudaMalloc(&p->k0b.minmax, 2 * sizeof(unsigned int)));
         A(cudaMalloc(&p->k0b.grid_a, ncell * sizeof(float2)));
         A(cudaMalloc(&p->k0b.grid_b, ncell * sizeof(float2)));
+        A(cudaMalloc(&p->k0b.bins, npx * sizeof(short)));
         A(cudaMalloc(&p->k0b.zf, npx * sizeof(float)));
         A(cudaMalloc(&p->k0b.edge, npx));
         A(cudaMalloc(&p->k0b.DX, npx * sizeof(float4)));
@@ -561,7 +562,7 @@ tsdf_status tsdf_destroy(tsdf_handle h) {
     cudaFree(p->mc_count); cudaFree(p->mc_off); cudaFree(p->mc_tmp); cudaFree(p->mesh_xyz); cudaFree(p->mc_cells); cudaFree(p->mc_cell_counter);
     cudaFree(p->color); cudaFree(p->rgb4_buf[0]); cudaFree(p->rgb4_buf[1]); cudaFree(p->rgb_stage);
     cudaFree(p->cosn_buf[0]); cudaFree(p->cosn_buf[1]);
-    cudaFree(p->k0b.minmax); cudaFree(p->k0b.grid_a); cudaFree(p->k0b.grid_b); cudaFree(p->k0b.zf); cudaFree(p->k0b.edge);
+    cudaFree(p->k0b.minmax); cudaFree(p->k0b.grid_a); cudaFree(p->k0b.grid_b); cudaFree(p->k0b.bins); cudaFree(p->k0b.zf); cudaFree(p->k0b.edge);
     cudaFree(p->k0b.DX); cudaFree(p->k0b.DY); cudaFree(p->k0b.normals);
     cudaFree(p->grid); cudaFree(p->depth_stage); cudaFree(p->pose_dev);
     cudaFreeHost(p->pose_pin); cudaFreeHost(p->ring_pin); cudaFree(p->partials); cudaFree(p->ticket);

@@ -93,6 +93,7 @@ struct K0Params {
 struct K0Buffers {
     unsigned int* minmax;                  /* [0] ~bits(zmin), [1] bits(zmax) */
     float2 *grid_a, *grid_b;               /* bilateral grid, (sum z, count) per cell */
+    short* bins;                           /* depth bin of every pixel (-1 = none) */
     float* zf;                             /* filtered depth */
     uint8_t* edge;                         /* depth-discontinuity map */
     float4 *DX, *DY;                       /* central-difference 3-D gradients (+ validity) */

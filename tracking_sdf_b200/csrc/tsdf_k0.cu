@@ -15,7 +15,7 @@
  * atomics, compiled -fmad=false.  Optional stage (tsdf_config.preprocess): the benchmark inputs are noise free and
  * use K1's own normals; K0 is for real (noisy) sensor data.
  *
- * Seven small launches on the preprocessing stream, ahead of K1; they overlap the previous frame's tracking and
+ * Twelve small launches on the preprocessing stream, ahead of K1; they overlap the previous frame's tracking and
  * fusion like K1 does.
  */
 #include "tsdf_internal.h"
@@ -56,28 +56,50 @@ __global__ void __launch_bounds__(256) k0_minmax(K0Params P, const float* __rest
     }
 }
 
+/* depth bin of every pixel (-1 = no measurement): (int)((z - zmin) / sigma_r + 0.5f) + pad, clamped to the last bin */
+__global__ void __launch_bounds__(256) k0_bins(K0Params P, const float* __restrict__ depth, const unsigned int* mm, short* __restrict__ bins) {
+    const int n = P.img_w * P.img_h;
+    K0Dims d;
+    const bool okd = k0_dims(P, mm, d);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const float z = depth[p];
+        int bz = -1;
+        if (okd && k0_valid(z)) {
+            bz = (int)((z - d.zmin) / P.sigma_r + 0.5f) + K0_PAD;
+            if (bz > d.sd - 1 - K0_PAD) bz = d.sd - 1 - K0_PAD;
+        }
+        bins[p] = (short)bz;
+    }
+}
+
 /* splat: one thread per grid cell; the cell adds ITS pixels in row-major order (the oracle's order for that cell).
- * Writes every cell of both buffers (value / zero), so no clearing pass is needed. */
-__global__ void __launch_bounds__(128) k0_splat(K0Params P, const float* __restrict__ depth, const unsigned int* mm, float2* ga, float2* gb) {
+ * The pixels of a cell's column are the u (v) with (int)(u / sigma_s + 0.5f) == cu (cv): found once per thread as two
+ * bit masks over the candidate range, then the depth bin of each (precomputed) decides.  Writes every cell of both
+ * buffers (value / zero), so no clearing pass is needed. */
+__global__ void __launch_bounds__(128) k0_splat(K0Params P, const float* __restrict__ depth, const short* __restrict__ bins,
+                                                const unsigned int* mm, float2* ga, float2* gb) {
     K0Dims d;
     if (!k0_dims(P, mm, d)) return;
     const int sz = blockIdx.x * blockDim.x + threadIdx.x, sy = blockIdx.y, sx = blockIdx.z;
     if (sz >= d.sd || sy >= d.sh || sx >= d.sw) return;
     float sum = 0.0f, cnt = 0.0f;
-    const int cu = sx - K0_PAD, cv = sy - K0_PAD;            /* pixels u with (int)(u / sigma_s + 0.5f) == cu */
+    const int cu = sx - K0_PAD, cv = sy - K0_PAD;
     if (cu >= 0 && cv >= 0 && sz >= K0_PAD && sz <= d.sd - 1 - K0_PAD) {
-        const int span = (int)P.sigma_s + 2;
-        const int u_lo = max(0, (int)((float)cu * P.sigma_s) - span), u_hi = min(P.img_w - 1, (int)((float)cu * P.sigma_s) + span);
-        const int v_lo = max(0, (int)((float)cv * P.sigma_s) - span), v_hi = min(P.img_h - 1, (int)((float)cv * P.sigma_s) + span);
-        for (int v = v_lo; v <= v_hi; v++) {
-            if ((int)((float)v / P.sigma_s + 0.5f) != cv) continue;
-            for (int u = u_lo; u <= u_hi; u++) {
-                if ((int)((float)u / P.sigma_s + 0.5f) != cu) continue;
-                const float z = __ldg(&depth[(size_t)v * P.img_w + u]);
-                if (!k0_valid(z)) continue;
-                int bz = (int)((z - d.zmin) / P.sigma_r + 0.5f) + K0_PAD;
-                if (bz > d.sd - 1 - K0_PAD) bz = d.sd - 1 - K0_PAD;
-                if (bz == sz) { sum = sum + z; cnt = cnt + 1.0f; }
+        const int span = (int)P.sigma_s + 2;                 /* candidates: centre +- span (<= 31 each side for sigma_s <= 29) */
+        const int uc = (int)((float)cu * P.sigma_s), vc = (int)((float)cv * P.sigma_s);
+        unsigned long long mu = 0ull, mv = 0ull;
+        for (int q = 0; q <= 2 * span; q++) {
+            const int u = uc - span + q, v = vc - span + q;
+            if (u >= 0 && u < P.img_w && (int)((float)u / P.sigma_s + 0.5f) == cu) mu |= 1ull << q;
+            if (v >= 0 && v < P.img_h && (int)((float)v / P.sigma_s + 0.5f) == cv) mv |= 1ull << q;
+        }
+        for (int qv = 0; qv <= 2 * span; qv++) {
+            if (!((mv >> qv) & 1ull)) continue;
+            const size_t row = (size_t)(vc - span + qv) * P.img_w;
+            for (int qu = 0; qu <= 2 * span; qu++) {
+                if (!((mu >> qu) & 1ull)) continue;
+                const size_t p = row + (uc - span + qu);
+                if ((int)__ldg(&bins[p]) == sz) { sum = sum + __ldg(&depth[p]); cnt = cnt + 1.0f; }
             }
         }
     }
@@ -177,11 +199,14 @@ __global__ void __launch_bounds__(256) k0_normals(K0Params P, const float* __res
     __shared__ uint8_t s_edge[TH][TW];
     const int W = P.img_w, H = P.img_h;
     const int u0 = blockIdx.x * 32 - R, v0 = blockIdx.y * 8 - R;
+    int n_edge = 0;
     for (int t = threadIdx.x; t < TW * TH; t += 256) {
         const int tx = t % TW, ty = t / TW, uu = u0 + tx, vv = v0 + ty;
-        s_edge[ty][tx] = (uu >= 0 && vv >= 0 && uu < W && vv < H) ? edge[(size_t)vv * W + uu] : 0;   /* outside the image: no discontinuity */
+        const uint8_t e = (uu >= 0 && vv >= 0 && uu < W && vv < H) ? edge[(size_t)vv * W + uu] : 0;   /* outside the image: no discontinuity */
+        s_edge[ty][tx] = e;
+        n_edge += e;
     }
-    __syncthreads();
+    const bool any_edge = __syncthreads_or(n_edge) != 0;     /* smooth regions (most blocks): every distance is the cap */
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
     const int u = blockIdx.x * 32 + lx, v = blockIdx.y * 8 + ly;
     if (u >= W || v >= H) return;
@@ -192,6 +217,7 @@ __global__ void __launch_bounds__(256) k0_normals(K0Params P, const float* __res
     if (z == z) {
         float dist = P.smoothing;
         const int Rs = (int)P.smoothing;                     /* <= K0_RADIUS (checked at create) */
+        if (any_edge)
         for (int dv = -Rs; dv <= Rs; dv++)
             for (int du = -Rs; du <= Rs; du++) {
                 if (!s_edge[ly + R + dv][lx + R + du]) continue;
@@ -237,7 +263,8 @@ int launch_k0(const K0Params& P, const K0Buffers& B, const float* depth, cudaStr
     k0_minmax<<<64, 256, 0, s>>>(P, depth, B.minmax);
     const int sw = (int)((float)(P.img_w - 1) / P.sigma_s) + 1 + 2 * K0_PAD, sh = (int)((float)(P.img_h - 1) / P.sigma_s) + 1 + 2 * K0_PAD;
     const dim3 gcells((K0_SD_MAX + 127) / 128, sh, sw);
-    k0_splat<<<gcells, 128, 0, s>>>(P, depth, B.minmax, B.grid_a, B.grid_b);
+    k0_bins<<<148 * 2, 256, 0, s>>>(P, depth, B.minmax, B.bins);
+    k0_splat<<<gcells, 128, 0, s>>>(P, depth, B.bins, B.minmax, B.grid_a, B.grid_b);
     float2 *src = B.grid_a, *dst = B.grid_b;
     for (int dim = 0; dim < 3; dim++)
         for (int it = 0; it < 2; it++) {
@@ -249,7 +276,7 @@ int launch_k0(const K0Params& P, const K0Buffers& B, const float* depth, cudaStr
     k0_grad<<<gpx, 256, 0, s>>>(P, B.zf, B.edge, B.DX, B.DY);
     k0_normals<<<gpx, 256, 0, s>>>(P, B.zf, B.edge, B.DX, B.DY, B.normals);
     note_cuda(cudaGetLastError());
-    return 11;
+    return 12;
 }
 
 }  // namespace tsdf

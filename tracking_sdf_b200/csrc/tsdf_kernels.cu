@@ -94,6 +94,13 @@ __global__ void __launch_bounds__(256) k_prep(GridParams g, const float* __restr
 
 void launch_prep(const GridParams& g, const float* depth, const float4* nrm_in, PixRec* pix, float2* cert0, float4* pts, const uint8_t* rgb3, uchar4* rgb4, double* cosn, cudaStream_t s) {
     dim3 grid((g.img_w + 31) / 32, (g.img_h + 7) / 8);
+    if (nrm_in) {
+        /* K0 ran just before on this stream: its outputs are read through the read-only path here, so this launch
+         * is an ordinary one (it starts after K0 has completed), not a programmatic dependent launch */
+        k_prep<<<grid, 256, 0, s>>>(g, depth, nrm_in, pix, cert0, pts, rgb3, rgb4, cosn);
+        note_cuda(cudaGetLastError());
+        return;
+    }
     launch_pdl(k_prep, grid, dim3(256), s, g, depth, nrm_in, pix, cert0, pts, rgb3, rgb4, cosn);
 }
 
@@ -478,7 +485,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
             double vx, vy, vz;
             sample_coords_off(g, M, sT, off_x, off_y, off_z, (double)x, (double)y, (double)z, vx, vy, vz);
             /* camera_tracking.cpp:261-268: only the centre sample's (s = 0) verdict is used */
-            oob = (fmin(fmin(vx, vy), vz) < 0.0) | (fmax(fmax(vx, vy), vz) >= dm);
+            oob = (vx < 0.0) | (vy < 0.0) | (vz < 0.0) | (vx >= dm) | (vy >= dm) | (vz >= dm);   /* six compares: :261-268 verbatim */
             bool is_interp;
             val = interpolate_distance(vx, vy, vz, fetch, is_interp);
             ok = is_interp;
