@@ -40,6 +40,18 @@ def test_mesh_bit_exact(gpu_lib, frames, K, m):
     g.close(); o.close()
 
 
+def test_mesh_list_overflow_falls_back_to_two_sweeps(gpu_lib, frames, K, monkeypatch):
+    """The one-sweep mesher appends surface cells to a compact list; when the list is too small the extraction falls
+    back to the second sweep over the store and grows the list for the next call.  Both paths give the oracle's mesh."""
+    monkeypatch.setenv("TSDF_B200_MC_CELLS", "64")
+    o, g = fused_pair(64, K, frames, 3, color=False)
+    xo = o.mesh(0.0)[0]
+    x1 = g.mesh(0.0)[0]                      # list of 64 cells overflows: two-sweep fallback
+    x2 = g.mesh(0.0)[0]                      # list grown: one sweep + list emit
+    assert len(xo) > 3000 and np.array_equal(xo, x1) and np.array_equal(xo, x2)
+    g.close(); o.close()
+
+
 def test_mesh_of_empty_and_partially_seen_volume(gpu_lib, frames, K):
     depth, Rs, ts = frames
     g = T.Tsdf(T.default_config(m=32)); g.set_intrinsics(K)

@@ -91,6 +91,33 @@ def test_cross_device_exchange(gpu_lib, frames, K, n_dev):
     one.close(); grp.close()
 
 
+def test_dead_peer_is_reported_not_solved(gpu_lib, frames, K):
+    """A peer rank that never delivers its normal equations (here: its kernel is simply never launched).  The mailbox
+    wait is bounded (2 s); the rank must NOT solve with partial sums: the pose stays, the frame's GN loop ends and
+    the status is TSDF_ERR_PEER — through the synchronous call and through the pose ring of the streaming path alike
+    (ADVICE round 1).  Needs two devices."""
+    if gpu_lib.tsdf_device_count() < 2:
+        pytest.skip("needs 2 devices")
+    depth, Rs, ts = frames
+    kw = dict(m=64, gauss_newton_max_iteration=10, maximum_twist_diff=float("-inf"))
+    grp = T.ShardGroup(2, devices=[0, 1], **kw); grp.set_intrinsics(K)
+    grp.set_pose(Rs[0], ts[0]); grp.frame(depth[0], track=False, fuse=True)
+    a = grp.shards[0]                                  # drive rank 0 alone: rank 1 never joins
+    R0, t0 = a.get_pose()
+    with pytest.raises(T.TsdfError) as e:
+        a.track(depth[1])
+    assert e.value.status == 7
+    R1, t1 = a.get_pose()
+    assert np.array_equal(R0, R1) and np.array_equal(t0, t1)          # pose kept
+    dev = a.dev_alloc(depth[1].nbytes); a.dev_upload(dev, depth[1])
+    a.enqueue_frame(dev, track=1, slot=5); a.sync()
+    with pytest.raises(T.TsdfError) as e:
+        a.read_pose_ring(5)
+    assert e.value.status == 7
+    a.dev_free(dev)
+    grp.close()
+
+
 def test_too_small_halo_is_detected(gpu_lib, frames, K):
     depth, Rs, ts = frames
     grp = T.ShardGroup(4, m=128, halo=0)

@@ -1,6 +1,8 @@
 """Small end-to-end pass over every kernel family (64^3) for compute-sanitizer:
-prep, pyramid, linearize (+ GN update), fusion (tables, plan, cert, exact, items with skewed K), colour fusion,
-colour sampling, mesher, accessors, in-process z-slab shards.  Run as
+prep, pyramid, linearize (+ GN update), fusion (tables, plan, cert with affine end points, exact, items with skewed K),
+colour fusion (incl. the dense pose: rows certified free straight from the item list), colour sampling, the one-sweep
+mesher (list emit, and the two-sweep fallback on a list overflow), K0 (bilateral grid + window normals), accessors,
+in-process z-slab shards (micro-tile sweeps).  Run as
     compute-sanitizer --tool memcheck|racecheck|initcheck python tools/sanitize_probe.py"""
 import sys
 import numpy as np
@@ -30,6 +32,17 @@ Ks = K.copy(); Ks[1] = 2.0
 g = T.Tsdf(T.default_config(**kw)); g.set_intrinsics(Ks)
 g.fuse(depth[0], Rs[0], ts[0]); g.fuse_rgb(depth[1], synth.synth_rgb(depth[1], Rs[1], ts[1]), Rs[1], ts[1])
 g.close()
+# K0 on noisy / ragged depth, through the frame path
+gk = T.Tsdf(T.default_config(preprocess=1, **kw)); gk.set_intrinsics(K)
+noisy = synth.add_sensor_noise(depth, seed=3, dropout=0.02)
+gk.preprocess(noisy[0]); gk.fuse(noisy[0], Rs[0], ts[0]); gk.track_and_fuse(noisy[1])
+gk.preprocess(np.full_like(depth[0], np.nan))
+gk.close()
+# dense pose with colour: every row certified free -> exact<colour> consumes items directly; large mesh -> list overflow fallback
+gd = T.Tsdf(T.default_config(m=128)); gd.set_intrinsics(K); gd.enable_color()
+Rd = np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0]], float); td = np.array([0.0, -12.0, 1.25])
+gd.fuse_rgb(np.full((480, 640), 40.0, np.float32), np.full((480, 640, 3), 128, np.uint8), Rd, td)
+gd.close()
 grp = T.ShardGroup(2, **kw); grp.set_intrinsics(K); grp.set_pose(Rs[0], ts[0])
 grp.frame(depth[0], track=False, fuse=True); grp.frame(depth[1], track=True, fuse=True)
 grp.close()

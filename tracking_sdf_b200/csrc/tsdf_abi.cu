@@ -875,6 +875,8 @@ tsdf_status tsdf_mesh_extract(tsdf_handle h, float iso_level, int64_t* n_vertice
     }
     if (!p->mc_cells) {
         p->mc_cell_cap = 1u << 20;                                    /* grows to fit the surface, see below */
+        const char* cap_env = getenv("TSDF_B200_MC_CELLS");           /* tests: a tiny list forces the overflow fallback */
+        if (cap_env && atoi(cap_env) > 0) p->mc_cell_cap = (unsigned int)atoi(cap_env);
         CK(cudaMalloc(&p->mc_cells, (size_t)p->mc_cell_cap * sizeof(unsigned long long)));
     }
     McParams P;
