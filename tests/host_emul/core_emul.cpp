@@ -441,6 +441,72 @@ void emul_brick_stats(const GridParams* gp, const float* pix, const PoseState* p
     for (int q = 0; q < 16; q++) out[q] = c[q];
 }
 
+/* how many UNKNOWN units would per-VOXEL certificates resolve?  out: [0] units UNKNOWN at unit level, [1] of those: all four
+ * voxels individually certified SKIP, [2] all four individually certified (skip or front), [3] all four FRONT */
+void emul_voxel_cert_stats(const GridParams* gp, const float* pix, const PoseState* pose, int64_t out[8]) {
+    const GridParams& g = *gp;
+    const int m = g.m;
+    const double* Ri = pose->Rinv; const double* ti = pose->tinv;
+    const K1Params kp = k1_params(g.K);
+    CertPyramid P;
+    std::vector<std::vector<float>> zf(CERT_LEVELS), zb(CERT_LEVELS);
+    for (int l = 0; l < CERT_LEVELS; l++) {
+        P.w[l] = (g.img_w + (1 << l) - 1) >> l; P.h[l] = (g.img_h + (1 << l) - 1) >> l; P.off[l] = 0;
+        zf[l].assign((size_t)P.w[l] * P.h[l], 3.402823466e+38f); zb[l].assign((size_t)P.w[l] * P.h[l], -3.402823466e+38f);
+    }
+    for (int v = 0; v < g.img_h; v++)
+        for (int u = 0; u < g.img_w; u++) {
+            const float* q = pix + 4 * ((size_t)v * g.img_w + u);
+            PixRec r; r.z = q[0]; r.nx = q[1]; r.ny = q[2]; r.nz = q[3];
+            cert_pixel(g, kp, u, v, r, zf[0][(size_t)v * P.w[0] + u], zb[0][(size_t)v * P.w[0] + u]);
+        }
+    for (int l = 1; l < CERT_LEVELS; l++)
+        for (int y = 0; y < P.h[l - 1]; y++)
+            for (int x = 0; x < P.w[l - 1]; x++) {
+                const size_t o = (size_t)(y >> 1) * P.w[l] + (x >> 1), i = (size_t)y * P.w[l - 1] + x;
+                zf[l][o] = fminf(zf[l][o], zf[l - 1][i]); zb[l][o] = fmaxf(zb[l][o], zb[l - 1][i]);
+            }
+    auto fetch = [&](int level, int x, int y, float& f, float& b) { f = zf[level][(size_t)y * P.w[level] + x]; b = zb[level][(size_t)y * P.w[level] + x]; };
+    int64_t c[8] = {0};
+#pragma omp parallel
+    {
+        int64_t lc[8] = {0};
+#pragma omp for schedule(dynamic, 1)
+        for (int k = g.ks0; k < g.ks1; k++) {
+            const double gz = voxel_centre(g.vs_z, k, g.origin[2]);
+            const double pz0 = Ri[2] * gz, pz1 = Ri[5] * gz, pz2 = Ri[8] * gz;
+            for (int j = 0; j < m; j++) {
+                const double gy = voxel_centre(g.vs_y, j, g.origin[1]);
+                const double py0 = Ri[1] * gy, py1 = Ri[4] * gy, py2 = Ri[7] * gy;
+                int ilo = 0, ihi = m;
+                row_clip(g, Ri, ti, py0, py1, py2, pz0, pz1, pz2, ilo, ihi);
+                auto cam = [&](int x, double& X, double& Y, double& Z) {
+                    const double gx = voxel_centre(g.vs_x, x, g.origin[0]);
+                    X = ((Ri[0] * gx + py0) + pz0) + ti[0]; Y = ((Ri[3] * gx + py1) + pz1) + ti[1]; Z = ((Ri[6] * gx + py2) + pz2) + ti[2];
+                };
+                for (int x0 = ilo; x0 < ihi; x0 += 4) {
+                    double ax, ay, az, bx, by, bz;
+                    cam(x0, ax, ay, az); cam(x0 + 3, bx, by, bz);
+                    if (unit_certificate(g, P, ax, ay, az, bx, by, bz, fetch) != UNIT_UNKNOWN) continue;
+                    lc[0]++;
+                    int ns = 0, nf = 0;
+                    for (int v = 0; v < 4; v++) {
+                        cam(x0 + v, ax, ay, az);
+                        const int vv = unit_certificate(g, P, ax, ay, az, ax, ay, az, fetch);
+                        ns += vv == UNIT_SKIP; nf += vv == UNIT_FRONT;
+                    }
+                    if (ns == 4) lc[1]++;
+                    if (ns + nf == 4) lc[2]++;
+                    if (nf == 4) lc[3]++;
+                }
+            }
+        }
+#pragma omp critical
+        for (int q = 0; q < 8; q++) c[q] += lc[q];
+    }
+    for (int q = 0; q < 8; q++) out[q] = c[q];
+}
+
 /* SDF::interpolate_color through the kernels' core (k_sample_color) */
 void emul_interpolate_color(const GridParams* gp, const float* color, int64_t n, const double* gpts, float* rgba) {
     const GridParams& g = *gp;
