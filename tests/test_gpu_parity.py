@@ -170,6 +170,34 @@ def test_async_stream_path_equals_sync_path(gpu_lib, frames, K):
     a.close(); b.close()
 
 
+def test_submit_frame_buffer_ring_may_be_recycled_as_documented(gpu_lib, frames, K):
+    """tsdf_submit_frame: "the host buffer must stay valid until 4 later submissions returned".  A caller that takes
+    the contract literally keeps a ring of FIVE pinned buffers and overwrites buffer n % 5 right after submission
+    n + 4 has returned — far ahead of the GPU unless the library makes the host wait.  Poses and grid must equal the
+    run with one distinct buffer per frame (the lifetime rule was documented but not enforced)."""
+    from tracking_sdf_b200 import capi
+    depth, Rs, ts = frames
+    kw = dict(gauss_newton_max_iteration=10, maximum_twist_diff=float("-inf"))
+    a = T.Tsdf(T.default_config(m=128, **kw)); b = T.Tsdf(T.default_config(m=128, **kw))
+    for x in (a, b):
+        x.set_intrinsics(K); x.set_pose(Rs[0], ts[0])
+    n, NR = 12, 5
+    ring = capi.pinned_empty((NR,) + depth[0].shape, np.float32)
+    for f in range(n):
+        ring[f % NR][...] = depth[f]                      # overwrite the slot whose 4-later submission has returned
+        a.submit_frame(ring[f % NR], track=0 if f == 0 else 1, slot=f)
+        ring[f % NR - 4][...] = np.nan if f >= 4 else ring[f % NR - 4]   # poison the buffer of submission f - 4: it must be consumed by now
+    a.sync()
+    b.fuse(depth[0])
+    for f in range(1, n):
+        Rb, tb, sb, _ = b.track_and_fuse(depth[f])
+        Ra, ta, sa = a.read_pose_ring(f)
+        assert np.array_equal(Ra, Rb) and np.array_equal(ta, tb), f
+    Da, Wa = a.download(); Db, Wb = b.download()
+    assert np.array_equal(Da, Db) and np.array_equal(Wa, Wb)
+    a.close(); b.close()
+
+
 def test_host_streaming_path_equals_sync_path(gpu_lib, frames, K):
     """tsdf_submit_frame (copy stream + device frame ring, H2D of frame n+1 under compute of frame n)
     gives the same poses and grid as the synchronous host-buffer call."""

@@ -118,6 +118,22 @@ def test_dead_peer_is_reported_not_solved(gpu_lib, frames, K):
     grp.close()
 
 
+def test_group_handles_may_be_destroyed_in_any_order(gpu_lib, frames, K):
+    """Same-device shards share one stream (program order is the cross-shard dependency).  It is reference counted:
+    destroying shard 0 first must leave the others usable, and attaching twice is harmless."""
+    depth, Rs, ts = frames
+    grp = T.ShardGroup(3, m=64)
+    grp._ck(grp.L.tsdf_shard_attach_local(grp.arr, 3))            # second attach: no-op
+    grp.set_intrinsics(K); grp.set_pose(Rs[0], ts[0])
+    grp.frame(depth[0], track=False, fuse=True)
+    grp.shards[0].close()
+    R, t = grp.shards[1].get_pose()                               # syncs and copies on the shared stream
+    assert np.array_equal(R, Rs[0]) and np.array_equal(t, ts[0])
+    d, w = grp.shards[2].download()
+    assert d.shape[2] == grp.shards[2].stored_range()[1] - grp.shards[2].stored_range()[0]
+    grp.shards[2].close(); grp.shards[1].close()
+
+
 def test_too_small_halo_is_detected(gpu_lib, frames, K):
     depth, Rs, ts = frames
     grp = T.ShardGroup(4, m=128, halo=0)
