@@ -373,6 +373,42 @@ def k0_bench(T, m, K, n_frames, hbm):
     return out
 
 
+def ragged_bench(T, m, K, n_frames):
+    """The benchmark frames are complete (every pixel hits the analytic scene).  This sub-record pays for the invalid
+    paths too: the same frames with 5 % NaN speckle, a NaN block, a zero block and the outermost 12 pixel rings
+    missing (seed 99) — frames/s and the tracked path's error, device-resident."""
+    from tools import synth, evaluate_ate
+    depth, Rs, ts = synth.render_sequence(n_frames)
+    rng = np.random.default_rng(99)
+    d = depth.copy()
+    d[rng.random(d.shape) < 0.05] = np.nan
+    d[:, 100:160, 200:330] = np.nan
+    d[:, 300:330, 10:120] = 0.0
+    d[:, :12, :] = np.nan; d[:, -12:, :] = np.nan; d[:, :, :12] = np.nan; d[:, :, -12:] = np.nan
+    g = T.Tsdf(T.default_config(m=m, gauss_newton_max_iteration=GN_ITERS, maximum_twist_diff=float("-inf")))
+    g.set_intrinsics(K)
+    ring = g.pose_ring_capacity()
+    dev = g.dev_alloc(d.nbytes); g.dev_upload(dev, d)
+    fb = d[0].nbytes
+    g.set_pose(Rs[0], ts[0])
+    g.enqueue_frame(dev, track=0, slot=0)
+    for f in range(1, 5):
+        g.enqueue_frame(dev + f * fb, track=1, slot=f)
+    g.sync()
+    g.timer_begin()
+    for f in range(5, n_frames):
+        g.enqueue_frame(dev + f * fb, track=1, slot=f % ring)
+    ms = g.timer_end()
+    g.sync()
+    est = np.array([g.read_pose_ring(f % ring)[1] for f in range(1, n_frames)])
+    st = g.read_pose_ring((n_frames - 1) % ring)[2]
+    ate, _ = evaluate_ate.ate_rmse(est, ts[1:n_frames], do_align=True)
+    g.dev_free(dev); g.close()
+    return {"frames": n_frames, "invalid_pixel_fraction": float((~(np.isfinite(d) & (d > 0))).mean()),
+            "frames_per_s": (n_frames - 5) / (ms * 1e-3), "ate_rmse_m": ate, "n_valid_last": int(st["n_valid"]),
+            "note": "same trajectory frames with NaN speckle, NaN / zero blocks and a missing border: what the invalid-pixel paths cost"}
+
+
 def main_cuda(args):
     rank, world, local = dist_env()
     if world != args.gpus and world > 1:
@@ -567,6 +603,7 @@ def main_cuda(args):
         out["mesh"] = mesh
     if rank == 0 and n_gpus == 1 and not args.no_k0:
         out["preprocess_k0"] = k0_bench(T, m, K, 200, hbm)
+        out["ragged_depth"] = ragged_bench(T, m, K, 200)
     if rank == 0 and n_gpus == 1 and not args.no_cpu:
         nb = min(n_frames, 40)
         out["cpu_baseline"] = run_cpu_baseline(depth[:nb], Rs[:nb], ts[:nb], m, budget_s=args.cpu_budget, max_frames=nb - 1)

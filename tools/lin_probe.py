@@ -8,8 +8,10 @@ m = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 depth, Rs, ts = synth.render_sequence(8)
 g = T.Tsdf(T.default_config(m=m, gauss_newton_max_iteration=10, maximum_twist_diff=float("-inf")))
 g.set_intrinsics(synth.K_DEFAULT); g.set_pose(Rs[0], ts[0]); g.fuse(depth[0])
+import os
 for f in range(1, 6):
-    g.track_and_fuse(depth[f])
+    if os.environ.get("LIN_PROBE_GT"): g.fuse(depth[f], Rs[f], ts[f])      # experiment builds that cannot track
+    else: g.track_and_fuse(depth[f])
 for rep in range(4):
     t = g.debug_phase_times(depth[6])
     print("main loop %.2f us | to final block %.2f | reduce %.2f | update %.2f | total %.2f" % tuple(

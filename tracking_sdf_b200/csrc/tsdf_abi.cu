@@ -1433,6 +1433,40 @@ tsdf_status tsdf_debug_stream_rmw(tsdf_handle h, int32_t reps, float* ms) {
     return TSDF_OK;
 }
 
+#ifdef TSDF_SWZ_EXPERIMENT
+/* layout experiment (variant builds only): time `reps` linearisations (no pose update) at the current pose on the
+ * store as it is and on a swizzled copy; out_ms[0], out_ms[1] = mean ms per launch; sums_equal = the 30 sums match bitwise */
+tsdf_status tsdf_debug_swizzle_probe(tsdf_handle h, const float* depth, int32_t mem, int32_t reps, float out_ms[2], int32_t* sums_equal) {
+    Impl* p = I(h);
+    CK(cudaSetDevice(p->device));
+    const float* dptr;
+    tsdf_status st = stage_depth(p, depth, mem, &dptr);
+    if (st != TSDF_OK) return st;
+    float2* swz = nullptr;
+    CK(cudaMalloc(&swz, (size_t)p->n_stored * sizeof(float2)));
+    launch_swizzle(p->g, p->grid, swz, p->stream);
+    enqueue_prep(p, dptr, 1);
+    double sums[2][30];
+    for (int v = 0; v < 2; v++) {
+        LinearizeArgs a = lin_args(p, 0, false);
+        if (v == 1) a.grid = swz;
+        auto go = [&]() { if (v == 0) launch_linearize(a, p->lin_blocks, 0, 0ull, p->stream); else launch_linearize_swz(a, p->lin_blocks, p->stream); };
+        go(); go();
+        CK(cudaEventRecord(p->tmr[0], p->stream));
+        for (int r = 0; r < reps; r++) go();
+        CK(cudaEventRecord(p->tmr[1], p->stream));
+        CK(cudaEventSynchronize(p->tmr[1]));
+        float t = 0; CK(cudaEventElapsedTime(&t, p->tmr[0], p->tmr[1]));
+        out_ms[v] = t / reps;
+        st = fetch_pose(p); if (st != TSDF_OK) return st;
+        memcpy(sums[v], p->pose_pin->sums, sizeof sums[v]);
+    }
+    *sums_equal = memcmp(sums[0], sums[1], sizeof sums[0]) == 0 ? 1 : 0;
+    cudaFree(swz);
+    return launch_status();
+}
+#endif
+
 tsdf_status tsdf_total_updates(tsdf_handle h, int32_t reset, int64_t* total) {
     if (!h) return bad("null handle");
     Impl* p = I(h);

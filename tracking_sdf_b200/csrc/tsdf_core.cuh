@@ -101,8 +101,8 @@ TSDF_HD float rcp_rn_small(float x) {
 /* ---- the reference's (int) casts: x86 cvttss2si — truncation toward zero, NaN and
  * out-of-range give INT_MIN.  sdf.cpp:143-145 ---- */
 TSDF_HD int trunc_f2i(float v) {
-    if (!(v >= -2147483648.0f && v < 2147483648.0f)) return INT_MIN;
-    return (int)v;
+    /* |v| < 2^31, else INT_MIN (v = -2^31 converts to INT_MIN either way; NaN fails the compare): one compare + select */
+    return (fabsf(v) < 2147483648.0f) ? (int)v : INT_MIN;
 }
 
 /* `volume < 0.00001` compares the float promoted to double against a double literal
@@ -703,6 +703,8 @@ TSDF_HD void row_clip(const GridParams& g, const double* Ri, const double* ti,
     const double Wd = (double)g.img_w, Hd = (double)g.img_h;
     clip_constraint(az, bz, span, lo, hi, empty);                               /* z >= 0 */
     if (g.k_simple) {
+        /* all five constraints are evaluated without early exits: their divisions are independent and overlap
+         * (early returns were measured slower: they serialise the chain in a latency-bound kernel) */
         const double a0 = g.K[0] * ax + g.K[2] * az, b0 = g.K[0] * bx + g.K[2] * bz;   /* ij0 */
         const double a1 = g.K[4] * ay + g.K[5] * az, b1 = g.K[4] * by + g.K[5] * bz;   /* ij1 */
         clip_constraint(a0 + az, b0 + bz, span, lo, hi, empty);                 /* u > -1     */

@@ -21,7 +21,7 @@ constexpr int LIN_TW = LIN_TW_DEF, LIN_TH = LIN_TH_DEF;      /* strided-pixel ti
 constexpr int LIN_PARTIAL_STRIDE = 32;    /* doubles per block partial (30 used) */
 constexpr int MAX_WORLD = 16;
 #ifndef LIN_GROUP_DEF
-#define LIN_GROUP_DEF 16
+#define LIN_GROUP_DEF 32
 #endif
 constexpr int LIN_GROUP = LIN_GROUP_DEF;  /* blocks per first-level reduction group */
 constexpr int FUSE_THREADS = 128;
@@ -109,6 +109,10 @@ void launch_pyramid(const CertPyramid& P, float2* cert, unsigned int* ticket, cu
  * launch_gn_combine sums in rank order).  seqno labels the exchange. */
 void launch_linearize(const LinearizeArgs& a, int nblk, int exchange_mode, unsigned long long seqno, cudaStream_t s);
 void launch_gn_combine(const LinearizeArgs& a, unsigned long long seqno, cudaStream_t s);
+#ifdef TSDF_SWZ_EXPERIMENT
+void launch_swizzle(const GridParams& g, const float2* src, float2* dst, cudaStream_t s);
+void launch_linearize_swz(const LinearizeArgs& a, int nblk, cudaStream_t s);
+#endif
 struct FuseArgs {
     GridParams g;
     float2* grid;

@@ -124,7 +124,33 @@ void launch_cloud(const GridParams& g, const PixRec* pix, float* cloud, float* n
 /* ------------------------------------------------------------------------------------------
  * voxel fetch used by the tracker and the sampler: {D,W} interleaved, x-fastest, read-only path
  * ------------------------------------------------------------------------------------------ */
-template <bool IDX32 = false>
+#ifdef TSDF_SWZ_EXPERIMENT
+#define SWZ_TPARAM , bool SWZ = false
+#define SWZ_ON SWZ
+#else
+#define SWZ_TPARAM
+#define SWZ_ON false
+#endif
+#ifdef TSDF_SWZ_EXPERIMENT
+#ifndef TSDF_SWZ_MODE
+#define TSDF_SWZ_MODE 0
+#endif
+/* experimental layouts (element index of voxel (i, j, kk = k - ks0)):
+ * 0: 2 x 2 (j,k) micro-tiles interleaved per i     1: 4 x 4 (j,k) tiles interleaved per i
+ * 2: 4 x 4 x 4 bricks, i fastest inside a brick     3: 8(i) x 2 x 2 bricks */
+__host__ __device__ __forceinline__ unsigned swz_index(unsigned um, unsigned i, unsigned j, unsigned k) {
+#if TSDF_SWZ_MODE == 0
+    return (((k >> 1) * (um >> 1) + (j >> 1)) * um + i) * 4u + ((k & 1u) << 1) + (j & 1u);
+#elif TSDF_SWZ_MODE == 1
+    return (((k >> 2) * (um >> 2) + (j >> 2)) * um + i) * 16u + ((k & 3u) << 2) + (j & 3u);
+#elif TSDF_SWZ_MODE == 2
+    return ((((k >> 2) * (um >> 2) + (j >> 2)) * (um >> 2) + (i >> 2)) << 6) + ((k & 3u) << 4) + ((j & 3u) << 2) + (i & 3u);
+#else
+    return ((((k >> 1) * (um >> 1) + (j >> 1)) * (um >> 3) + (i >> 3)) << 5) + ((k & 1u) << 4) + ((j & 1u) << 3) + (i & 7u);
+#endif
+}
+#endif
+template <bool IDX32 = false SWZ_TPARAM>
 struct GridFetchT {
     const float2* grid;                                   /* written by the previous frame's fusion: ordinary loads (ld_dep) */
     int m, ks0, ks1;
@@ -132,6 +158,15 @@ struct GridFetchT {
     __device__ __forceinline__ bool operator()(int ci, int cj, int ck, float& d, float& w) const {
         if ((unsigned)ci >= (unsigned)m || (unsigned)cj >= (unsigned)m || (unsigned)ck >= (unsigned)m) return false;   /* sdf.h:114-119 */
         if (ck < ks0 || ck >= ks1) { *miss = 1; d = 0.0f; w = 0.0f; return true; }   /* not held by this shard */
+        if (SWZ_ON) {      /* experiment: 2 x 2 (j,k) micro-tiles interleaved per i */
+#ifdef TSDF_SWZ_EXPERIMENT
+            const float2 dws = ld_dep(&grid[swz_index((unsigned)m, (unsigned)ci, (unsigned)cj, (unsigned)(ck - ks0))]);
+#else
+            const float2 dws = make_float2(0.f, 0.f);
+#endif
+            d = dws.x; w = dws.y;
+            return true;
+        }
         const float2 dw = ld_dep(&grid[((size_t)(ck - ks0) * m + cj) * m + ci]);
         d = dw.x; w = dw.y;
         return true;
@@ -144,9 +179,27 @@ struct GridFetchT {
      * pointers is one IMAD.WIDE (index * 8 + base) instead of a chain of 64-bit multiplies and adds. */
     __device__ __forceinline__ void load8(int bi, int bj, int bk, float* d, float* w) const {
         const float2 *p00, *p01, *p10, *p11;                           /* rows (jo, ko) */
+        if (SWZ_ON) {
+#ifdef TSDF_SWZ_EXPERIMENT
+            const unsigned um = (unsigned)m, i0 = (unsigned)bi, j0 = (unsigned)bj, k0 = (unsigned)(bk - ks0);
+            const float2 v0 = ld_dep(grid + swz_index(um, i0, j0, k0)), v1 = ld_dep(grid + swz_index(um, i0, j0, k0 + 1));
+            const float2 v2 = ld_dep(grid + swz_index(um, i0, j0 + 1, k0)), v3 = ld_dep(grid + swz_index(um, i0, j0 + 1, k0 + 1));
+            const float2 v4 = ld_dep(grid + swz_index(um, i0 + 1, j0, k0)), v5 = ld_dep(grid + swz_index(um, i0 + 1, j0, k0 + 1));
+            const float2 v6 = ld_dep(grid + swz_index(um, i0 + 1, j0 + 1, k0)), v7 = ld_dep(grid + swz_index(um, i0 + 1, j0 + 1, k0 + 1));
+#else
+            const float2 v0 = make_float2(0.f, 0.f), v1 = v0, v2 = v0, v3 = v0, v4 = v0, v5 = v0, v6 = v0, v7 = v0;
+#endif
+            d[0] = v0.x; w[0] = v0.y; d[1] = v1.x; w[1] = v1.y; d[2] = v2.x; w[2] = v2.y; d[3] = v3.x; w[3] = v3.y;
+            d[4] = v4.x; w[4] = v4.y; d[5] = v5.x; w[5] = v5.y; d[6] = v6.x; w[6] = v6.y; d[7] = v7.x; w[7] = v7.y;
+            return;
+        }
         if (IDX32) {
             const unsigned um = (unsigned)m;
+#ifdef TSDF_X_HOTLOAD   /* experiment: every gather falls into the same four lines ("perfect memory") */
+            const unsigned i00 = (((unsigned)(bk - ks0) * um + (unsigned)bj) * um + (unsigned)bi) & 7u;
+#else
             const unsigned i00 = ((unsigned)(bk - ks0) * um + (unsigned)bj) * um + (unsigned)bi;
+#endif
             const unsigned smm = um * um;
             p00 = grid + i00; p01 = grid + (i00 + smm); p10 = grid + (i00 + um); p11 = grid + (i00 + um + smm);
         } else {
@@ -384,7 +437,7 @@ __device__ void gn_update_warp(const GridParams& g, PoseState* pose, const doubl
     }
 }
 
-template <bool IDX32>
+template <bool IDX32 SWZ_TPARAM>
 __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(LinearizeArgs a, int exchange_mode, unsigned long long seqno) {
     __shared__ double sM[7][9];
     __shared__ double sT[3];
@@ -395,6 +448,80 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
 
     const GridParams& g = a.g;
     PoseState* pose = a.pose;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = lane >> 4, s = lane & 15, base = grp << 4;
+    const bool sharded = (g.ko0 > 0 || g.ko1 < g.m);
+    /* rot, trans and the six perturbed rotations (camera_tracking.cpp:92-145: (I +- w_h [e_k]x) * rot) into shared memory */
+    auto stage_pose = [&]() {
+        if (tid < 9) sM[0][tid] = pose->R[tid];
+        if (tid < 3) sT[tid] = pose->t[tid];
+        if (tid >= 32 && tid < 32 + 54) {
+            const int q = (tid - 32) / 9, e = (tid - 32) % 9, r = e / 3, c = e % 3;
+            const double w_h = (double)g.w_h;
+            /* row r of the perturbation matrix q; same values and product order as perturbed_rot() */
+            double d0 = (r == 0) ? 1.0 : 0.0, d1 = (r == 1) ? 1.0 : 0.0, d2 = (r == 2) ? 1.0 : 0.0;
+            const double sgn = (q & 1) ? -1.0 : 1.0;
+            const int axis = q >> 1;
+            if (axis == 0) { if (r == 1) d2 = -sgn * w_h; if (r == 2) d1 = sgn * w_h; }
+            if (axis == 1) { if (r == 0) d2 = sgn * w_h; if (r == 2) d0 = -sgn * w_h; }
+            if (axis == 2) { if (r == 0) d1 = -sgn * w_h; if (r == 1) d0 = sgn * w_h; }
+            sM[1 + q][e] = (d0 * pose->R[c] + d1 * pose->R[3 + c]) + d2 * pose->R[6 + c];
+        }
+    };
+    /* each block owns a LIN_TW x LIN_TH tile of the strided pixel grid (columns x rows), so its
+     * samples touch a compact piece of the volume and share voxel lines in L1.
+     *
+     * Sharded volumes: a rank linearises only the pixels whose centre cell it owns — a compact region of the image —
+     * and with one tile per block the launch would still last as long as its slowest (fully owned) tile.  So the
+     * sweeps of a block are spread over the image instead: sweep q of block b takes the 4 x 4 micro-tile
+     * b + q * gridDim.x, owned micro-tiles end up evenly over all blocks and a rank that owns 1/G of the pixels
+     * finishes its pixel loop in about 1/G of the time.  (Same pixels, same per-block order every launch: the
+     * reduction stays deterministic.) */
+    constexpr int PX_SWEEP = (LIN_THREADS / 32) * 2;                         /* 16 pixels per sweep */
+    constexpr int STAGED = ((LIN_TW * LIN_TH + PX_SWEEP - 1) / PX_SWEEP) * PX_SWEEP;
+    __shared__ float4 sPts[STAGED];
+    const int tiles_y = (g.nj + LIN_TH - 1) / LIN_TH;
+    const int tile_x = blockIdx.x / tiles_y, tile_y = blockIdx.x - tile_x * tiles_y;
+    const int mty = (g.nj + 3) >> 2, n_micro = ((g.ni + 3) >> 2) * mty;
+    const int n_sweeps = sharded ? (n_micro + (int)gridDim.x - 1) / (int)gridDim.x : (LIN_TW * LIN_TH + PX_SWEEP - 1) / PX_SWEEP;
+    /* pixel tl of sweep q -> strided pixel (ii, jj); false when the slot is empty */
+    auto pixel_of = [&](int q, int tl, int& ii, int& jj) -> bool {
+        if (sharded) {
+            const int mt = (int)blockIdx.x + q * (int)gridDim.x;
+            const int mx = mt / mty, my = mt - mx * mty;
+            ii = (mx << 2) + (tl >> 2); jj = (my << 2) + (tl & 3);
+            return (PX_SWEEP == 16) & (mt < n_micro) & (ii < g.ni) & (jj < g.nj);
+        }
+        const int t = q * PX_SWEEP + tl;
+        ii = tile_x * LIN_TW + t / LIN_TH; jj = tile_y * LIN_TH + t % LIN_TH;
+        return (t < LIN_TW * LIN_TH) & (ii < g.ni) & (jj < g.nj);
+    };
+    /* everything that does not depend on the pose is set up before the dependency wait */
+    const int a0 = c_slot_a[s], b0 = c_slot_b[s];
+    const int a1 = c_slot_a[s + 16], b1 = c_slot_b[s + 16], k1 = c_slot_k[s + 16];
+    const K1Params kp = k1_params(g.K);
+    const float step = (s == 0) ? g.v_h2_width : (s == 1) ? g.v_h2_height : (s == 2) ? g.v_h2_depth : g.two_w_h;
+    const double* M = sM[(s < 7) ? 0 : (s - 6)];
+    int miss = 0;
+#ifdef TSDF_SWZ_EXPERIMENT
+    GridFetchT<IDX32, SWZ> fetch{a.grid, g.m, g.ks0, g.ks1, &miss};
+#else
+    GridFetchT<IDX32> fetch{a.grid, g.m, g.ks0, g.ks1, &miss};
+#endif
+
+    const double dm = (double)g.m;
+    double off_x, off_y, off_z;
+    sample_offsets(g, s, off_x, off_y, off_z);
+    /* The back-projected points come from the preprocessing stream (joined by an event before the frame's first
+     * launch), not from the predecessor in the PDL chain: the block stages its pixels in shared memory BEFORE the
+     * dependency wait, in the shadow of the previous launch's reduction and solve, and no sweep starts with an L2
+     * round trip. */
+    for (int e = tid; e < STAGED; e += LIN_THREADS) {
+        int ii, jj;
+        float4 pt = make_float4(0.0f, 0.0f, __int_as_float(0x7fc00000), 0.0f);
+        if (e < n_sweeps * PX_SWEEP && pixel_of(e / PX_SWEEP, e % PX_SWEEP, ii, jj)) pt = __ldg(&a.pts[ii * g.nj + jj]);
+        sPts[e] = pt;
+    }
     pdl_wait();
     pdl_release();
     /* a.first: first launch of a frame; the per-frame state (iterations, stopped, singular,
@@ -402,71 +529,23 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
      * another stream and never touches the pose block */
     if (a.do_update && !a.first && pose->stopped) return;  /* loop condition of camera_tracking.cpp:79 */
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (a.dbg_times && tid == 0) atomicMin(&a.dbg_times[0], gtime());
-    if (tid < 9) sM[0][tid] = pose->R[tid];
-    if (tid < 3) sT[tid] = pose->t[tid];
+    stage_pose();
     if (tid == 0) sMiss = 0;
-    if (tid >= 32 && tid < 32 + 54) {                     /* camera_tracking.cpp:92-145: (I +- w_h [e_k]x) * rot */
-        const int q = (tid - 32) / 9, e = (tid - 32) % 9, r = e / 3, c = e % 3;
-        const double w_h = (double)g.w_h;
-        /* row r of the perturbation matrix q; same values and product order as perturbed_rot() */
-        double d0 = (r == 0) ? 1.0 : 0.0, d1 = (r == 1) ? 1.0 : 0.0, d2 = (r == 2) ? 1.0 : 0.0;
-        const double sgn = (q & 1) ? -1.0 : 1.0;
-        const int axis = q >> 1;
-        if (axis == 0) { if (r == 1) d2 = -sgn * w_h; if (r == 2) d1 = sgn * w_h; }
-        if (axis == 1) { if (r == 0) d2 = sgn * w_h; if (r == 2) d0 = -sgn * w_h; }
-        if (axis == 2) { if (r == 0) d1 = -sgn * w_h; if (r == 1) d0 = sgn * w_h; }
-        sM[1 + q][e] = (d0 * pose->R[c] + d1 * pose->R[3 + c]) + d2 * pose->R[6 + c];
-    }
     __syncthreads();
 
-    const int grp = lane >> 4, s = lane & 15, base = grp << 4;
-    const int a0 = c_slot_a[s], b0 = c_slot_b[s];
-    const int a1 = c_slot_a[s + 16], b1 = c_slot_b[s + 16], k1 = c_slot_k[s + 16];
-    const K1Params kp = k1_params(g.K);
-    const float step = (s == 0) ? g.v_h2_width : (s == 1) ? g.v_h2_height : (s == 2) ? g.v_h2_depth : g.two_w_h;
-    const double* M = sM[(s < 7) ? 0 : (s - 6)];
-    int miss = 0;
-    GridFetchT<IDX32> fetch{a.grid, g.m, g.ks0, g.ks1, &miss};
-
-    const bool sharded = (g.ko0 > 0 || g.ko1 < g.m);
-    const double dm = (double)g.m;
-    double off_x, off_y, off_z;
-    sample_offsets(g, s, off_x, off_y, off_z);
-    /* each block owns a LIN_TW x LIN_TH tile of the strided pixel grid (columns x rows), so its
-     * samples touch a compact piece of the volume and share voxel lines in L1 */
-    const int tiles_y = (g.nj + LIN_TH - 1) / LIN_TH;
-    const int tile_x = blockIdx.x / tiles_y, tile_y = blockIdx.x - tile_x * tiles_y;
     double acc0 = 0.0, acc1 = 0.0;
-
-    /* Sharded volumes: a rank linearises only the pixels whose centre cell it owns — a compact region of the image —
-     * and with one tile per block the launch would still last as long as its slowest (fully owned) tile.  So the
-     * sweeps of a block are spread over the image instead: sweep q of block b takes the 4 x 4 micro-tile
-     * b + q * gridDim.x, owned micro-tiles end up evenly over all blocks and a rank that owns 1/G of the pixels
-     * finishes its pixel loop in about 1/G of the time.  (Same pixels, same per-block order every launch: the
-     * reduction stays deterministic.) */
-    constexpr int PX_SWEEP = (LIN_THREADS / 32) * 2;                         /* 16 pixels per sweep */
-    const int mty = (g.nj + 3) >> 2, n_micro = ((g.ni + 3) >> 2) * mty;
-    const int n_sweeps = sharded ? (n_micro + (int)gridDim.x - 1) / (int)gridDim.x : (LIN_TW * LIN_TH + PX_SWEEP - 1) / PX_SWEEP;
     for (int q = 0; q < n_sweeps; q++) {                                     /* warp-uniform trip count */
-        const int t0 = q * PX_SWEEP;
-        const int t = t0 + warp * 2 + grp;
+        const int tl = warp * 2 + grp;
         int ii, jj;
-        bool have;
-        if (sharded) {
-            const int mt = (int)blockIdx.x + q * (int)gridDim.x, tl = warp * 2 + grp;
-            const int mx = mt / mty, my = mt - mx * mty;
-            ii = (mx << 2) + (tl >> 2); jj = (my << 2) + (tl & 3);
-            have = (PX_SWEEP == 16) & (mt < n_micro) & (ii < g.ni) & (jj < g.nj);
-        } else {
-            ii = tile_x * LIN_TW + t / LIN_TH; jj = tile_y * LIN_TH + t % LIN_TH;
-            have = (t < LIN_TW * LIN_TH) & (ii < g.ni) & (jj < g.nj);
-        }
+        const bool have = pixel_of(q, tl, ii, jj);
         const int p = ii * g.nj + jj;                                        /* reference loop order, camera_tracking.cpp:162-163 */
         float x = 0.0f, y = 0.0f, z = __int_as_float(0x7fc00000);
-        if (have) {
-            const float4 pt = __ldg(&a.pts[p]);                              /* back-projected by k_prep; z = NaN when invalid */
+        if (q * PX_SWEEP < STAGED) {
+            const float4 pt = sPts[q * PX_SWEEP + tl];                       /* back-projected by k_prep; z = NaN when invalid */
+            x = pt.x; y = pt.y; z = pt.z;
+        } else if (have) {                                                   /* more sweeps than staged slots (sharded, small grids) */
+            const float4 pt = __ldg(&a.pts[p]);
             x = pt.x; y = pt.y; z = pt.z;
         }
         const bool valid_pt = have && (z == z);                              /* camera_tracking.cpp:168 */
@@ -485,7 +564,20 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
             double vx, vy, vz;
             sample_coords_off(g, M, sT, off_x, off_y, off_z, (double)x, (double)y, (double)z, vx, vy, vz);
             /* camera_tracking.cpp:261-268: only the centre sample's (s = 0) verdict is used */
-            oob = (vx < 0.0) | (vy < 0.0) | (vz < 0.0) | (vx >= dm) | (vy >= dm) | (vz >= dm);   /* six compares: :261-268 verbatim */
+            /* camera_tracking.cpp:261-268 verbatim: six ordered compares (false for NaN), chained on one predicate —
+             * written out because the compiler otherwise folds them into fp64 min/max with NaN fix-ups (~30 instructions) */
+            {
+                unsigned o;
+                asm("{\n\t.reg .pred p;\n\t"
+                    "setp.lt.f64 p, %1, 0d0000000000000000;\n\t"
+                    "setp.lt.or.f64 p, %2, 0d0000000000000000, p;\n\t"
+                    "setp.lt.or.f64 p, %3, 0d0000000000000000, p;\n\t"
+                    "setp.ge.or.f64 p, %1, %4, p;\n\t"
+                    "setp.ge.or.f64 p, %2, %4, p;\n\t"
+                    "setp.ge.or.f64 p, %3, %4, p;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(o) : "d"(vx), "d"(vy), "d"(vz), "d"(dm));
+                oob = o != 0u;
+            }
             bool is_interp;
             val = interpolate_distance(vx, vy, vz, fetch, is_interp);
             ok = is_interp;
@@ -640,6 +732,21 @@ void launch_linearize(const LinearizeArgs& a, int nblk, int exchange_mode, unsig
     if (n_stored < (1ull << 32) && !a.force_idx64) launch_pdl(k_linearize<true>, dim3(nblk), dim3(LIN_THREADS), s, a, exchange_mode, seqno);
     else launch_pdl(k_linearize<false>, dim3(nblk), dim3(LIN_THREADS), s, a, exchange_mode, seqno);
 }
+#ifdef TSDF_SWZ_EXPERIMENT
+/* layout experiment: a swizzled COPY of the store (2 x 2 (j,k) micro-tiles interleaved per i) for the tracker only */
+__global__ void k_swizzle(GridParams g, const float2* __restrict__ src, float2* __restrict__ dst) {
+    const unsigned um = (unsigned)g.m;
+    const size_t n = (size_t)(g.ks1 - g.ks0) * um * um;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const unsigned i = (unsigned)(q % um), j = (unsigned)((q / um) % um), k = (unsigned)(q / ((size_t)um * um));
+        dst[swz_index(um, i, j, k)] = src[q];
+    }
+}
+void launch_swizzle(const GridParams& g, const float2* src, float2* dst, cudaStream_t s) { k_swizzle<<<148 * 8, 256, 0, s>>>(g, src, dst); }
+void launch_linearize_swz(const LinearizeArgs& a, int nblk, cudaStream_t s) {
+    launch_pdl(k_linearize<true, true>, dim3(nblk), dim3(LIN_THREADS), s, a, 0, 0ull);
+}
+#endif
 void launch_gn_combine(const LinearizeArgs& a, unsigned long long seqno, cudaStream_t s) {
     launch_pdl(k_gn_combine, dim3(1), dim3(32), s, a, seqno);
 }
