@@ -28,6 +28,7 @@ void emul_params(int m, float width, float height, float depth, const double ori
     g->metric = metric; g->img_w = img_w; g->img_h = img_h; g->stride = stride;
     g->ni = (img_w + stride - 1) / stride; g->nj = (img_h + stride - 1) / stride;
     g->m_div_height = m / height; g->m_div_width = m / width; g->m_div_depth = m / depth;
+    g->m_div_d[0] = (double)g->m_div_width; g->m_div_d[1] = (double)g->m_div_height; g->m_div_d[2] = (double)g->m_div_depth;
     g->vs_x = width / ((float)m); g->vs_y = height / ((float)m); g->vs_z = depth / ((float)m);
     g->delta = delta; g->eps = eps; g->v_h = v_h; g->w_h = w_h;
     const float v_h2 = 2 * v_h;

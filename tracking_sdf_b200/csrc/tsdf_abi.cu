@@ -160,6 +160,7 @@ void build_params(const tsdf_config& c, GridParams& g) {
     g.m_div_height = c.m / c.height;                       /* sdf.cpp:19-21 */
     g.m_div_width = c.m / c.width;
     g.m_div_depth = c.m / c.depth;
+    g.m_div_d[0] = (double)g.m_div_width; g.m_div_d[1] = (double)g.m_div_height; g.m_div_d[2] = (double)g.m_div_depth;
     g.vs_x = c.width / ((float)c.m);                       /* sdf.h:154-156 */
     g.vs_y = c.height / ((float)c.m);
     g.vs_z = c.depth / ((float)c.m);

@@ -35,6 +35,8 @@ struct GridParams {
     int32_t stride;            /* pixel stride of the tracker */
     int32_t ni, nj;            /* strided pixel grid (columns, rows) */
     float m_div_width, m_div_height, m_div_depth;      /* sdf.cpp:19-21 (fp32) */
+    double m_div_d[3];         /* the same three fp32 values widened once on the host: a constant-bank operand instead of a
+                                * float -> double conversion per use */
     float vs_x, vs_y, vs_z;    /* extent / (float)m, the fp32 quotient of sdf.h:154-156 */
     float delta, eps;          /* sdf.cpp:8 */
     float v_h, w_h;            /* camera_tracking.cpp:11-12 */
@@ -113,9 +115,9 @@ TSDF_HD int trunc_f2i(float v) {
 /* sdf.h:143-147 */
 TSDF_HD void world_to_voxel(const GridParams& g, double wx, double wy, double wz,
                             double& vx, double& vy, double& vz) {
-    vx = ((wx - g.origin[0]) * (double)g.m_div_width - 0.5);
-    vy = ((wy - g.origin[1]) * (double)g.m_div_height - 0.5);
-    vz = ((wz - g.origin[2]) * (double)g.m_div_depth - 0.5);
+    vx = ((wx - g.origin[0]) * g.m_div_d[0] - 0.5);
+    vy = ((wy - g.origin[1]) * g.m_div_d[1] - 0.5);
+    vz = ((wz - g.origin[2]) * g.m_div_d[2] - 0.5);
 }
 /* sdf.h:153-157, one axis */
 TSDF_HD double voxel_centre(float vs, int idx, double org) {

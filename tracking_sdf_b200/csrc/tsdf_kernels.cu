@@ -234,9 +234,9 @@ __global__ void k_sample_color(GridParams g, const float4* __restrict__ color, i
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     /* get_voxel_coordinates, sdf.h:143-147 */
-    const double vx = ((gpts[3 * q] - g.origin[0]) * (double)g.m_div_width - 0.5);
-    const double vy = ((gpts[3 * q + 1] - g.origin[1]) * (double)g.m_div_height - 0.5);
-    const double vz = ((gpts[3 * q + 2] - g.origin[2]) * (double)g.m_div_depth - 0.5);
+    const double vx = ((gpts[3 * q] - g.origin[0]) * g.m_div_d[0] - 0.5);
+    const double vy = ((gpts[3 * q + 1] - g.origin[1]) * g.m_div_d[1] - 0.5);
+    const double vz = ((gpts[3 * q + 2] - g.origin[2]) * g.m_div_d[2] - 0.5);
     const int m = g.m, ks0 = g.ks0, ks1 = g.ks1;
     auto fetch = [&](int ci, int cj, int ck, float& cw, float& r, float& gg, float& b) {
         if ((unsigned)ci >= (unsigned)m || (unsigned)cj >= (unsigned)m || (unsigned)ck >= (unsigned)m) return false;
@@ -437,6 +437,11 @@ __device__ void gn_update_warp(const GridParams& g, PoseState* pose, const doubl
     }
 }
 
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
 template <bool IDX32 SWZ_TPARAM>
 __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(LinearizeArgs a, int exchange_mode, unsigned long long seqno) {
     __shared__ double sM[7][9];
@@ -497,11 +502,16 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
         return (t < LIN_TW * LIN_TH) & (ii < g.ni) & (jj < g.nj);
     };
     /* everything that does not depend on the pose is set up before the dependency wait */
-    const int a0 = c_slot_a[s], b0 = c_slot_b[s];
-    const int a1 = c_slot_a[s + 16], b1 = c_slot_b[s + 16], k1 = c_slot_k[s + 16];
+    /* the lane's two reduction slots (operand lanes a, b; kind k of the second), packed into one register so the loop
+     * never goes back to the constant bank for them */
+    const unsigned slots = (unsigned)c_slot_a[s] | ((unsigned)c_slot_b[s] << 4) | ((unsigned)c_slot_a[s + 16] << 8) |
+                           ((unsigned)c_slot_b[s + 16] << 12) | ((unsigned)c_slot_k[s + 16] << 16);
     const K1Params kp = k1_params(g.K);
     const float step = (s == 0) ? g.v_h2_width : (s == 1) ? g.v_h2_height : (s == 2) ? g.v_h2_depth : g.two_w_h;
-    const double* M = sM[(s < 7) ? 0 : (s - 6)];
+    /* 32-bit shared addresses of this lane's rotation (rot for s = 0..6, a perturbed one for s = 7..12) and of trans,
+     * taken once: the loop reads them with ld.shared and no address arithmetic */
+    const unsigned m_sh = (unsigned)__cvta_generic_to_shared(sM[(s < 7) ? 0 : (s - 6)]);
+    const unsigned t_sh = (unsigned)__cvta_generic_to_shared(sT);
     int miss = 0;
 #ifdef TSDF_SWZ_EXPERIMENT
     GridFetchT<IDX32, SWZ> fetch{a.grid, g.m, g.ks0, g.ks1, &miss};
@@ -554,7 +564,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
         if (sharded && valid_pt) {
             /* pixel owner = the slab holding the centre sample's base cell */
             const double wz = ((sM[0][6] * (double)x + sM[0][7] * (double)y) + sM[0][8] * (double)z) + sT[2];
-            const double vzc = ((wz - g.origin[2]) * (double)g.m_div_depth - 0.5);
+            const double vzc = ((wz - g.origin[2]) * g.m_div_d[2] - 0.5);
             int kc = trunc_f2i((float)vzc);
             kc = kc < 0 ? 0 : (kc > g.m - 1 ? g.m - 1 : kc);
             mine = (kc >= g.ko0 && kc < g.ko1);
@@ -562,7 +572,12 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
         ok = (s >= 13);                                                      /* idle lanes never veto the pixel */
         if ((s < 13) & valid_pt & mine) {                                    /* one divergent region per sweep */
             double vx, vy, vz;
-            sample_coords_off(g, M, sT, off_x, off_y, off_z, (double)x, (double)y, (double)z, vx, vy, vz);
+            double Mr[9], Tr[3];
+#pragma unroll
+            for (int e = 0; e < 9; e++) Mr[e] = lds_f64(m_sh + 8u * e);
+#pragma unroll
+            for (int e = 0; e < 3; e++) Tr[e] = lds_f64(t_sh + 8u * e);
+            sample_coords_off(g, Mr, Tr, off_x, off_y, off_z, (double)x, (double)y, (double)z, vx, vy, vz);
             /* camera_tracking.cpp:261-268: only the centre sample's (s = 0) verdict is used */
             /* camera_tracking.cpp:261-268 verbatim: six ordered compares (false for NaN), chained on one predicate —
              * written out because the compiler otherwise folds them into fp64 min/max with NaN fix-ups (~30 instructions) */
@@ -595,10 +610,11 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
         const float psi = __shfl_sync(0xffffffffu, val, base);
         const float Ja = (vplus - vminus) / step;
         const float xv = (s < 6) ? Ja : psi;                                 /* lane 6 (and up) holds psi */
-        const double xa0 = (double)__shfl_sync(0xffffffffu, xv, base + a0);
-        const double xb0 = (double)__shfl_sync(0xffffffffu, xv, base + b0);
-        const double xa1 = (double)__shfl_sync(0xffffffffu, xv, base + a1);
-        const double xb1 = (double)__shfl_sync(0xffffffffu, xv, base + b1);
+        const int k1 = (int)(slots >> 16);
+        const double xa0 = (double)__shfl_sync(0xffffffffu, xv, base + (int)(slots & 15u));
+        const double xb0 = (double)__shfl_sync(0xffffffffu, xv, base + (int)((slots >> 4) & 15u));
+        const double xa1 = (double)__shfl_sync(0xffffffffu, xv, base + (int)((slots >> 8) & 15u));
+        const double xb1 = (double)__shfl_sync(0xffffffffu, xv, base + (int)((slots >> 12) & 15u));
         {
             /* camera_tracking.cpp:178-182, branch-free: the addend is selected (an invalid pixel's products may be
              * NaN), and adding +0.0 leaves a sum unchanged */
