@@ -1253,19 +1253,17 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
         act = x0 < ihi;                                   /* interval ends are multiples of 4 */
         return reinterpret_cast<float4*>(&grid[((size_t)(k - g.ks0) * m + j) * m + (act ? x0 : xs)]);
     };
-    /* pipeline prologue */
-    unsigned int it = gw;
-    unsigned long long item_cur = it < n_items ? ld_dep(&items[it]) : 0ull;
-    unsigned long long item_nxt = it + total_warps < n_items ? ld_dep(&items[it + total_warps]) : 0ull;
-    /* the row constant of the affine certificates is fetched only for items that need per-unit certificates
-     * (row- or item-certified work, e.g. the dense case, never touches it) */
+    /* Item descriptors and row constants arrive a BATCH at a time: lane L of the warp fetches the warp's L-th next item
+     * (and, only when that item needs per-unit certificates, its row constant), 32 items per round trip, and every
+     * iteration takes its descriptor from the holding lane with shuffles — no global load sits between two items.
+     * (Row- or item-certified work, e.g. the dense case, never touches the row constants.) */
     int k, j, x0; bool act;
-    float4* ptr = decode_ptr(item_cur, k, j, x0, act);
+    float4* ptr = nullptr;
     /* deferred completion: the voxel loads of a unit certified as free space are issued right after
      * its verdict and consumed one item later, after the next item's certificate arithmetic, so the
      * HBM latency is hidden without loading anything for units that end up skipped or queued */
     bool pend = false;
-    float4* pptr = ptr;
+    float4* pptr = nullptr;
     float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
     auto complete = [&]() {
         if (pend) {
@@ -1277,68 +1275,74 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
             pptr[0] = p0; pptr[1] = p1;
         }
     };
-    for (; it < n_items; it += total_warps) {
-        /* stage A: descriptor two items ahead */
-        const unsigned int it2 = it + 2 * total_warps;
-        const unsigned long long item_nn = it2 < n_items ? ld_dep(&items[it2]) : 0ull;
-        int kn = 0, jn = 0, x0n = 0; bool actn = false;
-        float4* ptrn = decode_ptr(item_nxt, kn, jn, x0n, actn);
-        /* stage B: certificate of the current unit (unless the whole row was already judged) */
-        int verdict = UNIT_SKIP;
-        const int rowv = (int)(item_cur >> 61) & 3;
-        if (act && rowv != UNIT_UNKNOWN) verdict = rowv;
+    for (unsigned int base = gw; base < n_items; base += 32u * (unsigned int)total_warps) {
+        const unsigned int mine = base + (unsigned int)lane * (unsigned int)total_warps;
+        const unsigned long long b_item = mine < n_items ? ld_dep(&items[mine]) : 0ull;
+        float b_cx = 0.0f, b_cy = 0.0f, b_cz = 0.0f;
 #ifndef TSDF_AFFINE_OUT
-        else if (act && affine) {
-            /* end points of the lane's four voxels by the fp32 affine form of the row: six FFMA instead of twelve
-             * table loads and eighteen double additions */
-            const float4 c0_cur = ld_dep(&item_c[it]);       /* only items with per-unit certificates touch it (never the dense case) */
-            verdict = unit_certificate_affine(g, P, c0_cur.x, c0_cur.y, c0_cur.z, stx, sty, stz, x0, fetch);
+        if (mine < n_items && affine && ((int)(b_item >> 61) & 3) == UNIT_UNKNOWN) {
+            const float4 c = ld_dep(&item_c[mine]);
+            b_cx = c.x; b_cy = c.y; b_cz = c.z;
         }
+#endif
+        const unsigned int left = (n_items - base + (unsigned int)total_warps - 1u) / (unsigned int)total_warps;
+        const int nb = left < 32u ? (int)left : 32;       /* warp-uniform */
+        for (int r = 0; r < nb; r++) {
+            const unsigned long long item_cur = __shfl_sync(0xffffffffu, b_item, r);
+            const float c0x = __shfl_sync(0xffffffffu, b_cx, r), c0y = __shfl_sync(0xffffffffu, b_cy, r), c0z = __shfl_sync(0xffffffffu, b_cz, r);
+            ptr = decode_ptr(item_cur, k, j, x0, act);
+            /* certificate of the current unit (unless the whole row was already judged) */
+            int verdict = UNIT_SKIP;
+            const int rowv = (int)(item_cur >> 61) & 3;
+            if (act && rowv != UNIT_UNKNOWN) verdict = rowv;
+#ifndef TSDF_AFFINE_OUT
+            else if (act && affine) {
+                /* end points of the lane's four voxels by the fp32 affine form of the row: six FFMA instead of twelve
+                 * table loads and eighteen double additions */
+                verdict = unit_certificate_affine(g, P, c0x, c0y, c0z, stx, sty, stz, x0, fetch);
+            }
 #endif
 #ifndef TSDF_DOUBLE_OUT
-        else if (act) {
-            const double qy0 = ld_dep(T + (3u * um + j)), qy1 = ld_dep(T + (4u * um + j)), qy2 = ld_dep(T + (5u * um + j));
-            const double pz0 = ld_dep(T + (6u * um + k)), pz1 = ld_dep(T + (7u * um + k)), pz2 = ld_dep(T + (8u * um + k));
-            const double ax = ((ld_dep(T + (unsigned int)x0) + qy0) + pz0) + ti0, bx = ((ld_dep(T + (unsigned int)x0 + 3) + qy0) + pz0) + ti0;
-            const double ay = ((ld_dep(T + (um + x0)) + qy1) + pz1) + ti1, by = ((ld_dep(T + (um + x0 + 3)) + qy1) + pz1) + ti1;
-            const double az = ((ld_dep(T + (2u * um + x0)) + qy2) + pz2) + ti2, bz = ((ld_dep(T + (2u * um + x0 + 3)) + qy2) + pz2) + ti2;
-            verdict = unit_certificate(g, P, ax, ay, az, bx, by, bz, fetch);
-        }
-#endif
-        /* colour fusion needs every updated voxel's pixel (normal, rgb): certified free space is
-         * queued for the exact pass too; only the skip certificate is used */
-        /* ... except whole rows certified as free space: the colour pass takes those straight from the item list
-         * (no 8-byte queue entry per unit, no staging) */
-        if (queue_front && rowv == UNIT_FRONT && !CHECK) verdict = UNIT_SKIP;
-        const bool front_queued = queue_front && verdict == UNIT_FRONT;     /* queued WITH its certificate */
-        if (CHECK) {
-            /* self-check build: queue EVERY unit with its verdict; pass 2 compares, nothing is written */
-            const unsigned int mask = __ballot_sync(0xffffffffu, act);
-            if (act) stage[staged + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, verdict);
-            __syncwarp();
-            staged += __popc(mask);
-            flush(63);
-        } else {
-            complete();                                   /* the previous item's free-space units */
-            pend = (verdict == UNIT_FRONT) && !front_queued;
-            if (pend) {
-                pptr = ptr;
-                p0 = ld_f4(ptr); p1 = ld_f4(ptr + 1);
-                if (k >= g.ko0 && k < g.ko1) my_updates += 4u;
+            else if (act) {
+                const double qy0 = ld_dep(T + (3u * um + j)), qy1 = ld_dep(T + (4u * um + j)), qy2 = ld_dep(T + (5u * um + j));
+                const double pz0 = ld_dep(T + (6u * um + k)), pz1 = ld_dep(T + (7u * um + k)), pz2 = ld_dep(T + (8u * um + k));
+                const double ax = ((ld_dep(T + (unsigned int)x0) + qy0) + pz0) + ti0, bx = ((ld_dep(T + (unsigned int)x0 + 3) + qy0) + pz0) + ti0;
+                const double ay = ((ld_dep(T + (um + x0)) + qy1) + pz1) + ti1, by = ((ld_dep(T + (um + x0 + 3)) + qy1) + pz1) + ti1;
+                const double az = ((ld_dep(T + (2u * um + x0)) + qy2) + pz2) + ti2, bz = ((ld_dep(T + (2u * um + x0 + 3)) + qy2) + pz2) + ti2;
+                verdict = unit_certificate(g, P, ax, ay, az, bx, by, bz, fetch);
             }
-            const bool to_queue = (verdict == UNIT_UNKNOWN) | front_queued;
-            const unsigned int mask = __ballot_sync(0xffffffffu, to_queue);
-            if (mask) {
-                if (to_queue) stage[staged + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, verdict);
+#endif
+            /* colour fusion needs every updated voxel's pixel (normal, rgb): certified free space is
+             * queued for the exact pass too; only the skip certificate is used */
+            /* ... except whole rows certified as free space: the colour pass takes those straight from the item list
+             * (no 8-byte queue entry per unit, no staging) */
+            if (queue_front && rowv == UNIT_FRONT && !CHECK) verdict = UNIT_SKIP;
+            const bool front_queued = queue_front && verdict == UNIT_FRONT;     /* queued WITH its certificate */
+            if (CHECK) {
+                /* self-check build: queue EVERY unit with its verdict; pass 2 compares, nothing is written */
+                const unsigned int mask = __ballot_sync(0xffffffffu, act);
+                if (act) stage[staged + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, verdict);
                 __syncwarp();
                 staged += __popc(mask);
                 flush(63);
+            } else {
+                complete();                                   /* the previous item's free-space units */
+                pend = (verdict == UNIT_FRONT) && !front_queued;
+                if (pend) {
+                    pptr = ptr;
+                    p0 = ld_f4(ptr); p1 = ld_f4(ptr + 1);
+                    if (k >= g.ko0 && k < g.ko1) my_updates += 4u;
+                }
+                const bool to_queue = (verdict == UNIT_UNKNOWN) | front_queued;
+                const unsigned int mask = __ballot_sync(0xffffffffu, to_queue);
+                if (mask) {
+                    if (to_queue) stage[staged + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, verdict);
+                    __syncwarp();
+                    staged += __popc(mask);
+                    flush(63);
+                }
             }
         }
-        /* rotate the pipeline */
-        item_cur = item_nxt;
-        item_nxt = item_nn;
-        k = kn; j = jn; x0 = x0n; act = actn; ptr = ptrn;
     }
     if (!CHECK) complete();
     flush(0);
@@ -1392,9 +1396,17 @@ __global__ void __launch_bounds__(FUSE_THREADS, COLOR ? FUSE_COLOR_MIN_BLOCKS : 
         }
         my_updates += apply_four(g, ptr, q0, q1, k, upd, dnew, wnew);
     };
-    for (unsigned int q = blockIdx.x * FUSE_THREADS + threadIdx.x; q < n_units; q += gridDim.x * FUSE_THREADS) {
-        const unsigned long long unit = ld_dep(&units[q]);
-        process((int)(unit & 0xfff), (int)((unit >> 12) & 0xfff), (int)((unit >> 24) & 0x3ff) << 2, (int)((unit >> 34) & 3));
+    {
+        /* the descriptor of the thread's next unit is fetched one unit ahead: the queue read is off the dependent chain
+         * (descriptor -> tables -> projection -> pixel record -> verdict) */
+        const unsigned int stride = gridDim.x * FUSE_THREADS;
+        unsigned int q = blockIdx.x * FUSE_THREADS + threadIdx.x;
+        unsigned long long unit = q < n_units ? ld_dep(&units[q]) : 0ull;
+        for (; q < n_units; q += stride) {
+            const unsigned long long unit_nxt = (q + stride < n_units) ? ld_dep(&units[q + stride]) : 0ull;
+            process((int)(unit & 0xfff), (int)((unit >> 12) & 0xfff), (int)((unit >> 24) & 0x3ff) << 2, (int)((unit >> 34) & 3));
+            unit = unit_nxt;
+        }
     }
     if (COLOR && !CHECK && item_count[2] != 0u) {
         /* rows certified as free space as a whole (the dense case): straight from the item list, a warp per item */
