@@ -218,5 +218,83 @@ inline int64_t SDF::update(CameraTracking* camera_tracking, const float* depth, 
     return n;
 }
 
+/* One volume cut into z slabs, one slab per shard, driven from ONE host thread (the C++ counterpart of
+ * tracking_sdf_b200/sharding.py, which does the same across processes with torch.distributed for the rendezvous).
+ * Shards are placed round-robin on `devices`; shards on different devices all-reduce the 6x6 normal equations inside
+ * the tracking kernel over NVLink peer memory (tsdf_shard_attach_local), shards sharing a device (a single-GPU box)
+ * use the deferred same-device combine.  The per-frame call sequence is the node's (sdf_reconstruction.cpp:61-74):
+ * set_camera_transformation on the first frame, estimate_new_position_and_update afterwards.  Every shard holds the
+ * same pose; n_updated sums the voxels each shard owns.
+ *   cost_weights: optional per-z-layer fusion cost (m values) for work-balanced slabs (tsdf_balanced_slabs); nullptr =
+ *   equal thickness. */
+class ShardedSDF {
+public:
+    ShardedSDF(int n_shards, const std::vector<int>& devices, int m, float width, float height, float depth,
+               const double sdf_origin[3], float distance_delta, float distance_epsilon,
+               int gauss_newton_max_iteration, float maximum_twist_diff, float v_h, float w_h,
+               int image_width = 640, int image_height = 480, const double* cost_weights = nullptr) {
+        if (n_shards < 1 || devices.empty()) throw Error(TSDF_ERR_BAD_ARG, "ShardedSDF: need at least one shard and one device");
+        tsdf_config c;
+        tsdf_default_config(&c);
+        c.m = m; c.width = width; c.height = height; c.depth = depth;
+        for (int q = 0; q < 3; q++) c.origin[q] = sdf_origin[q];
+        c.distance_delta = distance_delta; c.distance_epsilon = distance_epsilon;
+        c.gauss_newton_max_iteration = gauss_newton_max_iteration; c.maximum_twist_diff = maximum_twist_diff;
+        c.v_h = v_h; c.w_h = w_h; c.image_width = image_width; c.image_height = image_height;
+        c.n_shards = n_shards;
+        std::vector<int32_t> bounds;
+        if (cost_weights && n_shards > 1) {
+            int32_t plan[5];
+            c.shard_rank = 0;
+            check(tsdf_slab_plan(&c, plan));
+            bounds.resize((size_t)n_shards + 1);
+            check(tsdf_balanced_slabs(m, n_shards, cost_weights, 8, plan[4], bounds.data()));
+        }
+        try {
+            for (int r = 0; r < n_shards; r++) {
+                c.shard_rank = r;
+                c.device = devices[(size_t)r % devices.size()];
+                if (!bounds.empty()) { c.slab_k_begin = bounds[(size_t)r]; c.slab_k_end = bounds[(size_t)r + 1]; }
+                tsdf_handle h = nullptr;
+                check(tsdf_create(&c, &h));
+                h_.push_back(h);
+            }
+            if (n_shards > 1) check(tsdf_shard_attach_local(h_.data(), n_shards));
+        } catch (...) {
+            for (tsdf_handle h : h_) tsdf_destroy(h);
+            throw;
+        }
+    }
+    ~ShardedSDF() { for (tsdf_handle h : h_) tsdf_destroy(h); }
+    ShardedSDF(const ShardedSDF&) = delete;
+    ShardedSDF& operator=(const ShardedSDF&) = delete;
+
+    int n_shards() const { return (int)h_.size(); }
+    void camera_info_cb(const double K_row_major[9]) { check(tsdf_group_set_intrinsics(h_.data(), n_shards(), K_row_major)); }
+    void set_camera_transformation(const double rot[9], const double trans[3]) { check(tsdf_group_set_pose(h_.data(), n_shards(), rot, trans)); }
+    /* sdf->update at the current pose (frame 1 of the node) */
+    int64_t update(const float* depth, double R_out[9] = nullptr, double t_out[3] = nullptr) {
+        int64_t n = 0;
+        check(tsdf_group_frame(h_.data(), n_shards(), depth, TSDF_HOST, 0, 1, R_out, t_out, nullptr, &n));
+        return n;
+    }
+    /* estimate_new_position + update (sdf_reconstruction.cpp:69-74) on every shard in lock step */
+    int64_t estimate_new_position_and_update(const float* depth, double R_out[9], double t_out[3], tsdf_track_stats* stats = nullptr) {
+        int64_t n = 0;
+        check(tsdf_group_frame(h_.data(), n_shards(), depth, TSDF_HOST, 1, 1, R_out, t_out, stats, &n));
+        return n;
+    }
+    /* owned z layers [begin, end) of shard r */
+    void owned_layers(int r, int32_t& begin, int32_t& end) const {
+        int32_t kb, ke;
+        check(tsdf_stored_range(h_.at((size_t)r), &kb, &ke, &begin, &end));
+    }
+    /* the slab of shard r in the reference's layout (its STORED layers, halo included): see tsdf_download */
+    tsdf_handle shard(int r) const { return h_.at((size_t)r); }
+
+private:
+    std::vector<tsdf_handle> h_;
+};
+
 }  // namespace b200
 #endif
