@@ -524,9 +524,18 @@ tsdf_status tsdf_create(const tsdf_config* cfg, tsdf_handle* out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     const int sms = prop.multiProcessorCount;
-    /* K2: one block per LIN_TW x LIN_TH tile of the strided pixel grid */
+    /* K2: one block per LIN_TW x LIN_TH tile of the strided pixel grid; LIN_MICRO: one block per SM slot, each with a
+     * contiguous run of 4 x 4 micro-tiles (tsdf_kernels.cu: k_linearize, "Work distribution") */
+#ifdef LIN_MICRO
+    const int n_micro = ((p->g.ni + 3) / 4) * ((p->g.nj + 3) / 4);
+    int lb = linearize_blocks_per_sm();
+    if (lb < 1) lb = 1;
+    const int nb = n_micro < sms * lb ? n_micro : sms * lb;
+    const int ppb = ((n_micro + nb - 1) / nb) * 16;
+#else
     const int ppb = LIN_TW * LIN_TH;
     const int nb = ((p->g.ni + LIN_TW - 1) / LIN_TW) * ((p->g.nj + LIN_TH - 1) / LIN_TH);
+#endif
     if ((nb + LIN_GROUP - 1) / LIN_GROUP > MAX_LIN_GROUPS) { g_err = "image too large for the reduction tree"; tsdf_destroy(reinterpret_cast<tsdf_handle>(p)); return TSDF_ERR_BAD_ARG; }
     p->px_per_block = ppb; p->lin_blocks = nb;
     A(cudaMalloc(&p->partials, (size_t)nb * LIN_PARTIAL_STRIDE * sizeof(double)));

@@ -7,21 +7,38 @@
 
 namespace tsdf {
 
+/* K2 launch shape.  Default (LIN_MICRO): ONE 768-thread block per SM (24 warps at 72 registers fill the register file
+ * about as far as three 256-thread blocks did), each with a contiguous run of 4 x 4 micro-tiles of the strided pixel
+ * grid.  148 blocks means 148 partial sums: ONE ticket level instead of two (three dependent global round trips
+ * instead of six between the slowest block's last pixel and the solve) — 22.6 -> 21.4 us per iteration.
+ * -DLIN_TILES selects the previous shape: one 256-thread block per LIN_TW x LIN_TH pixel tile, groups of LIN_GROUP. */
+#ifndef LIN_TILES
+#define LIN_MICRO 1
+#endif
 #ifndef LIN_THREADS_DEF
+#ifdef LIN_MICRO
+#define LIN_THREADS_DEF 768
+#else
 #define LIN_THREADS_DEF 256
 #endif
-constexpr int LIN_THREADS = LIN_THREADS_DEF;   /* 8 warps, 16 pixels per sweep */
+#endif
+constexpr int LIN_THREADS = LIN_THREADS_DEF;   /* a multiple of 256: two pixels per warp, 16 pixels per micro-tile */
+static_assert(LIN_THREADS % 256 == 0 && LIN_THREADS <= 1024, "k_linearize: whole micro-tiles per sweep");
 #ifndef LIN_TW_DEF
 #define LIN_TW_DEF 8
 #endif
 #ifndef LIN_TH_DEF
 #define LIN_TH_DEF 10
 #endif
-constexpr int LIN_TW = LIN_TW_DEF, LIN_TH = LIN_TH_DEF;      /* strided-pixel tile per block (columns x rows) = 80 pixels = 5 sweeps of 16 */
+constexpr int LIN_TW = LIN_TW_DEF, LIN_TH = LIN_TH_DEF;      /* LIN_TILES: strided-pixel tile per block (columns x rows) = 80 pixels = 5 sweeps of 16 */
 constexpr int LIN_PARTIAL_STRIDE = 32;    /* doubles per block partial (30 used) */
 constexpr int MAX_WORLD = 16;
 #ifndef LIN_GROUP_DEF
+#ifdef LIN_MICRO
+#define LIN_GROUP_DEF 256               /* >= the block count of any current GPU: a single reduction level */
+#else
 #define LIN_GROUP_DEF 32
+#endif
 #endif
 constexpr int LIN_GROUP = LIN_GROUP_DEF;  /* blocks per first-level reduction group */
 constexpr int FUSE_THREADS = 128;
@@ -36,7 +53,11 @@ constexpr int FUSE_THREADS = 128;
 #define CERT_MIN_BLOCKS 8
 #endif
 #ifndef LIN_MIN_BLOCKS
+#ifdef LIN_MICRO
+#define LIN_MIN_BLOCKS 1
+#else
 #define LIN_MIN_BLOCKS 3
+#endif
 #endif
 
 /* cross-shard exchange of the reduced normal equations (one slot per rank, double-buffered

@@ -473,29 +473,42 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
             sM[1 + q][e] = (d0 * pose->R[c] + d1 * pose->R[3 + c]) + d2 * pose->R[6 + c];
         }
     };
-    /* each block owns a LIN_TW x LIN_TH tile of the strided pixel grid (columns x rows), so its
-     * samples touch a compact piece of the volume and share voxel lines in L1.
-     *
-     * Sharded volumes: a rank linearises only the pixels whose centre cell it owns — a compact region of the image —
-     * and with one tile per block the launch would still last as long as its slowest (fully owned) tile.  So the
-     * sweeps of a block are spread over the image instead: sweep q of block b takes the 4 x 4 micro-tile
-     * b + q * gridDim.x, owned micro-tiles end up evenly over all blocks and a rank that owns 1/G of the pixels
-     * finishes its pixel loop in about 1/G of the time.  (Same pixels, same per-block order every launch: the
-     * reduction stays deterministic.) */
-    constexpr int PX_SWEEP = (LIN_THREADS / 32) * 2;                         /* 16 pixels per sweep */
+    /* Work distribution.  The strided pixel grid is cut into 4 x 4 micro-tiles (16 pixels = 8 warps' worth), numbered
+     * column by column; a sweep of the block processes PX_SWEEP pixels = MT_SWEEP micro-tiles.
+     *   default     each block owns a LIN_TW x LIN_TH tile (columns x rows): its samples touch a compact piece of the
+     *               volume and share voxel lines in L1.
+     *   LIN_MICRO   the grid is ONE block per SM slot and each block owns a contiguous run of micro-tiles, so the
+     *               number of blocks (= partial sums to reduce) no longer depends on the image size.
+     *   sharded     a rank linearises only the pixels whose centre cell it owns — a compact region of the image — and
+     *               with one compact tile per block the launch would last as long as its slowest (fully owned) tile.
+     *               So the micro-tiles of a block are spread over the image: slot sl of block b is micro-tile
+     *               b + sl * gridDim.x, owned micro-tiles end up evenly over all blocks and a rank that owns 1/G of the
+     *               pixels finishes its pixel loop in about 1/G of the time.
+     * Same pixels, same per-block order every launch: the reduction stays deterministic. */
+    constexpr int PX_SWEEP = (LIN_THREADS / 32) * 2;                         /* pixels per sweep: two per warp */
+    constexpr int MT_SWEEP = PX_SWEEP / 16;                                  /* micro-tiles per sweep (0: fewer than 8 warps) */
+#ifdef LIN_MICRO
+    constexpr bool MICRO = true;
+    constexpr int STAGED = 5 * PX_SWEEP;
+#else
+    constexpr bool MICRO = false;
     constexpr int STAGED = ((LIN_TW * LIN_TH + PX_SWEEP - 1) / PX_SWEEP) * PX_SWEEP;
+#endif
     __shared__ float4 sPts[STAGED];
     const int tiles_y = (g.nj + LIN_TH - 1) / LIN_TH;
     const int tile_x = blockIdx.x / tiles_y, tile_y = blockIdx.x - tile_x * tiles_y;
     const int mty = (g.nj + 3) >> 2, n_micro = ((g.ni + 3) >> 2) * mty;
-    const int n_sweeps = sharded ? (n_micro + (int)gridDim.x - 1) / (int)gridDim.x : (LIN_TW * LIN_TH + PX_SWEEP - 1) / PX_SWEEP;
+    const int n_slots = (n_micro + (int)gridDim.x - 1) / (int)gridDim.x;     /* micro-tiles per block (MICRO, sharded) */
+    const int n_sweeps = (sharded || MICRO) ? (MT_SWEEP > 0 ? (n_slots + MT_SWEEP - 1) / (MT_SWEEP > 0 ? MT_SWEEP : 1) : 0)
+                                            : (LIN_TW * LIN_TH + PX_SWEEP - 1) / PX_SWEEP;
     /* pixel tl of sweep q -> strided pixel (ii, jj); false when the slot is empty */
     auto pixel_of = [&](int q, int tl, int& ii, int& jj) -> bool {
-        if (sharded) {
-            const int mt = (int)blockIdx.x + q * (int)gridDim.x;
+        if (sharded || MICRO) {
+            const int sl = q * MT_SWEEP + (tl >> 4);
+            const int mt = sharded ? (int)blockIdx.x + sl * (int)gridDim.x : (int)blockIdx.x * n_slots + sl;
             const int mx = mt / mty, my = mt - mx * mty;
-            ii = (mx << 2) + (tl >> 2); jj = (my << 2) + (tl & 3);
-            return (PX_SWEEP == 16) & (mt < n_micro) & (ii < g.ni) & (jj < g.nj);
+            ii = (mx << 2) + ((tl & 15) >> 2); jj = (my << 2) + (tl & 3);
+            return (sl < n_slots) & (mt < n_micro) & (ii < g.ni) & (jj < g.nj);
         }
         const int t = q * PX_SWEEP + tl;
         ii = tile_x * LIN_TW + t / LIN_TH; jj = tile_y * LIN_TH + t % LIN_TH;
@@ -528,8 +541,11 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
      * round trip. */
     for (int e = tid; e < STAGED; e += LIN_THREADS) {
         int ii, jj;
-        float4 pt = make_float4(0.0f, 0.0f, __int_as_float(0x7fc00000), 0.0f);
-        if (e < n_sweeps * PX_SWEEP && pixel_of(e / PX_SWEEP, e % PX_SWEEP, ii, jj)) pt = __ldg(&a.pts[ii * g.nj + jj]);
+        float4 pt = make_float4(0.0f, 0.0f, __int_as_float(0x7fc00000), __int_as_float(-1));
+        if (e < n_sweeps * PX_SWEEP && pixel_of(e / PX_SWEEP, e % PX_SWEEP, ii, jj)) {
+            pt = __ldg(&a.pts[ii * g.nj + jj]);
+            pt.w = __int_as_float(ii * g.nj + jj);                           /* the pixel's index rides along (-1: empty slot) */
+        }
         sPts[e] = pt;
     }
     pdl_wait();
@@ -547,16 +563,21 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     double acc0 = 0.0, acc1 = 0.0;
     for (int q = 0; q < n_sweeps; q++) {                                     /* warp-uniform trip count */
         const int tl = warp * 2 + grp;
-        int ii, jj;
-        const bool have = pixel_of(q, tl, ii, jj);
-        const int p = ii * g.nj + jj;                                        /* reference loop order, camera_tracking.cpp:162-163 */
+        int p;                                                               /* ii * nj + jj: reference loop order, camera_tracking.cpp:162-163 */
+        bool have;
         float x = 0.0f, y = 0.0f, z = __int_as_float(0x7fc00000);
         if (q * PX_SWEEP < STAGED) {
             const float4 pt = sPts[q * PX_SWEEP + tl];                       /* back-projected by k_prep; z = NaN when invalid */
             x = pt.x; y = pt.y; z = pt.z;
-        } else if (have) {                                                   /* more sweeps than staged slots (sharded, small grids) */
-            const float4 pt = __ldg(&a.pts[p]);
-            x = pt.x; y = pt.y; z = pt.z;
+            p = __float_as_int(pt.w); have = p >= 0;
+        } else {                                                             /* more sweeps than staged slots (small grids, few blocks) */
+            int ii, jj;
+            have = pixel_of(q, tl, ii, jj);
+            p = ii * g.nj + jj;
+            if (have) {
+                const float4 pt = __ldg(&a.pts[p]);
+                x = pt.x; y = pt.y; z = pt.z;
+            }
         }
         const bool valid_pt = have && (z == z);                              /* camera_tracking.cpp:168 */
         float val = 0.0f;
