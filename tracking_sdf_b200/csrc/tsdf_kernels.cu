@@ -682,8 +682,17 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     {
         const int slot = tid & 31, sub = tid >> 5;           /* one warp per stripe of the group's blocks */
         double v = 0.0;
-        for (int bq = sub; bq < gsize; bq += LIN_THREADS / 32)
-            v = v + __ldcg(&a.partials[(size_t)(grp_id * LIN_GROUP + bq) * LIN_PARTIAL_STRIDE + slot]);
+        constexpr int NW = LIN_THREADS / 32;
+        for (int b0 = sub; b0 < gsize; b0 += 8 * NW) {       /* eight loads in flight per thread: one L2 round trip for 148 blocks */
+            double x[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int bq = b0 + u * NW;
+                x[u] = bq < gsize ? __ldcg(&a.partials[(size_t)(grp_id * LIN_GROUP + bq) * LIN_PARTIAL_STRIDE + slot]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) v = v + x[u];        /* same order as one at a time (+0.0 for the absent ones) */
+        }
         __syncthreads();
         sRed[sub][slot] = v;
         __syncthreads();
