@@ -477,8 +477,8 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
      * column by column; a sweep of the block processes PX_SWEEP pixels = MT_SWEEP micro-tiles.
      *   default     each block owns a LIN_TW x LIN_TH tile (columns x rows): its samples touch a compact piece of the
      *               volume and share voxel lines in L1.
-     *   LIN_MICRO   the grid is ONE block per SM slot and each block owns a contiguous run of micro-tiles, so the
-     *               number of blocks (= partial sums to reduce) no longer depends on the image size.
+     *   LIN_MICRO   the grid is ONE block per SM slot, so the number of blocks (= partial sums to reduce) no longer
+     *               depends on the image size; a sweep takes MT_SWEEP adjacent micro-tiles, sweeps are spread.
      *   sharded     a rank linearises only the pixels whose centre cell it owns — a compact region of the image — and
      *               with one compact tile per block the launch would last as long as its slowest (fully owned) tile.
      *               So the micro-tiles of a block are spread over the image: slot sl of block b is micro-tile
@@ -504,11 +504,14 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     /* pixel tl of sweep q -> strided pixel (ii, jj); false when the slot is empty */
     auto pixel_of = [&](int q, int tl, int& ii, int& jj) -> bool {
         if (sharded || MICRO) {
+            /* sharded: slot sl of block b = micro-tile b + sl * gridDim.x;  unsharded: sweep q of block b = the MT_SWEEP
+             * adjacent micro-tiles (q * gridDim.x + b) * MT_SWEEP ... (one compact strip per sweep, sweeps spread over the
+             * image: slow regions — samples leaving the volume take the per-voxel path — do not pile up in a few blocks) */
             const int sl = q * MT_SWEEP + (tl >> 4);
-            const int mt = sharded ? (int)blockIdx.x + sl * (int)gridDim.x : (int)blockIdx.x * n_slots + sl;
+            const int mt = sharded ? (int)blockIdx.x + sl * (int)gridDim.x : (q * (int)gridDim.x + (int)blockIdx.x) * MT_SWEEP + (tl >> 4);
             const int mx = mt / mty, my = mt - mx * mty;
             ii = (mx << 2) + ((tl & 15) >> 2); jj = (my << 2) + (tl & 3);
-            return (sl < n_slots) & (mt < n_micro) & (ii < g.ni) & (jj < g.nj);
+            return (sharded ? sl < n_slots : true) & (mt < n_micro) & (ii < g.ni) & (jj < g.nj);
         }
         const int t = q * PX_SWEEP + tl;
         ii = tile_x * LIN_TW + t / LIN_TH; jj = tile_y * LIN_TH + t % LIN_TH;
