@@ -518,17 +518,19 @@ def main_cuda(args):
                  "note": "algorithmic bytes = 16 B x voxels updated (read+write D,W); skipped voxels move no bytes. On this workload only ~5 % of the "
                          "134 M voxels are in view, so the stage is bound by certificate/fp64 latency on in-view voxels, not by HBM: see dense_fuse for the "
                          "HBM-bound case (every voxel updated), which is where north_star's >= 70 % target is defined"}
-    # floor of one GN iteration: the pixel loop cannot beat the L1 data pipe (ncu: 17.5 k LSU data-pipe wavefronts
-    # per SM per launch = 8.9 us at one wavefront per clock, 1965 MHz), and the serial tail is five dependent global round trips
-    # (partial -> ticket -> group sum -> ticket -> final sum, ~0.7 us each), a ~2 us chain of dependent fp64 divisions (6x6 LU,
-    # exp map, 3x3 inverse) and the dependent launch (~1 us)
-    floor_us = 8.9 + 3.5 + 2.0 + 1.0
-    roof_track = {"bound": "l1-data-pipe + dependent-latency chain", "kernel": "k_linearize", "achieved": gather, "peak": hbm, "unit": "GB/s",
+    # floor of one GN iteration.  Measured this round: with every gather forced into the same four lines ("perfect
+    # memory", -DTSDF_X_HOTLOAD) the pixel loop loses only 1.9 us, and four alternative voxel layouts gain 9-11 %: the loop is bound by
+    # instruction issue and dependent-instruction latency, not by the L1 data pipe as round 1 assumed.  Hard floor of the loop =
+    # 7.11 M warp-instructions (ncu) / (148 SMs x 4 schedulers x 1 instruction per clock) = 6.1 us at 1965 MHz.  Serial tail: three
+    # dependent global round trips (block partial + fence -> ticket -> read of the 148 partials, ~0.7 us each), a ~2 us chain of
+    # dependent fp64 divisions (6x6 LU pivots, exp map, 3x3 inverse), the dependent launch and the reload of the pose (~1.6 us).
+    floor_us = 6.1 + 2.1 + 2.0 + 1.6
+    roof_track = {"bound": "instruction issue + dependent-latency chain", "kernel": "k_linearize", "achieved": gather, "peak": hbm, "unit": "GB/s",
                   "frac": gather / hbm, "ms_per_launch": t_track * 1e3 / GN_ITERS, "launches_per_frame": GN_ITERS,
                   "floor_us_per_launch": floor_us, "frac_of_floor": floor_us / (t_track * 1e6 / GN_ITERS),
                   "note": "832 B gathered per valid pixel-iteration (13 samples x 8 neighbours x {D,W}); the working set is L2-resident, so the HBM "
-                          "peak (achieved/peak/frac) is only a yardstick; the bound that applies is floor_us_per_launch: L1 data-pipe wavefronts of "
-                          "the gathers (8.9 us) + the serial reduction/solve/launch tail (6.5 us); frac_of_floor = floor / measured"}
+                          "peak (achieved/peak/frac) is only a yardstick; the bound that applies is floor_us_per_launch: issue slots of the pixel "
+                          "loop (6.1 us for 7.11 M warp-instructions) + the serial reduction/solve/launch tail (5.7 us); frac_of_floor = floor / measured"}
     share = {"prep": t_prep, "track": t_track, "fuse": t_fuse}
     tot = sum(share.values())
     share = {k: v / tot for k, v in share.items()}
