@@ -487,7 +487,7 @@ def main_cuda(args):
         t_mesh = min(tm)
         mesh = {"kernel": "k_mc_sweep (count + surface-cell list) + cub scan + k_mc_emit_list", "ms_per_extraction": t_mesh * 1e3, "triangles": nv // 3,
                 "store_read_gbs": 8.0 * m ** 3 / t_mesh / 1e9, "peak": hbm, "frac": 8.0 * m ** 3 / t_mesh / 1e9 / hbm,
-                "note": "host wall clock around tsdf_mesh_extract (ONE sweep over the 8 B/voxel store + scan + list emit + allocation + two syncs); "
+                "note": "host wall clock around tsdf_mesh_extract (ONE sweep over the 8 B/voxel store + scan + list emit enqueued behind it + one sync); "
                         "algorithmic bytes = 8 B x m^3 (every voxel read once); cub::DeviceScan is library code, off the frame path"}
     value = n_gpus * Ksteps / (ms_total * 1e-3)
     # stage breakdown: a SECOND pass over the same frames with the per-stage CUDA events on (an event record between

@@ -82,6 +82,7 @@ struct Impl {
     double* fuse_tables = nullptr;
     unsigned long long* fuse_items = nullptr;
     float4* fuse_item_c = nullptr;
+    unsigned int mc_last_cells = 0, mc_emit_threads = 0;   /* mesher: list length of the last extraction / threads of the speculative emit */
     unsigned int* fuse_item_count = nullptr;      /* [0] items, [1] units */
     unsigned long long* fuse_units = nullptr;
     float2* cert = nullptr;
@@ -893,11 +894,28 @@ tsdf_status tsdf_mesh_extract(tsdf_handle h, float iso_level, int64_t* n_vertice
     P.width = p->cfg.width; P.height = p->cfg.height; P.depth = p->cfg.depth; P.iso = iso_level;
     launch_mesh_count(p->g, P, p->grid, p->mc_count, p->mc_off, p->mc_tmp, p->mc_tmp_bytes, p->mc_cells, p->mc_cell_counter, p->mc_cell_cap, p->stream);
     p->launches += 2;
+    /* The emit is enqueued right behind the sweep, before the host knows the counts: it takes the list length from the
+     * device and stays inside the capacities of this moment.  One synchronisation per extraction; the emit is repeated
+     * (with larger buffers) only when the surface outgrew them. */
+    const unsigned int cell_cap0 = p->mc_cell_cap;
+    const int64_t vtx_cap0 = p->mesh_cap;
+    const bool speculated = p->mesh_xyz != nullptr && vtx_cap0 > 0 && cell_cap0 > 0;
+    if (speculated) {
+        /* threads: the last list length with head room (the surface grows slowly), at most the list capacity */
+        unsigned int nt = p->mc_last_cells ? p->mc_last_cells + p->mc_last_cells / 8 + 4096u : cell_cap0;
+        if (nt > cell_cap0) nt = cell_cap0;
+        p->mc_emit_threads = nt;
+        launch_mesh_emit_list(p->g, P, p->grid, p->mc_cells, p->mc_cell_counter, nt, p->mc_off, p->mesh_xyz, cell_cap0,
+                              (unsigned int)(vtx_cap0 > 0xffffffffll ? 0xffffffffll : vtx_cap0), p->stream);
+        p->launches++;
+    }
     unsigned int total = 0, n_cells = 0;
     CK(cudaMemcpyAsync(&total, p->mc_off + (n_rows - 1), sizeof total, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaMemcpyAsync(&n_cells, p->mc_cell_counter, sizeof n_cells, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    if (total) {
+    p->mc_last_cells = n_cells;
+    const bool emitted = speculated && (int64_t)total <= vtx_cap0 && n_cells <= cell_cap0 && n_cells <= p->mc_emit_threads;
+    if (total && !emitted) {
         if ((int64_t)total > p->mesh_cap) {                          /* grow with head room: the next mesh is usually a bit larger */
             cudaFree(p->mesh_xyz); p->mesh_xyz = nullptr; p->mesh_cap = 0;
             const int64_t cap = (int64_t)total + (int64_t)total / 4 + 1024;
@@ -907,7 +925,8 @@ tsdf_status tsdf_mesh_extract(tsdf_handle h, float iso_level, int64_t* n_vertice
         }
         if (n_cells <= p->mc_cell_cap) {
             /* one sweep: the triangles come from the listed surface cells */
-            launch_mesh_emit_list(p->g, P, p->grid, p->mc_cells, p->mc_cell_counter, n_cells, p->mc_off, p->mesh_xyz, p->stream);
+            launch_mesh_emit_list(p->g, P, p->grid, p->mc_cells, p->mc_cell_counter, n_cells, p->mc_off, p->mesh_xyz, p->mc_cell_cap,
+                                  (unsigned int)(p->mesh_cap > 0xffffffffll ? 0xffffffffll : p->mesh_cap), p->stream);
         } else {
             /* the list overflowed: second sweep over the store this time, a larger list for the next extraction */
             launch_mesh_emit(p->g, P, p->grid, p->mc_off, p->mesh_xyz, p->stream);

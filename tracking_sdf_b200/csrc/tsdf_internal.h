@@ -176,7 +176,7 @@ int mesh_zsplit();
 void launch_mesh_count(const GridParams& g, const McParams& P, const float2* grid, unsigned int* row_count, unsigned int* row_off,
                        void* scan_tmp, size_t scan_bytes, unsigned long long* cells, unsigned int* cell_counter, unsigned int cell_cap, cudaStream_t s);
 void launch_mesh_emit_list(const GridParams& g, const McParams& P, const float2* grid, const unsigned long long* cells, const unsigned int* cell_counter,
-                           unsigned int n_cells, const unsigned int* row_off, float* xyz, cudaStream_t s);
+                           unsigned int n_threads, const unsigned int* row_off, float* xyz, unsigned int cell_cap, unsigned int vtx_cap, cudaStream_t s);
 void launch_mesh_emit(const GridParams& g, const McParams& P, const float2* grid, const unsigned int* row_off, float* xyz, cudaStream_t s);
 void launch_mesh_world(const GridParams& g, const float* xyz, int64_t n, double* world, cudaStream_t s);
 int  fuse_blocks_per_sm();

@@ -134,8 +134,13 @@ __global__ void __launch_bounds__(MC_WARPS * 32) k_mc_sweep(GridParams g, McPara
 /* pass 2 of the one-sweep path: one thread per listed surface cell */
 __global__ void __launch_bounds__(128) k_mc_emit_list(GridParams g, McParams P, const float2* __restrict__ grid, int k_lo_all, int k_hi_all, int nz,
                                                       const unsigned long long* __restrict__ cells, const unsigned int* __restrict__ cell_counter,
-                                                      const unsigned int* __restrict__ row_off, float* __restrict__ xyz) {
-    const unsigned int n = *cell_counter;
+                                                      const unsigned int* __restrict__ row_off, float* __restrict__ xyz,
+                                                      unsigned int cell_cap, unsigned int vtx_cap) {
+    /* launched BEFORE the host knows the counts (no sync between the sweep and the emit): the list length comes from the
+     * device counter, and nothing is read or written beyond the capacities the buffers had at launch — the host checks
+     * the counts afterwards and repeats the emit with larger buffers if either was exceeded */
+    const unsigned int n_all = *cell_counter;
+    const unsigned int n = n_all < cell_cap ? n_all : cell_cap;
     const unsigned int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const unsigned long long c = cells[q];
@@ -152,7 +157,9 @@ __global__ void __launch_bounds__(128) k_mc_emit_list(GridParams g, McParams P, 
     const unsigned long long row = c_mc_tri[ci];
     const int nv = mc_vertex_count(row);
     const float fm = (float)m;
-    float* o = xyz + 3 * (size_t)(row_off[((size_t)i * m + j) * nz + zc] + off);
+    const unsigned int v0 = row_off[((size_t)i * m + j) * nz + zc] + off;
+    if (v0 + (unsigned int)nv > vtx_cap) return;
+    float* o = xyz + 3 * (size_t)v0;
     for (int t = 0; t < nv; t++) {
         float v[3];
         mc_edge_vertex(P, fm, i, j, k, (int)((row >> (4 * t)) & 0xFull), d, v);
@@ -211,11 +218,11 @@ void launch_mesh_emit(const GridParams& g, const McParams& P, const float2* grid
 }
 /* pass 2 of the one-sweep path (n_cells <= the list's capacity) */
 void launch_mesh_emit_list(const GridParams& g, const McParams& P, const float2* grid, const unsigned long long* cells, const unsigned int* cell_counter,
-                           unsigned int n_cells, const unsigned int* row_off, float* xyz, cudaStream_t s) {
+                           unsigned int n_threads, const unsigned int* row_off, float* xyz, unsigned int cell_cap, unsigned int vtx_cap, cudaStream_t s) {
     int k_lo, k_hi;
     mesh_k_range(g, k_lo, k_hi);
-    if (k_hi < k_lo || n_cells == 0) return;
-    k_mc_emit_list<<<(n_cells + 127) / 128, 128, 0, s>>>(g, P, grid, k_lo, k_hi, MC_ZSPLIT, cells, cell_counter, row_off, xyz);
+    if (k_hi < k_lo || n_threads == 0) return;
+    k_mc_emit_list<<<(n_threads + 127) / 128, 128, 0, s>>>(g, P, grid, k_lo, k_hi, MC_ZSPLIT, cells, cell_counter, row_off, xyz, cell_cap, vtx_cap);
 }
 
 }  // namespace tsdf
