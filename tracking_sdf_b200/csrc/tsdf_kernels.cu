@@ -1251,20 +1251,29 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
     const float stx = (float)T[9 * (size_t)m + 4], sty = (float)T[9 * (size_t)m + 5], stz = (float)T[9 * (size_t)m + 6];
     const float neg_delta = -g.delta;
     unsigned int my_updates = 0;
-    /* queue appends are staged per warp in shared memory and flushed 32+ at a time, so the
+    /* queue appends are staged per warp in shared memory and flushed 64 at a time, so the
      * atomicAdd round trip is paid once per several items and is off the per-item critical path */
-    __shared__ unsigned long long s_stage[FUSE_THREADS / 32][96];
+#ifndef CERT_FLUSH_N
+#define CERT_FLUSH_N 64
+#endif
+    /* one atomicAdd on the queue counter per CERT_FLUSH_N entries: the counter is ONE address, and with a flush per 32
+     * entries its ~80 k atomics per frame were a serial resource of their own (32 -> 64 entries: -4 us per frame; 128 and
+     * 256 cost shared memory and shifting and are slower again, measured) */
+    constexpr int FLUSH_N = CERT_FLUSH_N;
+    __shared__ unsigned long long s_stage[FUSE_THREADS / 32][FLUSH_N + 32];
     unsigned long long* stage = s_stage[threadIdx.x >> 5];
     int staged = 0;                                       /* warp-uniform */
     auto flush = [&](int keep_below) {
         while (staged > keep_below) {
-            const int n = staged < 32 ? staged : 32;      /* flush the oldest n entries */
+            const int n = staged < FLUSH_N ? staged : FLUSH_N;      /* flush the oldest n entries */
             unsigned int base = 0;
             if (lane == 0) base = atomicAdd(unit_count, (unsigned int)n);
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (lane < n) units[base + lane] = stage[lane];
+#pragma unroll
+            for (int q0 = 0; q0 < FLUSH_N; q0 += 32)
+                if (q0 + lane < n) units[base + q0 + lane] = stage[q0 + lane];
             __syncwarp();
-            const int rem = staged - n;                   /* warp-uniform: shift the remainder down */
+            const int rem = staged - n;                   /* warp-uniform (< 32 in the loop): shift the remainder down */
             for (int b0 = 0; b0 < rem; b0 += 32) {
                 const int q = b0 + lane;
                 const unsigned long long v = q < rem ? stage[n + q] : 0ull;
@@ -1357,7 +1366,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
                 if (act) stage[staged + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, verdict);
                 __syncwarp();
                 staged += __popc(mask);
-                flush(63);
+                flush(FLUSH_N - 1);
             } else {
                 complete();                                   /* the previous item's free-space units */
                 pend = (verdict == UNIT_FRONT) && !front_queued;
@@ -1372,7 +1381,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
                     if (to_queue) stage[staged + __popc(mask & ((1u << lane) - 1u))] = pack_unit(k, j, x0, verdict);
                     __syncwarp();
                     staged += __popc(mask);
-                    flush(63);
+                    flush(FLUSH_N - 1);
                 }
             }
         }
