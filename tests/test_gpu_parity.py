@@ -101,6 +101,34 @@ def test_linearisation_parity(gpu_lib, frames, K, metric):
     g.close(); o.close()
 
 
+@pytest.mark.parametrize("wh", [(320, 240), (100, 75), (76, 58), (64, 48), (1280, 960)])
+def test_linearisation_parity_other_image_sizes(gpu_lib, wh):
+    """The tracker's work distribution (4 x 4 micro-tiles of the strided pixel grid, three per sweep, one block per SM)
+    on image sizes whose strided grid is not a multiple of 4, has fewer micro-tiles than blocks, or needs more sweeps
+    than the staged slots: per-pixel J / psi / flag bit-equal to the oracle, sums to rounding, one tracked frame."""
+    w, h = wh
+    s = w / 640.0
+    Ks = np.array([525.0 * s, 0.0, (w - 1) / 2.0, 0.0, 525.0 * s, (h - 1) / 2.0, 0.0, 0.0, 1.0])
+    depth, Rs, ts = synth.render_sequence(6, K=Ks, w=w, h=h)
+    kw = dict(m=64, image_width=w, image_height=h, gauss_newton_max_iteration=6, maximum_twist_diff=float("-inf"))
+    o = po.Oracle(use_coord_table=0, **kw); o.set_intrinsics(Ks)
+    g = T.Tsdf(T.default_config(**kw)); g.set_intrinsics(Ks)
+    for f in range(4):
+        o.set_pose(Rs[f], ts[f]); o.fuse(depth[f]); g.fuse(depth[f], Rs[f], ts[f])
+    o.set_pose(Rs[4], ts[4]); g.set_pose(Rs[4], ts[4])
+    Jo, po_, fo = o.linearize_pixels(depth[4]); Jg, pg, fg = g.linearize_pixels(depth[4])
+    assert fo.size == ((w + 2) // 3) * ((h + 2) // 3)
+    assert np.array_equal(fo, fg) and np.array_equal(Jo, Jg) and np.array_equal(po_, pg)
+    A, b, st = o.linearize(depth[4]); Ag, bg, sg = g.linearize(depth[4])
+    assert sg["n_valid"] == st["n_valid"] > 0
+    assert ab_rel(Ag, A) <= 1e-12 and ab_rel(bg, b) <= 1e-12
+    st = o.track(depth[5]); Rg, tg, sg = g.track(depth[5])
+    Ro, to = o.get_pose()
+    assert sg["iterations"] == st["iterations"] == 6 and sg["n_valid"] == st["n_valid"]
+    assert np.abs(tg - to).max() < 1e-9 and np.abs(Rg - Ro).max() < 1e-9
+    g.close(); o.close()
+
+
 @pytest.mark.parametrize("fixed", [True, False])
 def test_tracking_parity(gpu_lib, frames, K, fixed):
     depth, Rs, ts = frames
