@@ -7,7 +7,8 @@
  *   K3 k_fuse       per-voxel TSDF integration, scan-line clipped     (sdf.cpp:224-292)
  *
  * Neither path is a dense contraction, so tensor cores are not used (BASELINE.json
- * north_star); K3 is HBM/fp64-issue bound, K2 is L1/L2-gather-latency bound.
+ * north_star); K3 is HBM bound where voxels are updated in bulk and issue bound on the trajectory workload,
+ * K2 is bound by instruction issue and dependent latency plus a serial reduce/solve tail.
  * Compiled with -fmad=false: see tsdf_core.cuh.
  */
 #include <stdlib.h>
@@ -475,9 +476,9 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     };
     /* Work distribution.  The strided pixel grid is cut into 4 x 4 micro-tiles (16 pixels = 8 warps' worth), numbered
      * column by column; a sweep of the block processes PX_SWEEP pixels = MT_SWEEP micro-tiles.
-     *   default     each block owns a LIN_TW x LIN_TH tile (columns x rows): its samples touch a compact piece of the
+     *   LIN_TILES   each block owns a LIN_TW x LIN_TH tile (columns x rows): its samples touch a compact piece of the
      *               volume and share voxel lines in L1.
-     *   LIN_MICRO   the grid is ONE block per SM slot, so the number of blocks (= partial sums to reduce) no longer
+     *   default     (LIN_MICRO) the grid is ONE block per SM slot, so the number of blocks (= partial sums to reduce) no longer
      *               depends on the image size; a sweep takes MT_SWEEP adjacent micro-tiles, sweeps are spread.
      *   sharded     a rank linearises only the pixels whose centre cell it owns — a compact region of the image — and
      *               with one compact tile per block the launch would last as long as its slowest (fully owned) tile.
