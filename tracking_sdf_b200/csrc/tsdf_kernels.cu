@@ -1233,7 +1233,7 @@ __device__ __forceinline__ unsigned long long pack_unit(int k, int j, int x0, in
  * loads of a certified unit are issued right after its verdict and completed after the NEXT item's
  * certificate arithmetic, so HBM latency is hidden and nothing is loaded for skipped or queued units. */
 template <int CHECK>
-__global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(GridParams g, CertPyramid P, float2* __restrict__ grid,
+__global__ void __launch_bounds__(CERT_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(GridParams g, CertPyramid P, float2* __restrict__ grid,
                                                                const float2* __restrict__ cert, const double* T,
                                                                const unsigned long long* items, const float4* item_c,
                                                                const unsigned int* item_count,
@@ -1242,8 +1242,8 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
     pdl_wait();
     pdl_release();
     const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * (FUSE_THREADS / 32) + (threadIdx.x >> 5);
-    const int total_warps = gridDim.x * (FUSE_THREADS / 32);
+    const int gw = blockIdx.x * (CERT_THREADS / 32) + (threadIdx.x >> 5);
+    const int total_warps = gridDim.x * (CERT_THREADS / 32);
     const int m = g.m;
     const unsigned int um = (unsigned int)m;
     const unsigned int n_items = *item_count;
@@ -1261,7 +1261,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, CERT_MIN_BLOCKS) k_fuse_cert(Gri
      * entries its ~80 k atomics per frame were a serial resource of their own (32 -> 64 entries: -4 us per frame; 128 and
      * 256 cost shared memory and shifting and are slower again, measured) */
     constexpr int FLUSH_N = CERT_FLUSH_N;
-    __shared__ unsigned long long s_stage[FUSE_THREADS / 32][FLUSH_N + 32];
+    __shared__ unsigned long long s_stage[CERT_THREADS / 32][FLUSH_N + 32];
     unsigned long long* stage = s_stage[threadIdx.x >> 5];
     int staged = 0;                                       /* warp-uniform */
     auto flush = [&](int keep_below) {
@@ -1487,12 +1487,12 @@ int launch_fuse(const FuseArgs& f, cudaStream_t s) {
         return 3;
     }
     if (f.check) {
-        launch_pdl(k_fuse_cert<1>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_c, f.item_count, f.units, f.unit_count, f.n_updated, 0);
+        launch_pdl(k_fuse_cert<1>, dim3(f.nblk_cert), dim3(CERT_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_c, f.item_count, f.units, f.unit_count, f.n_updated, 0);
         if (g.metric == 0) launch_pdl(k_fuse_exact<0, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn, f.items, f.item_count);
         else launch_pdl(k_fuse_exact<1, 1>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn, f.items, f.item_count);
         return 4;
     }
-    launch_pdl(k_fuse_cert<0>, dim3(f.nblk_cert), dim3(FUSE_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_c, f.item_count, f.units, f.unit_count, f.n_updated, color ? 1 : 0);
+    launch_pdl(k_fuse_cert<0>, dim3(f.nblk_cert), dim3(CERT_THREADS), s, g, f.pyr, f.grid, f.cert, f.tables, f.items, f.item_c, f.item_count, f.units, f.unit_count, f.n_updated, color ? 1 : 0);
     if (color) launch_pdl(k_fuse_exact<0, 0, true>, dim3(f.nblk_color), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn, f.items, f.item_count);
     else if (g.metric == 0) launch_pdl(k_fuse_exact<0, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn, f.items, f.item_count);
     else launch_pdl(k_fuse_exact<1, 0>, dim3(f.nblk), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.units, f.unit_count, f.n_updated, f.color, f.rgb4, f.cosn, f.items, f.item_count);
@@ -1512,7 +1512,7 @@ int fuse_blocks_per_sm() {
 }
 int fuse_cert_blocks_per_sm() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fuse_cert<0>, FUSE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fuse_cert<0>, CERT_THREADS, 0);
     return n;
 }
 
