@@ -863,7 +863,10 @@ __device__ __forceinline__ unsigned long long pack_item(int k, int j, int xs, in
            ((unsigned long long)ilo << 36) | ((unsigned long long)ihi << 48);
 }
 
-__global__ void __launch_bounds__(256) k_fuse_plan(GridParams g, CertPyramid P, const float2* __restrict__ cert, int check,
+#ifndef PLAN_THREADS
+#define PLAN_THREADS 256
+#endif
+__global__ void __launch_bounds__(PLAN_THREADS) k_fuse_plan(GridParams g, CertPyramid P, const float2* __restrict__ cert, int check,
                                                    const PoseState* pose,      /* written by the PDL predecessor: no __restrict__/nc */
                                                    const double* T, unsigned long long* __restrict__ items,
                                                    float4* __restrict__ item_c, unsigned int* item_count) {
@@ -1478,7 +1481,7 @@ int launch_fuse(const FuseArgs& f, cudaStream_t s) {
     const GridParams& g = f.g;
     launch_pdl(k_fuse_tables, dim3((g.m + 127) / 128), dim3(128), s, g, f.pose, f.tables, f.n_updated, f.item_count, f.unit_count);
     const int nrows = (g.ks1 - g.ks0) * g.m;
-    launch_pdl(k_fuse_plan, dim3((nrows + 255) / 256), dim3(256), s, g, f.pyr, f.cert, f.check, f.pose, f.tables, f.items, f.item_c, f.item_count);
+    launch_pdl(k_fuse_plan, dim3((nrows + PLAN_THREADS - 1) / PLAN_THREADS), dim3(PLAN_THREADS), s, g, f.pyr, f.cert, f.check, f.pose, f.tables, f.items, f.item_c, f.item_count);
     const bool color = f.color != nullptr;      /* plane metric only (checked by the caller) */
     if (!g.k_simple) {          /* skewed intrinsics: the exact path for every in-view voxel */
         if (color) launch_pdl(k_fuse_items<0, 0, true>, dim3(f.nblk_color), dim3(FUSE_THREADS), s, g, f.grid, f.pix, f.tables, f.items, f.item_count, f.n_updated, f.color, f.rgb4, f.cosn);
