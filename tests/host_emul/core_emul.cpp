@@ -563,4 +563,17 @@ void emul_exp_map(const double twist[6], double R[9], double t[3]) { exp_map(twi
 double emul_weight_exp(double x) { return weight_exp(x); }
 int emul_trunc_f2i(float v) { return trunc_f2i(v); }
 
+/* k_linearize's work distribution (tsdf_core.cuh: lin_layout / lin_pixel_of), walked exactly as the kernel's blocks do:
+ * count[ii * nj + jj] += 1 for every (block, sweep, slot) that yields a pixel.  Returns the number of sweeps. */
+int emul_lin_coverage(int ni, int nj, int nblocks, int mt_sweep, int sharded, int32_t* count) {
+    const LinLayout L = lin_layout(ni, nj, nblocks, mt_sweep);
+    for (int b = 0; b < nblocks; b++)
+        for (int q = 0; q < L.n_sweeps; q++)
+            for (int tl = 0; tl < 16 * mt_sweep; tl++) {
+                int ii, jj;
+                if (lin_pixel_of(L, ni, nj, nblocks, b, mt_sweep, sharded != 0, q, tl, ii, jj)) count[ii * nj + jj]++;
+            }
+    return L.n_sweeps;
+}
+
 }  // extern "C"

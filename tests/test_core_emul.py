@@ -199,3 +199,22 @@ def test_color_fusion_sampling_and_mesh_core_bit_exact(frames, K, m):
         assert np.array_equal(o.mesh(iso)[0], e.mesh(iso))
     assert len(e.mesh(0.0)) > 500 and len(e.mesh(1.0)) == 0
     o.close()
+
+
+@pytest.mark.parametrize("sharded", [0, 1])
+def test_tracker_work_distribution_covers_every_pixel_once(sharded):
+    """tsdf_core.cuh: lin_layout / lin_pixel_of (the code k_linearize's blocks run): for any image size, block count and
+    block size, every strided pixel is visited by exactly one (block, sweep, slot)."""
+    import ctypes
+    L = emul.lib()
+    L.emul_lin_coverage.restype = ctypes.c_int
+    for w, h in [(640, 480), (320, 240), (1280, 960), (100, 75), (76, 58), (64, 48), (37, 29), (3, 3), (1, 1), (641, 479)]:
+        ni, nj = (w + 2) // 3, (h + 2) // 3
+        for nblocks in (1, 7, 24, 148, 444, 1000):
+            for mt_sweep in (1, 2, 3, 4):
+                count = np.zeros(ni * nj, np.int32)
+                n_sweeps = L.emul_lin_coverage(ni, nj, nblocks, mt_sweep, sharded, count.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+                assert (count == 1).all(), (w, h, nblocks, mt_sweep, sharded, int(count.min()), int(count.max()))
+                # no more sweeps than the work needs (rounded up to whole sweeps of whole micro-tiles)
+                n_micro = ((ni + 3) // 4) * ((nj + 3) // 4)
+                assert n_sweeps == -(-(-(-n_micro // nblocks)) // mt_sweep)

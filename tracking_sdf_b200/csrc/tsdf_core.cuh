@@ -763,6 +763,30 @@ TSDF_HD void perturbed_rot(const GridParams& g, const double* rot, int q, double
     matmul3(Rd, rot, out);
 }
 
+/* ---- k_linearize's work distribution (tsdf_kernels.cu: "Work distribution"): the strided pixel grid (ni columns x nj
+ * rows) is cut into 4 x 4 micro-tiles numbered column by column; a sweep of a block covers mt_sweep micro-tiles, one
+ * pixel per thread pair.  lin_layout: the numbers every block derives from the launch; lin_pixel_of: strided pixel
+ * (ii, jj) of slot tl (0 .. 16 * mt_sweep - 1) in sweep q of block b, false when the slot is empty.
+ *   unsharded: sweep q of block b = the mt_sweep ADJACENT micro-tiles (q * nblocks + b) * mt_sweep ...
+ *   sharded:   slot sl of block b = micro-tile b + sl * nblocks (spread: a rank owns a compact image region)
+ * Shared with the host build (tests/host_emul): every pixel must be covered exactly once for any image size. */
+struct LinLayout { int mty, n_micro, n_slots, n_sweeps; };
+TSDF_HD LinLayout lin_layout(int ni, int nj, int nblocks, int mt_sweep) {
+    LinLayout L;
+    L.mty = (nj + 3) >> 2;
+    L.n_micro = ((ni + 3) >> 2) * L.mty;
+    L.n_slots = (L.n_micro + nblocks - 1) / nblocks;                         /* micro-tiles per block */
+    L.n_sweeps = mt_sweep > 0 ? (L.n_slots + mt_sweep - 1) / mt_sweep : 0;
+    return L;
+}
+TSDF_HD bool lin_pixel_of(const LinLayout& L, int ni, int nj, int nblocks, int b, int mt_sweep, bool sharded, int q, int tl, int& ii, int& jj) {
+    const int sl = q * mt_sweep + (tl >> 4);
+    const int mt = sharded ? b + sl * nblocks : (q * nblocks + b) * mt_sweep + (tl >> 4);
+    const int mx = mt / L.mty, my = mt - mx * L.mty;
+    ii = (mx << 2) + ((tl & 15) >> 2); jj = (my << 2) + (tl & 3);
+    return (sharded ? sl < L.n_slots : true) & (mt < L.n_micro) & (ii < ni) & (jj < nj);
+}
+
 /* slot layout of the reduced normal equations */
 enum { SLOT_A = 0, SLOT_B = 21, SLOT_RES = 27, SLOT_NVALID = 28, SLOT_NOOB = 29, N_SLOTS = 30, SLOT_MISS = 30 /* local, not exchanged */ };
 

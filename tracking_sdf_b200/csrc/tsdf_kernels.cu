@@ -498,22 +498,11 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MIN_BLOCKS) k_linearize(Linea
     __shared__ float4 sPts[STAGED];
     const int tiles_y = (g.nj + LIN_TH - 1) / LIN_TH;
     const int tile_x = blockIdx.x / tiles_y, tile_y = blockIdx.x - tile_x * tiles_y;
-    const int mty = (g.nj + 3) >> 2, n_micro = ((g.ni + 3) >> 2) * mty;
-    const int n_slots = (n_micro + (int)gridDim.x - 1) / (int)gridDim.x;     /* micro-tiles per block (MICRO, sharded) */
-    const int n_sweeps = (sharded || MICRO) ? (MT_SWEEP > 0 ? (n_slots + MT_SWEEP - 1) / (MT_SWEEP > 0 ? MT_SWEEP : 1) : 0)
-                                            : (LIN_TW * LIN_TH + PX_SWEEP - 1) / PX_SWEEP;
+    const LinLayout LL = lin_layout(g.ni, g.nj, (int)gridDim.x, MT_SWEEP);
+    const int n_sweeps = (sharded || MICRO) ? LL.n_sweeps : (LIN_TW * LIN_TH + PX_SWEEP - 1) / PX_SWEEP;
     /* pixel tl of sweep q -> strided pixel (ii, jj); false when the slot is empty */
     auto pixel_of = [&](int q, int tl, int& ii, int& jj) -> bool {
-        if (sharded || MICRO) {
-            /* sharded: slot sl of block b = micro-tile b + sl * gridDim.x;  unsharded: sweep q of block b = the MT_SWEEP
-             * adjacent micro-tiles (q * gridDim.x + b) * MT_SWEEP ... (one compact strip per sweep, sweeps spread over the
-             * image: slow regions — samples leaving the volume take the per-voxel path — do not pile up in a few blocks) */
-            const int sl = q * MT_SWEEP + (tl >> 4);
-            const int mt = sharded ? (int)blockIdx.x + sl * (int)gridDim.x : (q * (int)gridDim.x + (int)blockIdx.x) * MT_SWEEP + (tl >> 4);
-            const int mx = mt / mty, my = mt - mx * mty;
-            ii = (mx << 2) + ((tl & 15) >> 2); jj = (my << 2) + (tl & 3);
-            return (sharded ? sl < n_slots : true) & (mt < n_micro) & (ii < g.ni) & (jj < g.nj);
-        }
+        if (sharded || MICRO) return lin_pixel_of(LL, g.ni, g.nj, (int)gridDim.x, (int)blockIdx.x, MT_SWEEP, sharded, q, tl, ii, jj);
         const int t = q * PX_SWEEP + tl;
         ii = tile_x * LIN_TW + t / LIN_TH; jj = tile_y * LIN_TH + t % LIN_TH;
         return (t < LIN_TW * LIN_TH) & (ii < g.ni) & (jj < g.nj);
